@@ -1,0 +1,189 @@
+/*
+ * tib.h - C ABI of libtib.so, the B200-native (sm_100a) sampling hot path of
+ * olsson-group/thermodynamic-interpolation.
+ *
+ * The reference has no FFI of its own: its seams are three Python call signatures
+ * (SURVEY.md section 8b).  Each entry point below names the reference interface it sits under
+ * (paths relative to the reference repo).  All pointers are plain device or host pointers; no
+ * torch types cross this boundary.  Conventions:
+ *   - the caller owns every buffer; the library keeps nothing past a call except the
+ *     tib_model handle (repacked weights) created by tib_model_create;
+ *   - every call is asynchronous on the given CUDA stream (`stream` is a cudaStream_t passed
+ *     as void*), except where stated (dopri5 reads one scalar back per attempted step,
+ *     exactly like torchdiffeq's accept/reject);
+ *   - return value 0 = ok, negative = error; the message is in tib_last_error() (thread local);
+ *   - a handle is bound to one device and is not thread-safe.
+ */
+#ifndef TIB_H_
+#define TIB_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TIB_ABI_VERSION 1
+
+/* ---- model ------------------------------------------------------------------------------- */
+
+enum { TIB_VARIANT_AMBIENT = 0,       /* T0 and T1 encoders   (mdqm9/thermo/ambient/models/cpainn.py:67-90) */
+       TIB_VARIANT_LATENT_MULTI_T = 1,/* one encoder on T     (mdqm9/thermo/latent/models/cpainn.py:43-58)  */
+       TIB_VARIANT_LATENT_SINGLE_T = 2/* no temperature input (mdqm9/thermo/latent/models/cpainn.py:59-72)  */ };
+
+/* GEMM arithmetic of the MLP / equivariant-linear layers. */
+enum { TIB_MATH_FP32_SIMT = 0,        /* fp32 FMA on CUDA cores: the bit-faithful reference mode            */
+       TIB_MATH_BF16X3_TC = 1,        /* tcgen05, operands split hi+lo bf16, 3 MMAs, fp32 accumulate (~2^-16) */
+       TIB_MATH_BF16_TC = 2           /* tcgen05, single bf16 pass, fp32 accumulate (~2^-8): opt-in only     */ };
+
+typedef struct tib_model tib_model;
+
+/* Constructor arguments of cPaiNN (ambient cpainn.py:23-32, latent cpainn.py:22-31) plus the
+ * constants its sub-modules hard-code (PaiNNBase length_scale=10, cpainn.py:127; edge-type
+ * vocabulary 4, cpainn.py:70; TemperatureEncoder mean/range, embedding.py:208-209). */
+typedef struct {
+  int32_t abi_version;     /* = TIB_ABI_VERSION */
+  int32_t variant;         /* TIB_VARIANT_* */
+  int32_t n_features;      /* F: 32, 64, 128 or 256 */
+  int32_t n_layers;        /* score_layers L */
+  int32_t n_types;         /* atom-id vocabulary (25) */
+  int32_t n_edge_types;    /* 4 */
+  float   temp_length;     /* PositionalEncoder max_length for temperatures */
+  float   time_length;     /* ... for t */
+  float   length_scale;    /* ... for edge distances */
+  float   temp_mean;       /* mean(temperatures)          = 650 */
+  float   temp_range;      /* max - min of temperatures   = 700 */
+} tib_model_desc;
+
+/* Number of floats tib_model_create expects in `packed_weights` for this descriptor.
+ * Packing order ([out,in] row-major, exactly the reference's state_dict tensors):
+ *   edge_emb[n_edge_types,F], atom_emb[n_types,F], MLP(combine: (2+n_temp)F -> F -> F),
+ *   per layer: MLP(phi: 2F->F->5F), MLP(w: F->F->5F), U[F,F], V[F,F], MLP(update: 2F->F->3F),
+ *   MLP(readout: F->F->2), Vout[1,F]
+ * where MLP(in->h->out) = W1[h,in] b1[h] ln1_w[h] ln1_b[h] W2[h,h] b2[h] ln2_w[h] ln2_b[h] W3[out,h] b3[out]
+ * (embedding.py:26-34). */
+size_t tib_packed_weight_count(const tib_model_desc* desc);
+
+/* Replaces cPaiNN(...).load_state_dict(sd).to(device)  (mdqm9/sample_ambient.py:125-131,72).
+ * `packed_weights` is a HOST pointer; the weights are copied to `device` and repacked once. */
+int  tib_model_create(tib_model** out, const tib_model_desc* desc, const float* packed_weights,
+                      size_t n_floats, int device);
+void tib_model_destroy(tib_model* m);
+int  tib_model_set_math(tib_model* m, int math_mode);     /* TIB_MATH_*; default FP32_SIMT */
+
+/* ---- batch ------------------------------------------------------------------------------- */
+
+/* The batch contract of MDQM9SamplerDataset.process + PyG collate
+ * (mdqm9/data/mdqm9_ambient.py:160-170; latent mdqm9/data/mdqm9_latent.py:188-205), reduced to
+ * what the drift reads.  The graph must be the complete digraph per molecule with edges in
+ * (src,dst)-lexicographic order (what `coalesce` produces, mdqm9/thermo/utils.py:74-78); edge row
+ * of (i -> j) in molecule m is  edge_ptr[m] + i*(n_m-1) + j - (j>i).  All pointers are DEVICE pointers. */
+typedef struct {
+  int32_t        n_mol;
+  int32_t        n_nodes;      /* N = sum n_m */
+  int64_t        n_edges;      /* E = sum n_m (n_m - 1) */
+  int32_t        max_atoms;    /* max n_m (<= 64) */
+  const int32_t* mol_ptr;      /* [n_mol+1] node offsets  (batch.ptr) */
+  const int64_t* edge_ptr;     /* [n_mol+1] edge-row offsets */
+  const int32_t* atom_id;      /* [N]  batch.atoms / batch.atom_number */
+  const uint8_t* edge_type;    /* [E]  batch.edge_type in {0..3} */
+  const float*   temp0;        /* [N]  batch.T0 (ambient) or batch.T (latent multi-T); may be NULL for single-T */
+  const float*   temp1;        /* [N]  batch.T1 (ambient); NULL otherwise */
+} tib_batch;
+
+/* Scratch the caller must provide to tib_drift / tib_rollout_* for this batch shape. */
+size_t tib_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges);
+
+/* ---- the drift: cPaiNN.forward via ODEWrapper.forward --------------------------------------
+ * Replaces  ODEWrapper(b).forward(t, x, batch)  with return_dlogp=False
+ * (mdqm9/thermo/ambient/models/ode_wrapper.py:51-57 -> cpainn.py:93-115).
+ *   x [N,3] fp32 (device), t scalar, out_b [N,3] fp32 (device). */
+int tib_drift(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b,
+              void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- K1: fused integrator state updates ---------------------------------------------------
+ * One explicit Euler / Euler-Maruyama update over a flat state of n floats:
+ *     x_out = x + dt*b                       [+ dt*eps*score] [+ sqrt(2*eps*dt)*noise]
+ * with the product and the sum rounded separately (torchdiffeq fixed-grid `y0 + dt*f0`,
+ * solvers.py FixedGridODESolver.integrate / Euler._step_func).  `score`, `noise` may be NULL
+ * (then the result is bit-identical to the Euler path); `frame` (may be NULL) receives a copy of
+ * x_out - the saved trajectory frame.  x_out may alias x. */
+int tib_step_euler(const float* x, const float* b, const float* score, const float* noise,
+                   float dt, float eps, float* x_out, float* frame, size_t n, void* stream);
+
+/* ---- rollouts: MoleculeIntegrator.rollout ------------------------------------------------- */
+
+enum { TIB_METHOD_EULER = 0, TIB_METHOD_MIDPOINT = 1, TIB_METHOD_RK4 = 2 };
+
+typedef struct {
+  int32_t      method;        /* TIB_METHOD_* (torchdiffeq fixed-grid solvers) */
+  int32_t      n_times;       /* T = len(t_grid) = n_step */
+  const float* t_grid;        /* HOST [T], torch.linspace(start,end,n_step) in fp32 */
+  int32_t      save_frames;   /* 1: out_xts is [T,N,3]; 0: out_xts is [N,3] (final state only) */
+  float        eps;           /* Euler-Maruyama diffusion (0 = ODE); EULER only */
+  const float* noise;         /* DEVICE [T-1,N,3] pre-drawn N(0,1), or NULL */
+  tib_model*   score_model;   /* second network standing in for the score, or NULL (extension; no reference oracle) */
+} tib_fixed_opts;
+
+/* Replaces MoleculeIntegrator(b, method in {'euler','midpoint','rk4'}, n_step).rollout(batch)
+ * with return_dlogp=False (mdqm9/thermo/ambient/integrators.py:28-33,55-68).  No host sync. */
+int tib_rollout_fixed(tib_model* m, const tib_batch* b, const float* x0, const tib_fixed_opts* o,
+                      float* out_xts, void* workspace, size_t workspace_bytes, void* stream);
+
+typedef struct {
+  double       rtol, atol;
+  int32_t      n_times;       /* T */
+  const float* t_grid;        /* HOST [T] fp32, increasing */
+  int32_t      save_frames;   /* 1: out_xts [T,N,3]; 0: [N,3] final state */
+  int32_t      max_attempts;  /* safety bound on attempted steps (0 = 100000) */
+  /* Optional hook run after the local error sums are on the host: all-reduce {sum_sq, count} so
+   * that shards share one step sequence (torchdiffeq's RMS norm is over the whole batch).
+   * NULL = local norm. */
+  void       (*norm_allreduce)(double* sum_sq_and_count /*[2]*/, void* user);
+  void*        norm_user;
+} tib_dopri5_opts;
+
+typedef struct { int32_t nfe, attempts, accepted; double last_dt; } tib_dopri5_stats;
+
+/* Replaces MoleculeIntegrator(b, 'dopri5', n_step, atol, rtol).rollout(batch), return_dlogp=False
+ * (mdqm9/thermo/ambient/integrators.py:55-68 -> torchdiffeq 0.2.5 dopri5).  Synchronises the stream
+ * once per attempted step to read the error ratio (as torchdiffeq does). */
+int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const tib_dopri5_opts* o,
+                       float* out_xts, tib_dopri5_stats* stats,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- reweighting statistics ---------------------------------------------------------------
+ * Partial sums behind calc_ti_weights / calc_ESS / calc_tfep_dF
+ * (mdqm9/analysis/utils/ess.py:8-10,32-35; free_energy.py:41-46):
+ *   phi_i = E1_i - E0_i + neg_dlogp_i ; w_i = exp(-phi_i)
+ *   out[0] = sum w, out[1] = sum w^2, out[2] = sum exp(-phi)*weight_i (weight = 1 if NULL),
+ *   out[3] = sum weight_i, out[4] = n.    All device pointers; out is DEVICE double[5].
+ * These are the quantities all-reduced across ranks. */
+int tib_reweight_stats(const double* E0, const double* E1, const double* neg_dlogp, const double* weight,
+                       size_t n, double* out, void* stream);
+
+/* ---- ADW: FCNetMultiBeta drift + exact 1-D divergence ---------------------------------------
+ * Replaces ODEWrapper(b, return_dlogp=True).forward for the 1-D double well
+ * (adw/thermo/models/ode_wrapper.py:38-47,55-67; adw/thermo/models/simple.py:38-41).
+ * fp64 weights, packed host array: beta_embed (3->H->H->1) then net (3->H x num_layers ->1), each layer W[out,in], b[out]. */
+typedef struct tib_adw_model tib_adw_model;
+int  tib_adw_create(tib_adw_model** out, int32_t hidden, int32_t num_layers, const double* packed_weights,
+                    size_t n_doubles, int device);
+void tib_adw_destroy(tib_adw_model* m);
+/* x [B] fp64 (the fp32 state widened; torchdiffeq's fixed-grid solvers let the state drift to fp64 with an
+ * fp64 model), beta0/beta1 [B] fp64, t scalar (fp32 value) -> b [B] fp64 and div [B] fp64 (= d b/d x,
+ * unscaled; may be NULL). */
+int  tib_adw_drift_div(tib_adw_model* m, const double* x, const double* beta0, const double* beta1, float t,
+                       double* out_b, double* out_div, size_t n, void* stream);
+
+/* ---- misc -------------------------------------------------------------------------------- */
+const char* tib_last_error(void);
+int         tib_abi_version(void);
+/* Number of kernel launches issued by this library on the calling thread since the last reset. */
+uint64_t    tib_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TIB_H_ */

@@ -1,0 +1,200 @@
+"""TEST INFRASTRUCTURE ONLY (oracle/).  Generates tests/golden/*.npz by running the UNMODIFIED
+reference modules from /root/reference (imported through oracle/stubs) on seeded synthetic inputs.
+Runs in the build container only; the committed .npz files are what travels to the GPU box.
+
+    python -m oracle.make_golden            # regenerate every fixture
+
+Weights: small models are stored in the fixture; large ones are regenerated from
+(torch.manual_seed(seed); construct; tests._util.perturb_(model, seed+1, 0.05)) and pinned by a
+sha256 of the state_dict.  The product's parameter holders reproduce the reference's construction
+order, so the same recipe yields the same weights without the reference (asserted here).
+"""
+from __future__ import annotations
+
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(HERE)
+sys.path.insert(0, REPO)
+
+from oracle import ref_loader  # noqa: E402
+from tests._util import perturb_, state_sha  # noqa: E402
+from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch, synthetic_latent_batch  # noqa: E402
+
+GOLDEN = os.path.join(REPO, "tests", "golden")
+PERTURB = 0.05
+
+
+def to_ref_batch(tg, mb):
+    b = tg.data.Batch()
+    for k in mb.keys():
+        b[k] = mb[k].clone() if torch.is_tensor(mb[k]) else mb[k]
+    return b
+
+
+def check_graph_contract(ns, n_atoms):
+    """The reference's own AddRadiusGraph + AddBondGraph + Coalesce on one molecule must give the
+    edge_index / edge_type the synthetic builder emits (mdqm9/data/mdqm9_ambient.py:160-170)."""
+    tg = ns.torch_geometric
+    mb = synthetic_ambient_batch(1, n_atoms, seed=3)
+    n = n_atoms
+    a = torch.arange(n - 1)
+    bond_index = torch.stack([torch.cat([a, a + 1]), torch.cat([a + 1, a])])
+    orders = torch.tensor([(1, 2, 1, 3)[i % 4] for i in range(n - 1)])
+    d = tg.data.Data(x=mb.x0, x0=mb.x0, atoms=torch.arange(n), bond_index=bond_index, bonds=torch.cat([orders, orders]))
+    b = tg.data.Batch.from_data_list([d])
+    b = ns.utils.Coalesce()(ns.utils.AddBondGraph()(ns.utils.AddRadiusGraph(cutoff=1000)(b)))
+    assert torch.equal(b.edge_index, mb.edge_index) and torch.equal(b.edge_type, mb.edge_type), "batch contract drifted"
+
+
+def make_model(ref_cls, seed, **kw):
+    torch.manual_seed(seed)
+    m = ref_cls(**kw)
+    perturb_(m, seed + 1, PERTURB)
+    return m.eval()
+
+
+def sd_arrays(sd):
+    return {"w::" + k: v.detach().numpy() for k, v in sd.items()}
+
+
+def ambient_case(ns, name, F, L, n_mol, n_atoms, seed, store_weights, n_frames=11, with_dopri=True, with_div=False):
+    tg = ns.torch_geometric
+    kw = dict(n_features=F, score_layers=L, temp_length=100)
+    model = make_model(ns.ambient_cpainn.cPaiNN, seed, **kw)
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN as Mine
+    mine = make_model(Mine, seed, **kw)
+    assert state_sha(mine.state_dict()) == state_sha(model.state_dict()), "seeded weight recipe diverged"
+    mb = synthetic_ambient_batch(n_mol, n_atoms, seed=seed + 10)
+    out = dict(kind="ambient", F=F, L=L, temp_length=100, seed=seed, perturb=PERTURB, n_mol=n_mol,
+               n_atoms=np.array([n_atoms] * n_mol if isinstance(n_atoms, int) else n_atoms), batch_seed=seed + 10,
+               sha=state_sha(model.state_dict()))
+    for k in ("x0", "T0", "T1", "atoms", "edge_index", "edge_type", "batch", "ptr"):
+        out["in::" + k] = mb[k].numpy()
+    wrap = ns.ambient_ode_wrapper.ODEWrapper(model)
+    ts = [0.0, 0.37, 1.0]
+    with torch.no_grad():
+        drifts = [wrap(torch.tensor(t), mb.x0.clone(), to_ref_batch(tg, mb), [0]).numpy() for t in ts]
+    out["drift_t"] = np.array(ts, dtype=np.float32)
+    out["drift"] = np.stack(drifts)
+    integ = ns.ambient_integrators.MoleculeIntegrator(model, method="euler", n_step=n_frames)
+    xts, dlogp, nfe, bvec = integ.rollout(to_ref_batch(tg, mb))
+    out["euler_xts"] = xts.numpy()
+    out["euler_nfe"] = nfe
+    if with_dopri:
+        integ = ns.ambient_integrators.MoleculeIntegrator(model, method="dopri5", n_step=6, atol=1e-5, rtol=1e-5)
+        xts, dlogp, nfe, _ = integ.rollout(to_ref_batch(tg, mb))
+        out["dopri5_xts"] = xts.numpy()
+        out["dopri5_nfe"] = nfe
+        for meth in ("midpoint", "rk4"):
+            integ = ns.ambient_integrators.MoleculeIntegrator(model, method=meth, n_step=5)
+            out[f"{meth}_xts"] = integ.rollout(to_ref_batch(tg, mb))[0].numpy()
+    if with_div:
+        wrapd = ns.ambient_ode_wrapper.ODEWrapper(model, return_dlogp=True)
+        b_, negdiv = wrapd(torch.tensor(0.37), (mb.x0.clone(), torch.zeros(n_mol)), to_ref_batch(tg, mb), [0])
+        out["div_t037_scaled"] = (-negdiv).detach().numpy()     # divergence * 1e-2
+        integ = ns.ambient_integrators.MoleculeIntegrator(model, method="euler", n_step=3, return_dlogp=True)
+        xts, dlogp, nfe, _ = integ.rollout(to_ref_batch(tg, mb))
+        out["euler_dlogp_xts"] = xts.detach().numpy()
+        out["euler_dlogp"] = dlogp.detach().numpy()
+    if store_weights:
+        out.update(sd_arrays(model.state_dict()))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "drift |mean|", float(np.abs(out["drift"]).mean()), "bytes", os.path.getsize(os.path.join(GOLDEN, name + ".npz")))
+
+
+def latent_case(ns, name, F, L, n_list, seed, temperatures, temp_length=75):
+    tg = ns.torch_geometric
+    kw = dict(n_features=F, score_layers=L, temp_length=temp_length, temperatures=temperatures)
+    model = make_model(ns.latent_cpainn.cPaiNN, seed, **kw)
+    from thermodynamic_interpolation_b200.latent.models.cpainn import cPaiNN as Mine
+    mine = make_model(Mine, seed, **kw)
+    assert state_sha(mine.state_dict()) == state_sha(model.state_dict())
+    multi = len(temperatures) > 1
+    mb = synthetic_latent_batch(len(n_list), n_list, T=800 if multi else None, seed=seed + 10)
+    out = dict(kind="latent", F=F, L=L, temp_length=temp_length, seed=seed, perturb=PERTURB,
+               temperatures=np.array(temperatures), n_atoms=np.array(n_list), batch_seed=seed + 10,
+               sha=state_sha(model.state_dict()))
+    for k in mb.keys():
+        out["in::" + k] = mb[k].numpy()
+    wrap = ns.latent_ode_wrapper.ODEWrapper(model)
+    ts = [0.0, 0.5, 1.0]
+    with torch.no_grad():
+        out["drift"] = np.stack([wrap(torch.tensor(t), mb.x0.clone(), to_ref_batch(tg, mb)).numpy() for t in ts])
+    out["drift_t"] = np.array(ts, dtype=np.float32)
+    if len(set(n_list)) == 1:   # the reference rollout needs equal sizes (latent/integrators.py:51)
+        integ = ns.latent_integrators.MoleculeIntegrator(model, method="euler", n_step=9)
+        xts, dlogp, bvec = integ.rollout(to_ref_batch(tg, mb))
+        out["euler_xts"] = xts.numpy()
+    out.update(sd_arrays(model.state_dict()))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "drift |mean|", float(np.abs(out["drift"]).mean()), "bytes", os.path.getsize(os.path.join(GOLDEN, name + ".npz")))
+
+
+def adw_case(name="adw"):
+    ns = ref_loader.load_adw()
+    torch.manual_seed(5)
+    model = ns.simple.FCNetMultiBeta(1, 1, 256, 5).double()
+    perturb_(model, 6, 0.02)
+    from thermodynamic_interpolation_b200.adw.models.simple import FCNetMultiBeta as Mine
+    torch.manual_seed(5)
+    mine = Mine(1, 1, 256, 5).double()
+    perturb_(mine, 6, 0.02)
+    assert state_sha(mine.state_dict()) == state_sha(model.state_dict())
+    gen = torch.Generator().manual_seed(7)
+    B = 64
+    x0 = torch.randn(B, 1, generator=gen)
+    beta0 = torch.full((B, 1), 1.0, dtype=torch.float64)
+    beta1 = torch.full((B, 1), 1.25, dtype=torch.float64)
+    out = dict(kind="adw", seed=5, perturb=0.02, sha=state_sha(model.state_dict()))
+    out["in::x0"], out["in::beta0"], out["in::beta1"] = x0.numpy(), beta0.numpy(), beta1.numpy()
+    wrap = ns.ode_wrapper.ODEWrapper(model, return_dlogp=True)
+    b, negdiv = wrap(torch.tensor(0.3), (x0.clone(), torch.zeros(B, 1)), x0, beta0, beta1)
+    out["drift_t03"] = b.detach().numpy()
+    out["div_t03_scaled"] = (-negdiv).detach().numpy()
+    for meth, n_step in (("euler", 11), ("dopri5", 9)):
+        integ = ns.integrators.StandardIntegrator(model, method=meth, n_step=n_step, atol=1e-4, rtol=1e-4, return_dlogp=True)
+        x, dlogp = integ.rollout(x0.clone(), beta0, beta1)
+        out[f"{meth}_x"] = x.detach().numpy()
+        out[f"{meth}_dlogp"] = dlogp.detach().numpy()
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "bytes", os.path.getsize(os.path.join(GOLDEN, name + ".npz")))
+
+
+def stats_case(name="stats"):
+    ns = ref_loader.load_analysis()
+    rng = np.random.default_rng(11)
+    n = 4096
+    E0 = rng.normal(10.0, 2.0, n)
+    E1 = E0 + rng.normal(0.3, 0.8, n)
+    nd = rng.normal(0.0, 0.5, n)
+    w = ns.ess.calc_ti_weights(E0, E1, nd)
+    phis, keep = ns.free_energy.calc_phis_tfep(E0, E1, nd, k=None)
+    out = dict(E0=E0, E1=E1, neg_dlogp=nd, weights=w, ess=ns.ess.calc_ESS(w),
+               dF=ns.free_energy.calc_tfep_dF(phis, np.ones_like(phis)),
+               keep_k3=ns.sensitivity.filter_iqr(w, k=3))
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "ess", out["ess"], "dF", out["dF"])
+
+
+def main():
+    os.makedirs(GOLDEN, exist_ok=True)
+    torch.set_num_threads(8)
+    ns = ref_loader.load_mdqm9()
+    for n in (9, 25):
+        check_graph_contract(ns, n)
+    ambient_case(ns, "ambient_f32", F=32, L=2, n_mol=3, n_atoms=9, seed=0, store_weights=True, with_div=True)
+    ambient_case(ns, "ambient_f128", F=128, L=5, n_mol=4, n_atoms=9, seed=1, store_weights=False)
+    ambient_case(ns, "ambient_f256", F=256, L=2, n_mol=2, n_atoms=25, seed=2, store_weights=False, n_frames=4, with_dopri=False)
+    latent_case(ns, "latent_multi_f64", F=64, L=2, n_list=[9, 12, 25, 9], seed=3, temperatures=[300, 400, 500, 600, 700, 800, 900, 1000])
+    latent_case(ns, "latent_single_f32", F=32, L=2, n_list=[9, 9, 9], seed=4, temperatures=[800])
+    adw_case()
+    stats_case()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,665 @@
+// tib_api.cu - extern "C" entry points of libtib.so (see include/tib.h).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/tib.h"
+#include "simt_drift.cuh"
+#include "steps.cuh"
+#include "adw.cuh"
+
+namespace {
+
+thread_local std::string g_err;
+thread_local uint64_t g_launches = 0;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_err = buf;
+  return -1;
+}
+
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+#define LAUNCH_CHECK()                                                                        \
+  do {                                                                                        \
+    ++g_launches;                                                                             \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+
+// ---- packed-weight walking ---------------------------------------------------------------------
+struct MlpShape { int k_in, h, n_out; };
+size_t mlp_floats(const MlpShape& s) {
+  return (size_t)s.h * s.k_in + 3 * (size_t)s.h + (size_t)s.h * s.h + 3 * (size_t)s.h + (size_t)s.n_out * s.h + s.n_out;
+}
+int n_temp_of(int variant) {
+  return variant == TIB_VARIANT_AMBIENT ? 2 : (variant == TIB_VARIANT_LATENT_MULTI_T ? 1 : 0);
+}
+
+struct HostMlp { tib::MlpW w; };
+
+}  // namespace
+
+struct tib_model {
+  tib_model_desc d;
+  int device = 0;
+  int math = TIB_MATH_FP32_SIMT;
+  int n_temp = 0;
+  float* dev = nullptr;   // one allocation holding every repacked tensor
+  size_t dev_floats = 0;
+  const float* edge_emb = nullptr;
+  const float* atom_emb = nullptr;
+  tib::MlpW combine{};
+  struct Layer { tib::MlpW phi, w, upd; const float *Ut, *Vt; };
+  std::vector<Layer> layers;
+  tib::MlpW readout{};
+  const float* Vout = nullptr;
+  bool attrs_set = false;
+};
+
+namespace {
+
+// Copies one reference MLP into `dst` (host staging) in device layout and records device pointers.
+//   in : W1[h,k] b1 g1 be1 W2[h,h] b2 g2 be2 W3[o,h] b3     (row-major [out,in])
+//   out: W1t[k][h] b1 g1 be1 W2t[h][h] b2 g2 be2 W3t[h][o] (or W3 untransposed) b3
+const float* repack_mlp(const float* src, const MlpShape& s, std::vector<float>& stage, float* dev_base,
+                        tib::MlpW* out, bool transpose_w3) {
+  auto push_T = [&](const float* W, int rows_out, int cols_in) {  // W[rows_out][cols_in] -> [cols_in][rows_out]
+    size_t off = stage.size();
+    stage.resize(off + (size_t)rows_out * cols_in);
+    for (int o = 0; o < rows_out; ++o)
+      for (int k = 0; k < cols_in; ++k) stage[off + (size_t)k * rows_out + o] = W[(size_t)o * cols_in + k];
+    return dev_base + off;
+  };
+  auto push = [&](const float* v, size_t n) {
+    size_t off = stage.size();
+    // keep every tensor 16-byte aligned for 128-bit loads
+    stage.insert(stage.end(), v, v + n);
+    while (stage.size() % 4) stage.push_back(0.0f);
+    return dev_base + off;
+  };
+  const int h = s.h;
+  out->k_in = s.k_in;
+  out->n_out = s.n_out;
+  out->W1t = push_T(src, h, s.k_in); src += (size_t)h * s.k_in;
+  out->b1 = push(src, h); src += h;
+  out->g1 = push(src, h); src += h;
+  out->be1 = push(src, h); src += h;
+  out->W2t = push_T(src, h, h); src += (size_t)h * h;
+  out->b2 = push(src, h); src += h;
+  out->g2 = push(src, h); src += h;
+  out->be2 = push(src, h); src += h;
+  if (transpose_w3) out->W3t = push_T(src, s.n_out, h);
+  else out->W3t = push(src, (size_t)s.n_out * h);
+  src += (size_t)s.n_out * h;
+  out->b3 = push(src, s.n_out); src += s.n_out;
+  return src;
+}
+
+template <typename K>
+int set_smem(K kernel, size_t bytes) {
+  cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) return fail("cudaFuncSetAttribute(%zu B smem): %s", bytes, cudaGetErrorString(e));
+  return 0;
+}
+
+// Per-F tile heights (rows per thread): message / node kernels.  See simt_drift.cuh for the budgets.
+template <int F> struct Tiles;
+template <> struct Tiles<32>  { static constexpr int MSG = 9, NODE = 4; };
+template <> struct Tiles<64>  { static constexpr int MSG = 9, NODE = 4; };
+template <> struct Tiles<128> { static constexpr int MSG = 9, NODE = 4; };
+template <> struct Tiles<256> { static constexpr int MSG = 5, NODE = 2; };
+
+struct Workspace {
+  float *s[2], *v[2], *e, *drift, *score;
+  float *k;          // [7][3N] dopri stages / rk4 stages
+  float *ytmp, *ycur, *ynew;
+  double *partial, *scalar;
+  static constexpr int kPartials = 1024;
+  static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
+  static size_t bytes(int F, int n_nodes, long long n_edges) {
+    size_t b = 0;
+    b += 2 * align(sizeof(float) * (size_t)n_nodes * F);
+    b += 2 * align(sizeof(float) * (size_t)n_nodes * 3 * F);
+    b += align(sizeof(float) * (size_t)n_edges * F);
+    b += 12 * align(sizeof(float) * (size_t)n_nodes * 3);   // drift, score, k[7], ytmp, ycur, ynew
+    b += align(sizeof(double) * kPartials * 5) + align(sizeof(double) * 8);
+    return b;
+  }
+  void carve(void* base, int F, int n_nodes, long long n_edges) {
+    char* p = (char*)base;
+    auto take = [&](size_t nbytes) { char* r = p; p += align(nbytes); return r; };
+    s[0] = (float*)take(sizeof(float) * (size_t)n_nodes * F);
+    s[1] = (float*)take(sizeof(float) * (size_t)n_nodes * F);
+    v[0] = (float*)take(sizeof(float) * (size_t)n_nodes * 3 * F);
+    v[1] = (float*)take(sizeof(float) * (size_t)n_nodes * 3 * F);
+    e = (float*)take(sizeof(float) * (size_t)n_edges * F);
+    const size_t st = sizeof(float) * (size_t)n_nodes * 3;
+    drift = (float*)take(st);
+    score = (float*)take(st);
+    k = (float*)take(st);
+    for (int i = 1; i < 7; ++i) take(st);
+    ytmp = (float*)take(st);
+    ycur = (float*)take(st);
+    ynew = (float*)take(st);
+    partial = (double*)take(sizeof(double) * kPartials * 5);
+    scalar = (double*)take(sizeof(double) * 8);
+  }
+  static size_t kstride(int n_nodes) { return align(sizeof(float) * (size_t)n_nodes * 3) / sizeof(float); }
+};
+
+template <int F>
+int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float* out, Workspace& ws, cudaStream_t st) {
+  using namespace tib;
+  constexpr int RM = Tiles<F>::MSG, RN = Tiles<F>::NODE;
+  if (!m->attrs_set) {
+    if (set_smem(k_embed<F, RN>, smem_embed<F, RN>())) return -1;
+    if (set_smem(k_message<F, RM>, smem_message<F, RM>())) return -1;
+    if (set_smem(k_update<F, RN>, smem_update<F, RN>())) return -1;
+    if (set_smem(k_readout<F, RN>, smem_readout<F, RN>())) return -1;
+    m->attrs_set = true;
+  }
+  DriftBatch db{b->n_mol, b->n_nodes, (long long)b->n_edges, b->mol_ptr, (const long long*)b->edge_ptr,
+                b->atom_id, b->edge_type, b->temp0, b->temp1};
+  const int node_tiles = (b->n_nodes + 8 * RN - 1) / (8 * RN);
+
+  EmbedP ep{db, m->combine, m->atom_emb, m->n_temp, t, m->d.temp_mean, m->d.temp_range, m->d.temp_length,
+            m->d.time_length, ws.s[0]};
+  k_embed<F, RN><<<node_tiles, TIB_THREADS, smem_embed<F, RN>(), st>>>(ep);
+  LAUNCH_CHECK();
+  {
+    const long long total = (long long)b->n_edges * (F / 4);
+    const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    k_edge_init<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(b->edge_type, m->edge_emb, ws.e, (long long)b->n_edges, F);
+    LAUNCH_CHECK();
+  }
+  int cur = 0;
+  for (int l = 0; l < m->d.n_layers; ++l) {
+    const tib_model::Layer& L = m->layers[l];
+    MessageP mp{db, L.phi, L.w, x, ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->d.length_scale, l == 0};
+    k_message<F, RM><<<b->n_mol, TIB_THREADS, smem_message<F, RM>(), st>>>(mp);
+    LAUNCH_CHECK();
+    cur ^= 1;
+    UpdateP up{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]};
+    k_update<F, RN><<<node_tiles, TIB_THREADS, smem_update<F, RN>(), st>>>(up);
+    LAUNCH_CHECK();
+  }
+  ReadoutP rp{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], out};
+  k_readout<F, RN><<<node_tiles, TIB_THREADS, smem_readout<F, RN>(), st>>>(rp);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int check_batch(const tib_model* m, const tib_batch* b) {
+  if (!m || !b) return fail("null model or batch");
+  if (b->n_mol <= 0 || b->n_nodes <= 0) return fail("empty batch (n_mol=%d, n_nodes=%d)", b->n_mol, b->n_nodes);
+  if (b->max_atoms > TIB_MAX_ATOMS) return fail("max_atoms=%d exceeds the supported %d", b->max_atoms, TIB_MAX_ATOMS);
+  if (b->max_atoms < 2) return fail("molecules need at least 2 atoms (max_atoms=%d)", b->max_atoms);
+  if (!b->mol_ptr || !b->edge_ptr || !b->atom_id || !b->edge_type) return fail("batch pointers must not be null");
+  if (m->n_temp >= 1 && !b->temp0) return fail("temp0 is required for this model variant");
+  if (m->n_temp >= 2 && !b->temp1) return fail("temp1 is required for the ambient variant");
+  return 0;
+}
+
+int drift_dispatch(tib_model* m, const tib_batch* b, const float* x, float t, float* out, Workspace& ws, cudaStream_t st) {
+  if (m->math != TIB_MATH_FP32_SIMT) return fail("math mode %d is not built in this library version", m->math);
+  switch (m->d.n_features) {
+    case 32: return drift_simt<32>(m, b, x, t, out, ws, st);
+    case 64: return drift_simt<64>(m, b, x, t, out, ws, st);
+    case 128: return drift_simt<128>(m, b, x, t, out, ws, st);
+    case 256: return drift_simt<256>(m, b, x, t, out, ws, st);
+  }
+  return fail("unsupported n_features=%d", m->d.n_features);
+}
+
+int grid_for(size_t n, int threads = 256) {
+  size_t blocks = (n + threads - 1) / threads;
+  const size_t cap = 148 * 8;
+  return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
+}
+
+int prep_ws(const tib_model* m, const tib_batch* b, void* workspace, size_t workspace_bytes, Workspace& ws) {
+  const size_t need = Workspace::bytes(m->d.n_features, b->n_nodes, (long long)b->n_edges);
+  if (!workspace || workspace_bytes < need) return fail("workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  if (((uintptr_t)workspace & 255) != 0) return fail("workspace must be 256-byte aligned");
+  ws.carve(workspace, m->d.n_features, b->n_nodes, (long long)b->n_edges);
+  return 0;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* tib_last_error(void) { return g_err.c_str(); }
+int tib_abi_version(void) { return TIB_ABI_VERSION; }
+uint64_t tib_launch_count(int reset) {
+  uint64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+size_t tib_packed_weight_count(const tib_model_desc* d) {
+  if (!d) return 0;
+  const int F = d->n_features, nt = n_temp_of(d->variant);
+  size_t n = (size_t)d->n_edge_types * F + (size_t)d->n_types * F;
+  n += mlp_floats({(2 + nt) * F, F, F});
+  for (int l = 0; l < d->n_layers; ++l) {
+    n += mlp_floats({2 * F, F, 5 * F}) + mlp_floats({F, F, 5 * F}) + 2 * (size_t)F * F + mlp_floats({2 * F, F, 3 * F});
+  }
+  n += mlp_floats({F, F, 2}) + F;
+  return n;
+}
+
+int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, size_t n_floats, int device) {
+  if (!out || !d || !w) return fail("tib_model_create: null argument");
+  if (d->abi_version != TIB_ABI_VERSION) return fail("ABI mismatch: header %d, library %d", d->abi_version, TIB_ABI_VERSION);
+  const int F = d->n_features;
+  if (!(F == 32 || F == 64 || F == 128 || F == 256)) return fail("n_features must be 32, 64, 128 or 256 (got %d)", F);
+  if (d->variant < 0 || d->variant > 2) return fail("bad variant %d", d->variant);
+  if (d->n_layers < 1 || d->n_types < 1 || d->n_edge_types < 1) return fail("bad layer/type counts");
+  if (n_floats != tib_packed_weight_count(d))
+    return fail("packed weight count mismatch: got %zu, descriptor needs %zu", n_floats, tib_packed_weight_count(d));
+  CUDA_TRY(cudaSetDevice(device));
+  tib_model* m = new tib_model();
+  m->d = *d;
+  m->device = device;
+  m->n_temp = n_temp_of(d->variant);
+  const int nt = m->n_temp;
+
+  // upper bound of the staged size: every tensor padded to 4 floats
+  std::vector<float> stage;
+  stage.reserve(n_floats + 64 * (size_t)(d->n_layers + 2) * 10);
+  // device allocation first (pointers are computed relative to it); size known after staging, so
+  // stage against a null base and rebase afterwards.
+  float* base = nullptr;
+  auto push = [&](const float* v, size_t n) {
+    size_t off = stage.size();
+    stage.insert(stage.end(), v, v + n);
+    while (stage.size() % 4) stage.push_back(0.0f);
+    return base + off;
+  };
+  auto push_T = [&](const float* W, int rows_out, int cols_in) {
+    size_t off = stage.size();
+    stage.resize(off + (size_t)rows_out * cols_in);
+    for (int o = 0; o < rows_out; ++o)
+      for (int k = 0; k < cols_in; ++k) stage[off + (size_t)k * rows_out + o] = W[(size_t)o * cols_in + k];
+    while (stage.size() % 4) stage.push_back(0.0f);
+    return base + off;
+  };
+  const float* src = w;
+  m->edge_emb = push(src, (size_t)d->n_edge_types * F); src += (size_t)d->n_edge_types * F;
+  m->atom_emb = push(src, (size_t)d->n_types * F); src += (size_t)d->n_types * F;
+  src = repack_mlp(src, {(2 + nt) * F, F, F}, stage, base, &m->combine, true);
+  m->layers.resize(d->n_layers);
+  for (int l = 0; l < d->n_layers; ++l) {
+    auto& L = m->layers[l];
+    src = repack_mlp(src, {2 * F, F, 5 * F}, stage, base, &L.phi, true);
+    src = repack_mlp(src, {F, F, 5 * F}, stage, base, &L.w, true);
+    L.Ut = push_T(src, F, F); src += (size_t)F * F;
+    L.Vt = push_T(src, F, F); src += (size_t)F * F;
+    src = repack_mlp(src, {2 * F, F, 3 * F}, stage, base, &L.upd, true);
+  }
+  src = repack_mlp(src, {F, F, 2}, stage, base, &m->readout, false);
+  m->Vout = push(src, F); src += F;
+  if ((size_t)(src - w) != n_floats) { delete m; return fail("internal: weight walk consumed %zu of %zu", (size_t)(src - w), n_floats); }
+
+  m->dev_floats = stage.size();
+  cudaError_t e = cudaMalloc(&m->dev, sizeof(float) * m->dev_floats);
+  if (e != cudaSuccess) { delete m; return fail("cudaMalloc(%zu floats): %s", stage.size(), cudaGetErrorString(e)); }
+  e = cudaMemcpy(m->dev, stage.data(), sizeof(float) * m->dev_floats, cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(m->dev); delete m; return fail("cudaMemcpy weights: %s", cudaGetErrorString(e)); }
+  // rebase the recorded (null-relative) pointers onto the device allocation
+  auto rb = [&](const float*& p) { p = m->dev + (p - (const float*)nullptr); };
+  auto rb_mlp = [&](tib::MlpW& q) { rb(q.W1t); rb(q.b1); rb(q.g1); rb(q.be1); rb(q.W2t); rb(q.b2); rb(q.g2); rb(q.be2); rb(q.W3t); rb(q.b3); };
+  rb(m->edge_emb); rb(m->atom_emb); rb_mlp(m->combine);
+  for (auto& L : m->layers) { rb_mlp(L.phi); rb_mlp(L.w); rb_mlp(L.upd); rb(L.Ut); rb(L.Vt); }
+  rb_mlp(m->readout); rb(m->Vout);
+  *out = m;
+  return 0;
+}
+
+void tib_model_destroy(tib_model* m) {
+  if (!m) return;
+  if (m->dev) cudaFree(m->dev);
+  delete m;
+}
+
+int tib_model_set_math(tib_model* m, int math_mode) {
+  if (!m) return fail("null model");
+  if (math_mode != TIB_MATH_FP32_SIMT) return fail("math mode %d is not built in this library version", math_mode);
+  m->math = math_mode;
+  return 0;
+}
+
+size_t tib_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges) {
+  (void)n_mol;
+  if (!m) return 0;
+  return Workspace::bytes(m->d.n_features, n_nodes, (long long)n_edges);
+}
+
+int tib_drift(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, void* workspace,
+              size_t workspace_bytes, void* stream) {
+  if (check_batch(m, b)) return -1;
+  if (!x || !out_b) return fail("tib_drift: null x/out");
+  Workspace ws;
+  if (prep_ws(m, b, workspace, workspace_bytes, ws)) return -1;
+  return drift_dispatch(m, b, x, t, out_b, ws, (cudaStream_t)stream);
+}
+
+int tib_step_euler(const float* x, const float* b, const float* score, const float* noise, float dt, float eps,
+                   float* x_out, float* frame, size_t n, void* stream) {
+  if (!x || !b || !x_out) return fail("tib_step_euler: null pointer");
+  if (n == 0) return 0;
+  const float dt_eps = dt * eps;
+  const float sig = sqrtf(2.0f * eps * dt);
+  tib::k_step_euler<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, b, score, noise, dt, dt_eps, sig, x_out, frame, n);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int tib_rollout_fixed(tib_model* m, const tib_batch* b, const float* x0, const tib_fixed_opts* o, float* out_xts,
+                      void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_batch(m, b)) return -1;
+  if (!x0 || !o || !out_xts || !o->t_grid) return fail("tib_rollout_fixed: null argument");
+  if (o->n_times < 1) return fail("n_times must be >= 1");
+  if (o->method != TIB_METHOD_EULER && (o->eps != 0.0f || o->noise || o->score_model))
+    return fail("Euler-Maruyama terms are only defined for TIB_METHOD_EULER");
+  Workspace ws;
+  if (prep_ws(m, b, workspace, workspace_bytes, ws)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)b->n_nodes * 3;
+  const size_t ks = Workspace::kstride(b->n_nodes);
+  float* y = ws.ycur;
+  CUDA_TRY(cudaMemcpyAsync(y, x0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (o->save_frames) CUDA_TRY(cudaMemcpyAsync(out_xts, x0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  for (int j = 1; j < o->n_times; ++j) {
+    const float t0 = o->t_grid[j - 1], t1 = o->t_grid[j];
+    const float dt = t1 - t0;   // fp32, as `dt = t1 - t0` on the fp32 grid tensor
+    float* frame = o->save_frames ? out_xts + (size_t)j * n : nullptr;
+    if (o->method == TIB_METHOD_EULER) {
+      if (drift_dispatch(m, b, y, t0, ws.drift, ws, st)) return -1;
+      const float* sc = nullptr;
+      if (o->score_model && o->eps != 0.0f) {
+        if (o->score_model->d.n_features != m->d.n_features) return fail("score model must share n_features");
+        if (drift_dispatch(o->score_model, b, y, t0, ws.score, ws, st)) return -1;
+        sc = ws.score;
+      }
+      const float* nz = (o->noise && o->eps != 0.0f) ? o->noise + (size_t)(j - 1) * n : nullptr;
+      if (tib_step_euler(y, ws.drift, sc, nz, dt, o->eps, y, frame, n, stream)) return -1;
+    } else if (o->method == TIB_METHOD_MIDPOINT) {
+      const float half_dt = 0.5f * dt;
+      if (drift_dispatch(m, b, y, t0, ws.drift, ws, st)) return -1;
+      if (tib_step_euler(y, ws.drift, nullptr, nullptr, half_dt, 0.f, ws.ytmp, nullptr, n, stream)) return -1;
+      if (drift_dispatch(m, b, ws.ytmp, t0 + half_dt, ws.drift, ws, st)) return -1;
+      if (tib_step_euler(y, ws.drift, nullptr, nullptr, dt, 0.f, y, frame, n, stream)) return -1;
+    } else if (o->method == TIB_METHOD_RK4) {
+      float* k1 = ws.k; float* k2 = ws.k + ks; float* k3 = ws.k + 2 * ks; float* k4 = ws.k + 3 * ks;
+      const float third = (float)(1.0 / 3.0), two_thirds = (float)(2.0 / 3.0);
+      const int g = grid_for(n);
+      if (drift_dispatch(m, b, y, t0, k1, ws, st)) return -1;
+      tib::k_rk4_stage<<<g, 256, 0, st>>>(0, y, k1, k2, k3, k4, dt, ws.ytmp, nullptr, n); LAUNCH_CHECK();
+      if (drift_dispatch(m, b, ws.ytmp, t0 + dt * third, k2, ws, st)) return -1;
+      tib::k_rk4_stage<<<g, 256, 0, st>>>(1, y, k1, k2, k3, k4, dt, ws.ytmp, nullptr, n); LAUNCH_CHECK();
+      if (drift_dispatch(m, b, ws.ytmp, t0 + dt * two_thirds, k3, ws, st)) return -1;
+      tib::k_rk4_stage<<<g, 256, 0, st>>>(2, y, k1, k2, k3, k4, dt, ws.ytmp, nullptr, n); LAUNCH_CHECK();
+      if (drift_dispatch(m, b, ws.ytmp, t1, k4, ws, st)) return -1;
+      tib::k_rk4_stage<<<g, 256, 0, st>>>(3, y, k1, k2, k3, k4, dt, y, frame, n); LAUNCH_CHECK();
+    } else {
+      return fail("unknown fixed-grid method %d", o->method);
+    }
+  }
+  if (!o->save_frames) CUDA_TRY(cudaMemcpyAsync(out_xts, y, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// ---- dopri5 (torchdiffeq 0.2.5 RKAdaptiveStepsizeODESolver; restated in oracle/ode_oracle.py) ----
+namespace {
+const double DP_ALPHA[6] = {1 / 5., 3 / 10., 4 / 5., 8 / 9., 1., 1.};
+const double DP_BETA[6][6] = {
+    {1 / 5.},
+    {3 / 40., 9 / 40.},
+    {44 / 45., -56 / 15., 32 / 9.},
+    {19372 / 6561., -25360 / 2187., 64448 / 6561., -212 / 729.},
+    {9017 / 3168., -355 / 33., 46732 / 5247., 49 / 176., -5103 / 18656.},
+    {35 / 384., 0, 500 / 1113., 125 / 192., -2187 / 6784., 11 / 84.}};
+const double DP_C_ERROR[7] = {35 / 384. - 1951 / 21600., 0, 500 / 1113. - 22642 / 50085., 125 / 192. - 451 / 720.,
+                              -2187 / 6784. - -12231 / 42400., 11 / 84. - 649 / 6300., -1. / 60.};
+const double DP_C_MID[7] = {6025192743. / 30085553152. / 2, 0, 51252292925. / 65400821598. / 2,
+                            -2691868925. / 45128329728. / 2, 187940372067. / 1594534317056. / 2,
+                            -1776094331. / 19743644256. / 2, 11237099. / 235043384. / 2};
+
+struct Reducer {
+  Workspace* ws; cudaStream_t st; size_t n; const tib_dopri5_opts* o;
+  // rms = sqrt(mean(partials)) over the (optionally all-reduced) batch
+  int finish(double* rms) {
+    tib::k_reduce_partials<<<1, 256, 0, st>>>(ws->partial, Workspace::kPartials, ws->scalar);
+    LAUNCH_CHECK();
+    double h[2];
+    CUDA_TRY(cudaMemcpyAsync(&h[0], ws->scalar, sizeof(double), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    h[1] = (double)n;
+    if (o->norm_allreduce) o->norm_allreduce(h, o->norm_user);
+    *rms = std::sqrt(h[0] / h[1]);
+    return 0;
+  }
+};
+}  // namespace
+
+int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const tib_dopri5_opts* o, float* out_xts,
+                       tib_dopri5_stats* stats, void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_batch(m, b)) return -1;
+  if (!x0 || !o || !out_xts || !o->t_grid) return fail("tib_rollout_dopri5: null argument");
+  if (o->n_times < 1) return fail("n_times must be >= 1");
+  for (int i = 1; i < o->n_times; ++i)
+    if (!(o->t_grid[i] > o->t_grid[i - 1])) return fail("t_grid must be strictly increasing");
+  Workspace ws;
+  if (prep_ws(m, b, workspace, workspace_bytes, ws)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)b->n_nodes * 3;
+  const size_t ks = Workspace::kstride(b->n_nodes);
+  const int g = grid_for(n);
+  const int gp = Workspace::kPartials;   // reduction kernels use exactly kPartials blocks
+  const double rtol = o->rtol, atol = o->atol;
+  const int max_attempts = o->max_attempts > 0 ? o->max_attempts : 100000;
+  Reducer red{&ws, st, n, o};
+  int nfe = 0, attempts = 0, accepted = 0;
+
+  float* y = ws.ycur;
+  float* ynew = ws.ynew;
+  float* k = ws.k;   // k_s at k + s*ks
+  CUDA_TRY(cudaMemcpyAsync(y, x0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (o->save_frames) CUDA_TRY(cudaMemcpyAsync(out_xts, x0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+
+  // --- _before_integrate: f0 and Hairer's initial step (misc._select_initial_step, order = 4)
+  const double tstart = (double)o->t_grid[0];
+  if (drift_dispatch(m, b, y, (float)tstart, k, ws, st)) return -1;
+  ++nfe;
+  double d0, d1, d2, h0, h1, dt;
+  tib::k_scaled_sq<<<gp, 256, 0, st>>>(y, nullptr, y, rtol, atol, ws.partial, n); LAUNCH_CHECK();
+  if (red.finish(&d0)) return -1;
+  tib::k_scaled_sq<<<gp, 256, 0, st>>>(k, nullptr, y, rtol, atol, ws.partial, n); LAUNCH_CHECK();
+  if (red.finish(&d1)) return -1;
+  if (d0 < 1e-5 || d1 < 1e-5) h0 = (double)1e-6f; else h0 = 0.01 * d0 / d1;
+  h0 = std::fabs(h0);
+  // y1 = y0 + h0*f0 (h0 is a 0-dim fp64 tensor times an fp32 tensor -> fp32 arithmetic)
+  if (tib_step_euler(y, k, nullptr, nullptr, (float)h0, 0.f, ws.ytmp, nullptr, n, stream)) return -1;
+  if (drift_dispatch(m, b, ws.ytmp, (float)(tstart + h0), k + ks, ws, st)) return -1;
+  ++nfe;
+  tib::k_scaled_sq<<<gp, 256, 0, st>>>(k + ks, k, y, rtol, atol, ws.partial, n); LAUNCH_CHECK();
+  if (red.finish(&d2)) return -1;
+  d2 = std::fabs(d2 / h0);
+  if (d1 <= 1e-15 && d2 <= 1e-15) h1 = std::max((double)1e-6f, h0 * 1e-3);
+  else h1 = std::pow(0.01 / std::max(d1, d2), 1.0 / 5.0);
+  dt = std::min(100 * h0, std::fabs(h1));
+
+  double t0 = tstart, t1 = tstart;   // rk_state.t0, rk_state.t1
+  bool have_interp = false;
+  float dt_step = 0.f;               // fp32 dt of the last accepted step (for the dense output)
+  tib::StageCoef cmid{}; cmid.n = 7;
+  for (int i = 1; i < o->n_times; ++i) {
+    const double tn = (double)o->t_grid[i];
+    // collect the frames that fall inside the current accepted step before stepping further
+    while (tn > t1) {
+      if (attempts >= max_attempts) return fail("dopri5: exceeded %d attempted steps", max_attempts);
+      const double t_new = t1 + dt;
+      if (!(t1 + dt > t1)) return fail("dopri5: underflow in dt %g", dt);
+      const float t0_s = (float)t1, dt_s = (float)dt, t1_s = (float)t_new;
+      for (int s = 0; s < 6; ++s) {
+        tib::StageCoef c{}; c.n = s + 1;
+        for (int q = 0; q <= s; ++q) c.c[q] = (float)DP_BETA[s][q] * dt_s;   // beta_i (fp32) * dt (fp32)
+        float* yi = (s == 5) ? ynew : ws.ytmp;
+        tib::k_dopri_stage<<<g, 256, 0, st>>>(y, k, ks, c, yi, n); LAUNCH_CHECK();
+        float ti;
+        if (DP_ALPHA[s] == 1.0) ti = std::nextafterf(t1_s, t1_s - 1.0f);   // Perturb.PREV
+        else ti = t0_s + (float)DP_ALPHA[s] * dt_s;
+        if (drift_dispatch(m, b, yi, ti, k + (size_t)(s + 1) * ks, ws, st)) return -1;
+        ++nfe;
+      }
+      tib::StageCoef ce{}; ce.n = 7;
+      for (int q = 0; q < 7; ++q) ce.c[q] = dt_s * (float)DP_C_ERROR[q];
+      tib::k_dopri_error<<<gp, 256, 0, st>>>(y, ynew, k, ks, ce, rtol, atol, ws.partial, n); LAUNCH_CHECK();
+      double ratio;
+      if (red.finish(&ratio)) return -1;
+      ++attempts;
+      if (!(ratio == ratio)) return fail("dopri5: non-finite error ratio (state diverged)");
+      if (ratio <= 1.0) {
+        // accepted: the dense-output kernel needs (y, ynew, k) of THIS step; keep them by flushing the
+        // frames that fall inside [t1, t_new] right away.
+        ++accepted;
+        for (int q = 0; q < 7; ++q) cmid.c[q] = dt_s * (float)DP_C_MID[q];
+        dt_step = dt_s;
+        t0 = t1; t1 = t_new;
+        have_interp = true;
+        // frames i.. with t_grid <= t1
+        int j = i;
+        while (j < o->n_times && (double)o->t_grid[j] <= t1) {
+          tib::DenseArgs da{}; da.n = 0;
+          while (j < o->n_times && (double)o->t_grid[j] <= t1 && da.n < 8) {
+            const double xx = ((double)o->t_grid[j] - t0) / (t1 - t0);
+            da.xs[da.n] = (float)xx;
+            da.frames[da.n] = o->save_frames ? out_xts + (size_t)j * n : ((j == o->n_times - 1) ? out_xts : nullptr);
+            if (da.frames[da.n]) ++da.n;
+            ++j;
+          }
+          if (da.n > 0) { tib::k_dopri_dense<<<g, 256, 0, st>>>(y, ynew, k, ks, cmid, dt_step, da, n); LAUNCH_CHECK(); }
+        }
+        // FSAL: f0 <- f1 (k_6 -> k_0), y <- ynew
+        CUDA_TRY(cudaMemcpyAsync(k, k + 6 * ks, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+        std::swap(y, ynew);
+      }
+      // _optimal_step_size(dt, ratio, safety=0.9, ifactor=10, dfactor=0.2, order=5)
+      if (ratio == 0.0) dt = dt * 10.0;
+      else {
+        const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
+        const double factor = std::min(10.0, std::max(0.9 / std::pow(ratio, 0.2), dfactor));
+        dt = dt * factor;
+      }
+    }
+    (void)have_interp;
+  }
+  if (stats) { stats->nfe = nfe; stats->attempts = attempts; stats->accepted = accepted; stats->last_dt = dt; }
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+int tib_reweight_stats(const double* E0, const double* E1, const double* nd, const double* wt, size_t n, double* out,
+                       void* stream) {
+  if (!E0 || !E1 || !out) return fail("tib_reweight_stats: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = grid_for(n);
+  double* partial = nullptr;
+  CUDA_TRY(cudaMallocAsync(&partial, sizeof(double) * 5 * blocks, st));
+  tib::k_reweight_partials<<<blocks, 256, 0, st>>>(E0, E1, nd, wt, n, partial); LAUNCH_CHECK();
+  tib::k_reweight_final<<<1, 32, 0, st>>>(partial, blocks, out); LAUNCH_CHECK();
+  CUDA_TRY(cudaFreeAsync(partial, st));
+  return 0;
+}
+
+// ---- ADW -----------------------------------------------------------------------------------------
+struct tib_adw_model {
+  int hidden, num_layers, device;
+  double* dev;
+  tib::AdwW w;
+};
+
+int tib_adw_create(tib_adw_model** out, int32_t hidden, int32_t num_layers, const double* w, size_t n_doubles, int device) {
+  if (!out || !w) return fail("tib_adw_create: null argument");
+  if (hidden != 256) return fail("ADW kernel is built for hidden_size 256 (adw/config/settings.json:6), got %d", hidden);
+  if (num_layers < 1 || num_layers > 8) return fail("num_layers must be in [1,8]");
+  const size_t H = hidden;
+  const size_t need = (3 * H + H) + (H * H + H) + (H + 1) + (3 * H + H) + (size_t)(num_layers - 1) * (H * H + H) + (H + 1);
+  if (n_doubles != need) return fail("ADW packed weight count mismatch: got %zu, need %zu", n_doubles, need);
+  CUDA_TRY(cudaSetDevice(device));
+  // device layout: hidden->hidden matrices transposed to [in][out]; everything else as given
+  std::vector<double> stage;
+  stage.reserve(n_doubles);
+  tib_adw_model* m = new tib_adw_model();
+  m->hidden = hidden; m->num_layers = num_layers; m->device = device; m->dev = nullptr;
+  std::vector<size_t> offs;
+  auto push = [&](const double* v, size_t n) { offs.push_back(stage.size()); stage.insert(stage.end(), v, v + n); };
+  auto push_T = [&](const double* W) {
+    offs.push_back(stage.size());
+    size_t off = stage.size(); stage.resize(off + H * H);
+    for (size_t o = 0; o < H; ++o) for (size_t k = 0; k < H; ++k) stage[off + k * H + o] = W[o * H + k];
+  };
+  const double* src = w;
+  // beta_embed: Linear(3,H), Linear(H,H), Linear(H,1)
+  push(src, 3 * H); src += 3 * H; push(src, H); src += H;
+  push_T(src); src += H * H; push(src, H); src += H;
+  push(src, H); src += H; push(src, 1); src += 1;
+  // net: Linear(3,H), (num_layers-1) x Linear(H,H), Linear(H,1)
+  push(src, 3 * H); src += 3 * H; push(src, H); src += H;
+  for (int l = 0; l < num_layers - 1; ++l) { push_T(src); src += H * H; push(src, H); src += H; }
+  push(src, H); src += H; push(src, 1); src += 1;
+  cudaError_t e = cudaMalloc(&m->dev, sizeof(double) * stage.size());
+  if (e != cudaSuccess) { delete m; return fail("cudaMalloc: %s", cudaGetErrorString(e)); }
+  e = cudaMemcpy(m->dev, stage.data(), sizeof(double) * stage.size(), cudaMemcpyHostToDevice);
+  if (e != cudaSuccess) { cudaFree(m->dev); delete m; return fail("cudaMemcpy: %s", cudaGetErrorString(e)); }
+  size_t i = 0;
+  auto next = [&]() { return (const double*)(m->dev + offs[i++]); };
+  m->w.e_W1 = next(); m->w.e_b1 = next(); m->w.e_W2t = next(); m->w.e_b2 = next(); m->w.e_W3 = next(); m->w.e_b3 = next();
+  m->w.n_W1 = next(); m->w.n_b1 = next();
+  m->w.n_hidden = num_layers - 1;
+  for (int l = 0; l < num_layers - 1; ++l) { m->w.n_Wt[l] = next(); m->w.n_b[l] = next(); }
+  m->w.n_Wo = next(); m->w.n_bo = next();
+  *out = m;
+  return 0;
+}
+
+void tib_adw_destroy(tib_adw_model* m) {
+  if (!m) return;
+  if (m->dev) cudaFree(m->dev);
+  delete m;
+}
+
+int tib_adw_drift_div(tib_adw_model* m, const double* x, const double* beta0, const double* beta1, float t,
+                      double* out_b, double* out_div, size_t n, void* stream) {
+  if (!m || !x || !beta0 || !beta1 || !out_b) return fail("tib_adw_drift_div: null pointer");
+  if (n == 0) return 0;
+  static bool attr = false;
+  if (!attr) {
+    if (set_smem(tib::k_adw<256>, tib::adw_smem<256>())) return -1;
+    attr = true;
+  }
+  const int blocks = (int)((n + tib::kAdwRows - 1) / tib::kAdwRows);
+  tib::k_adw<256><<<blocks, 256, tib::adw_smem<256>(), (cudaStream_t)stream>>>(m->w, x, beta0, beta1, t, out_b, out_div, n);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+}  // extern "C"
