@@ -183,6 +183,14 @@ int         tib_abi_version(void);
 /* Number of kernel launches issued by this library on the calling thread since the last reset. */
 uint64_t    tib_launch_count(int reset);
 
+
+/* Per-kernel-class device time (CUDA event pairs around each launch on the launching stream) between
+ * begin and end, for bench.py's roofline line.  ms_sum / launches are HOST arrays [TIB_K_COUNT]. */
+enum { TIB_K_EMBED = 0, TIB_K_EDGE_INIT = 1, TIB_K_MESSAGE = 2, TIB_K_UPDATE = 3, TIB_K_READOUT = 4,
+       TIB_K_STEP = 5, TIB_K_COUNT = 6 };
+int tib_profile_begin(void);
+int tib_profile_end(double* ms_sum, uint64_t* launches);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,14 +88,21 @@ def oracle_temps(batch, hp):
     return dict(T=batch.T) if hp.n_temp_encoders == 1 else {}
 
 
-def oracle_drift(model, batch, x, t):
-    """Oracle drift for a product model holder + MolBatch (CPU tensors)."""
+def oracle_hp_sd(model):
+    """Oracle-side (Hyper, state_dict) of a product model holder."""
     from oracle import cpainn_oracle as co
     hp_p = model.hyper
     hp = co.Hyper(n_features=hp_p.n_features, score_layers=hp_p.score_layers, temp_length=hp_p.temp_length,
                   time_length=hp_p.time_length, n_types=hp_p.n_types, temperatures=list(hp_p.temperatures),
                   variant=hp_p.variant)
     sd = {k: v.detach().cpu() for k, v in model.state_dict().items()}
+    return hp, sd
+
+
+def oracle_drift(model, batch, x, t):
+    """Oracle drift for a product model holder + MolBatch (CPU tensors)."""
+    from oracle import cpainn_oracle as co
+    hp, sd = oracle_hp_sd(model)
     atoms = batch.atoms if hp.variant == "ambient" else batch.atom_number
     cpu = lambda v: v.detach().cpu()  # noqa: E731
     temps = {k: cpu(v) for k, v in oracle_temps(batch, hp).items()}

@@ -12,6 +12,9 @@ ABI_VERSION = 1
 VARIANT_AMBIENT, VARIANT_LATENT_MULTI_T, VARIANT_LATENT_SINGLE_T = 0, 1, 2
 MATH_FP32_SIMT, MATH_BF16X3_TC, MATH_BF16_TC = 0, 1, 2
 METHOD_EULER, METHOD_MIDPOINT, METHOD_RK4 = 0, 1, 2
+KERNEL_KINDS = ("embed", "edge_init", "message", "update", "readout", "step")
+N_KERNEL_KINDS = len(KERNEL_KINDS)
+MATH_NAMES = {0: "fp32_simt", 1: "bf16x3_tcgen05", 2: "bf16_tcgen05"}
 METHODS = {"euler": METHOD_EULER, "midpoint": METHOD_MIDPOINT, "rk4": METHOD_RK4}
 
 
@@ -65,6 +68,8 @@ SYMBOLS = [
     ("tib_last_error", C.c_char_p, []),
     ("tib_abi_version", C.c_int, []),
     ("tib_launch_count", C.c_uint64, [C.c_int]),
+    ("tib_profile_begin", C.c_int, []),
+    ("tib_profile_end", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
 ]
 
 _lib = None

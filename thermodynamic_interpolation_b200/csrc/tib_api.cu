@@ -28,6 +28,29 @@ int fail(const char* fmt, ...) {
   return -1;
 }
 
+// ---- optional per-kernel-class timing (tib_profile_begin/end): an event pair around each launch
+struct ProfState {
+  bool on = false;
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> ev[TIB_K_COUNT];
+  std::vector<std::pair<cudaEvent_t, cudaEvent_t>> pool;
+};
+thread_local ProfState g_prof;
+
+struct ProfScope {
+  int kind; cudaStream_t st; cudaEvent_t a = nullptr, b = nullptr;
+  ProfScope(int k, cudaStream_t s) : kind(k), st(s) {
+    if (!g_prof.on) return;
+    if (!g_prof.pool.empty()) { a = g_prof.pool.back().first; b = g_prof.pool.back().second; g_prof.pool.pop_back(); }
+    else { cudaEventCreate(&a); cudaEventCreate(&b); }
+    cudaEventRecord(a, st);
+  }
+  ~ProfScope() {
+    if (!a) return;
+    cudaEventRecord(b, st);
+    g_prof.ev[kind].push_back({a, b});
+  }
+};
+
 #define CUDA_TRY(expr)                                                                        \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -179,11 +202,12 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
 
   EmbedP ep{db, m->combine, m->atom_emb, m->n_temp, t, m->d.temp_mean, m->d.temp_range, m->d.temp_length,
             m->d.time_length, ws.s[0]};
-  k_embed<F, RN><<<node_tiles, TIB_THREADS, smem_embed<F, RN>(), st>>>(ep);
+  { ProfScope ps(TIB_K_EMBED, st); k_embed<F, RN><<<node_tiles, TIB_THREADS, smem_embed<F, RN>(), st>>>(ep); }
   LAUNCH_CHECK();
   {
     const long long total = (long long)b->n_edges * (F / 4);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+    ProfScope ps(TIB_K_EDGE_INIT, st);
     k_edge_init<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(b->edge_type, m->edge_emb, ws.e, (long long)b->n_edges, F);
     LAUNCH_CHECK();
   }
@@ -191,15 +215,15 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
   for (int l = 0; l < m->d.n_layers; ++l) {
     const tib_model::Layer& L = m->layers[l];
     MessageP mp{db, L.phi, L.w, x, ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->d.length_scale, l == 0};
-    k_message<F, RM><<<b->n_mol, TIB_THREADS, smem_message<F, RM>(), st>>>(mp);
+    { ProfScope ps(TIB_K_MESSAGE, st); k_message<F, RM><<<b->n_mol, TIB_THREADS, smem_message<F, RM>(), st>>>(mp); }
     LAUNCH_CHECK();
     cur ^= 1;
     UpdateP up{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]};
-    k_update<F, RN><<<node_tiles, TIB_THREADS, smem_update<F, RN>(), st>>>(up);
+    { ProfScope ps(TIB_K_UPDATE, st); k_update<F, RN><<<node_tiles, TIB_THREADS, smem_update<F, RN>(), st>>>(up); }
     LAUNCH_CHECK();
   }
   ReadoutP rp{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], out};
-  k_readout<F, RN><<<node_tiles, TIB_THREADS, smem_readout<F, RN>(), st>>>(rp);
+  { ProfScope ps(TIB_K_READOUT, st); k_readout<F, RN><<<node_tiles, TIB_THREADS, smem_readout<F, RN>(), st>>>(rp); }
   LAUNCH_CHECK();
   return 0;
 }
@@ -251,6 +275,30 @@ uint64_t tib_launch_count(int reset) {
   uint64_t v = g_launches;
   if (reset) g_launches = 0;
   return v;
+}
+
+int tib_profile_begin(void) {
+  for (auto& v : g_prof.ev) { for (auto& p : v) g_prof.pool.push_back(p); v.clear(); }
+  g_prof.on = true;
+  return 0;
+}
+
+int tib_profile_end(double* ms_sum, uint64_t* launches) {
+  g_prof.on = false;
+  for (int k = 0; k < TIB_K_COUNT; ++k) {
+    double tot = 0.0;
+    for (auto& p : g_prof.ev[k]) {
+      CUDA_TRY(cudaEventSynchronize(p.second));
+      float ms = 0.f;
+      CUDA_TRY(cudaEventElapsedTime(&ms, p.first, p.second));
+      tot += ms;
+      g_prof.pool.push_back(p);
+    }
+    if (ms_sum) ms_sum[k] = tot;
+    if (launches) launches[k] = g_prof.ev[k].size();
+    g_prof.ev[k].clear();
+  }
+  return 0;
 }
 
 size_t tib_packed_weight_count(const tib_model_desc* d) {
@@ -367,7 +415,8 @@ int tib_step_euler(const float* x, const float* b, const float* score, const flo
   if (n == 0) return 0;
   const float dt_eps = dt * eps;
   const float sig = sqrtf(2.0f * eps * dt);
-  tib::k_step_euler<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, b, score, noise, dt, dt_eps, sig, x_out, frame, n);
+  { ProfScope ps(TIB_K_STEP, (cudaStream_t)stream);
+    tib::k_step_euler<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, b, score, noise, dt, dt_eps, sig, x_out, frame, n); }
   LAUNCH_CHECK();
   return 0;
 }
