@@ -12,8 +12,10 @@ namespace tib {
 __global__ void k_step_euler(const float* __restrict__ x, const float* __restrict__ b,
                              const float* __restrict__ score, const float* __restrict__ noise,
                              float dt, float dt_eps, float sig, float* __restrict__ x_out,
-                             float* __restrict__ frame, size_t n) {
-  const size_t n4 = n / 4;
+                             float* __restrict__ frame, size_t n, int vec_ok) {
+  // 128-bit path only when every pointer is 16-byte aligned (frames of a [T,N,3] trajectory with
+  // 3N % 4 != 0 are not)
+  const size_t n4 = vec_ok ? n / 4 : 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n4; i += stride) {
     const float4 xv = reinterpret_cast<const float4*>(x)[i];

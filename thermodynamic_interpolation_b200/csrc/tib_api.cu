@@ -415,8 +415,10 @@ int tib_step_euler(const float* x, const float* b, const float* score, const flo
   if (n == 0) return 0;
   const float dt_eps = dt * eps;
   const float sig = sqrtf(2.0f * eps * dt);
+  const uintptr_t bits = (uintptr_t)x | (uintptr_t)b | (uintptr_t)score | (uintptr_t)noise | (uintptr_t)x_out | (uintptr_t)frame;
+  const int vec_ok = (bits & 15) == 0;
   { ProfScope ps(TIB_K_STEP, (cudaStream_t)stream);
-    tib::k_step_euler<<<grid_for((n + 3) / 4), 256, 0, (cudaStream_t)stream>>>(x, b, score, noise, dt, dt_eps, sig, x_out, frame, n); }
+    tib::k_step_euler<<<grid_for(vec_ok ? (n + 3) / 4 : n), 256, 0, (cudaStream_t)stream>>>(x, b, score, noise, dt, dt_eps, sig, x_out, frame, n, vec_ok); }
   LAUNCH_CHECK();
   return 0;
 }
