@@ -33,9 +33,10 @@ enum { TIB_VARIANT_AMBIENT = 0,       /* T0 and T1 encoders   (mdqm9/thermo/ambi
        TIB_VARIANT_LATENT_SINGLE_T = 2/* no temperature input (mdqm9/thermo/latent/models/cpainn.py:59-72)  */ };
 
 /* GEMM arithmetic of the MLP / equivariant-linear layers. */
-enum { TIB_MATH_FP32_SIMT = 0,        /* fp32 FMA on CUDA cores: the bit-faithful reference mode            */
-       TIB_MATH_BF16X3_TC = 1,        /* tcgen05, operands split hi+lo bf16, 3 MMAs, fp32 accumulate (~2^-16) */
-       TIB_MATH_BF16_TC = 2           /* tcgen05, single bf16 pass, fp32 accumulate (~2^-8): opt-in only     */ };
+enum { TIB_MATH_FP32_SIMT = 0,        /* fp32 FMA on CUDA cores: rounds like the reference op by op          */
+       TIB_MATH_F16X3_TC = 1,         /* tcgen05, operands split hi+lo f16 (22 bits), 3 MMAs, fp32 accumulate: */
+                                      /*   fp32-faithful (~2^-21 per product); n_features = 128 only          */
+       TIB_MATH_F16_TC = 2            /* tcgen05, single f16 pass (TF32-class, ~2^-11): opt-in only           */ };
 
 typedef struct tib_model tib_model;
 
@@ -71,6 +72,9 @@ int  tib_model_create(tib_model** out, const tib_model_desc* desc, const float* 
                       size_t n_floats, int device);
 void tib_model_destroy(tib_model* m);
 int  tib_model_set_math(tib_model* m, int math_mode);     /* TIB_MATH_*; default FP32_SIMT */
+/* Synchronises `stream` and reports (once) a device-side pipeline error recorded by the tensor-core
+ * kernels' bounded barrier waits.  0 = healthy. */
+int  tib_model_status(tib_model* m, void* stream);
 
 /* ---- batch ------------------------------------------------------------------------------- */
 
@@ -188,6 +192,11 @@ uint64_t    tib_launch_count(int reset);
  * begin and end, for bench.py's roofline line.  ms_sum / launches are HOST arrays [TIB_K_COUNT]. */
 enum { TIB_K_EMBED = 0, TIB_K_EDGE_INIT = 1, TIB_K_MESSAGE = 2, TIB_K_UPDATE = 3, TIB_K_READOUT = 4,
        TIB_K_STEP = 5, TIB_K_COUNT = 6 };
+/* Tensor-core plumbing self test: out = A * W^T (transposed = 0) or W * A^T (transposed = 1) through the
+ * same operand images, weight ring and TMEM addressing the drift kernels use.  A, out: DEVICE fp32
+ * [128][128]; W: HOST fp32 [128][128].  Synchronous. */
+int tib_selftest_gemm(const float* A, const float* W_host, float* out, int transposed, void* stream);
+
 int tib_profile_begin(void);
 int tib_profile_end(double* ms_sum, uint64_t* launches);
 

@@ -1,0 +1,110 @@
+"""GPU tier: the tcgen05 path (TIB_MATH_F16X3_TC / TIB_MATH_F16_TC) - plumbing self test, parity against the
+reference's frozen outputs, the CPU oracle and the fp32 SIMT path of this library."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import golden_batch, golden_model, load_golden, oracle_drift, perturb_
+from thermodynamic_interpolation_b200 import _lib
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.abs(a - b).max() / np.abs(b).max())
+
+
+@pytest.mark.parametrize("transposed", [False, True])
+def test_selftest_gemm_split_f16(transposed):
+    """One [128x128]x[128x128] product through the operand images, the bulk-copy weight ring, tcgen05.mma
+    (3 split-f16 passes) and tcgen05.ld: fp32-faithful (error ~2^-21 per product)."""
+    from thermodynamic_interpolation_b200.engine import selftest_gemm
+    gen = torch.Generator().manual_seed(3 + int(transposed))
+    A = torch.randn(128, 128, generator=gen)
+    W = torch.randn(128, 128, generator=gen) * 0.2
+    out = selftest_gemm(A.to(DEV), W, transposed).cpu().double()
+    ref = (W.double() @ A.double().T) if transposed else (A.double() @ W.double().T)
+    err = _rel(out.numpy(), ref.numpy())
+    print(f"[tc] selftest transposed={transposed}: max rel err {err:.3e}")
+    assert err < 2e-6
+
+
+def _tc_model(g, mode=_lib.MATH_F16X3_TC):
+    model = golden_model(g, DEV)
+    model.set_math(mode)
+    return model
+
+
+def test_tc_drift_matches_reference_golden():
+    g = load_golden("ambient_f128")
+    from thermodynamic_interpolation_b200.ambient.models.ode_wrapper import ODEWrapper
+    model = _tc_model(g)
+    batch = golden_batch(g).to(DEV)
+    wrap = ODEWrapper(model)
+    for t, ref in zip(g["drift_t"], g["drift"]):
+        out = wrap(torch.tensor(float(t)), batch.x0.clone(), batch, [0])
+        model.engine().status()
+        err = _rel(out.cpu().numpy(), ref)
+        print(f"[tc] ambient_f128 drift t={t}: max|diff|/max|ref| = {err:.3e}")
+        assert err < 2e-5
+
+
+def test_tc_euler_rollout_matches_reference_golden():
+    from thermodynamic_interpolation_b200.ambient.integrators import MoleculeIntegrator
+    g = load_golden("ambient_f128")
+    ref = g["euler_xts"]
+    model = _tc_model(g)
+    xts = MoleculeIntegrator(model, method="euler", n_step=ref.shape[0]).rollout(golden_batch(g).to(DEV))[0]
+    model.engine().status()
+    err = _rel(xts.cpu().numpy(), ref)
+    print(f"[tc] ambient_f128 euler frames: {err:.3e}")
+    np.testing.assert_allclose(xts.cpu().numpy(), ref, rtol=1e-4, atol=2e-5 * np.abs(ref).max())
+
+
+@pytest.mark.parametrize("n_list", [[9] * 40, [25, 9, 16, 2, 3, 12], [5] * 7])
+def test_tc_drift_vs_oracle_ragged(n_list):
+    """Tile tails, molecules straddling tiles, 2-atom molecules, more/fewer than 16 destination nodes per tile."""
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    torch.manual_seed(21)
+    model = perturb_(cPaiNN(n_features=128, score_layers=3, temp_length=100), 22).eval()
+    mb = synthetic_ambient_batch(len(n_list), n_list, seed=23, T0=900.0, T1=400.0)
+    ref, _, _ = oracle_drift(model, mb, mb.x0, 0.42)
+    model = model.to(DEV).set_math(_lib.MATH_F16X3_TC)
+    eng = model.engine()
+    out = eng.drift(eng.prepare(mb.to(DEV)), mb.x0, 0.42)
+    eng.status()
+    err = _rel(out.cpu().numpy(), ref.numpy())
+    print(f"[tc] ragged {n_list[:4]}..: {err:.3e}")
+    assert err < 2e-5
+
+
+def test_tc_full_size_agrees_with_simt_and_is_block_diagonal():
+    """BASELINE cfg 2 size.  The tensor-core drift agrees with this library's fp32 SIMT drift to fp32-level
+    error, and molecule i's drift does not depend on which other molecules share its tiles."""
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    torch.manual_seed(0)
+    model = perturb_(cPaiNN(n_features=128, score_layers=5, temp_length=100), 1).eval().to(DEV)
+    mb = synthetic_ambient_batch(4096, 9, seed=2).to(DEV)
+    eng = model.engine()
+    pb = eng.prepare(mb)
+    simt = eng.drift(pb, mb.x0, 0.3).clone()
+    model.set_math(_lib.MATH_F16X3_TC)
+    tc = eng.drift(pb, mb.x0, 0.3).clone()
+    eng.status()
+    err = _rel(tc.cpu().numpy(), simt.cpu().numpy())
+    print(f"[tc] cfg2 f16x3 vs fp32 SIMT: {err:.3e}")
+    assert err < 2e-5
+    x2 = mb.x0.clone()
+    x2[9:] = torch.roll(x2[9:], 9, 0)          # every other molecule changes
+    tc2 = eng.drift(pb, x2, 0.3)
+    assert torch.equal(tc2[:9], tc[:9])
+    model.set_math(_lib.MATH_F16_TC)
+    one = eng.drift(pb, mb.x0, 0.3).clone()
+    eng.status()
+    err1 = _rel(one.cpu().numpy(), simt.cpu().numpy())
+    print(f"[tc] cfg2 single-pass f16 vs fp32 SIMT: {err1:.3e}")
+    assert err1 < 5e-3

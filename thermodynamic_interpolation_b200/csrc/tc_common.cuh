@@ -1,0 +1,171 @@
+// tc_common.cuh - sm_100a primitives for the tensor-core path: mbarrier, bulk async copy (TMA unit,
+// SASS UBLKCP), tcgen05 (alloc / mma / commit / ld / fences), UMMA descriptors, and the split-f16
+// operand format.
+//
+// Arithmetic ("f16x3"): every fp32 value a is carried as a_hi = f16(a), a_lo = f16(a - a_hi)
+// (22 significand bits).  A product a*b is accumulated in fp32 on the tensor cores as
+//   a_hi*b_hi + a_hi*b_lo + a_lo*b_hi          (the dropped a_lo*b_lo term is ~2^-22 relative)
+// i.e. three tcgen05.mma.kind::f16 passes per K step into one TMEM accumulator.
+//
+// Shared-memory operand image (used for BOTH the A and the B operand, K-major, no swizzle -
+// UMMA "interleave" canonical layout  ((8,m),(8,k)) : ((16 B, SBO), (2 B, LBO))):
+//   byte(r, k) = (k / 8) * LBO + (r / 8) * 128 + (r % 8) * 16 + (k % 8) * 2
+// with rows r in [0,128), LBO = 2048 (one 8-column group of all 128 rows), SBO = 128.  A warp
+// that writes rows r..r+31 of one 8-column group writes 512 contiguous bytes.
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace tib {
+namespace tc {
+
+constexpr int kRows = 128;                    // rows of every operand image / MMA M and N
+constexpr uint32_t kLBO = 2048;               // bytes between 8-column groups
+constexpr uint32_t kSBO = 128;                // bytes between 8-row groups
+constexpr uint32_t kKStepBytes = 2 * kLBO;    // one MMA K step = 16 columns = two column groups
+constexpr int kChunkK = 32;                   // columns per streamed weight chunk
+constexpr uint32_t kChunkHalfBytes = kRows * kChunkK * 2;   // 8 KB (hi or lo image)
+constexpr uint32_t kChunkBytes = 2 * kChunkHalfBytes;       // 16 KB: hi image then lo image
+constexpr uint32_t kOperandHalfBytes = kRows * 128 * 2;     // 32 KB: [128 x 128] f16 image
+constexpr uint32_t kOperandBytes = 2 * kOperandHalfBytes;   // 64 KB: hi image then lo image
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- mbarrier -----------------------------------------------------------------------------------
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must not hang the GPU.  On time-out the error word is set and
+// every later wait returns at once, so the kernel drains (with garbage results) and the host
+// reports the failure.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err) {
+  if (mbar_try_wait(bar, parity)) return;
+  if (*err) return;
+  for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spins & 1023u) == 1023u && *err) return;
+  }
+  *err = 1;
+}
+
+// ---- bulk async copy global -> shared (TMA unit; completes on an mbarrier) -------------------------
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// generic-proxy smem writes -> visible to the async proxy (tcgen05.mma operand reads)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// ---- tcgen05 ------------------------------------------------------------------------------------
+__device__ __forceinline__ void tmem_alloc(uint32_t* slot, uint32_t ncols) {   // one full warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {  // the same warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// arrives on `bar` when every tcgen05.mma issued so far by this thread has completed
+__device__ __forceinline__ void tc_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T ; both operands K-major, f16 in, fp32 accumulate
+__device__ __forceinline__ void tc_mma_f16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                           uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 consecutive fp32 columns of this thread's TMEM lane (lane = 32 * (warp % 4) + laneid)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ---- UMMA descriptors ------------------------------------------------------------------------------
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
+// SBO>>4 [32,46), version=1 [46,48), layout_type=0 (no swizzle) [61,64)
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+  return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | ((uint64_t)(kLBO >> 4) << 16) | ((uint64_t)(kSBO >> 4) << 32) |
+         (1ull << 46);
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c_format=F32 [4,6), a/b_format=F16 (0),
+// a/b K-major (0), N>>3 [17,23), M>>4 [24,29)
+constexpr uint32_t kIdesc128x128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4) << 24);
+
+// One K range of `ksteps` 16-column steps: D (+)= A * B^T in f16x3.  a_hi / b_hi are the shared
+// addresses of the hi images at the first step; the lo images sit a_lo_off / b_lo_off bytes above.
+__device__ __forceinline__ void mma_f16x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo_off, uint32_t b_hi,
+                                          uint32_t b_lo_off, int ksteps, bool accumulate_first, int passes) {
+  uint32_t acc = accumulate_first ? 1u : 0u;
+  for (int ks = 0; ks < ksteps; ++ks) {
+    const uint64_t ah = make_desc(a_hi + ks * kKStepBytes), al = make_desc(a_hi + a_lo_off + ks * kKStepBytes);
+    const uint64_t bh = make_desc(b_hi + ks * kKStepBytes), bl = make_desc(b_hi + b_lo_off + ks * kKStepBytes);
+    tc_mma_f16(d_tmem, ah, bh, kIdesc128x128, acc);
+    if (passes == 3) {
+      tc_mma_f16(d_tmem, ah, bl, kIdesc128x128, 1u);
+      tc_mma_f16(d_tmem, al, bh, kIdesc128x128, 1u);
+    }
+    acc = 1u;
+  }
+}
+
+// ---- split-f16 packing ----------------------------------------------------------------------------
+__device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
+  const __half al = __float2half_rn(a - __half2float(ah)), bl = __float2half_rn(b - __half2float(bh));
+  hi = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
+  lo = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+}
+// 8 consecutive columns (one column group) of row r -> hi and lo images of an operand buffer
+__device__ __forceinline__ void store_group(unsigned char* op_hi, uint32_t lo_off, int r, int kgroup, const float (&v)[8]) {
+  uint4 h, l;
+  split2(v[0], v[1], h.x, l.x);
+  split2(v[2], v[3], h.y, l.y);
+  split2(v[4], v[5], h.z, l.z);
+  split2(v[6], v[7], h.w, l.w);
+  unsigned char* p = op_hi + (size_t)kgroup * kLBO + (size_t)r * 16;
+  *reinterpret_cast<uint4*>(p) = h;
+  *reinterpret_cast<uint4*>(p + lo_off) = l;
+}
+
+}  // namespace tc
+}  // namespace tib

@@ -12,6 +12,7 @@
 #include "simt_drift.cuh"
 #include "steps.cuh"
 #include "adw.cuh"
+#include "tc_message.cuh"
 
 namespace {
 
@@ -87,11 +88,16 @@ struct tib_model {
   const float* edge_emb = nullptr;
   const float* atom_emb = nullptr;
   tib::MlpW combine{};
-  struct Layer { tib::MlpW phi, w, upd; const float *Ut, *Vt; };
+  struct Layer { tib::MlpW phi, w, upd; const float *Ut, *Vt; const unsigned char* tc_msg = nullptr; };
   std::vector<Layer> layers;
   tib::MlpW readout{};
   const float* Vout = nullptr;
   bool attrs_set = false;
+  // tensor-core path (F = 128): per-layer streamed weight chunks in split-f16 operand images
+  unsigned char* tc_blob = nullptr;
+  bool tc_attrs_set = false;
+  int* dev_err = nullptr;     // device error word written by the bounded mbarrier waits
+  int n_sms = 148;
 };
 
 namespace {
@@ -147,11 +153,27 @@ template <> struct Tiles<64>  { static constexpr int MSG = 9, NODE = 4; };
 template <> struct Tiles<128> { static constexpr int MSG = 9, NODE = 4; };
 template <> struct Tiles<256> { static constexpr int MSG = 5, NODE = 2; };
 
+// One streamed weight chunk: rows [row0, row0+128) x columns [col0, col0+32) of the row-major matrix
+// W (leading dimension ld) as a split-f16 operand image, hi then lo (layout: csrc/tc_common.cuh).
+void pack_tc_chunk(uint16_t* out, const float* W, int ld, int row0, int col0) {
+  const size_t half = tib::tc::kChunkHalfBytes / 2;
+  for (int k = 0; k < tib::tc::kChunkK; ++k)
+    for (int r = 0; r < tib::tc::kRows; ++r) {
+      const float w = W[(size_t)(row0 + r) * ld + col0 + k];
+      const __half hi = __float2half_rn(w);
+      const __half lo = __float2half_rn(w - __half2float(hi));
+      const size_t idx = (size_t)(k / 8) * (tib::tc::kLBO / 2) + (size_t)r * 8 + (k % 8);
+      out[idx] = __half_as_ushort(hi);
+      out[half + idx] = __half_as_ushort(lo);
+    }
+}
+
 struct Workspace {
   float *s[2], *v[2], *e, *drift, *score;
   float *k;          // [7][3N] dopri stages / rk4 stages
   float *ytmp, *ycur, *ynew;
   double *partial, *scalar;
+  int *node_mol, *node_in_ptr;
   static constexpr int kPartials = 1024;
   static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
   static size_t bytes(int F, int n_nodes, long long n_edges) {
@@ -161,6 +183,7 @@ struct Workspace {
     b += align(sizeof(float) * (size_t)n_edges * F);
     b += 12 * align(sizeof(float) * (size_t)n_nodes * 3);   // drift, score, k[7], ytmp, ycur, ynew
     b += align(sizeof(double) * kPartials * 5) + align(sizeof(double) * 8);
+    b += 2 * align(sizeof(int) * ((size_t)n_nodes + 1));
     return b;
   }
   void carve(void* base, int F, int n_nodes, long long n_edges) {
@@ -181,6 +204,8 @@ struct Workspace {
     ynew = (float*)take(st);
     partial = (double*)take(sizeof(double) * kPartials * 5);
     scalar = (double*)take(sizeof(double) * 8);
+    node_mol = (int*)take(sizeof(int) * ((size_t)n_nodes + 1));
+    node_in_ptr = (int*)take(sizeof(int) * ((size_t)n_nodes + 1));
   }
   static size_t kstride(int n_nodes) { return align(sizeof(float) * (size_t)n_nodes * 3) / sizeof(float); }
 };
@@ -204,7 +229,23 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
             m->d.time_length, ws.s[0]};
   { ProfScope ps(TIB_K_EMBED, st); k_embed<F, RN><<<node_tiles, TIB_THREADS, smem_embed<F, RN>(), st>>>(ep); }
   LAUNCH_CHECK();
-  {
+  const bool use_tc = (F == 128) && m->math != TIB_MATH_FP32_SIMT;
+  int nodes_per_tile = 0, n_tiles = 0;
+  if (use_tc) {
+    if (b->n_edges >= (1ll << 31)) return fail("tensor-core path: n_edges=%lld exceeds int32 row indices", (long long)b->n_edges);
+    if (!m->tc_attrs_set) {
+      if (set_smem(tc::k_message_tc, tc::MsgSmem::TOTAL)) return -1;
+      m->tc_attrs_set = true;
+    }
+    nodes_per_tile = std::min(tc::kTileNodes, 128 / (b->max_atoms - 1));
+    n_tiles = (b->n_nodes + nodes_per_tile - 1) / nodes_per_tile;
+    tc::k_node_tables<<<(b->n_mol + 127) / 128, 128, 0, st>>>(b->mol_ptr, (const long long*)b->edge_ptr, b->n_mol,
+                                                              ws.node_mol, ws.node_in_ptr);
+    LAUNCH_CHECK();
+    ProfScope ps(TIB_K_EDGE_INIT, st);
+    tc::k_edge_init_dst<<<b->n_mol, 256, 0, st>>>(b->edge_type, m->edge_emb, b->mol_ptr, (const long long*)b->edge_ptr, ws.e, F);
+    LAUNCH_CHECK();
+  } else {
     const long long total = (long long)b->n_edges * (F / 4);
     const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
     ProfScope ps(TIB_K_EDGE_INIT, st);
@@ -214,9 +255,25 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
   int cur = 0;
   for (int l = 0; l < m->d.n_layers; ++l) {
     const tib_model::Layer& L = m->layers[l];
-    MessageP mp{db, L.phi, L.w, x, ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->d.length_scale, l == 0};
-    { ProfScope ps(TIB_K_MESSAGE, st); k_message<F, RM><<<b->n_mol, TIB_THREADS, smem_message<F, RM>(), st>>>(mp); }
-    LAUNCH_CHECK();
+    if (use_tc) {
+      tc::TcMsgP tp{};
+      tp.n_nodes = b->n_nodes; tp.n_tiles = n_tiles; tp.nodes_per_tile = nodes_per_tile;
+      tp.node_in_ptr = ws.node_in_ptr; tp.node_mol = ws.node_mol; tp.mol_ptr = b->mol_ptr;
+      tp.x = x; tp.s_old = ws.s[cur]; tp.v_old = ws.v[cur]; tp.s_new = ws.s[cur ^ 1]; tp.v_new = ws.v[cur ^ 1]; tp.e = ws.e;
+      tp.wblob = L.tc_msg;
+      tp.prm = tc::MsgParams{L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2, L.phi.b3,
+                             L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2, L.w.b3};
+      tp.length_scale = m->d.length_scale; tp.first_layer = (l == 0); tp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3;
+      tp.err = m->dev_err;
+      ProfScope ps(TIB_K_MESSAGE, st);
+      tc::k_message_tc<<<std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st>>>(tp);
+      LAUNCH_CHECK();
+    } else {
+      MessageP mp{db, L.phi, L.w, x, ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->d.length_scale, l == 0};
+      ProfScope ps(TIB_K_MESSAGE, st);
+      k_message<F, RM><<<b->n_mol, TIB_THREADS, smem_message<F, RM>(), st>>>(mp);
+      LAUNCH_CHECK();
+    }
     cur ^= 1;
     UpdateP up{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]};
     { ProfScope ps(TIB_K_UPDATE, st); k_update<F, RN><<<node_tiles, TIB_THREADS, smem_update<F, RN>(), st>>>(up); }
@@ -240,7 +297,8 @@ int check_batch(const tib_model* m, const tib_batch* b) {
 }
 
 int drift_dispatch(tib_model* m, const tib_batch* b, const float* x, float t, float* out, Workspace& ws, cudaStream_t st) {
-  if (m->math != TIB_MATH_FP32_SIMT) return fail("math mode %d is not built in this library version", m->math);
+  if (m->math != TIB_MATH_FP32_SIMT && m->d.n_features != 128)
+    return fail("the tensor-core math modes are built for n_features = 128 (got %d); use TIB_MATH_FP32_SIMT", m->d.n_features);
   switch (m->d.n_features) {
     case 32: return drift_simt<32>(m, b, x, t, out, ws, st);
     case 64: return drift_simt<64>(m, b, x, t, out, ws, st);
@@ -354,9 +412,12 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
   m->atom_emb = push(src, (size_t)d->n_types * F); src += (size_t)d->n_types * F;
   src = repack_mlp(src, {(2 + nt) * F, F, F}, stage, base, &m->combine, true);
   m->layers.resize(d->n_layers);
+  std::vector<const float*> phi_src(d->n_layers), w_src(d->n_layers);
   for (int l = 0; l < d->n_layers; ++l) {
     auto& L = m->layers[l];
+    phi_src[l] = src;
     src = repack_mlp(src, {2 * F, F, 5 * F}, stage, base, &L.phi, true);
+    w_src[l] = src;
     src = repack_mlp(src, {F, F, 5 * F}, stage, base, &L.w, true);
     L.Ut = push_T(src, F, F); src += (size_t)F * F;
     L.Vt = push_T(src, F, F); src += (size_t)F * F;
@@ -377,6 +438,40 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
   rb(m->edge_emb); rb(m->atom_emb); rb_mlp(m->combine);
   for (auto& L : m->layers) { rb_mlp(L.phi); rb_mlp(L.w); rb_mlp(L.upd); rb(L.Ut); rb(L.Vt); }
   rb_mlp(m->readout); rb(m->Vout);
+  {
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->n_sms = prop.multiProcessorCount;
+    e = cudaMalloc(&m->dev_err, sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(m->dev_err, 0, sizeof(int));
+    if (e != cudaSuccess) { tib_model_destroy(m); return fail("cudaMalloc(error word): %s", cudaGetErrorString(e)); }
+  }
+  if (F == 128) {
+    // tensor-core weight stream: per layer kChunksPerLayer chunks in consumption order (tc_message.cuh)
+    const size_t per_layer = (size_t)tib::tc::kChunksPerLayer * tib::tc::kChunkBytes;
+    std::vector<uint16_t> blob(per_layer / 2 * d->n_layers);
+    for (int l = 0; l < d->n_layers; ++l) {
+      uint16_t* out16 = blob.data() + per_layer / 2 * l;
+      const float* pW1 = phi_src[l];                                   // [F][2F]
+      const float* pW2 = pW1 + (size_t)F * 2 * F + 3 * F;              // [F][F]
+      const float* pW3 = pW2 + (size_t)F * F + 3 * F;                  // [5F][F]
+      const float* wW1 = w_src[l];                                     // [F][F]
+      const float* wW2 = wW1 + (size_t)F * F + 3 * F;
+      const float* wW3 = wW2 + (size_t)F * F + 3 * F;                  // [5F][F]
+      auto mat = [&](const float* W, int ld, int row0, int col0) {     // one [128 x 128] block = 4 chunks
+        for (int kb = 0; kb < 4; ++kb) { pack_tc_chunk(out16, W, ld, row0, col0 + 32 * kb); out16 += tib::tc::kChunkBytes / 2; }
+      };
+      mat(wW1, F, 0, 0);
+      mat(pW1, 2 * F, 0, 0);
+      mat(wW2, F, 0, 0);
+      mat(pW1, 2 * F, 0, F);
+      mat(pW2, F, 0, 0);
+      for (int sp = 0; sp < 5; ++sp) { mat(pW3, F, sp * F, 0); mat(wW3, F, sp * F, 0); }
+    }
+    e = cudaMalloc(&m->tc_blob, blob.size() * 2);
+    if (e == cudaSuccess) e = cudaMemcpy(m->tc_blob, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { tib_model_destroy(m); return fail("tensor-core weight upload: %s", cudaGetErrorString(e)); }
+    for (int l = 0; l < d->n_layers; ++l) m->layers[l].tc_msg = m->tc_blob + per_layer * l;
+  }
   *out = m;
   return 0;
 }
@@ -384,12 +479,28 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
 void tib_model_destroy(tib_model* m) {
   if (!m) return;
   if (m->dev) cudaFree(m->dev);
+  if (m->tc_blob) cudaFree(m->tc_blob);
+  if (m->dev_err) cudaFree(m->dev_err);
   delete m;
+}
+
+int tib_model_status(tib_model* m, void* stream) {
+  if (!m) return fail("null model");
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  int h = 0;
+  CUDA_TRY(cudaMemcpy(&h, m->dev_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h != 0) {
+    CUDA_TRY(cudaMemset(m->dev_err, 0, sizeof(int)));
+    return fail("device pipeline error %d: an mbarrier wait timed out inside a tensor-core kernel (results are invalid)", h);
+  }
+  return 0;
 }
 
 int tib_model_set_math(tib_model* m, int math_mode) {
   if (!m) return fail("null model");
-  if (math_mode != TIB_MATH_FP32_SIMT) return fail("math mode %d is not built in this library version", math_mode);
+  if (math_mode < TIB_MATH_FP32_SIMT || math_mode > TIB_MATH_F16_TC) return fail("unknown math mode %d", math_mode);
+  if (math_mode != TIB_MATH_FP32_SIMT && m->d.n_features != 128)
+    return fail("the tensor-core math modes are built for n_features = 128 (got %d)", m->d.n_features);
   m->math = math_mode;
   return 0;
 }
@@ -710,6 +821,29 @@ int tib_adw_drift_div(tib_adw_model* m, const double* x, const double* beta0, co
   const int blocks = (int)((n + tib::kAdwRows - 1) / tib::kAdwRows);
   tib::k_adw<256><<<blocks, 256, tib::adw_smem<256>(), (cudaStream_t)stream>>>(m->w, x, beta0, beta1, t, out_b, out_div, n);
   LAUNCH_CHECK();
+  return 0;
+}
+
+// Tensor-core plumbing self test (see k_tc_selftest): A, out are DEVICE fp32 [128][128]; W is HOST fp32 [128][128].
+int tib_selftest_gemm(const float* A, const float* W_host, float* out, int transposed, void* stream) {
+  if (!A || !W_host || !out) return fail("tib_selftest_gemm: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  std::vector<uint16_t> chunks(4 * tib::tc::kChunkBytes / 2);
+  for (int kb = 0; kb < 4; ++kb) pack_tc_chunk(chunks.data() + (size_t)kb * tib::tc::kChunkBytes / 2, W_host, 128, 0, 32 * kb);
+  unsigned char* dW = nullptr; int* derr = nullptr;
+  CUDA_TRY(cudaMalloc(&dW, chunks.size() * 2));
+  CUDA_TRY(cudaMalloc(&derr, sizeof(int)));
+  CUDA_TRY(cudaMemset(derr, 0, sizeof(int)));
+  CUDA_TRY(cudaMemcpy(dW, chunks.data(), chunks.size() * 2, cudaMemcpyHostToDevice));
+  const size_t smem = tib::tc::kOperandBytes + tib::tc::kStages * tib::tc::kChunkBytes + 256;
+  if (set_smem(tib::tc::k_tc_selftest, smem)) return -1;
+  tib::tc::k_tc_selftest<<<1, tib::tc::kThreads, smem, st>>>(A, dW, out, transposed, derr);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaStreamSynchronize(st));
+  int h = 0;
+  CUDA_TRY(cudaMemcpy(&h, derr, sizeof(int), cudaMemcpyDeviceToHost));
+  cudaFree(dW); cudaFree(derr);
+  if (h) return fail("tib_selftest_gemm: an mbarrier wait timed out (pipeline protocol error)");
   return 0;
 }
 

@@ -182,6 +182,11 @@ class DriftEngine:
     def set_math(self, mode: int):
         _lib.check(self.lib.tib_model_set_math(self.handle, mode), "tib_model_set_math")
 
+    def status(self):
+        """Synchronises the current stream and raises if a tensor-core kernel recorded a pipeline error."""
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tib_model_status(self.handle, self._stream()), "tib_model_status")
+
     def prepare(self, batch, validate: bool = True) -> PreparedBatch:
         return PreparedBatch(batch, self.hp, self.device, validate)
 
@@ -270,6 +275,18 @@ class DriftEngine:
                                                float(eps), out.data_ptr(), ptr(frame), x.numel(), self._stream()),
                        "tib_step_euler")
         return out
+
+
+def selftest_gemm(A: torch.Tensor, W: torch.Tensor, transposed: bool) -> torch.Tensor:
+    """Tensor-core plumbing self test: A (cuda fp32 [128,128]), W (fp32 [128,128]) -> A @ W.T or W @ A.T."""
+    lib = _lib.load()
+    A = A.contiguous()
+    Wh = np.ascontiguousarray(W.detach().to("cpu", torch.float32).numpy())
+    out = torch.empty(128, 128, dtype=torch.float32, device=A.device)
+    with torch.cuda.device(A.device):
+        _lib.check(lib.tib_selftest_gemm(A.data_ptr(), Wh.ctypes.data_as(C.c_void_p), out.data_ptr(), int(transposed),
+                                         C.c_void_p(torch.cuda.current_stream(A.device).cuda_stream)), "tib_selftest_gemm")
+    return out
 
 
 def launch_count(reset: bool = False) -> int:
