@@ -60,7 +60,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err) {
   if (mbar_try_wait(bar, parity)) return;
   if (*err) return;
-  for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
+  for (uint32_t spins = 0; spins < (1u << 21); ++spins) {
+    __nanosleep(40);
     if (mbar_try_wait(bar, parity)) return;
     if ((spins & 1023u) == 1023u && *err) return;
   }
@@ -150,10 +151,24 @@ __device__ __forceinline__ void mma_f16x3(uint32_t d_tmem, uint32_t a_hi, uint32
 
 // ---- split-f16 packing ----------------------------------------------------------------------------
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __half ah = __float2half_rn(a), bh = __float2half_rn(b);
-  const __half al = __float2half_rn(a - __half2float(ah)), bl = __float2half_rn(b - __half2float(bh));
-  hi = (uint32_t)__half_as_ushort(ah) | ((uint32_t)__half_as_ushort(bh) << 16);
-  lo = (uint32_t)__half_as_ushort(al) | ((uint32_t)__half_as_ushort(bl) << 16);
+  const __half2 h = __floats2half2_rn(a, b);            // one packed convert
+  const float2 hf = __half22float2(h);
+  const __half2 l = __floats2half2_rn(a - hf.x, b - hf.y);
+  hi = *reinterpret_cast<const uint32_t*>(&h);
+  lo = *reinterpret_cast<const uint32_t*>(&l);
+}
+// z * sigmoid(z) with the two MUFU approximations (ex2, rcp): ~2 ulp
+__device__ __forceinline__ float silu_fast(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return z * r;
+}
+__device__ __forceinline__ void smem_red_add(float* p, float v) {
+  asm volatile("red.shared.add.f32 [%0], %1;" ::"r"(smem_u32(p)), "f"(v) : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 // 8 consecutive columns (one column group) of row r -> hi and lo images of an operand buffer
 __device__ __forceinline__ void store_group(unsigned char* op_hi, uint32_t lo_off, int r, int kgroup, const float (&v)[8]) {

@@ -3,20 +3,24 @@
 // Work unit: a TILE = up to kTileNodes consecutive destination nodes and all their incoming edges
 // (<= 128 rows).  Edge features e[E][F] are kept in (dst, src)-lexicographic order inside the
 // library, so the rows of a tile are contiguous in HBM and every destination node is owned by
-// exactly one tile: the scatter-sum over incoming edges needs neither atomics nor a second pass.
+// exactly one tile: the scatter-sum over incoming edges needs neither global atomics nor a second pass.
 //
 // Per tile (F = 128):
-//   hidden layers   D[edge][feat] = A[edge][k] * W[feat][k]^T      (edge = TMEM lane: LayerNorm is thread-local)
+//   hidden layers   D[edge][feat] = A[edge][k] * W[feat][k]^T      (edge = TMEM lane: LayerNorm is row-local)
 //       w   : PE(d) -> LN/SiLU -> LN/SiLU                          (2 GEMMs)
 //       phi : cat[s[src], e] -> LN/SiLU -> LN/SiLU                 (3 GEMMs: the 2F input in two K halves)
-//   output layer    D^T[feat][edge] = W3[feat][k] * H2[edge][k]^T  (feat = TMEM lane: the gated
-//       scatter over the edges of a tile is a thread-local loop over TMEM columns), one 128-feature
-//       split (gates, scale_edge_dir, ds, de, cross_gates) at a time, phi and w side by side,
-//       double-buffered in TMEM so the MMAs of split i+1 overlap the scatter of split i.
-// Weights stream from L2 through a 4-stage ring of 16 KB chunks with cp.async.bulk (TMA unit).
+//   output layer    D^T[feat][edge] = W3[feat][k] * H2[edge][k]^T  (feat = TMEM lane: the gated scatter
+//       over the edges of a tile is a thread-local loop over TMEM columns), one 128-feature split
+//       (gates, scale_edge_dir, ds, de, cross_gates) at a time, phi and w side by side, double-buffered
+//       in TMEM so the MMAs of split i+1 overlap the scatter of split i.
+// Weights stream from L2 through a ring of 16 KB chunks with cp.async.bulk (TMA unit).
 //
-// Warp roles (192 threads): warps 0-3 operand builders / epilogue (thread = TMEM lane),
-// warp 4 weight producer (+ TMEM allocation), warp 5 MMA issuer.
+// Warp roles (576 threads): warps 0-15 = four epilogue groups (group g = warp / 4; a warp reads the
+// TMEM lane quarter warp % 4), warp 16 weight producer (+ TMEM allocation), warp 17 MMA issuer.
+//   hidden phase : groups 0,1 run the w chain (column halves 0-63 / 64-127 of every row),
+//                  groups 2,3 run the phi chain; LayerNorm statistics of a row are exchanged
+//                  between the two halves through shared memory.
+//   output phase : group g scatters TMEM columns (= edges) [32g, 32g+32) of every split.
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -25,9 +29,10 @@ namespace tib {
 namespace tc {
 
 constexpr int kF = 128;
-constexpr int kThreads = 192;
-constexpr int kStages = 4;
-constexpr int kTileNodes = 16;                 // destination nodes per tile (delta-v window in smem)
+constexpr int kEpiThreads = 512;
+constexpr int kThreads = kEpiThreads + 64;
+constexpr int kStages = 3;
+constexpr int kTileNodes = 16;                 // destination nodes per tile (delta-s / delta-v windows in smem)
 constexpr int kChunksPerLayer = 60;
 
 // streamed chunk order of one message layer (every entry is 4 chunks = one [128 x 128] matrix):
@@ -56,7 +61,8 @@ struct TcMsgP {
   int* err;
 };
 
-struct RowInfo { int src; int slot; float dx, dy, dz; int last; int dst; int pad; };   // 32 B
+struct RowA { int src; int dst; int slot_last; float dist; };   // slot | last << 8
+struct RowB { float dx, dy, dz, pad; };
 
 struct MsgSmem {
   // offsets (bytes) into dynamic shared memory
@@ -64,28 +70,30 @@ struct MsgSmem {
   static constexpr uint32_t Y = X + kOperandBytes;
   static constexpr uint32_t RING = Y + kOperandBytes;
   static constexpr uint32_t DV = RING + kStages * kChunkBytes;                 // [kTileNodes][3][F] fp32
-  static constexpr uint32_t ROWS = DV + kTileNodes * 3 * kF * 4;               // RowInfo[128]
-  static constexpr uint32_t BARS = ROWS + 128 * sizeof(RowInfo);
+  static constexpr uint32_t DS = DV + kTileNodes * 3 * kF * 4;                 // [kTileNodes][F] fp32
+  static constexpr uint32_t ROWA = DS + kTileNodes * kF * 4;                   // RowA[128]
+  static constexpr uint32_t ROWB = ROWA + 128 * 16;                            // RowB[128]
+  static constexpr uint32_t STAT = ROWB + 128 * 16;                            // [2 chains][2 kinds][2 halves][128] fp32
+  static constexpr uint32_t BARS = STAT + 2 * 2 * 2 * 128 * 4;
   static constexpr uint32_t TOTAL = BARS + 256;
 };
 // barrier indices
 enum { B_FULL = 0, B_EMPTY = B_FULL + kStages, B_XFULL = B_EMPTY + kStages, B_YFULL, B_YFREE, B_ACC0, B_ACC1,
        B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_COUNT };
+enum { NB_ALL = 1, NB_CHAIN_W = 2, NB_CHAIN_PHI = 3 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-
-// rows [32*warp, +32) x 16 column groups of an operand image from row-major fp32 global rows:
-// lane = (row & 7, group quad) so each 128 B line of a row is read by 4 lanes and every store
-// instruction writes 4 x 128 contiguous bytes.
+// rows [32*(warp%4), +32) x column groups [8*half, 8*half+8) of an operand image from row-major fp32
+// global rows: lane = (row & 7, group quad) so each 128 B line of a row is read by 4 lanes and every
+// store instruction writes 4 x 128 contiguous bytes.
 template <typename RowPtr>
-__device__ __forceinline__ void build_from_global(unsigned char* op, int warp, int lane, int rows, RowPtr row_ptr) {
-#pragma unroll 1
+__device__ __forceinline__ void build_from_global(unsigned char* op, int wq, int half, int lane, int rows, RowPtr row_ptr) {
+#pragma unroll
   for (int oct = 0; oct < 4; ++oct) {
-    const int r = 32 * warp + 8 * oct + (lane & 7);
+    const int r = 32 * wq + 8 * oct + (lane & 7);
     const float* src = r < rows ? row_ptr(r) : nullptr;
 #pragma unroll
-    for (int kq = 0; kq < 4; ++kq) {
-      const int g = 4 * kq + (lane >> 3);
+    for (int kq = 0; kq < 2; ++kq) {
+      const int g = 8 * half + 4 * kq + (lane >> 3);
       float v[8];
       if (src) {
         const float4 a = __ldg(reinterpret_cast<const float4*>(src + g * 8));
@@ -100,45 +108,49 @@ __device__ __forceinline__ void build_from_global(unsigned char* op, int warp, i
   }
 }
 
-// accumulator row (this thread's TMEM lane, 128 columns) -> + bias -> LayerNorm -> SiLU -> operand image
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, const float* __restrict__ b, const float* __restrict__ g,
-                                                const float* __restrict__ be, unsigned char* op, int row) {
-  float v[128];
+// Accumulator row `row` (TMEM lane), columns [64*half, +64): + bias -> LayerNorm over all 128 columns
+// (statistics exchanged with the thread that owns the other half) -> SiLU -> operand image.
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int half, int row, const float* __restrict__ b,
+                                                const float* __restrict__ g, const float* __restrict__ be,
+                                                unsigned char* op, float* stat, int bar_id) {
+  float v[64];
 #pragma unroll
-  for (int c = 0; c < 4; ++c) {
+  for (int c = 0; c < 2; ++c) {
     float t[32];
-    tmem_ld32(taddr + 32 * c, t);
+    tmem_ld32(taddr + 64 * half + 32 * c, t);
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[32 * c + i] = t[i];
   }
   float sum = 0.0f;
 #pragma unroll
-  for (int c = 0; c < 32; ++c) {
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(b) + c);
+  for (int c = 0; c < 16; ++c) {
+    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + 64 * half) + c);
     v[4 * c + 0] += bb.x; v[4 * c + 1] += bb.y; v[4 * c + 2] += bb.z; v[4 * c + 3] += bb.w;
     sum += (v[4 * c + 0] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);
   }
-  const float mean = sum * (1.0f / 128.0f);
+  stat[half * 128 + row] = sum;
+  named_bar_sync(bar_id, 256);
+  const float mean = (stat[row] + stat[128 + row]) * (1.0f / 128.0f);
   float ss = 0.0f;
 #pragma unroll
-  for (int i = 0; i < 128; ++i) {
+  for (int i = 0; i < 64; ++i) {
     v[i] -= mean;
     ss = fmaf(v[i], v[i], ss);
   }
-  const float rstd = rsqrtf(ss * (1.0f / 128.0f) + 1e-5f);
+  stat[256 + half * 128 + row] = ss;
+  named_bar_sync(bar_id, 256);
+  const float rstd = rsqrtf((stat[256 + row] + stat[384 + row]) * (1.0f / 128.0f) + 1e-5f);
 #pragma unroll
-  for (int kg = 0; kg < 16; ++kg) {
-    const float4 g0 = __ldg(reinterpret_cast<const float4*>(g) + 2 * kg), g1 = __ldg(reinterpret_cast<const float4*>(g) + 2 * kg + 1);
-    const float4 e0 = __ldg(reinterpret_cast<const float4*>(be) + 2 * kg), e1 = __ldg(reinterpret_cast<const float4*>(be) + 2 * kg + 1);
+  for (int kg = 0; kg < 8; ++kg) {
+    const float4* gp = reinterpret_cast<const float4*>(g + 64 * half) + 2 * kg;
+    const float4* ep = reinterpret_cast<const float4*>(be + 64 * half) + 2 * kg;
+    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), e0 = __ldg(ep), e1 = __ldg(ep + 1);
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     float y[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float z = fmaf(v[8 * kg + i] * rstd, gg[i], ee[i]);
-      y[i] = __fdividef(z, 1.0f + __expf(-z));
-    }
-    store_group(op, kOperandHalfBytes, row, kg, y);
+    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(v[8 * kg + i] * rstd, gg[i], ee[i]));
+    store_group(op, kOperandHalfBytes, row, 8 * half + kg, y);
   }
 }
 
@@ -148,7 +160,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   unsigned char* const Y = smem + MsgSmem::Y;
   unsigned char* const RING = smem + MsgSmem::RING;
   float* const DV = reinterpret_cast<float*>(smem + MsgSmem::DV);
-  RowInfo* const ROWS = reinterpret_cast<RowInfo*>(smem + MsgSmem::ROWS);
+  float* const DS = reinterpret_cast<float*>(smem + MsgSmem::DS);
+  RowA* const ROWA = reinterpret_cast<RowA*>(smem + MsgSmem::ROWA);
+  RowB* const ROWB = reinterpret_cast<RowB*>(smem + MsgSmem::ROWB);
+  float* const STAT = reinterpret_cast<float*>(smem + MsgSmem::STAT);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + MsgSmem::BARS);
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + MsgSmem::BARS + 8 * B_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -156,20 +171,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
 
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
-    mbar_init(&bars[B_XFULL], 128); mbar_init(&bars[B_YFULL], 128);
+    mbar_init(&bars[B_XFULL], 256); mbar_init(&bars[B_YFULL], 256);
     mbar_init(&bars[B_YFREE], 1); mbar_init(&bars[B_ACC0], 1); mbar_init(&bars[B_ACC1], 1);
     mbar_init(&bars[B_TFULL0], 1); mbar_init(&bars[B_TFULL1], 1);
-    mbar_init(&bars[B_TEMPTY0], 128); mbar_init(&bars[B_TEMPTY1], 128);
+    mbar_init(&bars[B_TEMPTY0], kEpiThreads); mbar_init(&bars[B_TEMPTY1], kEpiThreads);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 512);
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_splits = p.first_layer ? 3 : 5;
 
-  if (warp == 4) {
+  if (warp == 16) {
     // =========================== weight producer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
@@ -183,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         }
       }
     }
-  } else if (warp == 5) {
+  } else if (warp == 17) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
@@ -230,19 +245,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       }
     }
   } else {
-    // =========================== builders / epilogue (128 threads) ===========================
-    uint32_t pa0 = 0, pa1 = 0, pyf = 0, ptf[2] = {0, 0};
-    const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    const int f = tid;                                      // feature owned in the transposed epilogue
+    // =========================== builders / epilogue (512 threads) ===========================
+    const int grp = warp >> 2, wq = warp & 3;
+    const int row = 32 * wq + lane;                         // TMEM lane: edge row (hidden) / feature (output)
+    const int chain = grp >> 1, half = grp & 1;             // chain 0 = w, 1 = phi
+    float* const stat = STAT + chain * 512;
+    const int bar_id = chain ? NB_CHAIN_PHI : NB_CHAIN_W;
+    uint32_t pacc = 0, pyf = 0, ptf[2] = {0, 0};
+    const uint32_t lane_taddr = tmem + ((uint32_t)(wq * 32) << 16);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int node_lo = tile * p.nodes_per_tile;
       const int node_hi = min(node_lo + p.nodes_per_tile, p.n_nodes);
       const int row0 = __ldg(p.node_in_ptr + node_lo);
       const int rows = __ldg(p.node_in_ptr + node_hi) - row0;
-      epi_bar_sync();                                       // previous tile's readers of ROWS are done
-      float dist = 0.0f;
-      {
-        RowInfo ri; ri.src = 0; ri.slot = 0; ri.dx = ri.dy = ri.dz = 0.0f; ri.last = 0; ri.dst = node_lo; ri.pad = 0;
+      // ---- tile tables (the previous tile finished with an all-group barrier)
+      if (tid < 128) {
+        RowA ra; ra.src = 0; ra.dst = node_lo; ra.slot_last = 0; ra.dist = 0.0f;
+        RowB rb; rb.dx = rb.dy = rb.dz = rb.pad = 0.0f;
         if (tid < rows) {
           const int er = row0 + tid;
           int j = node_lo;
@@ -256,189 +275,142 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
           const float rx = __ldg(p.x + 3 * src + 0) - __ldg(p.x + 3 * j + 0);
           const float ry = __ldg(p.x + 3 * src + 1) - __ldg(p.x + 3 * j + 1);
           const float rz = __ldg(p.x + 3 * src + 2) - __ldg(p.x + 3 * j + 2);
-          dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
+          const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
           const float den = 1.0f + dist;
-          ri.src = src; ri.slot = j - node_lo; ri.dst = j; ri.last = (ip == n - 2);
-          ri.dx = __fdiv_rn(rx, den); ri.dy = __fdiv_rn(ry, den); ri.dz = __fdiv_rn(rz, den);
+          ra.src = src; ra.dst = j; ra.slot_last = (j - node_lo) | ((ip == n - 2) << 8); ra.dist = dist;
+          rb.dx = __fdiv_rn(rx, den); rb.dy = __fdiv_rn(ry, den); rb.dz = __fdiv_rn(rz, den);
         }
-        ROWS[tid] = ri;
+        ROWA[tid] = ra; ROWB[tid] = rb;
       }
-#pragma unroll
-      for (int i = 0; i < kTileNodes * 3; ++i) DV[i * kF + f] = 0.0f;
-      epi_bar_sync();
+      for (int i = tid; i < kTileNodes * 4 * kF; i += kEpiThreads) DV[i] = 0.0f;   // DV and DS are contiguous
+      named_bar_sync(NB_ALL, kEpiThreads);
 
-      // ---- E1: PositionalEncoder(edge_dist) -> X                                 (cpainn.py:283)
+      if (chain == 0) {
+        // ---- w chain.  E1: PositionalEncoder(edge_dist) -> X                      (cpainn.py:283)
+        const float dist = ROWA[row].dist;
 #pragma unroll 1
-      for (int kg = 0; kg < 16; ++kg) {
-        float v[8];
+        for (int kg = 8 * half; kg < 8 * half + 8; ++kg) {
+          float v[8];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          float sn = 0.0f, cs = 0.0f;
-          if (tid < rows) sincosf(pe_arg(dist, p.length_scale, 4 * kg + q + 1), &sn, &cs);
-          v[2 * q] = cs; v[2 * q + 1] = sn;
+          for (int q = 0; q < 4; ++q) {
+            float sn = 0.0f, cs = 0.0f;
+            if (row < rows) sincosf(pe_arg(dist, p.length_scale, 4 * kg + q + 1), &sn, &cs);
+            v[2 * q] = cs; v[2 * q + 1] = sn;
+          }
+          store_group(X, kOperandHalfBytes, row, kg, v);
         }
-        store_group(X, kOperandHalfBytes, tid, kg, v);
+        fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+        // E3: hidden 1 -> X
+        mbar_wait(&bars[B_ACC0], pacc, err); pacc ^= 1; tc_fence_after();
+        hidden_epilogue(lane_taddr, half, row, p.prm.w_b1, p.prm.w_g1, p.prm.w_be1, X, stat, bar_id);
+        tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+        // E5: hidden 2 -> X (final: B operand of the output layer)
+        mbar_wait(&bars[B_ACC0], pacc, err); pacc ^= 1; tc_fence_after();
+        hidden_epilogue(lane_taddr, half, row, p.prm.w_b2, p.prm.w_g2, p.prm.w_be2, X, stat, bar_id);
+        tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+      } else {
+        // ---- phi chain.  E2: s[src] -> Y                                          (cpainn.py:275-281)
+        build_from_global(Y, wq, half, lane, rows, [&](int r) { return p.s_old + (size_t)ROWA[r].src * kF; });
+        fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+        // E4: e rows -> Y (after the s[src] half has been consumed)
+        mbar_wait(&bars[B_YFREE], pyf, err); pyf ^= 1;
+        build_from_global(Y, wq, half, lane, rows, [&](int r) { return p.e + (size_t)(row0 + r) * kF; });
+        fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+        // E6: hidden 1 -> Y
+        mbar_wait(&bars[B_ACC1], pacc, err); pacc ^= 1; tc_fence_after();
+        hidden_epilogue(lane_taddr + 128, half, row, p.prm.phi_b1, p.prm.phi_g1, p.prm.phi_be1, Y, stat, bar_id);
+        tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+        // E7: hidden 2 -> Y (final)
+        mbar_wait(&bars[B_ACC1], pacc, err); pacc ^= 1; tc_fence_after();
+        hidden_epilogue(lane_taddr + 128, half, row, p.prm.phi_b2, p.prm.phi_g2, p.prm.phi_be2, Y, stat, bar_id);
+        tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
       }
-      fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
-      // ---- E2: s[src] -> Y                                                       (cpainn.py:275-281)
-      build_from_global(Y, warp, lane, rows, [&](int r) { return p.s_old + (size_t)ROWS[r].src * kF; });
-      fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
-      // ---- E3: w hidden 1 -> X
-      mbar_wait(&bars[B_ACC0], pa0, err); pa0 ^= 1; tc_fence_after();
-      hidden_epilogue(lane_taddr, p.prm.w_b1, p.prm.w_g1, p.prm.w_be1, X, tid);
-      tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
-      // ---- E4: e rows -> Y (after the s[src] half has been consumed)
-      mbar_wait(&bars[B_YFREE], pyf, err); pyf ^= 1;
-      build_from_global(Y, warp, lane, rows, [&](int r) { return p.e + (size_t)(row0 + r) * kF; });
-      fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
-      // ---- E5: w hidden 2 -> X (final: B operand of the output layer)
-      mbar_wait(&bars[B_ACC0], pa0, err); pa0 ^= 1; tc_fence_after();
-      hidden_epilogue(lane_taddr, p.prm.w_b2, p.prm.w_g2, p.prm.w_be2, X, tid);
-      tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
-      // ---- E6: phi hidden 1 -> Y
-      mbar_wait(&bars[B_ACC1], pa1, err); pa1 ^= 1; tc_fence_after();
-      hidden_epilogue(lane_taddr + 128, p.prm.phi_b1, p.prm.phi_g1, p.prm.phi_be1, Y, tid);
-      tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
-      // ---- E7: phi hidden 2 -> Y (final)
-      mbar_wait(&bars[B_ACC1], pa1, err); pa1 ^= 1; tc_fence_after();
-      hidden_epilogue(lane_taddr + 128, p.prm.phi_b2, p.prm.phi_g2, p.prm.phi_be2, Y, tid);
-      tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
 
-      // ---- E8..: output layer, transposed: this thread owns feature f, TMEM columns are edges.
-      // m = phi3 * w3, split order gates | scale_edge_dir | ds | de | cross_gates   (cpainn.py:285-290)
+      // ---- output layer, transposed: this thread owns feature f and the edges (TMEM columns)
+      // [32*grp, +32).  m = phi3 * w3, split order gates | scale_edge_dir | ds | de | cross_gates
+      // (cpainn.py:285-290)
+      const int f = row;
+      const int c0 = 32 * grp;
       for (int it = 0; it < n_splits; ++it) {
         const int sp = p.first_layer ? it + 1 : it;
         const int pb = it & 1;
-        const float bphi = __ldg(p.prm.phi_b3 + sp * kF + f), bw = __ldg(p.prm.w_b3 + sp * kF + f);
         mbar_wait(&bars[B_TFULL0 + pb], ptf[pb], err); ptf[pb] ^= 1; tc_fence_after();
-        const uint32_t tphi = lane_taddr + 256 * pb, tw = tphi + 128;
-        float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
-        float vj0 = 0.0f, vj1 = 0.0f, vj2 = 0.0f;
-        bool have_vj = false;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          if (32 * c >= rows) break;
+        if (c0 < rows) {
+          const float bphi = __ldg(p.prm.phi_b3 + sp * kF + f), bw = __ldg(p.prm.w_b3 + sp * kF + f);
           float P[32], Q[32];
-          tmem_ld32(tphi + 32 * c, P);
-          tmem_ld32(tw + 32 * c, Q);
+          tmem_ld32(lane_taddr + 256 * pb + c0, P);
+          tmem_ld32(lane_taddr + 256 * pb + 128 + c0, Q);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) {
-            const int r = 32 * c + q;
-            if (r < rows) {
-              const float m = __fmul_rn(P[q] + bphi, Q[q] + bw);
-              const RowInfo ri = ROWS[r];
-              if (sp == 0) {            // gates * v[src]
-                const float* vi = p.v_old + (size_t)ri.src * 3 * kF + f;
+          for (int q = 0; q < 32; ++q) P[q] = (c0 + q < rows) ? __fmul_rn(P[q] + bphi, Q[q] + bw) : 0.0f;
+          if (sp == 3) {
+            // e += de                                                                (cpainn.py:308)
+            float* ep = p.e + (size_t)(row0 + c0) * kF + f;
+#pragma unroll
+            for (int q = 0; q < 32; ++q) Q[q] = (c0 + q < rows) ? ep[(size_t)q * kF] : 0.0f;
+#pragma unroll
+            for (int q = 0; q < 32; ++q)
+              if (c0 + q < rows) ep[(size_t)q * kF] = Q[q] + P[q];
+          } else {
+            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+            float vj0 = 0.0f, vj1 = 0.0f, vj2 = 0.0f;
+            bool fresh = true;                              // first row of a destination group in this chunk
+#pragma unroll
+            for (int q = 0; q < 32; ++q) {
+              const float m = P[q];
+              const RowA ra = ROWA[c0 + q];
+              if (sp == 0) {              // gates * v[src]
+                const float* vi = p.v_old + (size_t)ra.src * 3 * kF + f;
                 a0 = fmaf(m, __ldg(vi), a0); a1 = fmaf(m, __ldg(vi + kF), a1); a2 = fmaf(m, __ldg(vi + 2 * kF), a2);
-              } else if (sp == 1) {     // scale_edge_dir * dir
-                a0 = fmaf(m, ri.dx, a0); a1 = fmaf(m, ri.dy, a1); a2 = fmaf(m, ri.dz, a2);
-              } else if (sp == 2) {     // ds
+              } else if (sp == 1) {       // scale_edge_dir * dir
+                const RowB rb = ROWB[c0 + q];
+                a0 = fmaf(m, rb.dx, a0); a1 = fmaf(m, rb.dy, a1); a2 = fmaf(m, rb.dz, a2);
+              } else if (sp == 2) {       // ds
                 a0 += m;
-              } else if (sp == 3) {     // e += de                                   (cpainn.py:308)
-                float* ep = p.e + (size_t)(row0 + r) * kF + f;
-                *ep = *ep + m;
-              } else {                  // cross_gates * (dir x v[dst])              (cpainn.py:296-300)
-                if (!have_vj) {
-                  const float* vj = p.v_old + (size_t)ri.dst * 3 * kF + f;
+              } else {                    // cross_gates * (dir x v[dst])              (cpainn.py:296-300)
+                const RowB rb = ROWB[c0 + q];
+                if (fresh) {
+                  const float* vj = p.v_old + (size_t)ra.dst * 3 * kF + f;
                   vj0 = __ldg(vj); vj1 = __ldg(vj + kF); vj2 = __ldg(vj + 2 * kF);
-                  have_vj = true;
                 }
-                const float c0 = __fmul_rn(ri.dy, vj2) - __fmul_rn(ri.dz, vj1);
-                const float c1 = __fmul_rn(ri.dz, vj0) - __fmul_rn(ri.dx, vj2);
-                const float c2 = __fmul_rn(ri.dx, vj1) - __fmul_rn(ri.dy, vj0);
-                a0 = fmaf(m, c0, a0); a1 = fmaf(m, c1, a1); a2 = fmaf(m, c2, a2);
+                const float x0 = __fmul_rn(rb.dy, vj2) - __fmul_rn(rb.dz, vj1);
+                const float x1 = __fmul_rn(rb.dz, vj0) - __fmul_rn(rb.dx, vj2);
+                const float x2 = __fmul_rn(rb.dx, vj1) - __fmul_rn(rb.dy, vj0);
+                a0 = fmaf(m, x0, a0); a1 = fmaf(m, x1, a1); a2 = fmaf(m, x2, a2);
               }
-              if (ri.last && sp != 3) {   // all incoming edges of this destination node seen
+              fresh = false;
+              if ((ra.slot_last >> 8) || q == 31) {   // destination group complete, or continues in the next chunk
+                const int slot = ra.slot_last & 0xFF;
                 if (sp == 2) {
-                  const size_t o = (size_t)ri.dst * kF + f;
-                  p.s_new[o] = __ldg(p.s_old + o) + a0;                               // cpainn.py:306
+                  smem_red_add(DS + slot * kF + f, a0);
                 } else {
-                  float* dv = DV + ri.slot * 3 * kF + f;
-                  dv[0] += a0; dv[kF] += a1; dv[2 * kF] += a2;
+                  float* dv = DV + slot * 3 * kF + f;
+                  smem_red_add(dv, a0); smem_red_add(dv + kF, a1); smem_red_add(dv + 2 * kF, a2);
                 }
                 a0 = a1 = a2 = 0.0f;
-                have_vj = false;
+                fresh = true;
               }
             }
           }
         }
         tc_fence_before(); mbar_arrive(&bars[B_TEMPTY0 + pb]);
       }
-      // ---- v_new = v_old + sum of the three equivariant contributions              (cpainn.py:305)
-      for (int j = node_lo; j < node_hi; ++j) {
-        const float* dv = DV + (j - node_lo) * 3 * kF + f;
-        const size_t o = (size_t)j * 3 * kF + f;
-#pragma unroll
-        for (int xyz = 0; xyz < 3; ++xyz)
-          p.v_new[o + xyz * kF] = (p.first_layer ? 0.0f : __ldg(p.v_old + o + xyz * kF)) + dv[xyz * kF];
+      // ---- s_new = s_old + sum ds (cpainn.py:306), v_new = v_old + sum dv (cpainn.py:305)
+      named_bar_sync(NB_ALL, kEpiThreads);
+      const int nn = node_hi - node_lo;
+      for (int i = tid; i < nn * kF; i += kEpiThreads) {
+        const size_t o = (size_t)node_lo * kF + i;
+        p.s_new[o] = __ldg(p.s_old + o) + DS[i];
       }
+      for (int i = tid; i < nn * 3 * kF; i += kEpiThreads) {
+        const size_t o = (size_t)node_lo * 3 * kF + i;
+        p.v_new[o] = (p.first_layer ? 0.0f : __ldg(p.v_old + o)) + DV[i];
+      }
+      named_bar_sync(NB_ALL, kEpiThreads);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 512);
-}
-
-// -------------------------------------------------------------------------------------------------
-// Self test of the tensor-core plumbing (descriptors, operand image, ring, TMEM addressing):
-//   transposed = 0:  out[r][c] = sum_k A[r][k] * W[c][k]      (lane = row of A)
-//   transposed = 1:  out[r][c] = sum_k W[r][k] * A[c][k]      (lane = row of W)
-// A is fp32 [128][128] row-major, wchunks = 4 packed chunks of W [128][128], out fp32 [128][128].
-__global__ void __launch_bounds__(kThreads, 1) k_tc_selftest(const float* __restrict__ A, const unsigned char* __restrict__ wchunks,
-                                                             float* __restrict__ out, int transposed, int* err_ptr) {
-  extern __shared__ __align__(1024) unsigned char smem[];
-  unsigned char* const X = smem;
-  unsigned char* const RING = smem + kOperandBytes;
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kOperandBytes + kStages * kChunkBytes);
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  volatile int* err = err_ptr;
-  if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) mbar_init(&bars[i], 1);
-    mbar_init(&bars[4], 128);   // operand full
-    mbar_init(&bars[5], 1);     // accumulator full
-    fence_mbar_init();
-  }
-  if (warp == 4) tmem_alloc(tmem_slot, 128);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = *tmem_slot;
-  if (warp == 4) {
-    if (lane == 0)
-      for (int c = 0; c < 4; ++c) {
-        mbar_arrive_expect_tx(&bars[c], kChunkBytes);
-        bulk_g2s(RING + c * kChunkBytes, wchunks + (size_t)c * kChunkBytes, kChunkBytes, &bars[c]);
-      }
-  } else if (warp == 5) {
-    if (lane == 0) {
-      mbar_wait(&bars[4], 0, err);
-      tc_fence_after();
-      for (int kb = 0; kb < 4; ++kb) {
-        mbar_wait(&bars[kb], 0, err);
-        tc_fence_after();
-        const uint32_t wst = smem_u32(RING) + kb * kChunkBytes, opk = smem_u32(X) + kb * (2 * kKStepBytes);
-        if (!transposed) mma_f16x3(tmem, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, kb > 0, 3);
-        else             mma_f16x3(tmem, wst, kChunkHalfBytes, opk, kOperandHalfBytes, 2, kb > 0, 3);
-      }
-      tc_commit(&bars[5]);
-    }
-  } else {
-    build_from_global(X, warp, lane, 128, [&](int r) { return A + (size_t)r * 128; });
-    fence_proxy_async();
-    mbar_arrive(&bars[4]);
-    mbar_wait(&bars[5], 0, err);
-    tc_fence_after();
-    const uint32_t lane_taddr = tmem + ((uint32_t)(warp * 32) << 16);
-    for (int c = 0; c < 4; ++c) {
-      float t[32];
-      tmem_ld32(lane_taddr + 32 * c, t);
-      for (int i = 0; i < 32; ++i) out[(size_t)tid * 128 + 32 * c + i] = t[i];
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == 16) tmem_dealloc(tmem, 512);
 }
 
 // ---- small helpers of the tensor-core drift ---------------------------------------------------------

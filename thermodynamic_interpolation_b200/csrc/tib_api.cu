@@ -13,6 +13,7 @@
 #include "steps.cuh"
 #include "adw.cuh"
 #include "tc_message.cuh"
+#include "tc_selftest.cuh"
 
 namespace {
 
@@ -835,9 +836,9 @@ int tib_selftest_gemm(const float* A, const float* W_host, float* out, int trans
   CUDA_TRY(cudaMalloc(&derr, sizeof(int)));
   CUDA_TRY(cudaMemset(derr, 0, sizeof(int)));
   CUDA_TRY(cudaMemcpy(dW, chunks.data(), chunks.size() * 2, cudaMemcpyHostToDevice));
-  const size_t smem = tib::tc::kOperandBytes + tib::tc::kStages * tib::tc::kChunkBytes + 256;
+  const size_t smem = tib::tc::kOperandBytes + tib::tc::kSelfStages * tib::tc::kChunkBytes + 256;
   if (set_smem(tib::tc::k_tc_selftest, smem)) return -1;
-  tib::tc::k_tc_selftest<<<1, tib::tc::kThreads, smem, st>>>(A, dW, out, transposed, derr);
+  tib::tc::k_tc_selftest<<<1, tib::tc::kSelfThreads, smem, st>>>(A, dW, out, transposed, derr);
   LAUNCH_CHECK();
   CUDA_TRY(cudaStreamSynchronize(st));
   int h = 0;
