@@ -197,6 +197,13 @@ enum { TIB_K_EMBED = 0, TIB_K_EDGE_INIT = 1, TIB_K_MESSAGE = 2, TIB_K_UPDATE = 3
  * [128][128]; W: HOST fp32 [128][128].  Synchronous. */
 int tib_selftest_gemm(const float* A, const float* W_host, float* out, int transposed, void* stream);
 
+/* Pipeline diagnostics of the tensor-core message kernel: enable = 1 allocates per-CTA stall counters that
+ * every later launch overwrites; `out` (HOST, [max_ctas][8] int64, may be NULL) receives, per CTA, cycles the
+ * MMA thread waited for {0: weights, 1: operands, 3: accumulator drain}, {2: the producer waited for a free
+ * ring slot}, {4: MMA thread total}, {5,6: an epilogue thread of the w / phi chain waited for accumulators},
+ * {7: ... for output-layer accumulators}.  Synchronises the device. */
+int tib_debug_counters(tib_model* m, int enable, long long* out, int max_ctas);
+
 int tib_profile_begin(void);
 int tib_profile_end(double* ms_sum, uint64_t* launches);
 

@@ -57,6 +57,7 @@ SYMBOLS = [
     ("tib_model_destroy", None, [C.c_void_p]),
     ("tib_model_set_math", C.c_int, [C.c_void_p, C.c_int]),
     ("tib_model_status", C.c_int, [C.c_void_p, C.c_void_p]),
+    ("tib_debug_counters", C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     ("tib_selftest_gemm", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("tib_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
     ("tib_drift", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -60,12 +60,19 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err) {
   if (mbar_try_wait(bar, parity)) return;
   if (*err) return;
-  for (uint32_t spins = 0; spins < (1u << 21); ++spins) {
-    __nanosleep(40);
-    if (mbar_try_wait(bar, parity)) return;
+  for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
+    if (mbar_try_wait(bar, parity)) return;       // try_wait itself suspends the thread for a bounded time
     if ((spins & 1023u) == 1023u && *err) return;
   }
   *err = 1;
+}
+
+// wait + add the stalled cycles to *acc (pipeline diagnostics; acc may be a dummy)
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, volatile int* err, long long& acc) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  mbar_wait(bar, parity, err);
+  acc += clock64() - t0;
 }
 
 // ---- bulk async copy global -> shared (TMA unit; completes on an mbarrier) -------------------------

@@ -59,9 +59,10 @@ struct TcMsgP {
   int first_layer;
   int passes;               // 3 = split-f16 (fp32-faithful), 1 = single f16 pass
   int* err;
+  long long* dbg;           // optional [gridDim.x][8] stall-cycle counters (diagnostics), or NULL
 };
 
-struct RowA { int src; int dst; int slot_last; float dist; };   // slot | last << 8
+struct RowA { int src; int dst; int slot_last; float dist; };   // slot | last << 8 | first << 9
 struct RowB { float dx, dy, dz, pad; };
 
 struct MsgSmem {
@@ -188,26 +189,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     // =========================== weight producer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
+      long long w_empty = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int c = 0; c < kChunksPerLayer; ++c) {
           if (p.first_layer && ((c >= 20 && c < 28) || c >= 52)) continue;   // splits 0 and 4 multiply v = 0
-          mbar_wait(&bars[B_EMPTY + stage], ph ^ 1, err);
+          mbar_wait_timed(&bars[B_EMPTY + stage], ph ^ 1, err, w_empty);
           mbar_arrive_expect_tx(&bars[B_FULL + stage], kChunkBytes);
           bulk_g2s(RING + stage * kChunkBytes, p.wblob + (size_t)c * kChunkBytes, kChunkBytes, &bars[B_FULL + stage]);
           if (++stage == kStages) { stage = 0; ph ^= 1; }
         }
       }
+      if (p.dbg) p.dbg[blockIdx.x * 8 + 2] = w_empty;
     }
   } else if (warp == 17) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
       uint32_t px = 0, py = 0, pte[2] = {0, 0};
+      long long w_weights = 0, w_operands = 0, w_tempty = 0;
+      const long long t_start = clock64();
       const uint32_t xa = smem_u32(X), ya = smem_u32(Y), ring = smem_u32(RING);
       // one [128 x 128] matrix = 4 chunks.  transposed = weights are the A operand.
       auto gemm = [&](uint32_t d, uint32_t op, bool transposed, bool accumulate) {
         for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait(&bars[B_FULL + stage], ph, err);
+          mbar_wait_timed(&bars[B_FULL + stage], ph, err, w_weights);
           tc_fence_after();
           const uint32_t wst = ring + stage * kChunkBytes, opk = op + kb * (2 * kKStepBytes);
           if (!transposed) mma_f16x3(d, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, accumulate || kb > 0, p.passes);
@@ -218,30 +223,34 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       };
       const uint32_t acc0 = tmem, acc1 = tmem + 128;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait(&bars[B_XFULL], px, err); px ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands); px ^= 1; tc_fence_after();
         gemm(acc0, xa, false, false);                       // w layer 1   : PE(d)
         tc_commit(&bars[B_ACC0]);
-        mbar_wait(&bars[B_YFULL], py, err); py ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands); py ^= 1; tc_fence_after();
         gemm(acc1, ya, false, false);                       // phi layer 1 : s[src] half
         tc_commit(&bars[B_YFREE]);
-        mbar_wait(&bars[B_XFULL], px, err); px ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands); px ^= 1; tc_fence_after();
         gemm(acc0, xa, false, false);                       // w layer 2
         tc_commit(&bars[B_ACC0]);
-        mbar_wait(&bars[B_YFULL], py, err); py ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands); py ^= 1; tc_fence_after();
         gemm(acc1, ya, false, true);                        // phi layer 1 : e half (accumulates)
         tc_commit(&bars[B_ACC1]);
-        mbar_wait(&bars[B_YFULL], py, err); py ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands); py ^= 1; tc_fence_after();
         gemm(acc1, ya, false, false);                       // phi layer 2
         tc_commit(&bars[B_ACC1]);
-        mbar_wait(&bars[B_YFULL], py, err); py ^= 1;
-        mbar_wait(&bars[B_XFULL], px, err); px ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands); py ^= 1;
+        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands); px ^= 1; tc_fence_after();
         for (int it = 0; it < n_splits; ++it) {
           const int pb = it & 1;
-          mbar_wait(&bars[B_TEMPTY0 + pb], pte[pb] ^ 1, err); pte[pb] ^= 1; tc_fence_after();
+          mbar_wait_timed(&bars[B_TEMPTY0 + pb], pte[pb] ^ 1, err, w_tempty); pte[pb] ^= 1; tc_fence_after();
           gemm(tmem + 256 * pb, ya, true, false);           // phi layer 3, one split (transposed)
           gemm(tmem + 256 * pb + 128, xa, true, false);     // w layer 3, same split
           tc_commit(&bars[B_TFULL0 + pb]);
         }
+      }
+      if (p.dbg) {
+        p.dbg[blockIdx.x * 8 + 0] = w_weights; p.dbg[blockIdx.x * 8 + 1] = w_operands;
+        p.dbg[blockIdx.x * 8 + 3] = w_tempty; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
       }
     }
   } else {
@@ -252,6 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     float* const stat = STAT + chain * 512;
     const int bar_id = chain ? NB_CHAIN_PHI : NB_CHAIN_W;
     uint32_t pacc = 0, pyf = 0, ptf[2] = {0, 0};
+    long long w_acc = 0, w_tfull = 0;
     const uint32_t lane_taddr = tmem + ((uint32_t)(wq * 32) << 16);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int node_lo = tile * p.nodes_per_tile;
@@ -277,7 +287,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
           const float rz = __ldg(p.x + 3 * src + 2) - __ldg(p.x + 3 * j + 2);
           const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
           const float den = 1.0f + dist;
-          ra.src = src; ra.dst = j; ra.slot_last = (j - node_lo) | ((ip == n - 2) << 8); ra.dist = dist;
+          ra.src = src; ra.dst = j; ra.slot_last = (j - node_lo) | ((ip == n - 2) << 8) | ((ip == 0) << 9); ra.dist = dist;
           rb.dx = __fdiv_rn(rx, den); rb.dy = __fdiv_rn(ry, den); rb.dz = __fdiv_rn(rz, den);
         }
         ROWA[tid] = ra; ROWB[tid] = rb;
@@ -301,11 +311,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         }
         fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         // E3: hidden 1 -> X
-        mbar_wait(&bars[B_ACC0], pacc, err); pacc ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr, half, row, p.prm.w_b1, p.prm.w_g1, p.prm.w_be1, X, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         // E5: hidden 2 -> X (final: B operand of the output layer)
-        mbar_wait(&bars[B_ACC0], pacc, err); pacc ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr, half, row, p.prm.w_b2, p.prm.w_g2, p.prm.w_be2, X, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
       } else {
@@ -313,15 +323,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         build_from_global(Y, wq, half, lane, rows, [&](int r) { return p.s_old + (size_t)ROWA[r].src * kF; });
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         // E4: e rows -> Y (after the s[src] half has been consumed)
-        mbar_wait(&bars[B_YFREE], pyf, err); pyf ^= 1;
+        mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc); pyf ^= 1;
         build_from_global(Y, wq, half, lane, rows, [&](int r) { return p.e + (size_t)(row0 + r) * kF; });
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         // E6: hidden 1 -> Y
-        mbar_wait(&bars[B_ACC1], pacc, err); pacc ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr + 128, half, row, p.prm.phi_b1, p.prm.phi_g1, p.prm.phi_be1, Y, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         // E7: hidden 2 -> Y (final)
-        mbar_wait(&bars[B_ACC1], pacc, err); pacc ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr + 128, half, row, p.prm.phi_b2, p.prm.phi_g2, p.prm.phi_be2, Y, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
       }
@@ -334,7 +344,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       for (int it = 0; it < n_splits; ++it) {
         const int sp = p.first_layer ? it + 1 : it;
         const int pb = it & 1;
-        mbar_wait(&bars[B_TFULL0 + pb], ptf[pb], err); ptf[pb] ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull); ptf[pb] ^= 1; tc_fence_after();
         if (c0 < rows) {
           const float bphi = __ldg(p.prm.phi_b3 + sp * kF + f), bw = __ldg(p.prm.w_b3 + sp * kF + f);
           float P[32], Q[32];
@@ -354,6 +364,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
             float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
             float vj0 = 0.0f, vj1 = 0.0f, vj2 = 0.0f;
             bool fresh = true;                              // first row of a destination group in this chunk
+            bool whole = false;                             // ... and the group started inside this chunk
 #pragma unroll
             for (int q = 0; q < 32; ++q) {
               const float m = P[q];
@@ -377,15 +388,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
                 const float x2 = __fmul_rn(rb.dx, vj1) - __fmul_rn(rb.dy, vj0);
                 a0 = fmaf(m, x0, a0); a1 = fmaf(m, x1, a1); a2 = fmaf(m, x2, a2);
               }
+              if (ra.slot_last & 0x200) whole = true;
               fresh = false;
-              if ((ra.slot_last >> 8) || q == 31) {   // destination group complete, or continues in the next chunk
+              if ((ra.slot_last & 0x100) || q == 31) {   // destination group complete, or continues in the next chunk
                 const int slot = ra.slot_last & 0xFF;
+                const bool exclusive = whole && (ra.slot_last & 0x100);   // no other group touches this slot
                 if (sp == 2) {
-                  smem_red_add(DS + slot * kF + f, a0);
+                  if (exclusive) DS[slot * kF + f] += a0; else smem_red_add(DS + slot * kF + f, a0);
                 } else {
                   float* dv = DV + slot * 3 * kF + f;
-                  smem_red_add(dv, a0); smem_red_add(dv + kF, a1); smem_red_add(dv + 2 * kF, a2);
+                  if (exclusive) { dv[0] += a0; dv[kF] += a1; dv[2 * kF] += a2; }
+                  else { smem_red_add(dv, a0); smem_red_add(dv + kF, a1); smem_red_add(dv + 2 * kF, a2); }
                 }
+                whole = false;
                 a0 = a1 = a2 = 0.0f;
                 fresh = true;
               }
@@ -406,6 +421,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         p.v_new[o] = (p.first_layer ? 0.0f : __ldg(p.v_old + o)) + DV[i];
       }
       named_bar_sync(NB_ALL, kEpiThreads);
+    }
+    if (p.dbg && (tid == 0 || tid == 256)) {
+      p.dbg[blockIdx.x * 8 + (tid ? 6 : 5)] = w_acc;
+      if (tid == 0) p.dbg[blockIdx.x * 8 + 7] = w_tfull;
     }
   }
   tc_fence_before();

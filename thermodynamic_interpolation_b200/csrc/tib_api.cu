@@ -99,6 +99,7 @@ struct tib_model {
   bool tc_attrs_set = false;
   int* dev_err = nullptr;     // device error word written by the bounded mbarrier waits
   int n_sms = 148;
+  long long* dev_dbg = nullptr;   // optional stall counters of the last tensor-core message launch
 };
 
 namespace {
@@ -265,7 +266,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       tp.prm = tc::MsgParams{L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2, L.phi.b3,
                              L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2, L.w.b3};
       tp.length_scale = m->d.length_scale; tp.first_layer = (l == 0); tp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3;
-      tp.err = m->dev_err;
+      tp.err = m->dev_err; tp.dbg = m->dev_dbg;
       ProfScope ps(TIB_K_MESSAGE, st);
       tc::k_message_tc<<<std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st>>>(tp);
       LAUNCH_CHECK();
@@ -482,6 +483,7 @@ void tib_model_destroy(tib_model* m) {
   if (m->dev) cudaFree(m->dev);
   if (m->tc_blob) cudaFree(m->tc_blob);
   if (m->dev_err) cudaFree(m->dev_err);
+  if (m->dev_dbg) cudaFree(m->dev_dbg);
   delete m;
 }
 
@@ -494,6 +496,20 @@ int tib_model_status(tib_model* m, void* stream) {
     CUDA_TRY(cudaMemset(m->dev_err, 0, sizeof(int)));
     return fail("device pipeline error %d: an mbarrier wait timed out inside a tensor-core kernel (results are invalid)", h);
   }
+  return 0;
+}
+
+int tib_debug_counters(tib_model* m, int enable, long long* out, int max_ctas) {
+  if (!m) return fail("null model");
+  if (enable && !m->dev_dbg) {
+    CUDA_TRY(cudaMalloc(&m->dev_dbg, sizeof(long long) * 8 * 1024));
+    CUDA_TRY(cudaMemset(m->dev_dbg, 0, sizeof(long long) * 8 * 1024));
+  }
+  if (out && m->dev_dbg) {
+    CUDA_TRY(cudaDeviceSynchronize());
+    CUDA_TRY(cudaMemcpy(out, m->dev_dbg, sizeof(long long) * 8 * (size_t)std::min(max_ctas, 1024), cudaMemcpyDeviceToHost));
+  }
+  if (!enable && m->dev_dbg) { cudaFree(m->dev_dbg); m->dev_dbg = nullptr; }
   return 0;
 }
 

@@ -1,0 +1,40 @@
+"""Diagnostics: where the tensor-core message kernel's pipeline waits (per-CTA stall-cycle counters,
+include/tib.h tib_debug_counters).  Run on a B200:  python tools/tc_pipeline_stalls.py [--math 1]"""
+import argparse
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests._util import perturb_  # noqa: E402
+from thermodynamic_interpolation_b200 import _lib  # noqa: E402
+from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN  # noqa: E402
+from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--math", type=int, default=1)
+ap.add_argument("--mols", type=int, default=4096)
+args = ap.parse_args()
+torch.manual_seed(0)
+model = perturb_(cPaiNN(n_features=128, score_layers=5, temp_length=100), 1).eval().to("cuda:0").set_math(args.math)
+mb = synthetic_ambient_batch(args.mols, 9, seed=2).to("cuda:0")
+eng = model.engine()
+pb = eng.prepare(mb)
+lib = _lib.load()
+for _ in range(3):
+    eng.drift(pb, mb.x0, 0.3)
+lib.tib_debug_counters(eng.handle, 1, None, 0)
+eng.drift(pb, mb.x0, 0.3)
+eng.status()
+n = 148
+buf = np.zeros((n, 8), dtype=np.int64)
+lib.tib_debug_counters(eng.handle, 1, buf.ctypes.data_as(C.c_void_p), n)
+names = ["mma:wait weights", "mma:wait operands", "producer:wait free slot", "mma:wait acc drain", "mma:total",
+         "epi(w chain):wait acc", "epi(phi chain):wait acc", "epi:wait output acc"]
+tot = buf[:, 4].mean()
+print("last message launch (layer 5), mean cycles per CTA over", n, "CTAs; tiles per CTA ~", 4096 * 9 / 16 / n)
+for i, nm in enumerate(names):
+    print(f"  {nm:28s} {buf[:, i].mean():12.0f}  ({100 * buf[:, i].mean() / tot:5.1f}% of mma total)")
