@@ -128,6 +128,38 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
   for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
 }
 
+// 8 consecutive fp32 columns of this thread's TMEM lane
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+  uint32_t r[8];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(taddr)
+               : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// sin and cos of a moderate fp32 argument (|a| < ~1e4): 3-term Cody-Waite reduction by pi/2 and the
+// minimax polynomials of the Cephes sinf / cosf kernels on [-pi/4, pi/4] (~1 ulp); no slow path, no stack.
+__device__ __forceinline__ void sincos_cw(float a, float& s, float& c) {
+  const float q = rintf(a * 0.636619772367581343f);
+  float r = fmaf(q, -1.5707962512969971f, a);
+  r = fmaf(q, -7.5497894158615964e-08f, r);
+  r = fmaf(q, -5.3903029534742384e-15f, r);
+  const float r2 = r * r;
+  float sp = fmaf(r2, -1.9515295891e-4f, 8.3321608736e-3f);
+  sp = fmaf(sp, r2, -1.6666654611e-1f);
+  const float sr = fmaf(sp * r2, r, r);
+  float cp = fmaf(r2, 2.443315711809948e-5f, -1.388731625493765e-3f);
+  cp = fmaf(cp, r2, 4.166664568298827e-2f);
+  const float cr = fmaf(cp * r2, r2, fmaf(r2, -0.5f, 1.0f));
+  const int n = (int)q;
+  const float ss = (n & 1) ? cr : sr, cc = (n & 1) ? sr : cr;
+  s = (n & 2) ? -ss : ss;
+  c = ((n + 1) & 2) ? -cc : cc;
+}
+
 // ---- UMMA descriptors ------------------------------------------------------------------------------
 // shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): start>>4 [0,14), LBO>>4 [16,30),
 // SBO>>4 [32,46), version=1 [46,48), layout_type=0 (no swizzle) [61,64)

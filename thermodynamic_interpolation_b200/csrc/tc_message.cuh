@@ -31,7 +31,10 @@ namespace tc {
 constexpr int kF = 128;
 constexpr int kEpiThreads = 512;
 constexpr int kThreads = kEpiThreads + 64;
-constexpr int kStages = 3;
+constexpr int kStages = 4;
+// fp32 layer parameters staged in shared memory once per CTA:
+//   [0,6F): w  {b1,g1,be1,b2,g2,be2}   [6F,12F): phi {b1,g1,be1,b2,g2,be2}   [12F,17F): phi b3   [17F,22F): w b3
+constexpr int kPrmW = 0, kPrmPhi = 6 * 128, kPrmB3 = 12 * 128, kPrmFloats = 22 * 128;
 constexpr int kTileNodes = 16;                 // destination nodes per tile (delta-s / delta-v windows in smem)
 constexpr int kChunksPerLayer = 60;
 
@@ -70,12 +73,12 @@ struct MsgSmem {
   static constexpr uint32_t X = 0;
   static constexpr uint32_t Y = X + kOperandBytes;
   static constexpr uint32_t RING = Y + kOperandBytes;
-  static constexpr uint32_t DV = RING + kStages * kChunkBytes;                 // [kTileNodes][3][F] fp32
-  static constexpr uint32_t DS = DV + kTileNodes * 3 * kF * 4;                 // [kTileNodes][F] fp32
-  static constexpr uint32_t ROWA = DS + kTileNodes * kF * 4;                   // RowA[128]
+  static constexpr uint32_t PRM = RING + kStages * kChunkBytes;                // layer parameters (fp32), see kPrm*
+  static constexpr uint32_t ROWA = PRM + kPrmFloats * 4;                       // RowA[128]
   static constexpr uint32_t ROWB = ROWA + 128 * 16;                            // RowB[128]
   static constexpr uint32_t STAT = ROWB + 128 * 16;                            // [2 chains][2 kinds][2 halves][128] fp32
-  static constexpr uint32_t BARS = STAT + 2 * 2 * 2 * 128 * 4;
+  static constexpr uint32_t SLOTROW = STAT + 2 * 2 * 2 * 128 * 4;              // int[kTileNodes + 1] first row of each slot
+  static constexpr uint32_t BARS = SLOTROW + 128;
   static constexpr uint32_t TOTAL = BARS + 256;
 };
 // barrier indices
@@ -111,8 +114,8 @@ __device__ __forceinline__ void build_from_global(unsigned char* op, int wq, int
 
 // Accumulator row `row` (TMEM lane), columns [64*half, +64): + bias -> LayerNorm over all 128 columns
 // (statistics exchanged with the thread that owns the other half) -> SiLU -> operand image.
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int half, int row, const float* __restrict__ b,
-                                                const float* __restrict__ g, const float* __restrict__ be,
+__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int half, int row, const float* b,
+                                                const float* g, const float* be,
                                                 unsigned char* op, float* stat, int bar_id) {
   float v[64];
 #pragma unroll
@@ -125,7 +128,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int half, int ro
   float sum = 0.0f;
 #pragma unroll
   for (int c = 0; c < 16; ++c) {
-    const float4 bb = __ldg(reinterpret_cast<const float4*>(b + 64 * half) + c);
+    const float4 bb = reinterpret_cast<const float4*>(b + 64 * half)[c];
     v[4 * c + 0] += bb.x; v[4 * c + 1] += bb.y; v[4 * c + 2] += bb.z; v[4 * c + 3] += bb.w;
     sum += (v[4 * c + 0] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);
   }
@@ -145,7 +148,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int half, int ro
   for (int kg = 0; kg < 8; ++kg) {
     const float4* gp = reinterpret_cast<const float4*>(g + 64 * half) + 2 * kg;
     const float4* ep = reinterpret_cast<const float4*>(be + 64 * half) + 2 * kg;
-    const float4 g0 = __ldg(gp), g1 = __ldg(gp + 1), e0 = __ldg(ep), e1 = __ldg(ep + 1);
+    const float4 g0 = gp[0], g1 = gp[1], e0 = ep[0], e1 = ep[1];
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     float y[8];
@@ -155,13 +158,13 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int half, int ro
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
+__global__ void __maxnreg__(112) k_message_tc(TcMsgP p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* const X = smem + MsgSmem::X;
   unsigned char* const Y = smem + MsgSmem::Y;
   unsigned char* const RING = smem + MsgSmem::RING;
-  float* const DV = reinterpret_cast<float*>(smem + MsgSmem::DV);
-  float* const DS = reinterpret_cast<float*>(smem + MsgSmem::DS);
+  float* const PRM = reinterpret_cast<float*>(smem + MsgSmem::PRM);
+  int* const SLOTROW = reinterpret_cast<int*>(smem + MsgSmem::SLOTROW);
   RowA* const ROWA = reinterpret_cast<RowA*>(smem + MsgSmem::ROWA);
   RowB* const ROWB = reinterpret_cast<RowB*>(smem + MsgSmem::ROWB);
   float* const STAT = reinterpret_cast<float*>(smem + MsgSmem::STAT);
@@ -179,6 +182,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, 512);
+  {
+    const float* src[22] = {p.prm.w_b1, p.prm.w_g1, p.prm.w_be1, p.prm.w_b2, p.prm.w_g2, p.prm.w_be2,
+                            p.prm.phi_b1, p.prm.phi_g1, p.prm.phi_be1, p.prm.phi_b2, p.prm.phi_g2, p.prm.phi_be2,
+                            p.prm.phi_b3, p.prm.phi_b3 + kF, p.prm.phi_b3 + 2 * kF, p.prm.phi_b3 + 3 * kF, p.prm.phi_b3 + 4 * kF,
+                            p.prm.w_b3, p.prm.w_b3 + kF, p.prm.w_b3 + 2 * kF, p.prm.w_b3 + 3 * kF, p.prm.w_b3 + 4 * kF};
+    for (int i = tid; i < kPrmFloats; i += kThreads) PRM[i] = __ldg(src[i >> 7] + (i & 127));
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -262,6 +272,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     const int bar_id = chain ? NB_CHAIN_PHI : NB_CHAIN_W;
     uint32_t pacc = 0, pyf = 0, ptf[2] = {0, 0};
     long long w_acc = 0, w_tfull = 0;
+    long long phc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = clock64();
+#define TIB_PHASE(i) do { const long long _t = clock64(); phc[i] += _t - tlast; tlast = _t; } while (0)
     const uint32_t lane_taddr = tmem + ((uint32_t)(wq * 32) << 16);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int node_lo = tile * p.nodes_per_tile;
@@ -292,8 +305,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         }
         ROWA[tid] = ra; ROWB[tid] = rb;
       }
-      for (int i = tid; i < kTileNodes * 4 * kF; i += kEpiThreads) DV[i] = 0.0f;   // DV and DS are contiguous
+      if (tid >= 128 && tid <= 128 + kTileNodes && node_lo + (tid - 128) <= node_hi)
+        SLOTROW[tid - 128] = __ldg(p.node_in_ptr + node_lo + (tid - 128)) - row0;
       named_bar_sync(NB_ALL, kEpiThreads);
+      TIB_PHASE(0);   // tile tables
 
       if (chain == 0) {
         // ---- w chain.  E1: PositionalEncoder(edge_dist) -> X                      (cpainn.py:283)
@@ -304,128 +319,146 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             float sn = 0.0f, cs = 0.0f;
-            if (row < rows) sincosf(pe_arg(dist, p.length_scale, 4 * kg + q + 1), &sn, &cs);
+            if (row < rows) sincos_cw(pe_arg(dist, p.length_scale, 4 * kg + q + 1), sn, cs);
             v[2 * q] = cs; v[2 * q + 1] = sn;
           }
           store_group(X, kOperandHalfBytes, row, kg, v);
         }
         fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+        TIB_PHASE(1);   // E1 / E2
         // E3: hidden 1 -> X
         mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr, half, row, p.prm.w_b1, p.prm.w_g1, p.prm.w_be1, X, stat, bar_id);
+        hidden_epilogue(lane_taddr, half, row, PRM + kPrmW, PRM + kPrmW + kF, PRM + kPrmW + 2 * kF, X, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+        TIB_PHASE(2);   // E3 / E4
         // E5: hidden 2 -> X (final: B operand of the output layer)
         mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr, half, row, p.prm.w_b2, p.prm.w_g2, p.prm.w_be2, X, stat, bar_id);
+        hidden_epilogue(lane_taddr, half, row, PRM + kPrmW + 3 * kF, PRM + kPrmW + 4 * kF, PRM + kPrmW + 5 * kF, X, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+        TIB_PHASE(3);   // E5 / E6
       } else {
         // ---- phi chain.  E2: s[src] -> Y                                          (cpainn.py:275-281)
         build_from_global(Y, wq, half, lane, rows, [&](int r) { return p.s_old + (size_t)ROWA[r].src * kF; });
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+        TIB_PHASE(1);
         // E4: e rows -> Y (after the s[src] half has been consumed)
         mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc); pyf ^= 1;
         build_from_global(Y, wq, half, lane, rows, [&](int r) { return p.e + (size_t)(row0 + r) * kF; });
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+        TIB_PHASE(2);
         // E6: hidden 1 -> Y
         mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr + 128, half, row, p.prm.phi_b1, p.prm.phi_g1, p.prm.phi_be1, Y, stat, bar_id);
+        hidden_epilogue(lane_taddr + 128, half, row, PRM + kPrmPhi, PRM + kPrmPhi + kF, PRM + kPrmPhi + 2 * kF, Y, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+        TIB_PHASE(3);
         // E7: hidden 2 -> Y (final)
         mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr + 128, half, row, p.prm.phi_b2, p.prm.phi_g2, p.prm.phi_be2, Y, stat, bar_id);
+        hidden_epilogue(lane_taddr + 128, half, row, PRM + kPrmPhi + 3 * kF, PRM + kPrmPhi + 4 * kF, PRM + kPrmPhi + 5 * kF, Y, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+        TIB_PHASE(4);   // E7
       }
 
-      // ---- output layer, transposed: this thread owns feature f and the edges (TMEM columns)
-      // [32*grp, +32).  m = phi3 * w3, split order gates | scale_edge_dir | ds | de | cross_gates
-      // (cpainn.py:285-290)
+      // ---- output layer, transposed: this thread owns feature f = TMEM lane; TMEM columns are edges.
+      // m = phi3 * w3, split order gates | scale_edge_dir | ds | de | cross_gates     (cpainn.py:285-290)
+      // Epilogue group g owns whole destination nodes (slots [g*per, g*per+per)), so the sums over
+      // incoming edges live in registers across all splits: no shared-memory scatter, no atomics.
       const int f = row;
-      const int c0 = 32 * grp;
+      const int nslots = node_hi - node_lo;
+      const int per = (nslots + 3) >> 2;                    // <= kTileNodes / 4 = 4 destination nodes per group
+      float acc_s[4], acc_v[4][3];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { acc_s[k] = 0.0f; acc_v[k][0] = acc_v[k][1] = acc_v[k][2] = 0.0f; }
       for (int it = 0; it < n_splits; ++it) {
         const int sp = p.first_layer ? it + 1 : it;
         const int pb = it & 1;
+        const float bphi = PRM[kPrmB3 + sp * kF + f], bw = PRM[kPrmB3 + 5 * kF + sp * kF + f];
         mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull); ptf[pb] ^= 1; tc_fence_after();
-        if (c0 < rows) {
-          const float bphi = __ldg(p.prm.phi_b3 + sp * kF + f), bw = __ldg(p.prm.w_b3 + sp * kF + f);
-          float P[32], Q[32];
-          tmem_ld32(lane_taddr + 256 * pb + c0, P);
-          tmem_ld32(lane_taddr + 256 * pb + 128 + c0, Q);
+        const uint32_t tphi = lane_taddr + 256 * pb, tw = tphi + 128;
 #pragma unroll
-          for (int q = 0; q < 32; ++q) P[q] = (c0 + q < rows) ? __fmul_rn(P[q] + bphi, Q[q] + bw) : 0.0f;
-          if (sp == 3) {
-            // e += de                                                                (cpainn.py:308)
-            float* ep = p.e + (size_t)(row0 + c0) * kF + f;
-#pragma unroll
-            for (int q = 0; q < 32; ++q) Q[q] = (c0 + q < rows) ? ep[(size_t)q * kF] : 0.0f;
-#pragma unroll
-            for (int q = 0; q < 32; ++q)
-              if (c0 + q < rows) ep[(size_t)q * kF] = Q[q] + P[q];
-          } else {
-            float a0 = 0.0f, a1 = 0.0f, a2 = 0.0f;
+        for (int k = 0; k < 4; ++k) {
+          const int slot = grp * per + k;
+          if (k < per && slot < nslots) {
+            const int rbeg = SLOTROW[slot], rend = SLOTROW[slot + 1];
             float vj0 = 0.0f, vj1 = 0.0f, vj2 = 0.0f;
-            bool fresh = true;                              // first row of a destination group in this chunk
-            bool whole = false;                             // ... and the group started inside this chunk
+            if (sp == 4) {
+              const float* vj = p.v_old + (size_t)(node_lo + slot) * 3 * kF + f;
+              vj0 = __ldg(vj); vj1 = __ldg(vj + kF); vj2 = __ldg(vj + 2 * kF);
+            }
+#pragma unroll 1
+            for (int r0 = rbeg; r0 < rend; r0 += 8) {
+              float P[8], Q[8];
+              tmem_ld8(tphi + r0, P);
+              tmem_ld8(tw + r0, Q);
+              const int nr = min(8, rend - r0);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const float m = P[q];
-              const RowA ra = ROWA[c0 + q];
-              if (sp == 0) {              // gates * v[src]
-                const float* vi = p.v_old + (size_t)ra.src * 3 * kF + f;
-                a0 = fmaf(m, __ldg(vi), a0); a1 = fmaf(m, __ldg(vi + kF), a1); a2 = fmaf(m, __ldg(vi + 2 * kF), a2);
-              } else if (sp == 1) {       // scale_edge_dir * dir
-                const RowB rb = ROWB[c0 + q];
-                a0 = fmaf(m, rb.dx, a0); a1 = fmaf(m, rb.dy, a1); a2 = fmaf(m, rb.dz, a2);
-              } else if (sp == 2) {       // ds
-                a0 += m;
-              } else {                    // cross_gates * (dir x v[dst])              (cpainn.py:296-300)
-                const RowB rb = ROWB[c0 + q];
-                if (fresh) {
-                  const float* vj = p.v_old + (size_t)ra.dst * 3 * kF + f;
-                  vj0 = __ldg(vj); vj1 = __ldg(vj + kF); vj2 = __ldg(vj + 2 * kF);
+              for (int q = 0; q < 8; ++q) P[q] = q < nr ? __fmul_rn(P[q] + bphi, Q[q] + bw) : 0.0f;
+              if (sp == 0) {            // gates * v[src]
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const float* vi = p.v_old + (size_t)ROWA[r0 + q].src * 3 * kF + f;
+                  acc_v[k][0] = fmaf(P[q], __ldg(vi), acc_v[k][0]);
+                  acc_v[k][1] = fmaf(P[q], __ldg(vi + kF), acc_v[k][1]);
+                  acc_v[k][2] = fmaf(P[q], __ldg(vi + 2 * kF), acc_v[k][2]);
                 }
-                const float x0 = __fmul_rn(rb.dy, vj2) - __fmul_rn(rb.dz, vj1);
-                const float x1 = __fmul_rn(rb.dz, vj0) - __fmul_rn(rb.dx, vj2);
-                const float x2 = __fmul_rn(rb.dx, vj1) - __fmul_rn(rb.dy, vj0);
-                a0 = fmaf(m, x0, a0); a1 = fmaf(m, x1, a1); a2 = fmaf(m, x2, a2);
-              }
-              if (ra.slot_last & 0x200) whole = true;
-              fresh = false;
-              if ((ra.slot_last & 0x100) || q == 31) {   // destination group complete, or continues in the next chunk
-                const int slot = ra.slot_last & 0xFF;
-                const bool exclusive = whole && (ra.slot_last & 0x100);   // no other group touches this slot
-                if (sp == 2) {
-                  if (exclusive) DS[slot * kF + f] += a0; else smem_red_add(DS + slot * kF + f, a0);
-                } else {
-                  float* dv = DV + slot * 3 * kF + f;
-                  if (exclusive) { dv[0] += a0; dv[kF] += a1; dv[2 * kF] += a2; }
-                  else { smem_red_add(dv, a0); smem_red_add(dv + kF, a1); smem_red_add(dv + 2 * kF, a2); }
+              } else if (sp == 1) {     // scale_edge_dir * dir
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const RowB rb = ROWB[r0 + q];
+                  acc_v[k][0] = fmaf(P[q], rb.dx, acc_v[k][0]);
+                  acc_v[k][1] = fmaf(P[q], rb.dy, acc_v[k][1]);
+                  acc_v[k][2] = fmaf(P[q], rb.dz, acc_v[k][2]);
                 }
-                whole = false;
-                a0 = a1 = a2 = 0.0f;
-                fresh = true;
+              } else if (sp == 2) {     // ds
+#pragma unroll
+                for (int q = 0; q < 8; ++q) acc_s[k] += P[q];
+              } else if (sp == 3) {     // e += de                                     (cpainn.py:308)
+                float* ep = p.e + (size_t)(row0 + r0) * kF + f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) Q[q] = q < nr ? ep[(size_t)q * kF] : 0.0f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (q < nr) ep[(size_t)q * kF] = Q[q] + P[q];
+              } else {                  // cross_gates * (dir x v[dst])                (cpainn.py:296-300)
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const RowB rb = ROWB[r0 + q];
+                  const float x0 = __fmul_rn(rb.dy, vj2) - __fmul_rn(rb.dz, vj1);
+                  const float x1 = __fmul_rn(rb.dz, vj0) - __fmul_rn(rb.dx, vj2);
+                  const float x2 = __fmul_rn(rb.dx, vj1) - __fmul_rn(rb.dy, vj0);
+                  acc_v[k][0] = fmaf(P[q], x0, acc_v[k][0]);
+                  acc_v[k][1] = fmaf(P[q], x1, acc_v[k][1]);
+                  acc_v[k][2] = fmaf(P[q], x2, acc_v[k][2]);
+                }
               }
             }
           }
         }
         tc_fence_before(); mbar_arrive(&bars[B_TEMPTY0 + pb]);
       }
+      TIB_PHASE(5);     // output layer (all splits, including waits)
       // ---- s_new = s_old + sum ds (cpainn.py:306), v_new = v_old + sum dv (cpainn.py:305)
-      named_bar_sync(NB_ALL, kEpiThreads);
-      const int nn = node_hi - node_lo;
-      for (int i = tid; i < nn * kF; i += kEpiThreads) {
-        const size_t o = (size_t)node_lo * kF + i;
-        p.s_new[o] = __ldg(p.s_old + o) + DS[i];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const int slot = grp * per + k;
+        if (k < per && slot < nslots) {
+          const size_t j = (size_t)(node_lo + slot);
+          p.s_new[j * kF + f] = __ldg(p.s_old + j * kF + f) + acc_s[k];
+#pragma unroll
+          for (int xyz = 0; xyz < 3; ++xyz) {
+            const size_t o = (j * 3 + xyz) * kF + f;
+            p.v_new[o] = (p.first_layer ? 0.0f : __ldg(p.v_old + o)) + acc_v[k][xyz];
+          }
+        }
       }
-      for (int i = tid; i < nn * 3 * kF; i += kEpiThreads) {
-        const size_t o = (size_t)node_lo * 3 * kF + i;
-        p.v_new[o] = (p.first_layer ? 0.0f : __ldg(p.v_old + o)) + DV[i];
-      }
-      named_bar_sync(NB_ALL, kEpiThreads);
+      named_bar_sync(NB_ALL, kEpiThreads);                  // every reader of this tile's tables is done
+      TIB_PHASE(6);     // write-back + end-of-tile barrier
     }
     if (p.dbg && (tid == 0 || tid == 256)) {
       p.dbg[blockIdx.x * 8 + (tid ? 6 : 5)] = w_acc;
       if (tid == 0) p.dbg[blockIdx.x * 8 + 7] = w_tfull;
+      for (int i = 0; i < 8; ++i) p.dbg[(size_t)(gridDim.x + blockIdx.x * 2 + (tid ? 1 : 0)) * 8 + i] = phc[i];
     }
+#undef TIB_PHASE
   }
   tc_fence_before();
   __syncthreads();

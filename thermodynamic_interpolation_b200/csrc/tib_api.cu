@@ -502,12 +502,12 @@ int tib_model_status(tib_model* m, void* stream) {
 int tib_debug_counters(tib_model* m, int enable, long long* out, int max_ctas) {
   if (!m) return fail("null model");
   if (enable && !m->dev_dbg) {
-    CUDA_TRY(cudaMalloc(&m->dev_dbg, sizeof(long long) * 8 * 1024));
-    CUDA_TRY(cudaMemset(m->dev_dbg, 0, sizeof(long long) * 8 * 1024));
+    CUDA_TRY(cudaMalloc(&m->dev_dbg, sizeof(long long) * 8 * 2048));
+    CUDA_TRY(cudaMemset(m->dev_dbg, 0, sizeof(long long) * 8 * 2048));
   }
   if (out && m->dev_dbg) {
     CUDA_TRY(cudaDeviceSynchronize());
-    CUDA_TRY(cudaMemcpy(out, m->dev_dbg, sizeof(long long) * 8 * (size_t)std::min(max_ctas, 1024), cudaMemcpyDeviceToHost));
+    CUDA_TRY(cudaMemcpy(out, m->dev_dbg, sizeof(long long) * 8 * (size_t)std::min(max_ctas, 2048), cudaMemcpyDeviceToHost));
   }
   if (!enable && m->dev_dbg) { cudaFree(m->dev_dbg); m->dev_dbg = nullptr; }
   return 0;

@@ -30,11 +30,20 @@ lib.tib_debug_counters(eng.handle, 1, None, 0)
 eng.drift(pb, mb.x0, 0.3)
 eng.status()
 n = 148
-buf = np.zeros((n, 8), dtype=np.int64)
-lib.tib_debug_counters(eng.handle, 1, buf.ctypes.data_as(C.c_void_p), n)
+buf_all = np.zeros((3 * n, 8), dtype=np.int64)
+lib.tib_debug_counters(eng.handle, 1, buf_all.ctypes.data_as(C.c_void_p), 3 * n)
+buf = buf_all[:n]
 names = ["mma:wait weights", "mma:wait operands", "producer:wait free slot", "mma:wait acc drain", "mma:total",
          "epi(w chain):wait acc", "epi(phi chain):wait acc", "epi:wait output acc"]
 tot = buf[:, 4].mean()
 print("last message launch (layer 5), mean cycles per CTA over", n, "CTAs; tiles per CTA ~", 4096 * 9 / 16 / n)
 for i, nm in enumerate(names):
     print(f"  {nm:28s} {buf[:, i].mean():12.0f}  ({100 * buf[:, i].mean() / tot:5.1f}% of mma total)")
+
+ph = buf_all[n:].reshape(n, 2, 8).mean(0)
+tiles = 4096 * 9 / 16 / n
+print("epilogue phases, mean cycles per tile (thread 0 = w chain | thread 256 = phi chain):")
+for i, nm in enumerate(["tile tables+barrier", "E1 PE | E2 s[src]", "E3 w hid1 | E4 e rows", "E5 w hid2 | E6 phi hid1", "-- | E7 phi hid2",
+                        "output layer", "write-back"]):
+    print(f"  {nm:28s} {ph[0, i] / tiles:10.0f} | {ph[1, i] / tiles:10.0f}")
+print("  total per tile               %10.0f | %10.0f" % (ph[0].sum() / tiles, ph[1].sum() / tiles))
