@@ -158,7 +158,7 @@ __device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int half, int ro
   }
 }
 
-__global__ void __maxnreg__(112) k_message_tc(TcMsgP p) {
+__global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* const X = smem + MsgSmem::X;
   unsigned char* const Y = smem + MsgSmem::Y;
