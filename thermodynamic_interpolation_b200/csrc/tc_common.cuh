@@ -57,14 +57,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must not hang the GPU.  On time-out the error word is set and
 // every later wait returns at once, so the kernel drains (with garbage results) and the host
 // reports the failure.
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err) {
-  if (mbar_try_wait(bar, parity)) return;
+__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, volatile int* err) {
   if (*err) return;
   for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
     if (mbar_try_wait(bar, parity)) return;       // try_wait itself suspends the thread for a bounded time
     if ((spins & 1023u) == 1023u && *err) return;
   }
   *err = 1;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volatile int* err) {
+  if (mbar_try_wait(bar, parity)) return;
+  mbar_wait_slow(bar, parity, err);
 }
 
 // wait + add the stalled cycles to *acc (pipeline diagnostics; acc may be a dummy)
@@ -176,6 +179,7 @@ constexpr uint32_t kIdesc128x128 = (1u << 4) | ((128u >> 3) << 17) | ((128u >> 4
 __device__ __forceinline__ void mma_f16x3(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo_off, uint32_t b_hi,
                                           uint32_t b_lo_off, int ksteps, bool accumulate_first, int passes) {
   uint32_t acc = accumulate_first ? 1u : 0u;
+#pragma unroll 1
   for (int ks = 0; ks < ksteps; ++ks) {
     const uint64_t ah = make_desc(a_hi + ks * kKStepBytes), al = make_desc(a_hi + a_lo_off + ks * kKStepBytes);
     const uint64_t bh = make_desc(b_hi + ks * kKStepBytes), bl = make_desc(b_hi + b_lo_off + ks * kKStepBytes);

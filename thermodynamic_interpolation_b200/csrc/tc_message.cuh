@@ -114,47 +114,78 @@ __device__ __forceinline__ void build_from_global(unsigned char* op, int wq, int
 
 // Accumulator row `row` (TMEM lane), columns [64*half, +64): + bias -> LayerNorm over all 128 columns
 // (statistics exchanged with the thread that owns the other half) -> SiLU -> operand image.
-__device__ __forceinline__ void hidden_epilogue(uint32_t taddr, int half, int row, const float* b,
-                                                const float* g, const float* be,
-                                                unsigned char* op, float* stat, int bar_id) {
-  float v[64];
-#pragma unroll
-  for (int c = 0; c < 2; ++c) {
-    float t[32];
-    tmem_ld32(taddr + 64 * half + 32 * c, t);
-#pragma unroll
-    for (int i = 0; i < 32; ++i) v[32 * c + i] = t[i];
-  }
+// The hot loops below are deliberately ROLLED (small bodies, TMEM re-read per pass): the straight-line
+// version of this kernel was ~220 KB of SASS and ran instruction-fetch bound (16 warps streaming
+// through code far larger than the 32 KB instruction cache).
+__device__ __noinline__ void hidden_epilogue(uint32_t taddr, int half, int row, const float* b,
+                                             const float* g, const float* be,
+                                             unsigned char* op, float* stat, int bar_id) {
+  const uint32_t t0 = taddr + 64 * half;
+  const float* bh = b + 64 * half;
   float sum = 0.0f;
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    const float4 bb = reinterpret_cast<const float4*>(b + 64 * half)[c];
-    v[4 * c + 0] += bb.x; v[4 * c + 1] += bb.y; v[4 * c + 2] += bb.z; v[4 * c + 3] += bb.w;
-    sum += (v[4 * c + 0] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);
+#pragma unroll 1
+  for (int kg = 0; kg < 8; ++kg) {
+    float t[8];
+    tmem_ld8(t0 + 8 * kg, t);
+    const float4 b0 = reinterpret_cast<const float4*>(bh)[2 * kg], b1 = reinterpret_cast<const float4*>(bh)[2 * kg + 1];
+    sum += ((t[0] + b0.x) + (t[1] + b0.y)) + ((t[2] + b0.z) + (t[3] + b0.w)) +
+           ((t[4] + b1.x) + (t[5] + b1.y)) + ((t[6] + b1.z) + (t[7] + b1.w));
   }
   stat[half * 128 + row] = sum;
   named_bar_sync(bar_id, 256);
   const float mean = (stat[row] + stat[128 + row]) * (1.0f / 128.0f);
   float ss = 0.0f;
+#pragma unroll 1
+  for (int kg = 0; kg < 8; ++kg) {
+    float t[8];
+    tmem_ld8(t0 + 8 * kg, t);
+    const float4 b0 = reinterpret_cast<const float4*>(bh)[2 * kg], b1 = reinterpret_cast<const float4*>(bh)[2 * kg + 1];
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-  for (int i = 0; i < 64; ++i) {
-    v[i] -= mean;
-    ss = fmaf(v[i], v[i], ss);
+    for (int i = 0; i < 8; ++i) { const float d = (t[i] + bb[i]) - mean; ss = fmaf(d, d, ss); }
   }
   stat[256 + half * 128 + row] = ss;
   named_bar_sync(bar_id, 256);
   const float rstd = rsqrtf((stat[256 + row] + stat[384 + row]) * (1.0f / 128.0f) + 1e-5f);
-#pragma unroll
+#pragma unroll 1
   for (int kg = 0; kg < 8; ++kg) {
+    float t[8];
+    tmem_ld8(t0 + 8 * kg, t);
+    const float4* bp = reinterpret_cast<const float4*>(bh) + 2 * kg;
     const float4* gp = reinterpret_cast<const float4*>(g + 64 * half) + 2 * kg;
     const float4* ep = reinterpret_cast<const float4*>(be + 64 * half) + 2 * kg;
-    const float4 g0 = gp[0], g1 = gp[1], e0 = ep[0], e1 = ep[1];
+    const float4 b0 = bp[0], b1 = bp[1], g0 = gp[0], g1 = gp[1], e0 = ep[0], e1 = ep[1];
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     float y[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(v[8 * kg + i] * rstd, gg[i], ee[i]));
+    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(((t[i] + bb[i]) - mean) * rstd, gg[i], ee[i]));
     store_group(op, kOperandHalfBytes, row, 8 * half + kg, y);
+  }
+}
+
+// rows [32*wq, +32) x column groups [8*half, +8) of an operand image from row-major fp32 global rows
+// `base + row_index(r) * 128`, where row_index(r) = gather ? ROWA[r].src : row0 + r.
+__device__ __noinline__ void build_rows(unsigned char* op, int wq, int half, int lane, int rows, const float* base,
+                                        const RowA* rowa, int gather, int row0) {
+  build_from_global(op, wq, half, lane, rows,
+                    [&](int r) { return base + (size_t)(gather ? rowa[r].src : row0 + r) * kF; });
+}
+
+// One [128 x 128] matrix = 4 streamed chunks; transposed = the weights are the A operand.
+struct MmaRing { int stage; uint32_t ph; long long w_weights; };
+__device__ __noinline__ void gemm_job(uint64_t* bars, uint32_t ring, MmaRing& st, uint32_t d, uint32_t op, int transposed,
+                                      int accumulate, int passes, volatile int* err) {
+#pragma unroll 1
+  for (int kb = 0; kb < 4; ++kb) {
+    mbar_wait_timed(&bars[B_FULL + st.stage], st.ph, err, st.w_weights);
+    tc_fence_after();
+    const uint32_t wst = ring + st.stage * kChunkBytes, opk = op + kb * (2 * kKStepBytes);
+    if (!transposed) mma_f16x3(d, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, accumulate || kb > 0, passes);
+    else             mma_f16x3(d, wst, kChunkHalfBytes, opk, kOperandHalfBytes, 2, accumulate || kb > 0, passes);
+    tc_commit(&bars[B_EMPTY + st.stage]);
+    if (++st.stage == kStages) { st.stage = 0; st.ph ^= 1; }
   }
 }
 
@@ -214,22 +245,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   } else if (warp == 17) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      int stage = 0; uint32_t ph = 0;
       uint32_t px = 0, py = 0, pte[2] = {0, 0};
-      long long w_weights = 0, w_operands = 0, w_tempty = 0;
+      long long w_operands = 0, w_tempty = 0;
       const long long t_start = clock64();
       const uint32_t xa = smem_u32(X), ya = smem_u32(Y), ring = smem_u32(RING);
-      // one [128 x 128] matrix = 4 chunks.  transposed = weights are the A operand.
+      MmaRing rs{0, 0u, 0};
       auto gemm = [&](uint32_t d, uint32_t op, bool transposed, bool accumulate) {
-        for (int kb = 0; kb < 4; ++kb) {
-          mbar_wait_timed(&bars[B_FULL + stage], ph, err, w_weights);
-          tc_fence_after();
-          const uint32_t wst = ring + stage * kChunkBytes, opk = op + kb * (2 * kKStepBytes);
-          if (!transposed) mma_f16x3(d, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, accumulate || kb > 0, p.passes);
-          else             mma_f16x3(d, wst, kChunkHalfBytes, opk, kOperandHalfBytes, 2, accumulate || kb > 0, p.passes);
-          tc_commit(&bars[B_EMPTY + stage]);
-          if (++stage == kStages) { stage = 0; ph ^= 1; }
-        }
+        gemm_job(bars, ring, rs, d, op, transposed, accumulate, p.passes, err);
       };
       const uint32_t acc0 = tmem, acc1 = tmem + 128;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -259,7 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         }
       }
       if (p.dbg) {
-        p.dbg[blockIdx.x * 8 + 0] = w_weights; p.dbg[blockIdx.x * 8 + 1] = w_operands;
+        p.dbg[blockIdx.x * 8 + 0] = rs.w_weights; p.dbg[blockIdx.x * 8 + 1] = w_operands;
         p.dbg[blockIdx.x * 8 + 3] = w_tempty; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
       }
     }
@@ -338,12 +360,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         TIB_PHASE(3);   // E5 / E6
       } else {
         // ---- phi chain.  E2: s[src] -> Y                                          (cpainn.py:275-281)
-        build_from_global(Y, wq, half, lane, rows, [&](int r) { return p.s_old + (size_t)ROWA[r].src * kF; });
+        build_rows(Y, wq, half, lane, rows, p.s_old, ROWA, 1, 0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(1);
         // E4: e rows -> Y (after the s[src] half has been consumed)
         mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc); pyf ^= 1;
-        build_from_global(Y, wq, half, lane, rows, [&](int r) { return p.e + (size_t)(row0 + r) * kF; });
+        build_rows(Y, wq, half, lane, rows, p.e, ROWA, 0, row0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(2);
         // E6: hidden 1 -> Y
@@ -365,6 +387,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       const int f = row;
       const int nslots = node_hi - node_lo;
       const int per = (nslots + 3) >> 2;                    // <= kTileNodes / 4 = 4 destination nodes per group
+      // accumulators of the (up to) 4 owned nodes: the node loop is rolled and always works on set 0,
+      // rotating the sets after every node (4 rotations restore the order)
       float acc_s[4], acc_v[4][3];
 #pragma unroll
       for (int k = 0; k < 4; ++k) { acc_s[k] = 0.0f; acc_v[k][0] = acc_v[k][1] = acc_v[k][2] = 0.0f; }
@@ -374,7 +398,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         const float bphi = PRM[kPrmB3 + sp * kF + f], bw = PRM[kPrmB3 + 5 * kF + sp * kF + f];
         mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull); ptf[pb] ^= 1; tc_fence_after();
         const uint32_t tphi = lane_taddr + 256 * pb, tw = tphi + 128;
-#pragma unroll
+#pragma unroll 1
         for (int k = 0; k < 4; ++k) {
           const int slot = grp * per + k;
           if (k < per && slot < nslots) {
@@ -395,22 +419,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
               if (sp == 0) {            // gates * v[src]
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  const float* vi = p.v_old + (size_t)ROWA[r0 + q].src * 3 * kF + f;
-                  acc_v[k][0] = fmaf(P[q], __ldg(vi), acc_v[k][0]);
-                  acc_v[k][1] = fmaf(P[q], __ldg(vi + kF), acc_v[k][1]);
-                  acc_v[k][2] = fmaf(P[q], __ldg(vi + 2 * kF), acc_v[k][2]);
+                  const float* vi = p.v_old + (size_t)(q < nr ? ROWA[r0 + q].src : 0) * 3 * kF + f;
+                  acc_v[0][0] = fmaf(P[q], __ldg(vi), acc_v[0][0]);
+                  acc_v[0][1] = fmaf(P[q], __ldg(vi + kF), acc_v[0][1]);
+                  acc_v[0][2] = fmaf(P[q], __ldg(vi + 2 * kF), acc_v[0][2]);
                 }
               } else if (sp == 1) {     // scale_edge_dir * dir
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  const RowB rb = ROWB[r0 + q];
-                  acc_v[k][0] = fmaf(P[q], rb.dx, acc_v[k][0]);
-                  acc_v[k][1] = fmaf(P[q], rb.dy, acc_v[k][1]);
-                  acc_v[k][2] = fmaf(P[q], rb.dz, acc_v[k][2]);
+                  const RowB rb = ROWB[(r0 + q) & 127];
+                  acc_v[0][0] = fmaf(P[q], rb.dx, acc_v[0][0]);
+                  acc_v[0][1] = fmaf(P[q], rb.dy, acc_v[0][1]);
+                  acc_v[0][2] = fmaf(P[q], rb.dz, acc_v[0][2]);
                 }
               } else if (sp == 2) {     // ds
 #pragma unroll
-                for (int q = 0; q < 8; ++q) acc_s[k] += P[q];
+                for (int q = 0; q < 8; ++q) acc_s[0] += P[q];
               } else if (sp == 3) {     // e += de                                     (cpainn.py:308)
                 float* ep = p.e + (size_t)(row0 + r0) * kF + f;
 #pragma unroll
@@ -421,16 +445,22 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
               } else {                  // cross_gates * (dir x v[dst])                (cpainn.py:296-300)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  const RowB rb = ROWB[r0 + q];
+                  const RowB rb = ROWB[(r0 + q) & 127];
                   const float x0 = __fmul_rn(rb.dy, vj2) - __fmul_rn(rb.dz, vj1);
                   const float x1 = __fmul_rn(rb.dz, vj0) - __fmul_rn(rb.dx, vj2);
                   const float x2 = __fmul_rn(rb.dx, vj1) - __fmul_rn(rb.dy, vj0);
-                  acc_v[k][0] = fmaf(P[q], x0, acc_v[k][0]);
-                  acc_v[k][1] = fmaf(P[q], x1, acc_v[k][1]);
-                  acc_v[k][2] = fmaf(P[q], x2, acc_v[k][2]);
+                  acc_v[0][0] = fmaf(P[q], x0, acc_v[0][0]);
+                  acc_v[0][1] = fmaf(P[q], x1, acc_v[0][1]);
+                  acc_v[0][2] = fmaf(P[q], x2, acc_v[0][2]);
                 }
               }
             }
+          }
+          {   // rotate the accumulator sets
+            const float ts = acc_s[0], t0 = acc_v[0][0], t1 = acc_v[0][1], t2 = acc_v[0][2];
+#pragma unroll
+            for (int j = 0; j < 3; ++j) { acc_s[j] = acc_s[j + 1]; acc_v[j][0] = acc_v[j + 1][0]; acc_v[j][1] = acc_v[j + 1][1]; acc_v[j][2] = acc_v[j + 1][2]; }
+            acc_s[3] = ts; acc_v[3][0] = t0; acc_v[3][1] = t1; acc_v[3][2] = t2;
           }
         }
         tc_fence_before(); mbar_arrive(&bars[B_TEMPTY0 + pb]);
