@@ -122,31 +122,30 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int half, int row, 
                                              unsigned char* op, float* stat, int bar_id) {
   const uint32_t t0 = taddr + 64 * half;
   const float* bh = b + 64 * half;
-  float sum = 0.0f;
+  // pass 1: sum and sum of squares of (x + bias) over this thread's 64 columns
+  float sum = 0.0f, ss = 0.0f;
 #pragma unroll 1
-  for (int kg = 0; kg < 8; ++kg) {
-    float t[8];
-    tmem_ld8(t0 + 8 * kg, t);
-    const float4 b0 = reinterpret_cast<const float4*>(bh)[2 * kg], b1 = reinterpret_cast<const float4*>(bh)[2 * kg + 1];
-    sum += ((t[0] + b0.x) + (t[1] + b0.y)) + ((t[2] + b0.z) + (t[3] + b0.w)) +
-           ((t[4] + b1.x) + (t[5] + b1.y)) + ((t[6] + b1.z) + (t[7] + b1.w));
-  }
-  stat[half * 128 + row] = sum;
-  named_bar_sync(bar_id, 256);
-  const float mean = (stat[row] + stat[128 + row]) * (1.0f / 128.0f);
-  float ss = 0.0f;
-#pragma unroll 1
-  for (int kg = 0; kg < 8; ++kg) {
-    float t[8];
-    tmem_ld8(t0 + 8 * kg, t);
-    const float4 b0 = reinterpret_cast<const float4*>(bh)[2 * kg], b1 = reinterpret_cast<const float4*>(bh)[2 * kg + 1];
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  for (int kg = 0; kg < 8; kg += 2) {
+    float t[8], u[8];
+    tmem_ld8x2(t0 + 8 * kg, t0 + 8 * kg + 8, 0, t, u);
+    const float4* bp = reinterpret_cast<const float4*>(bh) + 2 * kg;
+    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+    const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) { const float d = (t[i] + bb[i]) - mean; ss = fmaf(d, d, ss); }
+    for (int i = 0; i < 8; ++i) {
+      const float x0 = t[i] + bb[i], x1 = u[i] + bb[8 + i];
+      sum += x0 + x1;
+      ss = fmaf(x0, x0, fmaf(x1, x1, ss));
+    }
   }
-  stat[256 + half * 128 + row] = ss;
+  reinterpret_cast<float2*>(stat)[half * 128 + row] = make_float2(sum, ss);
   named_bar_sync(bar_id, 256);
-  const float rstd = rsqrtf((stat[256 + row] + stat[384 + row]) * (1.0f / 128.0f) + 1e-5f);
+  const float2 s0 = reinterpret_cast<const float2*>(stat)[row], s1 = reinterpret_cast<const float2*>(stat)[128 + row];
+  const float mean = (s0.x + s1.x) * (1.0f / 128.0f);
+  const float var = fmaxf((s0.y + s1.y) * (1.0f / 128.0f) - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float nmr = -mean * rstd;
+  // pass 2: normalise, affine, SiLU, split, store
 #pragma unroll 1
   for (int kg = 0; kg < 8; ++kg) {
     float t[8];
@@ -160,7 +159,7 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int half, int row, 
     const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     float y[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(((t[i] + bb[i]) - mean) * rstd, gg[i], ee[i]));
+    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(fmaf(t[i] + bb[i], rstd, nmr), gg[i], ee[i]));
     store_group(op, kOperandHalfBytes, row, 8 * half + kg, y);
   }
 }
@@ -403,16 +402,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
           const int slot = grp * per + k;
           if (k < per && slot < nslots) {
             const int rbeg = SLOTROW[slot], rend = SLOTROW[slot + 1];
-            float vj0 = 0.0f, vj1 = 0.0f, vj2 = 0.0f;
-            if (sp == 4) {
-              const float* vj = p.v_old + (size_t)(node_lo + slot) * 3 * kF + f;
-              vj0 = __ldg(vj); vj1 = __ldg(vj + kF); vj2 = __ldg(vj + 2 * kF);
-            }
+            float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;   // sp 4: sum of cross_gates * dir over the node's edges
 #pragma unroll 1
             for (int r0 = rbeg; r0 < rend; r0 += 8) {
               float P[8], Q[8];
-              tmem_ld8(tphi + r0, P);
-              tmem_ld8(tw + r0, Q);
+              tmem_ld8x2(tphi, tw, r0, P, Q);
               const int nr = min(8, rend - r0);
 #pragma unroll
               for (int q = 0; q < 8; ++q) P[q] = q < nr ? __fmul_rn(P[q] + bphi, Q[q] + bw) : 0.0f;
@@ -446,14 +440,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
                   const RowB rb = ROWB[(r0 + q) & 127];
-                  const float x0 = __fmul_rn(rb.dy, vj2) - __fmul_rn(rb.dz, vj1);
-                  const float x1 = __fmul_rn(rb.dz, vj0) - __fmul_rn(rb.dx, vj2);
-                  const float x2 = __fmul_rn(rb.dx, vj1) - __fmul_rn(rb.dy, vj0);
-                  acc_v[0][0] = fmaf(P[q], x0, acc_v[0][0]);
-                  acc_v[0][1] = fmaf(P[q], x1, acc_v[0][1]);
-                  acc_v[0][2] = fmaf(P[q], x2, acc_v[0][2]);
+                  d0 = fmaf(P[q], rb.dx, d0); d1 = fmaf(P[q], rb.dy, d1); d2 = fmaf(P[q], rb.dz, d2);
                 }
               }
+            }
+            if (sp == 4) {
+              // sum_i g_i (dir_i x v[dst]) = (sum_i g_i dir_i) x v[dst]: the cross product is linear in dir
+              const float* vj = p.v_old + (size_t)(node_lo + slot) * 3 * kF + f;
+              const float vj0 = __ldg(vj), vj1 = __ldg(vj + kF), vj2 = __ldg(vj + 2 * kF);
+              acc_v[0][0] += __fmul_rn(d1, vj2) - __fmul_rn(d2, vj1);
+              acc_v[0][1] += __fmul_rn(d2, vj0) - __fmul_rn(d0, vj2);
+              acc_v[0][2] += __fmul_rn(d0, vj1) - __fmul_rn(d1, vj0);
             }
           }
           {   // rotate the accumulator sets
