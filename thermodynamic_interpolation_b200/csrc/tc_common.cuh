@@ -143,29 +143,17 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
   for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
 }
 
-// two 8-column loads (phi and w accumulators of the same rows) under one wait; near the end of the
-// 128-column accumulator the tail is read column by column so no access leaves the allocation
+// two 8-column loads (e.g. the phi and w accumulators of the same rows) under one wait
 __device__ __forceinline__ void tmem_ld8x2(uint32_t ta, uint32_t tb, int col, float (&a)[8], float (&b)[8]) {
   uint32_t r[8], q[8];
-  if (col + 8 <= 128) {
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(ta + col)
-                 : "memory");
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
-                 : "r"(tb + col)
-                 : "memory");
-  } else {
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      r[i] = 0u; q[i] = 0u;
-      if (col + i < 128) {     // warp-uniform
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(r[i]) : "r"(ta + col + i) : "memory");
-        asm volatile("tcgen05.ld.sync.aligned.32x32b.x1.b32 {%0}, [%1];" : "=r"(q[i]) : "r"(tb + col + i) : "memory");
-      }
-    }
-  }
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "r"(ta + col)
+               : "memory");
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+               : "=r"(q[0]), "=r"(q[1]), "=r"(q[2]), "=r"(q[3]), "=r"(q[4]), "=r"(q[5]), "=r"(q[6]), "=r"(q[7])
+               : "r"(tb + col)
+               : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
   for (int i = 0; i < 8; ++i) { a[i] = __uint_as_float(r[i]); b[i] = __uint_as_float(q[i]); }

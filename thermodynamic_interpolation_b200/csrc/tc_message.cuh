@@ -404,16 +404,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
             const int rbeg = SLOTROW[slot], rend = SLOTROW[slot + 1];
             float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;   // sp 4: sum of cross_gates * dir over the node's edges
 #pragma unroll 1
-            for (int r0 = rbeg; r0 < rend; r0 += 8) {
+            for (int r0 = rbeg & ~7; r0 < rend; r0 += 8) {      // 8-column aligned TMEM pieces
               float P[8], Q[8];
               tmem_ld8x2(tphi, tw, r0, P, Q);
-              const int nr = min(8, rend - r0);
+              const int qlo = rbeg - r0, qhi = rend - r0;       // rows [qlo, qhi) of the piece belong to this node
 #pragma unroll
-              for (int q = 0; q < 8; ++q) P[q] = q < nr ? __fmul_rn(P[q] + bphi, Q[q] + bw) : 0.0f;
+              for (int q = 0; q < 8; ++q) P[q] = (q >= qlo && q < qhi) ? __fmul_rn(P[q] + bphi, Q[q] + bw) : 0.0f;
               if (sp == 0) {            // gates * v[src]
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  const float* vi = p.v_old + (size_t)(q < nr ? ROWA[r0 + q].src : 0) * 3 * kF + f;
+                  const float* vi = p.v_old + (size_t)ROWA[r0 + q].src * 3 * kF + f;
                   acc_v[0][0] = fmaf(P[q], __ldg(vi), acc_v[0][0]);
                   acc_v[0][1] = fmaf(P[q], __ldg(vi + kF), acc_v[0][1]);
                   acc_v[0][2] = fmaf(P[q], __ldg(vi + 2 * kF), acc_v[0][2]);
@@ -421,7 +421,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
               } else if (sp == 1) {     // scale_edge_dir * dir
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  const RowB rb = ROWB[(r0 + q) & 127];
+                  const RowB rb = ROWB[r0 + q];
                   acc_v[0][0] = fmaf(P[q], rb.dx, acc_v[0][0]);
                   acc_v[0][1] = fmaf(P[q], rb.dy, acc_v[0][1]);
                   acc_v[0][2] = fmaf(P[q], rb.dz, acc_v[0][2]);
@@ -432,14 +432,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
               } else if (sp == 3) {     // e += de                                     (cpainn.py:308)
                 float* ep = p.e + (size_t)(row0 + r0) * kF + f;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) Q[q] = q < nr ? ep[(size_t)q * kF] : 0.0f;
+                for (int q = 0; q < 8; ++q) Q[q] = (q >= qlo && q < qhi) ? ep[(size_t)q * kF] : 0.0f;
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
-                  if (q < nr) ep[(size_t)q * kF] = Q[q] + P[q];
+                  if (q >= qlo && q < qhi) ep[(size_t)q * kF] = Q[q] + P[q];
               } else {                  // cross_gates * (dir x v[dst])                (cpainn.py:296-300)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
-                  const RowB rb = ROWB[(r0 + q) & 127];
+                  const RowB rb = ROWB[r0 + q];
                   d0 = fmaf(P[q], rb.dx, d0); d1 = fmaf(P[q], rb.dy, d1); d2 = fmaf(P[q], rb.dz, d2);
                 }
               }

@@ -1,0 +1,304 @@
+// tc_update.cuh - Update.forward (cpainn.py:345-376) on the sm_100a tensor cores (F = 128).
+//
+//   vv = V v, uv = U v (per xyz plane);  q = |vv| over xyz;  (g, a, c) = split(MLP_{2F->F->F->3F}(cat[q, s]));
+//   v += uv * g;   s += q^2 * a + c
+//
+// Work unit: a tile of 128 consecutive nodes.  Every GEMM is D[node][feat] = A[node][k] * W[feat][k]^T
+// (node = TMEM lane), so LayerNorm, the norm over xyz and the gated residuals are all row-local:
+//   step 1: planes 0,1 -> operand images X,Y;   vv0, vv1 -> T0, T1          (V streamed once for both)
+//   step 2: plane 2 -> X;                        vv2 -> T2
+//   step 3: q = sqrt(T0^2+T1^2+T2^2) -> Y,  s -> X;   layer 1 = Y*W1[:, :F]^T + X*W1[:, F:]^T -> T3
+//   step 4: LN/SiLU(T3) -> X;                    layer 2 -> T3
+//   step 5: LN/SiLU(T3) -> X;                    a, c, g = X*W3{a,c,g}^T -> T0, T1, T2
+//   step 6: s_new = s + q^2 * a + c (q re-read from the Y image);  planes 0,1 -> X,Y;   uv0, uv1 -> T0, T1
+//   step 7: v_new[0,1] = v + uv * g;  plane 2 -> X;   uv2 -> T3
+//   step 8: v_new[2]
+// The epilogue (512 threads) and the MMA issuer alternate through one operand-ready / accumulator-ready
+// barrier pair; weights stream through the same bulk-copy ring as the message kernel.
+// Warp roles: warps 0-15 epilogue (group g = warp / 4 owns feature columns [32g, 32g+32) of every row),
+// warp 16 weight producer (+ TMEM allocation), warp 17 MMA issuer.
+#pragma once
+#include "common.cuh"
+#include "tc_common.cuh"
+#include "tc_message.cuh"
+
+namespace tib {
+namespace tc {
+
+constexpr int kUpdChunks = 40;     // streamed per tile: V | V | W1q | W1s | W2 | W3a | W3c | W3g | U | U
+// weight blob of one update layer (matrix index -> 4 chunks): 0 V, 1 W1[:, :F], 2 W1[:, F:], 3 W2,
+// 4 W3 rows [F,2F) (a), 5 W3 rows [2F,3F) (c), 6 W3 rows [0,F) (g), 7 U
+__constant__ int kUpdOrder[10] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 7};
+
+struct TcUpdP {
+  int n_nodes, n_tiles;
+  float* s;                 // [N][F]    in place
+  float* v;                 // [N][3][F] in place
+  const unsigned char* wblob;   // 8 matrices x 4 chunks
+  const float *b1, *g1, *be1, *b2, *g2, *be2, *b3;   // MLP parameters (fp32)
+  int passes;
+  int* err;
+};
+
+struct UpdSmem {
+  static constexpr uint32_t X = 0;
+  static constexpr uint32_t Y = X + kOperandBytes;
+  static constexpr uint32_t RING = Y + kOperandBytes;
+  static constexpr uint32_t PRM = RING + kStages * kChunkBytes;    // b1 g1 be1 b2 g2 be2 (6F) | b3 (3F)
+  static constexpr uint32_t STAT = PRM + 9 * 128 * 4;              // float2 [4 groups][128 rows]
+  static constexpr uint32_t BARS = STAT + 4 * 128 * 8;
+  static constexpr uint32_t TOTAL = BARS + 256;
+};
+enum { U_FULL = 0, U_EMPTY = U_FULL + kStages, U_OPS = U_EMPTY + kStages, U_ACC, U_COUNT };
+
+// rows [32*wq, +32) x column groups [4*grp, +4) of an operand image from fp32 global rows base + r*stride
+__device__ __noinline__ void upd_build(unsigned char* op, int wq, int grp, int lane, int rows, const float* base, size_t stride) {
+#pragma unroll
+  for (int oct = 0; oct < 4; ++oct) {
+    const int r = 32 * wq + 8 * oct + (lane & 7);
+    const int g = 4 * grp + (lane >> 3);
+    float v[8];
+    if (r < rows) {
+      const float* src = base + (size_t)r * stride + g * 8;
+      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+    }
+    store_group(op, kOperandHalfBytes, r, g, v);
+  }
+}
+
+// accumulator row, columns [32*grp, +32): + bias -> LayerNorm over all 128 columns (4-way statistics
+// exchange) -> SiLU -> operand image
+__device__ __noinline__ void upd_hidden(uint32_t taddr, int grp, int row, const float* b, const float* g, const float* be,
+                                        unsigned char* op, float2* stat) {
+  const uint32_t t0 = taddr + 32 * grp;
+  const float* bq = b + 32 * grp;
+  float sum = 0.0f, ss = 0.0f;
+#pragma unroll 1
+  for (int kg = 0; kg < 4; kg += 2) {
+    float t[8], u[8];
+    tmem_ld8x2(t0 + 8 * kg, t0 + 8 * kg + 8, 0, t, u);
+    const float4* bp = reinterpret_cast<const float4*>(bq) + 2 * kg;
+    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
+    const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const float x0 = t[i] + bb[i], x1 = u[i] + bb[8 + i];
+      sum += x0 + x1;
+      ss = fmaf(x0, x0, fmaf(x1, x1, ss));
+    }
+  }
+  stat[grp * 128 + row] = make_float2(sum, ss);
+  named_bar_sync(NB_ALL, kEpiThreads);
+  const float2 s0 = stat[row], s1 = stat[128 + row], s2 = stat[256 + row], s3 = stat[384 + row];
+  const float mean = ((s0.x + s1.x) + (s2.x + s3.x)) * (1.0f / 128.0f);
+  const float var = fmaxf(((s0.y + s1.y) + (s2.y + s3.y)) * (1.0f / 128.0f) - mean * mean, 0.0f);
+  const float rstd = rsqrtf(var + 1e-5f);
+  const float nmr = -mean * rstd;
+#pragma unroll 1
+  for (int kg = 0; kg < 4; ++kg) {
+    float t[8];
+    tmem_ld8(t0 + 8 * kg, t);
+    const float4* bp = reinterpret_cast<const float4*>(bq) + 2 * kg;
+    const float4* gp = reinterpret_cast<const float4*>(g + 32 * grp) + 2 * kg;
+    const float4* ep = reinterpret_cast<const float4*>(be + 32 * grp) + 2 * kg;
+    const float4 b0 = bp[0], b1 = bp[1], g0 = gp[0], g1 = gp[1], e0 = ep[0], e1 = ep[1];
+    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+    const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+    float y[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(fmaf(t[i] + bb[i], rstd, nmr), gg[i], ee[i]));
+    store_group(op, kOperandHalfBytes, row, 4 * grp + kg, y);
+  }
+  named_bar_sync(NB_ALL, kEpiThreads);     // `stat` may be rewritten by the next call
+}
+
+__global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
+  extern __shared__ __align__(1024) unsigned char smem[];
+  unsigned char* const X = smem + UpdSmem::X;
+  unsigned char* const Y = smem + UpdSmem::Y;
+  unsigned char* const RING = smem + UpdSmem::RING;
+  float* const PRM = reinterpret_cast<float*>(smem + UpdSmem::PRM);
+  float2* const STAT = reinterpret_cast<float2*>(smem + UpdSmem::STAT);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + UpdSmem::BARS);
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + UpdSmem::BARS + 8 * U_COUNT);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  volatile int* err = p.err;
+
+  if (tid == 0) {
+    for (int i = 0; i < kStages; ++i) { mbar_init(&bars[U_FULL + i], 1); mbar_init(&bars[U_EMPTY + i], 1); }
+    mbar_init(&bars[U_OPS], kEpiThreads);
+    mbar_init(&bars[U_ACC], 1);
+    fence_mbar_init();
+  }
+  if (warp == 16) tmem_alloc(tmem_slot, 512);
+  {
+    const float* src[9] = {p.b1, p.g1, p.be1, p.b2, p.g2, p.be2, p.b3, p.b3 + kF, p.b3 + 2 * kF};
+    for (int i = tid; i < 9 * kF; i += kThreads) PRM[i] = __ldg(src[i >> 7] + (i & 127));
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 16) {
+    // =========================== weight producer ===========================
+    if (lane == 0) {
+      int stage = 0; uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x)
+        for (int c = 0; c < kUpdChunks; ++c) {
+          mbar_wait(&bars[U_EMPTY + stage], ph ^ 1, err);
+          mbar_arrive_expect_tx(&bars[U_FULL + stage], kChunkBytes);
+          bulk_g2s(RING + stage * kChunkBytes, p.wblob + (size_t)(kUpdOrder[c >> 2] * 4 + (c & 3)) * kChunkBytes, kChunkBytes,
+                   &bars[U_FULL + stage]);
+          if (++stage == kStages) { stage = 0; ph ^= 1; }
+        }
+    }
+  } else if (warp == 17) {
+    // =========================== MMA issuer ===========================
+    if (lane == 0) {
+      int stage = 0; uint32_t ph = 0, pops = 0;
+      const uint32_t xa = smem_u32(X), ya = smem_u32(Y), ring = smem_u32(RING);
+      // one streamed [128 x 128] weight matrix against one or two operand images
+      auto gemm = [&](uint32_t d0, uint32_t op0, uint32_t d1, uint32_t op1, bool accumulate) {
+#pragma unroll 1
+        for (int kb = 0; kb < 4; ++kb) {
+          mbar_wait(&bars[U_FULL + stage], ph, err);
+          tc_fence_after();
+          const uint32_t wst = ring + stage * kChunkBytes, off = kb * (2 * kKStepBytes);
+          mma_f16x3(d0, op0 + off, kOperandHalfBytes, wst, kChunkHalfBytes, 2, accumulate || kb > 0, p.passes);
+          if (op1) mma_f16x3(d1, op1 + off, kOperandHalfBytes, wst, kChunkHalfBytes, 2, kb > 0, p.passes);
+          tc_commit(&bars[U_EMPTY + stage]);
+          if (++stage == kStages) { stage = 0; ph ^= 1; }
+        }
+      };
+      auto ops_ready = [&]() { mbar_wait(&bars[U_OPS], pops, err); pops ^= 1; tc_fence_after(); };
+      const uint32_t T0 = tmem, T1 = tmem + 128, T2 = tmem + 256, T3 = tmem + 384;
+      for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        ops_ready(); gemm(T0, xa, T1, ya, false); tc_commit(&bars[U_ACC]);                     // 1: vv0, vv1
+        ops_ready(); gemm(T2, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                       // 2: vv2
+        ops_ready(); gemm(T3, ya, 0, 0, false); gemm(T3, xa, 0, 0, true); tc_commit(&bars[U_ACC]);   // 3: layer 1
+        ops_ready(); gemm(T3, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                       // 4: layer 2
+        ops_ready(); gemm(T0, xa, 0, 0, false); gemm(T1, xa, 0, 0, false); gemm(T2, xa, 0, 0, false);
+        tc_commit(&bars[U_ACC]);                                                               // 5: a, c, g
+        ops_ready(); gemm(T0, xa, T1, ya, false); tc_commit(&bars[U_ACC]);                     // 6: uv0, uv1
+        ops_ready(); gemm(T3, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                       // 7: uv2
+      }
+    }
+  } else {
+    // =========================== builders / epilogue (512 threads) ===========================
+    const int grp = warp >> 2, wq = warp & 3;
+    const int row = 32 * wq + lane;
+    const uint32_t lt = tmem + ((uint32_t)(wq * 32) << 16);
+    const uint32_t T0 = lt, T1 = lt + 128, T2 = lt + 256, T3 = lt + 384;
+    uint32_t pacc = 0;
+    auto ops_done = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&bars[U_OPS]); };
+    auto acc_ready = [&]() { mbar_wait(&bars[U_ACC], pacc, err); pacc ^= 1; tc_fence_after(); };
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+      const int node0 = tile * 128;
+      const int rows = min(128, p.n_nodes - node0);
+      const float* vbase = p.v + (size_t)node0 * 3 * kF;
+      const bool live = row < rows;
+      const size_t node = (size_t)(node0 + row);
+      // step 1
+      upd_build(X, wq, grp, lane, rows, vbase, 3 * kF);
+      upd_build(Y, wq, grp, lane, rows, vbase + kF, 3 * kF);
+      ops_done();
+      // step 2
+      acc_ready();
+      upd_build(X, wq, grp, lane, rows, vbase + 2 * kF, 3 * kF);
+      ops_done();
+      // step 3: q = |V v| over xyz                                                   (cpainn.py:361)
+      acc_ready();
+#pragma unroll 1
+      for (int kg = 0; kg < 4; ++kg) {
+        float a[8], b[8], c[8];
+        tmem_ld8x2(T0, T1, 32 * grp + 8 * kg, a, b);
+        tmem_ld8(T2 + 32 * grp + 8 * kg, c);
+        float q[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) q[i] = __fsqrt_rn(fmaf(a[i], a[i], fmaf(b[i], b[i], c[i] * c[i])));
+        store_group(Y, kOperandHalfBytes, row, 4 * grp + kg, q);
+      }
+      upd_build(X, wq, grp, lane, rows, p.s + (size_t)node0 * kF, kF);
+      ops_done();
+      // step 4
+      acc_ready();
+      upd_hidden(T3, grp, row, PRM, PRM + kF, PRM + 2 * kF, X, STAT);
+      ops_done();
+      // step 5
+      acc_ready();
+      upd_hidden(T3, grp, row, PRM + 3 * kF, PRM + 4 * kF, PRM + 5 * kF, X, STAT);
+      ops_done();
+      // step 6: s += q^2 * a + c                                                      (cpainn.py:371,373)
+      acc_ready();
+#pragma unroll 1
+      for (int kg = 0; kg < 4; ++kg) {
+        const int col = 32 * grp + 8 * kg;
+        float a[8], c[8];
+        tmem_ld8x2(T0, T1, col, a, c);
+        if (live) {
+          const unsigned char* qp = Y + (size_t)(4 * grp + kg) * kLBO + (size_t)row * 16;
+          const uint4 qh = *reinterpret_cast<const uint4*>(qp), ql = *reinterpret_cast<const uint4*>(qp + kOperandHalfBytes);
+          const uint32_t hw[4] = {qh.x, qh.y, qh.z, qh.w}, lw[4] = {ql.x, ql.y, ql.z, ql.w};
+          float* sp = p.s + node * kF + col;
+          const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
+          const float so[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+          float o[8];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
+            const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
+            const float q0 = h.x + l.x, q1 = h.y + l.y;
+            o[2 * i] = so[2 * i] + fmaf(q0 * q0, a[2 * i] + PRM[7 * kF + col + 2 * i], c[2 * i] + PRM[8 * kF + col + 2 * i]);
+            o[2 * i + 1] = so[2 * i + 1] + fmaf(q1 * q1, a[2 * i + 1] + PRM[7 * kF + col + 2 * i + 1], c[2 * i + 1] + PRM[8 * kF + col + 2 * i + 1]);
+          }
+          *reinterpret_cast<float4*>(sp) = make_float4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<float4*>(sp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+        }
+      }
+      named_bar_sync(NB_ALL, kEpiThreads);                 // every reader of the q image in Y is done
+      upd_build(X, wq, grp, lane, rows, vbase, 3 * kF);
+      upd_build(Y, wq, grp, lane, rows, vbase + kF, 3 * kF);
+      ops_done();
+      // steps 7, 8: v += (U v) * g                                                    (cpainn.py:370,374)
+      auto gated = [&](uint32_t tuv, int xyz) {
+#pragma unroll 1
+        for (int kg = 0; kg < 4; ++kg) {
+          const int col = 32 * grp + 8 * kg;
+          float u[8], g[8];
+          tmem_ld8x2(tuv, T2, col, u, g);
+          if (live) {
+            float* vp = p.v + (node * 3 + xyz) * kF + col;
+            const float4 v0 = *reinterpret_cast<const float4*>(vp), v1 = *reinterpret_cast<const float4*>(vp + 4);
+            const float vo[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+            float o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = fmaf(u[i], g[i] + PRM[6 * kF + col + i], vo[i]);
+            *reinterpret_cast<float4*>(vp) = make_float4(o[0], o[1], o[2], o[3]);
+            *reinterpret_cast<float4*>(vp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+          }
+        }
+      };
+      acc_ready();
+      upd_build(X, wq, grp, lane, rows, vbase + 2 * kF, 3 * kF);   // plane 2 of the OLD v (only planes 0,1 are written below)
+      ops_done();
+      gated(T0, 0);
+      gated(T1, 1);
+      acc_ready();
+      gated(T3, 2);
+      tc_fence_before();
+      named_bar_sync(NB_ALL, kEpiThreads);                 // the tile's TMEM reads finish before the next tile's MMAs
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 16) tmem_dealloc(tmem, 512);
+}
+
+}  // namespace tc
+}  // namespace tib

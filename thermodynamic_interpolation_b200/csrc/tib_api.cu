@@ -14,6 +14,7 @@
 #include "adw.cuh"
 #include "tc_message.cuh"
 #include "tc_selftest.cuh"
+#include "tc_update.cuh"
 
 namespace {
 
@@ -89,7 +90,7 @@ struct tib_model {
   const float* edge_emb = nullptr;
   const float* atom_emb = nullptr;
   tib::MlpW combine{};
-  struct Layer { tib::MlpW phi, w, upd; const float *Ut, *Vt; const unsigned char* tc_msg = nullptr; };
+  struct Layer { tib::MlpW phi, w, upd; const float *Ut, *Vt; const unsigned char* tc_msg = nullptr; const unsigned char* tc_upd = nullptr; };
   std::vector<Layer> layers;
   tib::MlpW readout{};
   const float* Vout = nullptr;
@@ -237,6 +238,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     if (b->n_edges >= (1ll << 31)) return fail("tensor-core path: n_edges=%lld exceeds int32 row indices", (long long)b->n_edges);
     if (!m->tc_attrs_set) {
       if (set_smem(tc::k_message_tc, tc::MsgSmem::TOTAL)) return -1;
+      if (set_smem(tc::k_update_tc, tc::UpdSmem::TOTAL)) return -1;
       m->tc_attrs_set = true;
     }
     nodes_per_tile = std::min(tc::kTileNodes, 128 / (b->max_atoms - 1));
@@ -277,9 +279,21 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       LAUNCH_CHECK();
     }
     cur ^= 1;
-    UpdateP up{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]};
-    { ProfScope ps(TIB_K_UPDATE, st); k_update<F, RN><<<node_tiles, TIB_THREADS, smem_update<F, RN>(), st>>>(up); }
-    LAUNCH_CHECK();
+    if (use_tc) {
+      tc::TcUpdP up{};
+      up.n_nodes = b->n_nodes; up.n_tiles = (b->n_nodes + 127) / 128;
+      up.s = ws.s[cur]; up.v = ws.v[cur]; up.wblob = L.tc_upd;
+      up.b1 = L.upd.b1; up.g1 = L.upd.g1; up.be1 = L.upd.be1; up.b2 = L.upd.b2; up.g2 = L.upd.g2; up.be2 = L.upd.be2; up.b3 = L.upd.b3;
+      up.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3; up.err = m->dev_err;
+      ProfScope ps(TIB_K_UPDATE, st);
+      tc::k_update_tc<<<std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st>>>(up);
+      LAUNCH_CHECK();
+    } else {
+      UpdateP up{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]};
+      ProfScope ps(TIB_K_UPDATE, st);
+      k_update<F, RN><<<node_tiles, TIB_THREADS, smem_update<F, RN>(), st>>>(up);
+      LAUNCH_CHECK();
+    }
   }
   ReadoutP rp{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], out};
   { ProfScope ps(TIB_K_READOUT, st); k_readout<F, RN><<<node_tiles, TIB_THREADS, smem_readout<F, RN>(), st>>>(rp); }
@@ -414,13 +428,14 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
   m->atom_emb = push(src, (size_t)d->n_types * F); src += (size_t)d->n_types * F;
   src = repack_mlp(src, {(2 + nt) * F, F, F}, stage, base, &m->combine, true);
   m->layers.resize(d->n_layers);
-  std::vector<const float*> phi_src(d->n_layers), w_src(d->n_layers);
+  std::vector<const float*> phi_src(d->n_layers), w_src(d->n_layers), uv_src(d->n_layers);
   for (int l = 0; l < d->n_layers; ++l) {
     auto& L = m->layers[l];
     phi_src[l] = src;
     src = repack_mlp(src, {2 * F, F, 5 * F}, stage, base, &L.phi, true);
     w_src[l] = src;
     src = repack_mlp(src, {F, F, 5 * F}, stage, base, &L.w, true);
+    uv_src[l] = src;
     L.Ut = push_T(src, F, F); src += (size_t)F * F;
     L.Vt = push_T(src, F, F); src += (size_t)F * F;
     src = repack_mlp(src, {2 * F, F, 3 * F}, stage, base, &L.upd, true);
@@ -449,7 +464,9 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
   }
   if (F == 128) {
     // tensor-core weight stream: per layer kChunksPerLayer chunks in consumption order (tc_message.cuh)
-    const size_t per_layer = (size_t)tib::tc::kChunksPerLayer * tib::tc::kChunkBytes;
+    const size_t per_msg = (size_t)tib::tc::kChunksPerLayer * tib::tc::kChunkBytes;
+    const size_t per_upd = (size_t)32 * tib::tc::kChunkBytes;      // 8 matrices (tc_update.cuh)
+    const size_t per_layer = per_msg + per_upd;
     std::vector<uint16_t> blob(per_layer / 2 * d->n_layers);
     for (int l = 0; l < d->n_layers; ++l) {
       uint16_t* out16 = blob.data() + per_layer / 2 * l;
@@ -468,11 +485,25 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
       mat(pW1, 2 * F, 0, F);
       mat(pW2, F, 0, 0);
       for (int sp = 0; sp < 5; ++sp) { mat(pW3, F, sp * F, 0); mat(wW3, F, sp * F, 0); }
+      // update layer: U [F][F], V [F][F], MLP(2F -> F -> F -> 3F)
+      const float* U = uv_src[l];
+      const float* V = U + (size_t)F * F;
+      const float* uW1 = V + (size_t)F * F;                           // [F][2F]
+      const float* uW2 = uW1 + (size_t)F * 2 * F + 3 * F;
+      const float* uW3 = uW2 + (size_t)F * F + 3 * F;                 // [3F][F]: rows g | a | c
+      mat(V, F, 0, 0);
+      mat(uW1, 2 * F, 0, 0);
+      mat(uW1, 2 * F, 0, F);
+      mat(uW2, F, 0, 0);
+      mat(uW3, F, F, 0);
+      mat(uW3, F, 2 * F, 0);
+      mat(uW3, F, 0, 0);
+      mat(U, F, 0, 0);
     }
     e = cudaMalloc(&m->tc_blob, blob.size() * 2);
     if (e == cudaSuccess) e = cudaMemcpy(m->tc_blob, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { tib_model_destroy(m); return fail("tensor-core weight upload: %s", cudaGetErrorString(e)); }
-    for (int l = 0; l < d->n_layers; ++l) m->layers[l].tc_msg = m->tc_blob + per_layer * l;
+    for (int l = 0; l < d->n_layers; ++l) { m->layers[l].tc_msg = m->tc_blob + per_layer * l; m->layers[l].tc_upd = m->tc_blob + per_layer * l + per_msg; }
   }
   *out = m;
   return 0;
