@@ -327,7 +327,7 @@ def main():
     ap.add_argument("--atoms", type=int, default=9)
     ap.add_argument("--features", type=int, default=128)
     ap.add_argument("--layers", type=int, default=5)
-    ap.add_argument("--math", type=int, default=0, help="TIB_MATH_* (0 fp32 SIMT)")
+    ap.add_argument("--math", type=int, default=1, help="TIB_MATH_*: 0 fp32 SIMT, 1 split-f16 x3 tcgen05 (default), 2 single-pass f16")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--gather", type=int, default=1)

@@ -71,7 +71,7 @@ size_t tib_packed_weight_count(const tib_model_desc* desc);
 int  tib_model_create(tib_model** out, const tib_model_desc* desc, const float* packed_weights,
                       size_t n_floats, int device);
 void tib_model_destroy(tib_model* m);
-int  tib_model_set_math(tib_model* m, int math_mode);     /* TIB_MATH_*; default FP32_SIMT */
+int  tib_model_set_math(tib_model* m, int math_mode);     /* TIB_MATH_*; default: F16X3_TC if n_features == 128, else FP32_SIMT */
 /* Synchronises `stream` and reports (once) a device-side pipeline error recorded by the tensor-core
  * kernels' bounded barrier waits.  0 = healthy. */
 int  tib_model_status(tib_model* m, void* stream);

@@ -89,6 +89,7 @@ def test_tc_full_size_agrees_with_simt_and_is_block_diagonal():
     torch.manual_seed(0)
     model = perturb_(cPaiNN(n_features=128, score_layers=5, temp_length=100), 1).eval().to(DEV)
     mb = synthetic_ambient_batch(4096, 9, seed=2).to(DEV)
+    model.set_math(_lib.MATH_FP32_SIMT)
     eng = model.engine()
     pb = eng.prepare(mb)
     simt = eng.drift(pb, mb.x0, 0.3).clone()
@@ -108,3 +109,29 @@ def test_tc_full_size_agrees_with_simt_and_is_block_diagonal():
     err1 = _rel(one.cpu().numpy(), simt.cpu().numpy())
     print(f"[tc] cfg2 single-pass f16 vs fp32 SIMT: {err1:.3e}")
     assert err1 < 5e-3
+
+
+def test_tc_hundred_step_state_agreement_vs_oracle():
+    """BASELINE.json's bar for a tensor-core GEMM mode: state within rtol 1e-4 after 100 Euler steps
+    (F = 128, L = 5, the cfg-2 network) against the fp32 CPU oracle; the single-pass f16 mode is measured
+    against the same bound and reported (it is opt-in because it does not meet it)."""
+    from oracle import cpainn_oracle as co
+    from tests._util import oracle_hp_sd
+    from thermodynamic_interpolation_b200.ambient.integrators import MoleculeIntegrator
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    torch.manual_seed(0)
+    model = perturb_(cPaiNN(n_features=128, score_layers=5, temp_length=100), 1).eval()
+    mb = synthetic_ambient_batch(4, 9, seed=31)
+    hp, sd = oracle_hp_sd(model)
+    ref, _, _ = co.rollout(sd, hp, mb.x0, mb.atoms, mb.edge_index, mb.edge_type, mb.ptr.tolist(),
+                           method="euler", n_step=101, T0=mb.T0, T1=mb.T1)
+    model = model.to(DEV)
+    for mode, name in ((_lib.MATH_FP32_SIMT, "fp32 simt"), (_lib.MATH_F16X3_TC, "f16x3 tc"), (_lib.MATH_F16_TC, "f16 tc (1 pass)")):
+        model.set_math(mode)
+        xts = MoleculeIntegrator(model, method="euler", n_step=101).rollout(mb.clone().to(DEV))[0].cpu()
+        model.engine().status()
+        errs = [_rel(xts[k].numpy(), ref[k].numpy()) for k in (1, 10, 50, 100)]
+        print(f"[tc] 100-step state error vs oracle, {name}: " + ", ".join(f"{e:.2e}" for e in errs))
+        if mode != _lib.MATH_F16_TC:
+            np.testing.assert_allclose(xts[100].numpy(), ref[100].numpy(), rtol=1e-4, atol=2e-5 * float(ref[100].abs().max()))

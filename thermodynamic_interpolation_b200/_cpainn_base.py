@@ -21,7 +21,7 @@ class CPaiNNBase(nn.Module):
         super().__init__()
         self._engine: Optional[DriftEngine] = None
         self._engine_sig = None
-        self._math_mode = 0
+        self._math_mode = None     # None = the library default (tensor cores when n_features == 128)
 
     @property
     def device(self) -> torch.device:
@@ -34,7 +34,7 @@ class CPaiNNBase(nn.Module):
         sig = self._signature()
         if self._engine is None or sig != self._engine_sig:
             self._engine = DriftEngine(self.state_dict(), self.hyper, self.device)
-            if self._math_mode:
+            if self._math_mode is not None:
                 self._engine.set_math(self._math_mode)
             self._engine_sig = sig
         return self._engine

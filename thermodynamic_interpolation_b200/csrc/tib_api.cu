@@ -83,7 +83,7 @@ struct HostMlp { tib::MlpW w; };
 struct tib_model {
   tib_model_desc d;
   int device = 0;
-  int math = TIB_MATH_FP32_SIMT;
+  int math = TIB_MATH_FP32_SIMT;   // tib_model_create selects F16X3_TC when n_features == 128
   int n_temp = 0;
   float* dev = nullptr;   // one allocation holding every repacked tensor
   size_t dev_floats = 0;
@@ -401,6 +401,7 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
   m->d = *d;
   m->device = device;
   m->n_temp = n_temp_of(d->variant);
+  m->math = (F == 128) ? TIB_MATH_F16X3_TC : TIB_MATH_FP32_SIMT;
   const int nt = m->n_temp;
 
   // upper bound of the staged size: every tensor padded to 4 floats
