@@ -52,6 +52,17 @@ def message_flops_per_launch(n_mol, n, F):
     return n_mol * n * (n - 1) * 30 * F * F
 
 
+def load_traffic():
+    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture (None if absent)."""
+    p = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")
+    try:
+        with open(p) as f:
+            d = json.load(f)["k_message_tc"]
+        return d["dram_bytes_read"] + d["dram_bytes_write"]
+    except Exception:
+        return None
+
+
 def load_peaks():
     p = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -303,8 +314,9 @@ def run_b200(args):
             e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K,
                      seconds=e2e_s, api="ambient.integrators.MoleculeIntegrator.rollout(host batch) + D2H of all frames"),
             gpu_launches=n_launch, clocks=clk,
-            roofline=dict(kernel="k_message (SE3Message: phi/w edge MLPs + gated scatter)", bound="tensor",
-                          achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+            roofline=dict(kernel=("k_message_tc" if args.math != 0 else "k_message") + " (SE3Message: phi/w edge MLPs + gated scatter)", bound="tensor",
+                          achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
+                          traffic=load_traffic() if args.math != 0 else None,
                           peak_source=peaks["source"] + ", bf16 dense sustained", launches=msg_n,
                           avg_launch_ms=per_launch_ms, flops_per_launch=mflops, kernel_time_shares=shares),
             stats=dict(ess=tot["ess"], dF=tot["dF"], n=tot["n"]))
