@@ -48,9 +48,8 @@ struct MsgParams {
 struct TcMsgP {
   int n_nodes, n_tiles, nodes_per_tile;
   const int* node_in_ptr;   // [N+1] first (dst-major) edge row of each node
-  const int* node_mol;      // [N]
-  const int* mol_ptr;       // [B+1]
-  const float* x;           // [N][3]
+  const uint4* rowa;        // [E] RowA per (dst,src)-ordered edge row (k_edge_tables; slot filled per tile)
+  const uint4* rowb;        // [E] RowB
   const float* s_old;       // [N][F]
   const float* v_old;       // [N][3][F]
   float* s_new;
@@ -146,7 +145,7 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int half, int row, 
   const float rstd = rsqrtf(var + 1e-5f);
   const float nmr = -mean * rstd;
   // pass 2: normalise, affine, SiLU, split, store
-#pragma unroll 1
+#pragma unroll 2
   for (int kg = 0; kg < 8; ++kg) {
     float t[8];
     tmem_ld8(t0 + 8 * kg, t);
@@ -173,7 +172,7 @@ __device__ __noinline__ void build_rows(unsigned char* op, int wq, int half, int
 }
 
 // One [128 x 128] matrix = 4 streamed chunks; transposed = the weights are the A operand.
-struct MmaRing { int stage; uint32_t ph; long long w_weights; };
+struct MmaRing { int stage; uint32_t ph; long long w_weights; long long t_issue; long long t_commit; };
 __device__ __noinline__ void gemm_job(uint64_t* bars, uint32_t ring, MmaRing& st, uint32_t d, uint32_t op, int transposed,
                                       int accumulate, int passes, volatile int* err) {
 #pragma unroll 1
@@ -181,9 +180,12 @@ __device__ __noinline__ void gemm_job(uint64_t* bars, uint32_t ring, MmaRing& st
     mbar_wait_timed(&bars[B_FULL + st.stage], st.ph, err, st.w_weights);
     tc_fence_after();
     const uint32_t wst = ring + st.stage * kChunkBytes, opk = op + kb * (2 * kKStepBytes);
+    const long long ta = clock64();
     if (!transposed) mma_f16x3(d, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, accumulate || kb > 0, passes);
     else             mma_f16x3(d, wst, kChunkHalfBytes, opk, kOperandHalfBytes, 2, accumulate || kb > 0, passes);
+    const long long tb = clock64();
     tc_commit(&bars[B_EMPTY + st.stage]);
+    st.t_issue += tb - ta; st.t_commit += clock64() - tb;
     if (++st.stage == kStages) { st.stage = 0; st.ph ^= 1; }
   }
 }
@@ -248,7 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       long long w_operands = 0, w_tempty = 0;
       const long long t_start = clock64();
       const uint32_t xa = smem_u32(X), ya = smem_u32(Y), ring = smem_u32(RING);
-      MmaRing rs{0, 0u, 0};
+      MmaRing rs{0, 0u, 0, 0, 0};
       auto gemm = [&](uint32_t d, uint32_t op, bool transposed, bool accumulate) {
         gemm_job(bars, ring, rs, d, op, transposed, accumulate, p.passes, err);
       };
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       if (p.dbg) {
         p.dbg[blockIdx.x * 8 + 0] = rs.w_weights; p.dbg[blockIdx.x * 8 + 1] = w_operands;
         p.dbg[blockIdx.x * 8 + 3] = w_tempty; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
+        p.dbg[blockIdx.x * 8 + 5] = rs.t_issue; p.dbg[blockIdx.x * 8 + 6] = rs.t_commit;
       }
     }
   } else {
@@ -304,27 +307,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       const int rows = __ldg(p.node_in_ptr + node_hi) - row0;
       // ---- tile tables (the previous tile finished with an all-group barrier)
       if (tid < 128) {
-        RowA ra; ra.src = 0; ra.dst = node_lo; ra.slot_last = 0; ra.dist = 0.0f;
-        RowB rb; rb.dx = rb.dy = rb.dz = rb.pad = 0.0f;
+        uint4 ra = make_uint4(0u, (uint32_t)node_lo, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u);
         if (tid < rows) {
-          const int er = row0 + tid;
-          int j = node_lo;
-          while (j + 1 < node_hi && __ldg(p.node_in_ptr + j + 1) <= er) ++j;
-          const int mol = __ldg(p.node_mol + j);
-          const int n0 = __ldg(p.mol_ptr + mol), n = __ldg(p.mol_ptr + mol + 1) - n0;
-          const int jl = j - n0, ip = er - __ldg(p.node_in_ptr + j);
-          const int il = ip + (ip >= jl);
-          const int src = n0 + il;
-          // r = x[src] - x[dst], d = |r|, dir = r / (1 + d)                       (graph.py:27-29)
-          const float rx = __ldg(p.x + 3 * src + 0) - __ldg(p.x + 3 * j + 0);
-          const float ry = __ldg(p.x + 3 * src + 1) - __ldg(p.x + 3 * j + 1);
-          const float rz = __ldg(p.x + 3 * src + 2) - __ldg(p.x + 3 * j + 2);
-          const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
-          const float den = 1.0f + dist;
-          ra.src = src; ra.dst = j; ra.slot_last = (j - node_lo) | ((ip == n - 2) << 8) | ((ip == 0) << 9); ra.dist = dist;
-          rb.dx = __fdiv_rn(rx, den); rb.dy = __fdiv_rn(ry, den); rb.dz = __fdiv_rn(rz, den);
+          ra = __ldg(p.rowa + row0 + tid);
+          rb = __ldg(p.rowb + row0 + tid);
+          ra.z |= (uint32_t)((int)ra.y - node_lo);           // slot of the destination node inside this tile
         }
-        ROWA[tid] = ra; ROWB[tid] = rb;
+        reinterpret_cast<uint4*>(ROWA)[tid] = ra;
+        reinterpret_cast<uint4*>(ROWB)[tid] = rb;
       }
       if (tid >= 128 && tid <= 128 + kTileNodes && node_lo + (tid - 128) <= node_hi)
         SLOTROW[tid - 128] = __ldg(p.node_in_ptr + node_lo + (tid - 128)) - row0;
@@ -334,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       if (chain == 0) {
         // ---- w chain.  E1: PositionalEncoder(edge_dist) -> X                      (cpainn.py:283)
         const float dist = ROWA[row].dist;
-#pragma unroll 1
+#pragma unroll 2
         for (int kg = 8 * half; kg < 8 * half + 8; ++kg) {
           float v[8];
 #pragma unroll
@@ -481,8 +471,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       TIB_PHASE(6);     // write-back + end-of-tile barrier
     }
     if (p.dbg && (tid == 0 || tid == 256)) {
-      p.dbg[blockIdx.x * 8 + (tid ? 6 : 5)] = w_acc;
-      if (tid == 0) p.dbg[blockIdx.x * 8 + 7] = w_tfull;
+      if (tid == 0) p.dbg[blockIdx.x * 8 + 7] = w_tfull + w_acc;
       for (int i = 0; i < 8; ++i) p.dbg[(size_t)(gridDim.x + blockIdx.x * 2 + (tid ? 1 : 0)) * 8 + i] = phc[i];
     }
 #undef TIB_PHASE
@@ -493,15 +482,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
 }
 
 // ---- small helpers of the tensor-core drift ---------------------------------------------------------
-// node_mol[j], node_in_ptr[j] = first (dst,src)-ordered edge row of node j; node_in_ptr[N] = E
-__global__ void k_node_tables(const int* __restrict__ mol_ptr, const long long* __restrict__ edge_ptr, int n_mol,
-                              int* __restrict__ node_mol, int* __restrict__ node_in_ptr) {
-  const int m = blockIdx.x * blockDim.x + threadIdx.x;
-  if (m >= n_mol) return;
+// Per drift evaluation (geometry depends on x): node_in_ptr[j] = first (dst,src)-ordered edge row of node j
+// (node_in_ptr[N] = E) and, per edge row, RowA {src, dst, last << 8 | first << 9, dist} and RowB {dir, 0}:
+// r = x[src] - x[dst], d = |r|, dir = r / (1 + d)                                       (graph.py:27-29)
+__global__ void k_edge_tables(const int* __restrict__ mol_ptr, const long long* __restrict__ edge_ptr, int n_mol,
+                              const float* __restrict__ x, int* __restrict__ node_in_ptr, uint4* __restrict__ rowa,
+                              uint4* __restrict__ rowb) {
+  const int m = blockIdx.x;
   const int n0 = mol_ptr[m], n = mol_ptr[m + 1] - n0;
   const int e0 = (int)edge_ptr[m];
-  for (int j = 0; j < n; ++j) { node_mol[n0 + j] = m; node_in_ptr[n0 + j] = e0 + j * (n - 1); }
-  if (m == n_mol - 1) node_in_ptr[n0 + n] = (int)edge_ptr[n_mol];
+  for (int j = threadIdx.x; j < n; j += blockDim.x) node_in_ptr[n0 + j] = e0 + j * (n - 1);
+  if (m == n_mol - 1 && threadIdx.x == 0) node_in_ptr[n0 + n] = (int)edge_ptr[n_mol];
+  for (int row = threadIdx.x; row < n * (n - 1); row += blockDim.x) {
+    const int jl = row / (n - 1), ip = row % (n - 1), il = ip + (ip >= jl);
+    const int src = n0 + il, dst = n0 + jl;
+    const float rx = x[3 * src + 0] - x[3 * dst + 0];
+    const float ry = x[3 * src + 1] - x[3 * dst + 1];
+    const float rz = x[3 * src + 2] - x[3 * dst + 2];
+    const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
+    const float den = 1.0f + dist;
+    rowa[e0 + row] = make_uint4((uint32_t)src, (uint32_t)dst, (uint32_t)(((ip == n - 2) << 8) | ((ip == 0) << 9)),
+                                __float_as_uint(dist));
+    rowb[e0 + row] = make_uint4(__float_as_uint(__fdiv_rn(rx, den)), __float_as_uint(__fdiv_rn(ry, den)),
+                                __float_as_uint(__fdiv_rn(rz, den)), 0u);
+  }
 }
 
 // e0 = Emb4(edge_type) written in (dst,src) order; edge_type is given in the reference's (src,dst) order

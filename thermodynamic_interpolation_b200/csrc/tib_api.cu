@@ -176,7 +176,8 @@ struct Workspace {
   float *k;          // [7][3N] dopri stages / rk4 stages
   float *ytmp, *ycur, *ynew;
   double *partial, *scalar;
-  int *node_mol, *node_in_ptr;
+  int *node_in_ptr;
+  uint4 *rowa, *rowb;
   static constexpr int kPartials = 1024;
   static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
   static size_t bytes(int F, int n_nodes, long long n_edges) {
@@ -186,7 +187,7 @@ struct Workspace {
     b += align(sizeof(float) * (size_t)n_edges * F);
     b += 12 * align(sizeof(float) * (size_t)n_nodes * 3);   // drift, score, k[7], ytmp, ycur, ynew
     b += align(sizeof(double) * kPartials * 5) + align(sizeof(double) * 8);
-    b += 2 * align(sizeof(int) * ((size_t)n_nodes + 1));
+    b += align(sizeof(int) * ((size_t)n_nodes + 1)) + 2 * align(sizeof(uint4) * (size_t)n_edges);
     return b;
   }
   void carve(void* base, int F, int n_nodes, long long n_edges) {
@@ -207,8 +208,9 @@ struct Workspace {
     ynew = (float*)take(st);
     partial = (double*)take(sizeof(double) * kPartials * 5);
     scalar = (double*)take(sizeof(double) * 8);
-    node_mol = (int*)take(sizeof(int) * ((size_t)n_nodes + 1));
     node_in_ptr = (int*)take(sizeof(int) * ((size_t)n_nodes + 1));
+    rowa = (uint4*)take(sizeof(uint4) * (size_t)n_edges);
+    rowb = (uint4*)take(sizeof(uint4) * (size_t)n_edges);
   }
   static size_t kstride(int n_nodes) { return align(sizeof(float) * (size_t)n_nodes * 3) / sizeof(float); }
 };
@@ -243,8 +245,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     }
     nodes_per_tile = std::min(tc::kTileNodes, 128 / (b->max_atoms - 1));
     n_tiles = (b->n_nodes + nodes_per_tile - 1) / nodes_per_tile;
-    tc::k_node_tables<<<(b->n_mol + 127) / 128, 128, 0, st>>>(b->mol_ptr, (const long long*)b->edge_ptr, b->n_mol,
-                                                              ws.node_mol, ws.node_in_ptr);
+    tc::k_edge_tables<<<b->n_mol, 128, 0, st>>>(b->mol_ptr, (const long long*)b->edge_ptr, b->n_mol, x, ws.node_in_ptr,
+                                                ws.rowa, ws.rowb);
     LAUNCH_CHECK();
     ProfScope ps(TIB_K_EDGE_INIT, st);
     tc::k_edge_init_dst<<<b->n_mol, 256, 0, st>>>(b->edge_type, m->edge_emb, b->mol_ptr, (const long long*)b->edge_ptr, ws.e, F);
@@ -262,8 +264,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     if (use_tc) {
       tc::TcMsgP tp{};
       tp.n_nodes = b->n_nodes; tp.n_tiles = n_tiles; tp.nodes_per_tile = nodes_per_tile;
-      tp.node_in_ptr = ws.node_in_ptr; tp.node_mol = ws.node_mol; tp.mol_ptr = b->mol_ptr;
-      tp.x = x; tp.s_old = ws.s[cur]; tp.v_old = ws.v[cur]; tp.s_new = ws.s[cur ^ 1]; tp.v_new = ws.v[cur ^ 1]; tp.e = ws.e;
+      tp.node_in_ptr = ws.node_in_ptr; tp.rowa = ws.rowa; tp.rowb = ws.rowb;
+      tp.s_old = ws.s[cur]; tp.v_old = ws.v[cur]; tp.s_new = ws.s[cur ^ 1]; tp.v_new = ws.v[cur ^ 1]; tp.e = ws.e;
       tp.wblob = L.tc_msg;
       tp.prm = tc::MsgParams{L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2, L.phi.b3,
                              L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2, L.w.b3};

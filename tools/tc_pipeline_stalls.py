@@ -34,7 +34,7 @@ buf_all = np.zeros((3 * n, 8), dtype=np.int64)
 lib.tib_debug_counters(eng.handle, 1, buf_all.ctypes.data_as(C.c_void_p), 3 * n)
 buf = buf_all[:n]
 names = ["mma:wait weights", "mma:wait operands", "producer:wait free slot", "mma:wait acc drain", "mma:total",
-         "epi(w chain):wait acc", "epi(phi chain):wait acc", "epi:wait output acc"]
+         "mma:issuing tcgen05.mma", "mma:issuing tcgen05.commit", "epi(thread 0):wait accumulators"]
 tot = buf[:, 4].mean()
 print("last message launch (layer 5), mean cycles per CTA over", n, "CTAs; tiles per CTA ~", 4096 * 9 / 16 / n)
 for i, nm in enumerate(names):
