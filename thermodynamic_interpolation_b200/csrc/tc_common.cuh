@@ -72,7 +72,9 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, volati
 
 // wait + add the stalled cycles to *acc (pipeline diagnostics; acc may be a dummy)
 // (mbarrier.try_wait itself may block for a hardware time limit, so the clock brackets the first try too)
-__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, volatile int* err, long long& acc) {
+__device__ __forceinline__ void mbar_wait_timed(uint64_t* bar, uint32_t parity, volatile int* err, long long& acc,
+                                                bool diag = true) {
+  if (!diag) { mbar_wait(bar, parity, err); return; }
   const long long t0 = clock64();
   mbar_wait(bar, parity, err);
   acc += clock64() - t0;

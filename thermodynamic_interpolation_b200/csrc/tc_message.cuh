@@ -174,18 +174,18 @@ __device__ __noinline__ void build_rows(unsigned char* op, int wq, int half, int
 // One [128 x 128] matrix = 4 streamed chunks; transposed = the weights are the A operand.
 struct MmaRing { int stage; uint32_t ph; long long w_weights; long long t_issue; long long t_commit; };
 __device__ __noinline__ void gemm_job(uint64_t* bars, uint32_t ring, MmaRing& st, uint32_t d, uint32_t op, int transposed,
-                                      int accumulate, int passes, volatile int* err) {
+                                      int accumulate, int passes, volatile int* err, bool diag) {
 #pragma unroll 1
   for (int kb = 0; kb < 4; ++kb) {
-    mbar_wait_timed(&bars[B_FULL + st.stage], st.ph, err, st.w_weights);
+    mbar_wait_timed(&bars[B_FULL + st.stage], st.ph, err, st.w_weights, diag);
     tc_fence_after();
     const uint32_t wst = ring + st.stage * kChunkBytes, opk = op + kb * (2 * kKStepBytes);
-    const long long ta = clock64();
+    const long long ta = diag ? clock64() : 0;
     if (!transposed) mma_f16x3(d, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, accumulate || kb > 0, passes);
     else             mma_f16x3(d, wst, kChunkHalfBytes, opk, kOperandHalfBytes, 2, accumulate || kb > 0, passes);
-    const long long tb = clock64();
+    const long long tb = diag ? clock64() : 0;
     tc_commit(&bars[B_EMPTY + st.stage]);
-    st.t_issue += tb - ta; st.t_commit += clock64() - tb;
+    if (diag) { st.t_issue += tb - ta; st.t_commit += clock64() - tb; }
     if (++st.stage == kStages) { st.stage = 0; st.ph ^= 1; }
   }
 }
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + MsgSmem::BARS + 8 * B_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   volatile int* err = p.err;
+  const bool diag = p.dbg != nullptr;
 
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
@@ -235,7 +236,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int c = 0; c < kChunksPerLayer; ++c) {
           if (p.first_layer && ((c >= 20 && c < 28) || c >= 52)) continue;   // splits 0 and 4 multiply v = 0
-          mbar_wait_timed(&bars[B_EMPTY + stage], ph ^ 1, err, w_empty);
+          mbar_wait_timed(&bars[B_EMPTY + stage], ph ^ 1, err, w_empty, diag);
           mbar_arrive_expect_tx(&bars[B_FULL + stage], kChunkBytes);
           bulk_g2s(RING + stage * kChunkBytes, p.wblob + (size_t)c * kChunkBytes, kChunkBytes, &bars[B_FULL + stage]);
           if (++stage == kStages) { stage = 0; ph ^= 1; }
@@ -252,30 +253,30 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       const uint32_t xa = smem_u32(X), ya = smem_u32(Y), ring = smem_u32(RING);
       MmaRing rs{0, 0u, 0, 0, 0};
       auto gemm = [&](uint32_t d, uint32_t op, bool transposed, bool accumulate) {
-        gemm_job(bars, ring, rs, d, op, transposed, accumulate, p.passes, err);
+        gemm_job(bars, ring, rs, d, op, transposed, accumulate, p.passes, err, diag);
       };
       const uint32_t acc0 = tmem, acc1 = tmem + 128;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands); px ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
         gemm(acc0, xa, false, false);                       // w layer 1   : PE(d)
         tc_commit(&bars[B_ACC0]);
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands); py ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
         gemm(acc1, ya, false, false);                       // phi layer 1 : s[src] half
         tc_commit(&bars[B_YFREE]);
-        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands); px ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
         gemm(acc0, xa, false, false);                       // w layer 2
         tc_commit(&bars[B_ACC0]);
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands); py ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
         gemm(acc1, ya, false, true);                        // phi layer 1 : e half (accumulates)
         tc_commit(&bars[B_ACC1]);
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands); py ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
         gemm(acc1, ya, false, false);                       // phi layer 2
         tc_commit(&bars[B_ACC1]);
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands); py ^= 1;
-        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands); px ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1;
+        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
         for (int it = 0; it < n_splits; ++it) {
           const int pb = it & 1;
-          mbar_wait_timed(&bars[B_TEMPTY0 + pb], pte[pb] ^ 1, err, w_tempty); pte[pb] ^= 1; tc_fence_after();
+          mbar_wait_timed(&bars[B_TEMPTY0 + pb], pte[pb] ^ 1, err, w_tempty, diag); pte[pb] ^= 1; tc_fence_after();
           gemm(tmem + 256 * pb, ya, true, false);           // phi layer 3, one split (transposed)
           gemm(tmem + 256 * pb + 128, xa, true, false);     // w layer 3, same split
           tc_commit(&bars[B_TFULL0 + pb]);
@@ -298,7 +299,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     long long w_acc = 0, w_tfull = 0;
     long long phc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
-#define TIB_PHASE(i) do { const long long _t = clock64(); phc[i] += _t - tlast; tlast = _t; } while (0)
+#define TIB_PHASE(i) do { if (diag) { const long long _t = clock64(); phc[i] += _t - tlast; tlast = _t; } } while (0)
     const uint32_t lane_taddr = tmem + ((uint32_t)(wq * 32) << 16);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
       const int node_lo = tile * p.nodes_per_tile;
@@ -338,12 +339,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         TIB_PHASE(1);   // E1 / E2
         // E3: hidden 1 -> X
-        mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc, diag); pacc ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr, half, row, PRM + kPrmW, PRM + kPrmW + kF, PRM + kPrmW + 2 * kF, X, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         TIB_PHASE(2);   // E3 / E4
         // E5: hidden 2 -> X (final: B operand of the output layer)
-        mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc, diag); pacc ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr, half, row, PRM + kPrmW + 3 * kF, PRM + kPrmW + 4 * kF, PRM + kPrmW + 5 * kF, X, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         TIB_PHASE(3);   // E5 / E6
@@ -353,17 +354,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(1);
         // E4: e rows -> Y (after the s[src] half has been consumed)
-        mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc); pyf ^= 1;
+        mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc, diag); pyf ^= 1;
         build_rows(Y, wq, half, lane, rows, p.e, ROWA, 0, row0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(2);
         // E6: hidden 1 -> Y
-        mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc, diag); pacc ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr + 128, half, row, PRM + kPrmPhi, PRM + kPrmPhi + kF, PRM + kPrmPhi + 2 * kF, Y, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(3);
         // E7: hidden 2 -> Y (final)
-        mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc); pacc ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc, diag); pacc ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr + 128, half, row, PRM + kPrmPhi + 3 * kF, PRM + kPrmPhi + 4 * kF, PRM + kPrmPhi + 5 * kF, Y, stat, bar_id);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(4);   // E7
@@ -385,7 +386,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         const int sp = p.first_layer ? it + 1 : it;
         const int pb = it & 1;
         const float bphi = PRM[kPrmB3 + sp * kF + f], bw = PRM[kPrmB3 + 5 * kF + sp * kF + f];
-        mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull); ptf[pb] ^= 1; tc_fence_after();
+        mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull, diag); ptf[pb] ^= 1; tc_fence_after();
         const uint32_t tphi = lane_taddr + 256 * pb, tw = tphi + 128;
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
