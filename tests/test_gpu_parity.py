@@ -308,6 +308,27 @@ def test_adw_drift_and_divergence_match_reference_golden():
     np.testing.assert_allclose(div.cpu().numpy() * 1e-2, g["div_t03_scaled"], rtol=5e-7, atol=1e-12)
 
 
+@pytest.mark.parametrize("method,n_step", [("euler", 11), ("dopri5", 9)])
+def test_adw_rollout_matches_reference_golden(method, n_step):
+    """StandardIntegrator.rollout (adw/thermo/integrators.py:33-68) on the reference's fp64 model + fp32 state."""
+    from thermodynamic_interpolation_b200.adw.integrators import StandardIntegrator
+    from thermodynamic_interpolation_b200.adw.models.simple import FCNetMultiBeta
+    g = load_golden("adw")
+    torch.manual_seed(int(g["seed"]))
+    model = perturb_(FCNetMultiBeta(1, 1, 256, 5).double(), int(g["seed"]) + 1, float(g["perturb"])).to(DEV)
+    x0 = torch.from_numpy(g["in::x0"]).to(DEV)
+    b0 = torch.from_numpy(g["in::beta0"]).to(DEV)
+    b1 = torch.from_numpy(g["in::beta1"]).to(DEV)
+    integ = StandardIntegrator(model, method=method, n_step=n_step, atol=1e-4, rtol=1e-4, return_dlogp=True)
+    x, dlogp = integ.rollout(x0, b0, b1)
+    assert x.shape == (n_step, 64, 1) and dlogp.shape == (n_step, 64, 1)
+    tol = 1e-5 if method == "euler" else 2e-4        # dopri5: the solver's own tolerance (rtol = atol = 1e-4)
+    _close(x.cpu().numpy(), g[f"{method}_x"], rtol=tol, atol_rel=tol, what=f"adw {method} x")
+    _close(dlogp.cpu().numpy(), g[f"{method}_dlogp"], rtol=tol * 10, atol_rel=tol, what=f"adw {method} dlogp")
+    with pytest.raises(TypeError):
+        StandardIntegrator(model, method="euler", n_step=3).rollout(x0, b0, b1)
+
+
 def test_errors_are_loud():
     from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
     from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch

@@ -145,7 +145,7 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int half, int row, 
   const float rstd = rsqrtf(var + 1e-5f);
   const float nmr = -mean * rstd;
   // pass 2: normalise, affine, SiLU, split, store
-#pragma unroll 2
+#pragma unroll 1
   for (int kg = 0; kg < 8; ++kg) {
     float t[8];
     tmem_ld8(t0 + 8 * kg, t);
