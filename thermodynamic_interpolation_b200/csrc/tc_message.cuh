@@ -39,7 +39,8 @@ constexpr int kTileNodes = 16;                 // destination nodes per tile (de
 constexpr int kChunksPerLayer = 60;
 
 // streamed chunk order of one message layer (every entry is 4 chunks = one [128 x 128] matrix):
-//   0 w.W1 | 4 phi.W1[:, :F] | 8 w.W2 | 12 phi.W1[:, F:] | 16 phi.W2 | 20+8sp phi.W3[sp] | 24+8sp w.W3[sp]
+//   0 w.W1 | 4 phi.W1[:, :F] | 8 w.W2 | 12 phi.W1[:, F:] | 16 phi.W2 | 20+8sp: phi.W3[sp] and w.W3[sp] interleaved
+//   chunk by chunk (phi k0, w k0, phi k1, w k1, ...) so the two independent accumulators alternate in the MMA queue
 struct MsgParams {
   const float *phi_b1, *phi_g1, *phi_be1, *phi_b2, *phi_g2, *phi_be2, *phi_b3;
   const float *w_b1, *w_g1, *w_be1, *w_b2, *w_g2, *w_be2, *w_b3;
@@ -81,7 +82,7 @@ struct MsgSmem {
   static constexpr uint32_t TOTAL = BARS + 256;
 };
 // barrier indices
-enum { B_FULL = 0, B_EMPTY = B_FULL + kStages, B_XFULL = B_EMPTY + kStages, B_YFULL, B_YFREE, B_ACC0, B_ACC1,
+enum { B_FULL = 0, B_EMPTY = B_FULL + kStages /* one per PAIR of stages */, B_XFULL = B_EMPTY + kStages / 2, B_YFULL, B_YFREE, B_ACC0, B_ACC1,
        B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_COUNT };
 enum { NB_ALL = 1, NB_CHAIN_W = 2, NB_CHAIN_PHI = 3 };
 
@@ -184,9 +185,46 @@ __device__ __noinline__ void gemm_job(uint64_t* bars, uint32_t ring, MmaRing& st
     if (!transposed) mma_f16x3(d, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, accumulate || kb > 0, passes);
     else             mma_f16x3(d, wst, kChunkHalfBytes, opk, kOperandHalfBytes, 2, accumulate || kb > 0, passes);
     const long long tb = diag ? clock64() : 0;
-    tc_commit(&bars[B_EMPTY + st.stage]);
+    if (st.stage & 1) tc_commit(&bars[B_EMPTY + (st.stage >> 1)]);     // ring slots are released in pairs
     if (diag) { st.t_issue += tb - ta; st.t_commit += clock64() - tb; }
     if (++st.stage == kStages) { st.stage = 0; st.ph ^= 1; }
+  }
+}
+
+// Output layer of one split: D_phi^T = W3phi * Hphi^T and D_w^T = W3w * Hw^T, chunk pairs (phi k, w k) in
+// consecutive ring stages; the MMAs of the two independent accumulators are interleaved.
+__device__ __noinline__ void gemm_pair_job(uint64_t* bars, uint32_t ring, MmaRing& st, uint32_t d_phi, uint32_t op_phi,
+                                           uint32_t d_w, uint32_t op_w, int passes, volatile int* err, bool diag) {
+#pragma unroll 1
+  for (int kb = 0; kb < 4; ++kb) {
+    mbar_wait_timed(&bars[B_FULL + st.stage], st.ph, err, st.w_weights, diag);
+    mbar_wait_timed(&bars[B_FULL + st.stage + 1], st.ph, err, st.w_weights, diag);
+    tc_fence_after();
+    const uint32_t wp = ring + st.stage * kChunkBytes, ww = wp + kChunkBytes;
+    const uint32_t hp = op_phi + kb * (2 * kKStepBytes), hw = op_w + kb * (2 * kKStepBytes);
+    const long long ta = diag ? clock64() : 0;
+#pragma unroll 1
+    for (int ks = 0; ks < 2; ++ks) {
+      const uint32_t o = ks * kKStepBytes;
+      const uint32_t acc = (kb | ks) ? 1u : 0u;
+      const uint64_t wph = make_desc(wp + o), wpl = make_desc(wp + kChunkHalfBytes + o);
+      const uint64_t wwh = make_desc(ww + o), wwl = make_desc(ww + kChunkHalfBytes + o);
+      const uint64_t hph = make_desc(hp + o), hpl = make_desc(hp + kOperandHalfBytes + o);
+      const uint64_t hwh = make_desc(hw + o), hwl = make_desc(hw + kOperandHalfBytes + o);
+      tc_mma_f16(d_phi, wph, hph, kIdesc128x128, acc);
+      tc_mma_f16(d_w, wwh, hwh, kIdesc128x128, acc);
+      if (passes == 3) {
+        tc_mma_f16(d_phi, wph, hpl, kIdesc128x128, 1u);
+        tc_mma_f16(d_w, wwh, hwl, kIdesc128x128, 1u);
+        tc_mma_f16(d_phi, wpl, hph, kIdesc128x128, 1u);
+        tc_mma_f16(d_w, wwl, hwh, kIdesc128x128, 1u);
+      }
+    }
+    const long long tb = diag ? clock64() : 0;
+    tc_commit(&bars[B_EMPTY + (st.stage >> 1)]);
+    if (diag) { st.t_issue += tb - ta; st.t_commit += clock64() - tb; }
+    st.stage += 2;
+    if (st.stage == kStages) { st.stage = 0; st.ph ^= 1; }
   }
 }
 
@@ -207,7 +245,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   const bool diag = p.dbg != nullptr;
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars[B_FULL + i], 1); mbar_init(&bars[B_EMPTY + i], 1); }
+    for (int i = 0; i < kStages; ++i) mbar_init(&bars[B_FULL + i], 1);
+    for (int i = 0; i < kStages / 2; ++i) mbar_init(&bars[B_EMPTY + i], 1);
     mbar_init(&bars[B_XFULL], 256); mbar_init(&bars[B_YFULL], 256);
     mbar_init(&bars[B_YFREE], 1); mbar_init(&bars[B_ACC0], 1); mbar_init(&bars[B_ACC1], 1);
     mbar_init(&bars[B_TFULL0], 1); mbar_init(&bars[B_TFULL1], 1);
@@ -236,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int c = 0; c < kChunksPerLayer; ++c) {
           if (p.first_layer && ((c >= 20 && c < 28) || c >= 52)) continue;   // splits 0 and 4 multiply v = 0
-          mbar_wait_timed(&bars[B_EMPTY + stage], ph ^ 1, err, w_empty, diag);
+          if (!(stage & 1)) mbar_wait_timed(&bars[B_EMPTY + (stage >> 1)], ph ^ 1, err, w_empty, diag);
           mbar_arrive_expect_tx(&bars[B_FULL + stage], kChunkBytes);
           bulk_g2s(RING + stage * kChunkBytes, p.wblob + (size_t)c * kChunkBytes, kChunkBytes, &bars[B_FULL + stage]);
           if (++stage == kStages) { stage = 0; ph ^= 1; }
@@ -277,9 +316,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         for (int it = 0; it < n_splits; ++it) {
           const int pb = it & 1;
           mbar_wait_timed(&bars[B_TEMPTY0 + pb], pte[pb] ^ 1, err, w_tempty, diag); pte[pb] ^= 1; tc_fence_after();
-          gemm(tmem + 256 * pb, ya, true, false);           // phi layer 3, one split (transposed)
-          gemm(tmem + 256 * pb + 128, xa, true, false);     // w layer 3, same split
-          tc_commit(&bars[B_TFULL0 + pb]);
+          gemm_pair_job(bars, ring, rs, tmem + 256 * pb, ya, tmem + 256 * pb + 128, xa, p.passes, err, diag);
+          tc_commit(&bars[B_TFULL0 + pb]);                  // phi and w layer 3 of this split (transposed)
         }
       }
       if (p.dbg) {

@@ -487,7 +487,11 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
       mat(wW2, F, 0, 0);
       mat(pW1, 2 * F, 0, F);
       mat(pW2, F, 0, 0);
-      for (int sp = 0; sp < 5; ++sp) { mat(pW3, F, sp * F, 0); mat(wW3, F, sp * F, 0); }
+      for (int sp = 0; sp < 5; ++sp)            // output layer: phi and w chunks interleaved (tc_message.cuh)
+        for (int kb = 0; kb < 4; ++kb) {
+          pack_tc_chunk(out16, pW3, F, sp * F, 32 * kb); out16 += tib::tc::kChunkBytes / 2;
+          pack_tc_chunk(out16, wW3, F, sp * F, 32 * kb); out16 += tib::tc::kChunkBytes / 2;
+        }
       // update layer: U [F][F], V [F][F], MLP(2F -> F -> F -> 3F)
       const float* U = uv_src[l];
       const float* V = U + (size_t)F * F;
