@@ -17,10 +17,10 @@
 //
 // Warp roles (576 threads): warps 0-15 = four epilogue groups (group g = warp / 4; a warp reads the
 // TMEM lane quarter warp % 4), warp 16 weight producer (+ TMEM allocation), warp 17 MMA issuer.
-//   hidden phase : groups 0,1 run the w chain (column halves 0-63 / 64-127 of every row),
-//                  groups 2,3 run the phi chain; LayerNorm statistics of a row are exchanged
-//                  between the two halves through shared memory.
-//   output phase : group g scatters TMEM columns (= edges) [32g, 32g+32) of every split.
+//   hidden phase : every epilogue runs on all 16 warps (group g = feature columns [32g, 32g+32) of
+//                  every row; LayerNorm statistics exchanged through shared memory); the w and phi
+//                  chains are interleaved so that the MMAs of one run under the epilogue of the other.
+//   output phase : group g owns whole destination nodes and scatters their TMEM columns (= edges).
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -76,8 +76,8 @@ struct MsgSmem {
   static constexpr uint32_t PRM = RING + kStages * kChunkBytes;                // layer parameters (fp32), see kPrm*
   static constexpr uint32_t ROWA = PRM + kPrmFloats * 4;                       // RowA[128]
   static constexpr uint32_t ROWB = ROWA + 128 * 16;                            // RowB[128]
-  static constexpr uint32_t STAT = ROWB + 128 * 16;                            // [2 chains][2 kinds][2 halves][128] fp32
-  static constexpr uint32_t SLOTROW = STAT + 2 * 2 * 2 * 128 * 4;              // int[kTileNodes + 1] first row of each slot
+  static constexpr uint32_t STAT = ROWB + 128 * 16;                            // 2 x float2 [4 groups][128 rows] (alternating)
+  static constexpr uint32_t SLOTROW = STAT + 2 * 4 * 128 * 8;              // int[kTileNodes + 1] first row of each slot
   static constexpr uint32_t BARS = SLOTROW + 128;
   static constexpr uint32_t TOTAL = BARS + 256;
 };
@@ -86,49 +86,22 @@ enum { B_FULL = 0, B_EMPTY = B_FULL + kStages /* one per PAIR of stages */, B_XF
        B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_COUNT };
 enum { NB_ALL = 1, NB_CHAIN_W = 2, NB_CHAIN_PHI = 3 };
 
-// rows [32*(warp%4), +32) x column groups [8*half, 8*half+8) of an operand image from row-major fp32
-// global rows: lane = (row & 7, group quad) so each 128 B line of a row is read by 4 lanes and every
-// store instruction writes 4 x 128 contiguous bytes.
-template <typename RowPtr>
-__device__ __forceinline__ void build_from_global(unsigned char* op, int wq, int half, int lane, int rows, RowPtr row_ptr) {
-#pragma unroll
-  for (int oct = 0; oct < 4; ++oct) {
-    const int r = 32 * wq + 8 * oct + (lane & 7);
-    const float* src = r < rows ? row_ptr(r) : nullptr;
-#pragma unroll
-    for (int kq = 0; kq < 2; ++kq) {
-      const int g = 8 * half + 4 * kq + (lane >> 3);
-      float v[8];
-      if (src) {
-        const float4 a = __ldg(reinterpret_cast<const float4*>(src + g * 8));
-        const float4 b = __ldg(reinterpret_cast<const float4*>(src + g * 8 + 4));
-        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.0f;
-      }
-      store_group(op, kOperandHalfBytes, r, g, v);
-    }
-  }
-}
-
-// Accumulator row `row` (TMEM lane), columns [64*half, +64): + bias -> LayerNorm over all 128 columns
-// (statistics exchanged with the thread that owns the other half) -> SiLU -> operand image.
 // The hot loops below are deliberately ROLLED (small bodies, TMEM re-read per pass): the straight-line
 // version of this kernel was ~220 KB of SASS and ran instruction-fetch bound (16 warps streaming
 // through code far larger than the 32 KB instruction cache).
-__device__ __noinline__ void hidden_epilogue(uint32_t taddr, int half, int row, const float* b,
-                                             const float* g, const float* be,
-                                             unsigned char* op, float* stat, int bar_id) {
-  const uint32_t t0 = taddr + 64 * half;
-  const float* bh = b + 64 * half;
-  // pass 1: sum and sum of squares of (x + bias) over this thread's 64 columns
+__device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, const float* b, const float* g, const float* be,
+                                             unsigned char* op, float* stat_f) {
+  // Accumulator row `row` (TMEM lane), columns [32*grp, +32): + bias -> LayerNorm over all 128 columns
+  // (sum and sum of squares exchanged between the four threads of a row) -> SiLU -> operand image.
+  float2* stat = reinterpret_cast<float2*>(stat_f);
+  const uint32_t t0 = taddr + 32 * grp;
+  const float* bq = b + 32 * grp;
   float sum = 0.0f, ss = 0.0f;
 #pragma unroll 1
-  for (int kg = 0; kg < 8; kg += 2) {
+  for (int kg = 0; kg < 4; kg += 2) {
     float t[8], u[8];
     tmem_ld8x2(t0 + 8 * kg, t0 + 8 * kg + 8, 0, t, u);
-    const float4* bp = reinterpret_cast<const float4*>(bh) + 2 * kg;
+    const float4* bp = reinterpret_cast<const float4*>(bq) + 2 * kg;
     const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
     const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
 #pragma unroll
@@ -138,21 +111,20 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int half, int row, 
       ss = fmaf(x0, x0, fmaf(x1, x1, ss));
     }
   }
-  reinterpret_cast<float2*>(stat)[half * 128 + row] = make_float2(sum, ss);
-  named_bar_sync(bar_id, 256);
-  const float2 s0 = reinterpret_cast<const float2*>(stat)[row], s1 = reinterpret_cast<const float2*>(stat)[128 + row];
-  const float mean = (s0.x + s1.x) * (1.0f / 128.0f);
-  const float var = fmaxf((s0.y + s1.y) * (1.0f / 128.0f) - mean * mean, 0.0f);
+  stat[grp * 128 + row] = make_float2(sum, ss);
+  named_bar_sync(NB_ALL, kEpiThreads);
+  const float2 s0 = stat[row], s1 = stat[128 + row], s2 = stat[256 + row], s3 = stat[384 + row];
+  const float mean = ((s0.x + s1.x) + (s2.x + s3.x)) * (1.0f / 128.0f);
+  const float var = fmaxf(((s0.y + s1.y) + (s2.y + s3.y)) * (1.0f / 128.0f) - mean * mean, 0.0f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float nmr = -mean * rstd;
-  // pass 2: normalise, affine, SiLU, split, store
 #pragma unroll 1
-  for (int kg = 0; kg < 8; ++kg) {
+  for (int kg = 0; kg < 4; ++kg) {
     float t[8];
     tmem_ld8(t0 + 8 * kg, t);
-    const float4* bp = reinterpret_cast<const float4*>(bh) + 2 * kg;
-    const float4* gp = reinterpret_cast<const float4*>(g + 64 * half) + 2 * kg;
-    const float4* ep = reinterpret_cast<const float4*>(be + 64 * half) + 2 * kg;
+    const float4* bp = reinterpret_cast<const float4*>(bq) + 2 * kg;
+    const float4* gp = reinterpret_cast<const float4*>(g + 32 * grp) + 2 * kg;
+    const float4* ep = reinterpret_cast<const float4*>(be + 32 * grp) + 2 * kg;
     const float4 b0 = bp[0], b1 = bp[1], g0 = gp[0], g1 = gp[1], e0 = ep[0], e1 = ep[1];
     const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
@@ -160,16 +132,31 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int half, int row, 
     float y[8];
 #pragma unroll
     for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(fmaf(t[i] + bb[i], rstd, nmr), gg[i], ee[i]));
-    store_group(op, kOperandHalfBytes, row, 8 * half + kg, y);
+    store_group(op, kOperandHalfBytes, row, 4 * grp + kg, y);
   }
+  // Consecutive calls alternate between two `stat` buffers; a buffer is reused only after an MMA that
+  // needed every thread's operand-ready arrival has completed, i.e. after all of these reads.
 }
 
-// rows [32*wq, +32) x column groups [8*half, +8) of an operand image from row-major fp32 global rows
+// rows [32*wq, +32) x column groups [4*grp, +4) of an operand image from row-major fp32 global rows
 // `base + row_index(r) * 128`, where row_index(r) = gather ? ROWA[r].src : row0 + r.
-__device__ __noinline__ void build_rows(unsigned char* op, int wq, int half, int lane, int rows, const float* base,
+__device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int lane, int rows, const float* base,
                                         const RowA* rowa, int gather, int row0) {
-  build_from_global(op, wq, half, lane, rows,
-                    [&](int r) { return base + (size_t)(gather ? rowa[r].src : row0 + r) * kF; });
+#pragma unroll
+  for (int oct = 0; oct < 4; ++oct) {
+    const int r = 32 * wq + 8 * oct + (lane & 7);
+    const int g = 4 * grp + (lane >> 3);
+    float v[8];
+    if (r < rows) {
+      const float* src = base + (size_t)(gather ? rowa[r].src : row0 + r) * kF + g * 8;
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+    }
+    store_group(op, kOperandHalfBytes, r, g, v);
+  }
 }
 
 // One [128 x 128] matrix = 4 streamed chunks; transposed = the weights are the A operand.
@@ -247,7 +234,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) mbar_init(&bars[B_FULL + i], 1);
     for (int i = 0; i < kStages / 2; ++i) mbar_init(&bars[B_EMPTY + i], 1);
-    mbar_init(&bars[B_XFULL], 256); mbar_init(&bars[B_YFULL], 256);
+    mbar_init(&bars[B_XFULL], kEpiThreads); mbar_init(&bars[B_YFULL], kEpiThreads);
     mbar_init(&bars[B_YFREE], 1); mbar_init(&bars[B_ACC0], 1); mbar_init(&bars[B_ACC1], 1);
     mbar_init(&bars[B_TFULL0], 1); mbar_init(&bars[B_TFULL1], 1);
     mbar_init(&bars[B_TEMPTY0], kEpiThreads); mbar_init(&bars[B_TEMPTY1], kEpiThreads);
@@ -330,10 +317,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     // =========================== builders / epilogue (512 threads) ===========================
     const int grp = warp >> 2, wq = warp & 3;
     const int row = 32 * wq + lane;                         // TMEM lane: edge row (hidden) / feature (output)
-    const int chain = grp >> 1, half = grp & 1;             // chain 0 = w, 1 = phi
-    float* const stat = STAT + chain * 512;
-    const int bar_id = chain ? NB_CHAIN_PHI : NB_CHAIN_W;
-    uint32_t pacc = 0, pyf = 0, ptf[2] = {0, 0};
+    uint32_t pacc0 = 0, pacc1 = 0, pyf = 0, ptf[2] = {0, 0};
     long long w_acc = 0, w_tfull = 0;
     long long phc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = clock64();
@@ -360,11 +344,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       named_bar_sync(NB_ALL, kEpiThreads);
       TIB_PHASE(0);   // tile tables
 
-      if (chain == 0) {
-        // ---- w chain.  E1: PositionalEncoder(edge_dist) -> X                      (cpainn.py:283)
+      // ---- hidden phase: one sequence, every epilogue on all 16 warps (group g = feature columns
+      // [32g, 32g+32) of every row); the MMAs of one chain run under the epilogue of the other.
+      {
+        // E1: PositionalEncoder(edge_dist) -> X                                     (cpainn.py:283)
         const float dist = ROWA[row].dist;
 #pragma unroll 2
-        for (int kg = 8 * half; kg < 8 * half + 8; ++kg) {
+        for (int kg = 4 * grp; kg < 4 * grp + 4; ++kg) {
           float v[8];
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
@@ -375,35 +361,31 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
           store_group(X, kOperandHalfBytes, row, kg, v);
         }
         fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
-        TIB_PHASE(1);   // E1 / E2
-        // E3: hidden 1 -> X
-        mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc, diag); pacc ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr, half, row, PRM + kPrmW, PRM + kPrmW + kF, PRM + kPrmW + 2 * kF, X, stat, bar_id);
-        tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
-        TIB_PHASE(2);   // E3 / E4
-        // E5: hidden 2 -> X (final: B operand of the output layer)
-        mbar_wait_timed(&bars[B_ACC0], pacc, err, w_acc, diag); pacc ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr, half, row, PRM + kPrmW + 3 * kF, PRM + kPrmW + 4 * kF, PRM + kPrmW + 5 * kF, X, stat, bar_id);
-        tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
-        TIB_PHASE(3);   // E5 / E6
-      } else {
-        // ---- phi chain.  E2: s[src] -> Y                                          (cpainn.py:275-281)
-        build_rows(Y, wq, half, lane, rows, p.s_old, ROWA, 1, 0);
+        // E2: s[src] -> Y                                                            (cpainn.py:275-281)
+        build_rows(Y, wq, grp, lane, rows, p.s_old, ROWA, 1, 0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
-        TIB_PHASE(1);
+        TIB_PHASE(1);   // E1 + E2
+        // E3: w hidden 1 -> X
+        mbar_wait_timed(&bars[B_ACC0], pacc0, err, w_acc, diag); pacc0 ^= 1; tc_fence_after();
+        hidden_epilogue(lane_taddr, grp, row, PRM + kPrmW, PRM + kPrmW + kF, PRM + kPrmW + 2 * kF, X, STAT);
+        tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         // E4: e rows -> Y (after the s[src] half has been consumed)
         mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc, diag); pyf ^= 1;
-        build_rows(Y, wq, half, lane, rows, p.e, ROWA, 0, row0);
+        build_rows(Y, wq, grp, lane, rows, p.e, ROWA, 0, row0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
-        TIB_PHASE(2);
-        // E6: hidden 1 -> Y
-        mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc, diag); pacc ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr + 128, half, row, PRM + kPrmPhi, PRM + kPrmPhi + kF, PRM + kPrmPhi + 2 * kF, Y, stat, bar_id);
+        TIB_PHASE(2);   // E3 + E4
+        // E5: w hidden 2 -> X (final: B operand of the output layer)
+        mbar_wait_timed(&bars[B_ACC0], pacc0, err, w_acc, diag); pacc0 ^= 1; tc_fence_after();
+        hidden_epilogue(lane_taddr, grp, row, PRM + kPrmW + 3 * kF, PRM + kPrmW + 4 * kF, PRM + kPrmW + 5 * kF, X, STAT + 1024);
+        tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+        // E6: phi hidden 1 -> Y
+        mbar_wait_timed(&bars[B_ACC1], pacc1, err, w_acc, diag); pacc1 ^= 1; tc_fence_after();
+        hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi, PRM + kPrmPhi + kF, PRM + kPrmPhi + 2 * kF, Y, STAT);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
-        TIB_PHASE(3);
-        // E7: hidden 2 -> Y (final)
-        mbar_wait_timed(&bars[B_ACC1], pacc, err, w_acc, diag); pacc ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr + 128, half, row, PRM + kPrmPhi + 3 * kF, PRM + kPrmPhi + 4 * kF, PRM + kPrmPhi + 5 * kF, Y, stat, bar_id);
+        TIB_PHASE(3);   // E5 + E6
+        // E7: phi hidden 2 -> Y (final)
+        mbar_wait_timed(&bars[B_ACC1], pacc1, err, w_acc, diag); pacc1 ^= 1; tc_fence_after();
+        hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi + 3 * kF, PRM + kPrmPhi + 4 * kF, PRM + kPrmPhi + 5 * kF, Y, STAT + 1024);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(4);   // E7
       }
