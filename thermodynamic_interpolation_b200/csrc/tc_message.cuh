@@ -94,22 +94,16 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
   // Accumulator row `row` (TMEM lane), columns [32*grp, +32): + bias -> LayerNorm over all 128 columns
   // (sum and sum of squares exchanged between the four threads of a row) -> SiLU -> operand image.
   float2* stat = reinterpret_cast<float2*>(stat_f);
-  const uint32_t t0 = taddr + 32 * grp;
-  const float* bq = b + 32 * grp;
+  float v[32];
+  tmem_ld32(taddr + 32 * grp, v);                       // one TMEM read; the row quarter stays in registers
+  const float4* bp = reinterpret_cast<const float4*>(b + 32 * grp);
   float sum = 0.0f, ss = 0.0f;
-#pragma unroll 1
-  for (int kg = 0; kg < 4; kg += 2) {
-    float t[8], u[8];
-    tmem_ld8x2(t0 + 8 * kg, t0 + 8 * kg + 8, 0, t, u);
-    const float4* bp = reinterpret_cast<const float4*>(bq) + 2 * kg;
-    const float4 b0 = bp[0], b1 = bp[1], b2 = bp[2], b3 = bp[3];
-    const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
 #pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      const float x0 = t[i] + bb[i], x1 = u[i] + bb[8 + i];
-      sum += x0 + x1;
-      ss = fmaf(x0, x0, fmaf(x1, x1, ss));
-    }
+  for (int c = 0; c < 8; ++c) {
+    const float4 bb = bp[c];
+    v[4 * c + 0] += bb.x; v[4 * c + 1] += bb.y; v[4 * c + 2] += bb.z; v[4 * c + 3] += bb.w;
+    sum += (v[4 * c + 0] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);
+    ss = fmaf(v[4 * c + 0], v[4 * c + 0], fmaf(v[4 * c + 1], v[4 * c + 1], fmaf(v[4 * c + 2], v[4 * c + 2], fmaf(v[4 * c + 3], v[4 * c + 3], ss))));
   }
   stat[grp * 128 + row] = make_float2(sum, ss);
   named_bar_sync(NB_ALL, kEpiThreads);
@@ -118,20 +112,16 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
   const float var = fmaxf(((s0.y + s1.y) + (s2.y + s3.y)) * (1.0f / 128.0f) - mean * mean, 0.0f);
   const float rstd = rsqrtf(var + 1e-5f);
   const float nmr = -mean * rstd;
-#pragma unroll 1
+  const float4* gp = reinterpret_cast<const float4*>(g + 32 * grp);
+  const float4* ep = reinterpret_cast<const float4*>(be + 32 * grp);
+#pragma unroll
   for (int kg = 0; kg < 4; ++kg) {
-    float t[8];
-    tmem_ld8(t0 + 8 * kg, t);
-    const float4* bp = reinterpret_cast<const float4*>(bq) + 2 * kg;
-    const float4* gp = reinterpret_cast<const float4*>(g + 32 * grp) + 2 * kg;
-    const float4* ep = reinterpret_cast<const float4*>(be + 32 * grp) + 2 * kg;
-    const float4 b0 = bp[0], b1 = bp[1], g0 = gp[0], g1 = gp[1], e0 = ep[0], e1 = ep[1];
-    const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    const float4 g0 = gp[2 * kg], g1 = gp[2 * kg + 1], e0 = ep[2 * kg], e1 = ep[2 * kg + 1];
     const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
     const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     float y[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(fmaf(t[i] + bb[i], rstd, nmr), gg[i], ee[i]));
+    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(fmaf(v[8 * kg + i], rstd, nmr), gg[i], ee[i]));
     store_group(op, kOperandHalfBytes, row, 4 * grp + kg, y);
   }
   // Consecutive calls alternate between two `stat` buffers; a buffer is reused only after an MMA that
