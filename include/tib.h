@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TIB_ABI_VERSION 1
+#define TIB_ABI_VERSION 2
 
 /* ---- model ------------------------------------------------------------------------------- */
 
@@ -94,6 +94,14 @@ typedef struct {
   const uint8_t* edge_type;    /* [E]  batch.edge_type in {0..3} */
   const float*   temp0;        /* [N]  batch.T0 (ambient) or batch.T (latent multi-T); may be NULL for single-T */
   const float*   temp1;        /* [N]  batch.T1 (ambient); NULL otherwise */
+  /* Optional de-duplication of the x-independent node embedding s0 = MLP(cat[Emb(atom), PE(T0), PE(T1), PE(t)])
+   * (embedding.py:68-86,249-261): nodes with the same (atom_id, temp0, temp1) share one row.  embed_index == NULL
+   * (or n_embed_rows == 0) = evaluate every node. */
+  int32_t        n_embed_rows; /* U distinct (atom_id, temp0, temp1) triples */
+  const int32_t* embed_index;  /* [N]  row of each node in the U-row table */
+  const int32_t* embed_atom_id;/* [U] */
+  const float*   embed_temp0;  /* [U] or NULL */
+  const float*   embed_temp1;  /* [U] or NULL */
 } tib_batch;
 
 /* Scratch the caller must provide to tib_drift / tib_rollout_* for this batch shape. */

@@ -44,7 +44,7 @@ def test_packed_weight_count_matches_library(variant, temps, F, L):
         m = cPaiNN(n_features=F, score_layers=L, **({"temperatures": temps} if temps else {}))
     packed = pack_state_dict(m.state_dict(), m.hyper)
     hp = m.hyper
-    desc = _lib.ModelDesc(abi_version=1, variant=hp.c_variant, n_features=F, n_layers=L, n_types=25, n_edge_types=4)
+    desc = _lib.ModelDesc(abi_version=_lib.ABI_VERSION, variant=hp.c_variant, n_features=F, n_layers=L, n_types=25, n_edge_types=4)
     assert packed.size == _lib.load().tib_packed_weight_count(C.byref(desc))
     n_params = sum(p.numel() for p in m.parameters() if p.dim() > 0)
     assert packed.size == n_params
@@ -134,7 +134,7 @@ def test_no_cpu_fallback():
 
 def test_library_argument_errors_are_reported():
     lib = _lib.load()
-    desc = _lib.ModelDesc(abi_version=1, variant=0, n_features=48, n_layers=1, n_types=25, n_edge_types=4)
+    desc = _lib.ModelDesc(abi_version=_lib.ABI_VERSION, variant=0, n_features=48, n_layers=1, n_types=25, n_edge_types=4)
     h = C.c_void_p()
     w = np.zeros(8, dtype=np.float32)
     assert lib.tib_model_create(C.byref(h), C.byref(desc), w.ctypes.data_as(C.c_void_p), 8, 0) != 0

@@ -92,6 +92,18 @@ __global__ void __launch_bounds__(TIB_THREADS, 1) k_embed(EmbedP p) {
   }
 }
 
+// out[r][:] = table[index[r]][:]   (de-duplicated node embedding -> per-node rows)
+__global__ void k_gather_rows(const float* __restrict__ table, const int* __restrict__ index, float* __restrict__ out,
+                              int n_rows, int F) {
+  const long long total = (long long)n_rows * (F / 4);
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    const long long row = idx / (F / 4);
+    const int f4 = (int)(idx % (F / 4));
+    reinterpret_cast<float4*>(out + (size_t)row * F)[f4] =
+        __ldg(reinterpret_cast<const float4*>(table + (size_t)__ldg(index + row) * F) + f4);
+  }
+}
+
 // e0 = Emb4(edge_type)                                              (embedding.py:89-103, cpainn.py:70)
 __global__ void k_edge_init(const unsigned char* __restrict__ edge_type, const float* __restrict__ edge_emb,
                             float* __restrict__ e, long long n_edges, int F) {

@@ -230,10 +230,28 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
                 b->atom_id, b->edge_type, b->temp0, b->temp1};
   const int node_tiles = (b->n_nodes + 8 * RN - 1) / (8 * RN);
 
-  EmbedP ep{db, m->combine, m->atom_emb, m->n_temp, t, m->d.temp_mean, m->d.temp_range, m->d.temp_length,
-            m->d.time_length, ws.s[0]};
-  { ProfScope ps(TIB_K_EMBED, st); k_embed<F, RN><<<node_tiles, TIB_THREADS, smem_embed<F, RN>(), st>>>(ep); }
-  LAUNCH_CHECK();
+  if (b->embed_index && b->n_embed_rows > 0 && b->n_embed_rows <= b->n_nodes) {
+    // de-duplicated embedding: U distinct rows into ws.s[1] (free until the first message layer), then a gather
+    if (!b->embed_atom_id || (m->n_temp >= 1 && !b->embed_temp0) || (m->n_temp >= 2 && !b->embed_temp1))
+      return fail("embed_index given without the de-duplicated atom/temperature tables");
+    DriftBatch du = db;
+    du.n_nodes = b->n_embed_rows; du.atom_id = b->embed_atom_id; du.temp0 = b->embed_temp0; du.temp1 = b->embed_temp1;
+    EmbedP ep{du, m->combine, m->atom_emb, m->n_temp, t, m->d.temp_mean, m->d.temp_range, m->d.temp_length,
+              m->d.time_length, ws.s[1]};
+    ProfScope ps(TIB_K_EMBED, st);
+    k_embed<F, RN><<<(b->n_embed_rows + 8 * RN - 1) / (8 * RN), TIB_THREADS, smem_embed<F, RN>(), st>>>(ep);
+    LAUNCH_CHECK();
+    const long long total = (long long)b->n_nodes * (F / 4);
+    k_gather_rows<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(ws.s[1], b->embed_index, ws.s[0],
+                                                                                      b->n_nodes, F);
+    LAUNCH_CHECK();
+  } else {
+    EmbedP ep{db, m->combine, m->atom_emb, m->n_temp, t, m->d.temp_mean, m->d.temp_range, m->d.temp_length,
+              m->d.time_length, ws.s[0]};
+    ProfScope ps(TIB_K_EMBED, st);
+    k_embed<F, RN><<<node_tiles, TIB_THREADS, smem_embed<F, RN>(), st>>>(ep);
+    LAUNCH_CHECK();
+  }
   const bool use_tc = (F == 128) && m->math != TIB_MATH_FP32_SIMT;
   int nodes_per_tile = 0, n_tiles = 0;
   if (use_tc) {

@@ -133,12 +133,29 @@ class PreparedBatch:
             self.temp1 = batch.T1.to(device, torch.float32).contiguous()
         elif hp.n_temp_encoders == 1:
             self.temp0 = batch.T.to(device, torch.float32).contiguous()
+        # x-independent node embedding: one row per distinct (atom id, T0, T1) triple
+        keys = [self.atom_id.to(torch.int64)]
+        for tt in (self.temp0, self.temp1):
+            if tt is not None:
+                keys.append(tt.view(torch.int32).to(torch.int64))
+        uniq, inverse = torch.unique(torch.stack(keys, dim=1), dim=0, return_inverse=True)
+        self.n_embed_rows = int(uniq.shape[0])
+        self.embed_index = inverse.to(torch.int32).contiguous()
+        self.embed_atom_id = uniq[:, 0].to(torch.int32).contiguous()
+        self.embed_temp0 = uniq[:, 1].to(torch.int32).view(torch.float32).contiguous() if self.temp0 is not None else None
+        self.embed_temp1 = uniq[:, 2].to(torch.int32).view(torch.float32).contiguous() if self.temp1 is not None else None
+        dedupe = self.n_embed_rows * 2 <= N
         self.c = _lib.Batch(
             n_mol=n_mol, n_nodes=N, n_edges=self.n_edges, max_atoms=self.max_atoms,
             mol_ptr=self.mol_ptr.data_ptr(), edge_ptr=self.edge_ptr.data_ptr(),
             atom_id=self.atom_id.data_ptr(), edge_type=self.edge_type.data_ptr(),
             temp0=self.temp0.data_ptr() if self.temp0 is not None else None,
-            temp1=self.temp1.data_ptr() if self.temp1 is not None else None)
+            temp1=self.temp1.data_ptr() if self.temp1 is not None else None,
+            n_embed_rows=self.n_embed_rows if dedupe else 0,
+            embed_index=self.embed_index.data_ptr() if dedupe else None,
+            embed_atom_id=self.embed_atom_id.data_ptr() if dedupe else None,
+            embed_temp0=self.embed_temp0.data_ptr() if (dedupe and self.embed_temp0 is not None) else None,
+            embed_temp1=self.embed_temp1.data_ptr() if (dedupe and self.embed_temp1 is not None) else None)
 
 
 class DriftEngine:
