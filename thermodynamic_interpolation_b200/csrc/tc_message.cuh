@@ -130,29 +130,21 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
 
 // rows [32*wq, +32) x column groups [4*grp, +4) of an operand image from row-major fp32 global rows
 // `base + row_index(r) * 128`, where row_index(r) = gather ? ROWA[r].src : row0 + r.
-struct RowRegs { float4 a[4], b[4]; };
-__device__ __forceinline__ void rows_load(RowRegs& rr, int wq, int grp, int lane, int rows, const float* base,
-                                          const RowA* rowa, int gather, int row0) {
+__device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int lane, int rows, const float* base,
+                                        const RowA* rowa, int gather, int row0) {
 #pragma unroll
   for (int oct = 0; oct < 4; ++oct) {
     const int r = 32 * wq + 8 * oct + (lane & 7);
     const int g = 4 * grp + (lane >> 3);
+    float v[8];
     if (r < rows) {
       const float* src = base + (size_t)(gather ? rowa[r].src : row0 + r) * kF + g * 8;
-      rr.a[oct] = __ldg(reinterpret_cast<const float4*>(src));
-      rr.b[oct] = __ldg(reinterpret_cast<const float4*>(src + 4));
+      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
-      rr.a[oct] = make_float4(0.f, 0.f, 0.f, 0.f);
-      rr.b[oct] = rr.a[oct];
-    }
-  }
-}
-__device__ __forceinline__ void rows_store(const RowRegs& rr, unsigned char* op, int wq, int grp, int lane) {
 #pragma unroll
-  for (int oct = 0; oct < 4; ++oct) {
-    const int r = 32 * wq + 8 * oct + (lane & 7);
-    const int g = 4 * grp + (lane >> 3);
-    const float v[8] = {rr.a[oct].x, rr.a[oct].y, rr.a[oct].z, rr.a[oct].w, rr.b[oct].x, rr.b[oct].y, rr.b[oct].z, rr.b[oct].w};
+      for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+    }
     store_group(op, kOperandHalfBytes, r, g, v);
   }
 }
@@ -345,8 +337,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       // ---- hidden phase: one sequence, every epilogue on all 16 warps (group g = feature columns
       // [32g, 32g+32) of every row); the MMAs of one chain run under the epilogue of the other.
       {
-        RowRegs rr;
-        rows_load(rr, wq, grp, lane, rows, p.s_old, ROWA, 1, 0);      // E2's gather is in flight under E1's math
         // E1: PositionalEncoder(edge_dist) -> X                                     (cpainn.py:283)
         const float dist = ROWA[row].dist;
 #pragma unroll 2
@@ -362,9 +352,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         }
         fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         // E2: s[src] -> Y                                                            (cpainn.py:275-281)
-        rows_store(rr, Y, wq, grp, lane);
+        build_rows(Y, wq, grp, lane, rows, p.s_old, ROWA, 1, 0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
-        rows_load(rr, wq, grp, lane, rows, p.e, ROWA, 0, row0);       // E4's rows are in flight under E3
         TIB_PHASE(1);   // E1 + E2
         // E3: w hidden 1 -> X
         mbar_wait_timed(&bars[B_ACC0], pacc0, err, w_acc, diag); pacc0 ^= 1; tc_fence_after();
@@ -372,7 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         // E4: e rows -> Y (after the s[src] half has been consumed)
         mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc, diag); pyf ^= 1;
-        rows_store(rr, Y, wq, grp, lane);
+        build_rows(Y, wq, grp, lane, rows, p.e, ROWA, 0, row0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(2);   // E3 + E4
         // E5: w hidden 2 -> X (final: B operand of the output layer)
@@ -407,49 +396,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         const int sp = p.first_layer ? it + 1 : it;
         const int pb = it & 1;
         const float bphi = PRM[kPrmB3 + sp * kF + f], bw = PRM[kPrmB3 + 5 * kF + sp * kF + f];
-        const uint32_t tphi = lane_taddr + 256 * pb, tw = tphi + 128;
-        if (sp == 3) {
-          // e += de (cpainn.py:308).  The old e values do not depend on the MMAs: they are fetched
-          // before the wait for the split's accumulators, so the HBM latency hides behind it.
-          float pre[4][8];
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int slot = grp * per + k;
-            const bool on = k < per && slot < nslots;
-            const int rbeg = on ? SLOTROW[slot] : 0, rend = on ? SLOTROW[slot + 1] : 0;
-            const float* ep = p.e + (size_t)(row0 + (rbeg & ~7)) * kF + f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              const int r = (rbeg & ~7) + q;
-              pre[k][q] = (r >= rbeg && r < rend) ? ep[(size_t)q * kF] : 0.0f;
-            }
-          }
-          mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull, diag); ptf[pb] ^= 1; tc_fence_after();
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int slot = grp * per + k;
-            if (k < per && slot < nslots) {
-              const int rbeg = SLOTROW[slot], rend = SLOTROW[slot + 1];
-              for (int r0 = rbeg & ~7; r0 < rend; r0 += 8) {
-                float P[8], Q[8];
-                tmem_ld8x2(tphi, tw, r0, P, Q);
-                float* ep = p.e + (size_t)(row0 + r0) * kF + f;
-                const bool first = r0 == (rbeg & ~7);              // the prefetched piece
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                  const int r = r0 + q;
-                  if (r >= rbeg && r < rend) {
-                    const float old = first ? pre[k][q] : ep[(size_t)q * kF];
-                    ep[(size_t)q * kF] = old + __fmul_rn(P[q] + bphi, Q[q] + bw);
-                  }
-                }
-              }
-            }
-          }
-          tc_fence_before(); mbar_arrive(&bars[B_TEMPTY0 + pb]);
-          continue;
-        }
         mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull, diag); ptf[pb] ^= 1; tc_fence_after();
+        const uint32_t tphi = lane_taddr + 256 * pb, tw = tphi + 128;
 #pragma unroll 1
         for (int k = 0; k < 4; ++k) {
           const int slot = grp * per + k;
@@ -482,6 +430,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
               } else if (sp == 2) {     // ds
 #pragma unroll
                 for (int q = 0; q < 8; ++q) acc_s[0] += P[q];
+              } else if (sp == 3) {     // e += de                                     (cpainn.py:308)
+                float* ep = p.e + (size_t)(row0 + r0) * kF + f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) Q[q] = (q >= qlo && q < qhi) ? ep[(size_t)q * kF] : 0.0f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                  if (q >= qlo && q < qhi) ep[(size_t)q * kF] = Q[q] + P[q];
               } else {                  // cross_gates * (dir x v[dst])                (cpainn.py:296-300)
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
