@@ -151,7 +151,7 @@ __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int 
 
 // One [128 x 128] matrix = 4 streamed chunks; transposed = the weights are the A operand.
 struct MmaRing { int stage; uint32_t ph; long long w_weights; long long t_issue; long long t_commit; };
-__device__ __noinline__ void gemm_job(uint64_t* bars, uint32_t ring, MmaRing& st, uint32_t d, uint32_t op, int transposed,
+__device__ __forceinline__ void gemm_job(uint64_t* bars, uint32_t ring, MmaRing& st, uint32_t d, uint32_t op, int transposed,
                                       int accumulate, int passes, volatile int* err, bool diag) {
 #pragma unroll 1
   for (int kb = 0; kb < 4; ++kb) {
@@ -170,7 +170,7 @@ __device__ __noinline__ void gemm_job(uint64_t* bars, uint32_t ring, MmaRing& st
 
 // Output layer of one split: D_phi^T = W3phi * Hphi^T and D_w^T = W3w * Hw^T, chunk pairs (phi k, w k) in
 // consecutive ring stages; the MMAs of the two independent accumulators are interleaved.
-__device__ __noinline__ void gemm_pair_job(uint64_t* bars, uint32_t ring, MmaRing& st, uint32_t d_phi, uint32_t op_phi,
+__device__ __forceinline__ void gemm_pair_job(uint64_t* bars, uint32_t ring, MmaRing& st, uint32_t d_phi, uint32_t op_phi,
                                            uint32_t d_w, uint32_t op_w, int passes, volatile int* err, bool diag) {
 #pragma unroll 1
   for (int kb = 0; kb < 4; ++kb) {
