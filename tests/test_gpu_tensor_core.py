@@ -138,3 +138,54 @@ def test_tc_hundred_step_state_agreement_vs_oracle():
             assert errs[2] < 1e-4 and errs[3] < 1e-3, errs
         if mode == _lib.MATH_FP32_SIMT:
             assert errs[3] < 1e-4, errs
+
+
+@pytest.mark.parametrize("temperatures", [[300, 400, 500, 600, 700, 800, 900, 1000], [800]])
+def test_tc_latent_variants_vs_oracle(temperatures):
+    """Latent flow (one temperature encoder, or none for a single-temperature model), n_features = 128 on the
+    tensor cores, mixed molecule sizes (BASELINE cfg 3 shape at a size the oracle finishes in seconds)."""
+    from tests._util import oracle_drift
+    from thermodynamic_interpolation_b200.batch import synthetic_latent_batch
+    from thermodynamic_interpolation_b200.latent.models.cpainn import cPaiNN
+    torch.manual_seed(41)
+    model = perturb_(cPaiNN(n_features=128, score_layers=2, temp_length=75, temperatures=temperatures), 42).eval()
+    n_list = [9, 25, 17, 12, 9, 21, 10]
+    mb = synthetic_latent_batch(len(n_list), n_list, T=800 if len(temperatures) > 1 else None, seed=43)
+    ref, _, _ = oracle_drift(model, mb, mb.x0, 0.5)
+    model = model.to(DEV)
+    eng = model.engine()
+    out = eng.drift(eng.prepare(mb.to(DEV)), mb.x0, 0.5)
+    eng.status()
+    err = _rel(out.cpu().numpy(), ref.numpy())
+    print(f"[tc] latent {len(temperatures)} temperatures: {err:.3e}")
+    assert err < 2e-5
+
+
+def test_tc_cfg3_size_latent_mixed_batch():
+    """BASELINE cfg 3 at full size: 16 384 molecules with 9..25 atoms (latent multi-T, F = 128).  Size-independent
+    properties: finite output, and every molecule's drift equals the drift it gets in a batch of its own
+    neighbours only (block-diagonal graph), whatever tile it lands in."""
+    from thermodynamic_interpolation_b200.batch import synthetic_latent_batch
+    from thermodynamic_interpolation_b200.dist import shard_batch
+    from thermodynamic_interpolation_b200.latent.integrators import MoleculeIntegrator
+    from thermodynamic_interpolation_b200.latent.models.cpainn import cPaiNN
+    torch.manual_seed(51)
+    model = perturb_(cPaiNN(n_features=128, score_layers=5, temp_length=75), 52).eval().to(DEV)
+    gen = torch.Generator().manual_seed(53)
+    n_list = torch.randint(9, 26, (16384,), generator=gen).tolist()
+    mb = synthetic_latent_batch(len(n_list), n_list, T=800, seed=54).to(DEV)
+    eng = model.engine()
+    pb = eng.prepare(mb)
+    full = eng.drift(pb, mb.x0, 0.25).clone()
+    eng.status()
+    assert torch.isfinite(full).all()
+    sub = shard_batch(mb, 3, 64)                    # molecules [768, 1024)
+    lo = int(mb.ptr[768])
+    out_sub = eng.drift(eng.prepare(sub), sub.x0.contiguous(), 0.25)
+    eng.status()
+    ref = full[lo: lo + out_sub.shape[0]]
+    err = float((out_sub - ref).abs().max() / ref.abs().max())
+    print(f"[tc] cfg3: sub-batch vs full batch {err:.3e}")
+    assert err < 1e-5                                # different tiles -> different summation partners, same values
+    xts, dlogp, bvec = MoleculeIntegrator(model, method="euler", n_step=3, save_frames=False).rollout(sub)
+    assert xts.shape == sub.x0.shape and torch.isfinite(xts).all()
