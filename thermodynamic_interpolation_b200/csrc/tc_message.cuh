@@ -409,8 +409,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
               float P[8], Q[8];
               tmem_ld8x2(tphi, tw, r0, P, Q);
               const int qlo = rbeg - r0, qhi = rend - r0;       // rows [qlo, qhi) of the piece belong to this node
+              if (qlo <= 0 && qhi >= 8) {                       // whole piece belongs to the node (always, for n = 9)
 #pragma unroll
-              for (int q = 0; q < 8; ++q) P[q] = (q >= qlo && q < qhi) ? __fmul_rn(P[q] + bphi, Q[q] + bw) : 0.0f;
+                for (int q = 0; q < 8; ++q) P[q] = __fmul_rn(P[q] + bphi, Q[q] + bw);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 8; ++q) P[q] = (q >= qlo && q < qhi) ? __fmul_rn(P[q] + bphi, Q[q] + bw) : 0.0f;
+              }
               if (sp == 0) {            // gates * v[src]
 #pragma unroll
                 for (int q = 0; q < 8; ++q) {
