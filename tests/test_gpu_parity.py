@@ -344,3 +344,23 @@ def test_errors_are_loud():
     bad.edge_type = bad.edge_type[:-2]
     with pytest.raises(ValueError, match="complete digraph"):
         model(bad)
+
+
+def test_sampler_driver_writes_reference_file_format(tmp_path):
+    """sample() (driver loop of mdqm9/sample_ambient.py:18-119): files and shapes the reference analysis reads."""
+    import argparse
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    from thermodynamic_interpolation_b200.sample_ambient import sample
+    torch.manual_seed(3)
+    model = perturb_(cPaiNN(n_features=32, score_layers=2, temp_length=100), 4).eval()
+    loader = [synthetic_ambient_batch(5, 9, seed=s) for s in (1, 2)]
+    cfg = argparse.Namespace(seed=0, data_save_path=str(tmp_path), data_save_name="t", rtol=1e-4, atol=1e-4, n_steps=7,
+                             return_dlogp=0)
+    out = sample(cfg, model, loader, method="euler", verbose=False)
+    s = np.load(tmp_path / "samples_t.npy")
+    assert s.shape == (10, 7, 9, 3) and np.array_equal(s, out["samples"])
+    assert np.load(tmp_path / "latent_noises_t.npy").shape == (10, 9, 3)
+    assert np.load(tmp_path / "latent_dlogps_t.npy").shape == (10,)
+    x0 = torch.cat([b.x0 for b in loader]).reshape(10, 9, 3).numpy()
+    np.testing.assert_array_equal(s[:, 0], x0)       # frame 0 is the start conformer, molecule by molecule

@@ -163,3 +163,17 @@ def test_shard_range_and_shard_batch():
     for p in parts:                                 # each shard is a valid self-contained batch
         pb = PreparedBatch(p, hp, torch.device("cpu"))
         assert pb.n_mol == p.num_graphs
+
+
+def test_regroup_frames_matches_reference_loop():
+    """sample_ambient.py:93 regroups frames with a Python loop over molecules; ours is one reshape."""
+    from thermodynamic_interpolation_b200.sample_ambient import regroup_frames
+    rng = np.random.default_rng(0)
+    T, B, n = 5, 7, 9
+    xts = rng.normal(size=(T, B * n, 3)).astype(np.float32)
+    batch_idx = np.repeat(np.arange(B), n)
+    ref = np.array([xts[:, batch_idx == i] for i in range(batch_idx.max() + 1)])
+    got = regroup_frames(xts, batch_idx)
+    assert got.shape == (B, T, n, 3) and np.array_equal(got, ref)
+    with pytest.raises(ValueError):
+        regroup_frames(xts[:, :-1], batch_idx[:-1])
