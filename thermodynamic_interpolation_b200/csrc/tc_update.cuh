@@ -4,15 +4,15 @@
 //   v += uv * g;   s += q^2 * a + c
 //
 // Work unit: a tile of 128 consecutive nodes.  Every GEMM is D[node][feat] = A[node][k] * W[feat][k]^T
-// (node = TMEM lane), so LayerNorm, the norm over xyz and the gated residuals are all row-local:
-//   step 1: planes 0,1 -> operand images X,Y;   vv0, vv1 -> T0, T1          (V streamed once for both)
-//   step 2: plane 2 -> X;                        vv2 -> T2
-//   step 3: q = sqrt(T0^2+T1^2+T2^2) -> Y,  s -> X;   layer 1 = Y*W1[:, :F]^T + X*W1[:, F:]^T -> T3
-//   step 4: LN/SiLU(T3) -> X;                    layer 2 -> T3
-//   step 5: LN/SiLU(T3) -> X;                    a, c, g = X*W3{a,c,g}^T -> T0, T1, T2
-//   step 6: s_new = s + q^2 * a + c (q re-read from the Y image);  planes 0,1 -> X,Y;   uv0, uv1 -> T0, T1
-//   step 7: v_new[0,1] = v + uv * g;  plane 2 -> X;   uv2 -> T3
-//   step 8: v_new[2]
+// (node = TMEM lane), so LayerNorm, the norm over xyz and the gated residuals are all row-local.  Each plane
+// of v is turned into an operand image ONCE and multiplied by V and by U while it is resident:
+//   steps 1-3 (xyz = 0,1,2): plane -> X / Y / X;  vv = P V^T -> T0,  uv_xyz = P U^T -> T1+xyz;
+//                            epilogue: q2 += vv^2 (registers)
+//   step 4: q = sqrt(q2) -> X,  s -> Y;   layer 1 = X*W1[:, :F]^T + Y*W1[:, F:]^T -> T0
+//   step 5: LN/SiLU(T0) -> X;             layer 2 -> T0
+//   step 6: LN/SiLU(T0) -> X;             g = X*W3g^T -> T0
+//   step 7: v_new[xyz] = v + uv_xyz * g  (T1..T3, T0);      a, c = X*W3{a,c}^T -> T0, T1
+//   step 8: s_new = s + q2 * a + c
 // The epilogue (512 threads) and the MMA issuer alternate through one operand-ready / accumulator-ready
 // barrier pair; weights stream through the same bulk-copy ring as the message kernel.
 // Warp roles: warps 0-15 epilogue (group g = warp / 4 owns feature columns [32g, 32g+32) of every row),
@@ -25,10 +25,10 @@
 namespace tib {
 namespace tc {
 
-constexpr int kUpdChunks = 40;     // streamed per tile: V | V | W1q | W1s | W2 | W3a | W3c | W3g | U | U
+constexpr int kUpdChunks = 48;     // streamed per tile: (V | U) x 3 planes | W1q | W1s | W2 | W3g | W3a | W3c
 // weight blob of one update layer (matrix index -> 4 chunks): 0 V, 1 W1[:, :F], 2 W1[:, F:], 3 W2,
 // 4 W3 rows [F,2F) (a), 5 W3 rows [2F,3F) (c), 6 W3 rows [0,F) (g), 7 U
-__constant__ int kUpdOrder[10] = {0, 0, 1, 2, 3, 4, 5, 6, 7, 7};
+__constant__ int kUpdOrder[12] = {0, 7, 0, 7, 0, 7, 1, 2, 3, 6, 4, 5};
 
 struct TcUpdP {
   int n_nodes, n_tiles;
@@ -38,6 +38,7 @@ struct TcUpdP {
   const float *b1, *g1, *be1, *b2, *g2, *be2, *b3;   // MLP parameters (fp32)
   int passes;
   int* err;
+  long long* dbg;           // optional phase counters (diagnostics): [gridDim.x][16] cycles of thread 0 per step
 };
 
 struct UpdSmem {
@@ -179,14 +180,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
       auto ops_ready = [&]() { mbar_wait(&bars[U_OPS], pops, err); pops ^= 1; tc_fence_after(); };
       const uint32_t T0 = tmem, T1 = tmem + 128, T2 = tmem + 256, T3 = tmem + 384;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        ops_ready(); gemm(T0, xa, T1, ya, false); tc_commit(&bars[U_ACC]);                     // 1: vv0, vv1
-        ops_ready(); gemm(T2, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                       // 2: vv2
-        ops_ready(); gemm(T3, ya, 0, 0, false); gemm(T3, xa, 0, 0, true); tc_commit(&bars[U_ACC]);   // 3: layer 1
-        ops_ready(); gemm(T3, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                       // 4: layer 2
-        ops_ready(); gemm(T0, xa, 0, 0, false); gemm(T1, xa, 0, 0, false); gemm(T2, xa, 0, 0, false);
-        tc_commit(&bars[U_ACC]);                                                               // 5: a, c, g
-        ops_ready(); gemm(T0, xa, T1, ya, false); tc_commit(&bars[U_ACC]);                     // 6: uv0, uv1
-        ops_ready(); gemm(T3, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                       // 7: uv2
+        ops_ready(); gemm(T0, xa, 0, 0, false); gemm(T1, xa, 0, 0, false); tc_commit(&bars[U_ACC]);   // 1: vv, uv0 (plane 0 in X)
+        ops_ready(); gemm(T0, ya, 0, 0, false); gemm(T2, ya, 0, 0, false); tc_commit(&bars[U_ACC]);   // 2: vv, uv1 (plane 1 in Y)
+        ops_ready(); gemm(T0, xa, 0, 0, false); gemm(T3, xa, 0, 0, false); tc_commit(&bars[U_ACC]);   // 3: vv, uv2 (plane 2 in X)
+        ops_ready(); gemm(T0, xa, 0, 0, false); gemm(T0, ya, 0, 0, true); tc_commit(&bars[U_ACC]);    // 4: layer 1 (q in X, s in Y)
+        ops_ready(); gemm(T0, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                               // 5: layer 2
+        ops_ready(); gemm(T0, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                               // 6: g
+        ops_ready(); gemm(T0, xa, 0, 0, false); gemm(T1, xa, 0, 0, false); tc_commit(&bars[U_ACC]);   // 7: a, c
       }
     }
   } else {
@@ -194,8 +194,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
     const int grp = warp >> 2, wq = warp & 3;
     const int row = 32 * wq + lane;
     const uint32_t lt = tmem + ((uint32_t)(wq * 32) << 16);
-    const uint32_t T0 = lt, T1 = lt + 128, T2 = lt + 256, T3 = lt + 384;
+    const uint32_t T0 = lt, T1 = lt + 128;
     uint32_t pacc = 0;
+    const bool diag = p.dbg != nullptr && tid == 0;
+    long long phc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+    long long tlast = diag ? clock64() : 0;
+#define TIB_UPH(i) do { if (diag) { const long long _t = clock64(); phc[i] += _t - tlast; tlast = _t; } } while (0)
     auto ops_done = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&bars[U_OPS]); };
     auto acc_ready = [&]() { mbar_wait(&bars[U_ACC], pacc, err); pacc ^= 1; tc_fence_after(); };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
@@ -204,96 +208,115 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
       const float* vbase = p.v + (size_t)node0 * 3 * kF;
       const bool live = row < rows;
       const size_t node = (size_t)(node0 + row);
-      // step 1
+      // steps 1-3: planes of v; q2 = sum over xyz of (V v)^2                            (cpainn.py:358-361)
+      float q2[32];
+#pragma unroll
+      for (int i = 0; i < 32; ++i) q2[i] = 0.0f;
       upd_build(X, wq, grp, lane, rows, vbase, 3 * kF);
-      upd_build(Y, wq, grp, lane, rows, vbase + kF, 3 * kF);
       ops_done();
-      // step 2
-      acc_ready();
-      upd_build(X, wq, grp, lane, rows, vbase + 2 * kF, 3 * kF);
-      ops_done();
-      // step 3: q = |V v| over xyz                                                   (cpainn.py:361)
-      acc_ready();
+      upd_build(Y, wq, grp, lane, rows, vbase + kF, 3 * kF);          // under the MMAs of plane 0
+      TIB_UPH(0);
 #pragma unroll 1
+      for (int xyz = 0; xyz < 3; ++xyz) {
+        acc_ready();                                                  // vv, uv_xyz of plane xyz
+        TIB_UPH(1);
+        if (xyz == 0) upd_build(X, wq, grp, lane, rows, vbase + 2 * kF, 3 * kF);   // plane 2 (X is free again)
+        if (xyz == 1) upd_build(Y, wq, grp, lane, rows, p.s + (size_t)node0 * kF, kF);   // s (Y is free again)
+        float t[32];
+        tmem_ld32(T0 + 32 * grp, t);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) q2[i] = fmaf(t[i], t[i], q2[i]);
+        if (xyz < 2) ops_done();                                      // next plane's operand ready, T0 drained
+        TIB_UPH(2);
+      }
+      // step 4: q -> X (X is free: the MMAs of plane 2 have completed)
+#pragma unroll
       for (int kg = 0; kg < 4; ++kg) {
-        float a[8], b[8], c[8];
-        tmem_ld8x2(T0, T1, 32 * grp + 8 * kg, a, b);
-        tmem_ld8(T2 + 32 * grp + 8 * kg, c);
         float q[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = __fsqrt_rn(fmaf(a[i], a[i], fmaf(b[i], b[i], c[i] * c[i])));
-        store_group(Y, kOperandHalfBytes, row, 4 * grp + kg, q);
+        for (int i = 0; i < 8; ++i) q[i] = __fsqrt_rn(q2[8 * kg + i]);
+        store_group(X, kOperandHalfBytes, row, 4 * grp + kg, q);
       }
-      upd_build(X, wq, grp, lane, rows, p.s + (size_t)node0 * kF, kF);
       ops_done();
-      // step 4
-      acc_ready();
-      upd_hidden(T3, grp, row, PRM, PRM + kF, PRM + 2 * kF, X, STAT);
-      ops_done();
+      TIB_UPH(4);
       // step 5
       acc_ready();
-      upd_hidden(T3, grp, row, PRM + 3 * kF, PRM + 4 * kF, PRM + 5 * kF, X, STAT);
+      TIB_UPH(5);
+      upd_hidden(T0, grp, row, PRM, PRM + kF, PRM + 2 * kF, X, STAT);
       ops_done();
-      // step 6: s += q^2 * a + c                                                      (cpainn.py:371,373)
+      TIB_UPH(6);
+      // step 6
       acc_ready();
-#pragma unroll 1
-      for (int kg = 0; kg < 4; ++kg) {
-        const int col = 32 * grp + 8 * kg;
-        float a[8], c[8];
-        tmem_ld8x2(T0, T1, col, a, c);
-        if (live) {
-          const unsigned char* qp = Y + (size_t)(4 * grp + kg) * kLBO + (size_t)row * 16;
-          const uint4 qh = *reinterpret_cast<const uint4*>(qp), ql = *reinterpret_cast<const uint4*>(qp + kOperandHalfBytes);
-          const uint32_t hw[4] = {qh.x, qh.y, qh.z, qh.w}, lw[4] = {ql.x, ql.y, ql.z, ql.w};
-          float* sp = p.s + node * kF + col;
-          const float4 s0 = *reinterpret_cast<const float4*>(sp), s1 = *reinterpret_cast<const float4*>(sp + 4);
-          const float so[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-          float o[8];
+      TIB_UPH(7);
+      upd_hidden(T0, grp, row, PRM + 3 * kF, PRM + 4 * kF, PRM + 5 * kF, X, STAT);
+      ops_done();
+      TIB_UPH(8);
+      // step 7: v += (U v) * g                                                        (cpainn.py:370,374)
+      acc_ready();
+      TIB_UPH(9);
+      {
+        float g[32];
+        tmem_ld32(T0 + 32 * grp, g);
 #pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hw[i]));
-            const float2 l = __half22float2(*reinterpret_cast<const __half2*>(&lw[i]));
-            const float q0 = h.x + l.x, q1 = h.y + l.y;
-            o[2 * i] = so[2 * i] + fmaf(q0 * q0, a[2 * i] + PRM[7 * kF + col + 2 * i], c[2 * i] + PRM[8 * kF + col + 2 * i]);
-            o[2 * i + 1] = so[2 * i + 1] + fmaf(q1 * q1, a[2 * i + 1] + PRM[7 * kF + col + 2 * i + 1], c[2 * i + 1] + PRM[8 * kF + col + 2 * i + 1]);
+        for (int i = 0; i < 32; ++i) g[i] += PRM[6 * kF + 32 * grp + i];
+#pragma unroll 1
+        for (int xyz = 0; xyz < 3; ++xyz) {
+#pragma unroll 1
+          for (int kg = 0; kg < 4; kg += 2) {
+            float u0[8], u1[8];
+            tmem_ld8x2(lt + 128 * (1 + xyz), lt + 128 * (1 + xyz) + 8, 32 * grp + 8 * kg, u0, u1);
+            if (live) {
+              float* vp = p.v + (node * 3 + xyz) * kF + 32 * grp + 8 * kg;
+              const float4 v0 = *reinterpret_cast<const float4*>(vp), v1 = *reinterpret_cast<const float4*>(vp + 4);
+              const float4 v2 = *reinterpret_cast<const float4*>(vp + 8), v3 = *reinterpret_cast<const float4*>(vp + 12);
+              const float vo[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
+              float o[16];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                o[i] = fmaf(u0[i], kg == 0 ? g[i] : g[16 + i], vo[i]);
+                o[8 + i] = fmaf(u1[i], kg == 0 ? g[8 + i] : g[24 + i], vo[8 + i]);
+              }
+              *reinterpret_cast<float4*>(vp) = make_float4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<float4*>(vp + 4) = make_float4(o[4], o[5], o[6], o[7]);
+              *reinterpret_cast<float4*>(vp + 8) = make_float4(o[8], o[9], o[10], o[11]);
+              *reinterpret_cast<float4*>(vp + 12) = make_float4(o[12], o[13], o[14], o[15]);
+            }
           }
-          *reinterpret_cast<float4*>(sp) = make_float4(o[0], o[1], o[2], o[3]);
-          *reinterpret_cast<float4*>(sp + 4) = make_float4(o[4], o[5], o[6], o[7]);
         }
       }
-      named_bar_sync(NB_ALL, kEpiThreads);                 // every reader of the q image in Y is done
-      upd_build(X, wq, grp, lane, rows, vbase, 3 * kF);
-      upd_build(Y, wq, grp, lane, rows, vbase + kF, 3 * kF);
-      ops_done();
-      // steps 7, 8: v += (U v) * g                                                    (cpainn.py:370,374)
-      auto gated = [&](uint32_t tuv, int xyz) {
-#pragma unroll 1
-        for (int kg = 0; kg < 4; ++kg) {
-          const int col = 32 * grp + 8 * kg;
-          float u[8], g[8];
-          tmem_ld8x2(tuv, T2, col, u, g);
-          if (live) {
-            float* vp = p.v + (node * 3 + xyz) * kF + col;
-            const float4 v0 = *reinterpret_cast<const float4*>(vp), v1 = *reinterpret_cast<const float4*>(vp + 4);
-            const float vo[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-            float o[8];
+      ops_done();                                                     // T0..T3 drained: a, c may be written
+      TIB_UPH(10);
+      // step 8: s += q^2 * a + c                                                      (cpainn.py:371,373)
+      float so[32];
+      if (live) {
+        const float4* sp4 = reinterpret_cast<const float4*>(p.s + node * kF + 32 * grp);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) o[i] = fmaf(u[i], g[i] + PRM[6 * kF + col + i], vo[i]);
-            *reinterpret_cast<float4*>(vp) = make_float4(o[0], o[1], o[2], o[3]);
-            *reinterpret_cast<float4*>(vp + 4) = make_float4(o[4], o[5], o[6], o[7]);
-          }
+        for (int i = 0; i < 8; ++i) { const float4 t = sp4[i]; so[4 * i] = t.x; so[4 * i + 1] = t.y; so[4 * i + 2] = t.z; so[4 * i + 3] = t.w; }
+      }
+      acc_ready();
+      TIB_UPH(11);
+      {
+        float a[32];
+        tmem_ld32(T0 + 32 * grp, a);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) so[i] = fmaf(q2[i], a[i] + PRM[7 * kF + 32 * grp + i], so[i]);
+        tmem_ld32(T1 + 32 * grp, a);
+        if (live) {
+          float4* sp4 = reinterpret_cast<float4*>(p.s + node * kF + 32 * grp);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            sp4[i] = make_float4(so[4 * i] + (a[4 * i] + PRM[8 * kF + 32 * grp + 4 * i]),
+                                 so[4 * i + 1] + (a[4 * i + 1] + PRM[8 * kF + 32 * grp + 4 * i + 1]),
+                                 so[4 * i + 2] + (a[4 * i + 2] + PRM[8 * kF + 32 * grp + 4 * i + 2]),
+                                 so[4 * i + 3] + (a[4 * i + 3] + PRM[8 * kF + 32 * grp + 4 * i + 3]));
         }
-      };
-      acc_ready();
-      upd_build(X, wq, grp, lane, rows, vbase + 2 * kF, 3 * kF);   // plane 2 of the OLD v (only planes 0,1 are written below)
-      ops_done();
-      gated(T0, 0);
-      gated(T1, 1);
-      acc_ready();
-      gated(T3, 2);
+      }
       tc_fence_before();
       named_bar_sync(NB_ALL, kEpiThreads);                 // the tile's TMEM reads finish before the next tile's MMAs
+      TIB_UPH(14);
     }
+    if (diag) for (int i = 0; i < 16; ++i) p.dbg[(size_t)blockIdx.x * 16 + i] = phc[i];
+#undef TIB_UPH
   }
   tc_fence_before();
   __syncthreads();

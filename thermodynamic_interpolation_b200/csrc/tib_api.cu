@@ -305,6 +305,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       up.s = ws.s[cur]; up.v = ws.v[cur]; up.wblob = L.tc_upd;
       up.b1 = L.upd.b1; up.g1 = L.upd.g1; up.be1 = L.upd.be1; up.b2 = L.upd.b2; up.g2 = L.upd.g2; up.be2 = L.upd.be2; up.b3 = L.upd.b3;
       up.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3; up.err = m->dev_err;
+      up.dbg = m->dev_dbg ? m->dev_dbg + 8 * 1024 : nullptr;   // second half of the diagnostics buffer
       ProfScope ps(TIB_K_UPDATE, st);
       tc::k_update_tc<<<std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st>>>(up);
       LAUNCH_CHECK();
