@@ -255,60 +255,78 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
       acc_ready();
       TIB_UPH(9);
       {
+        // Row-per-thread global accesses would cost 32 wavefronts per instruction (rows are 1.5 KB apart), so
+        // each plane goes through the (free) Y buffer: coalesced load -> swizzled fp32 tile -> row-local
+        // update -> coalesced store.  16-byte chunk c of row r lives at chunk (c ^ (r & 31)).
         float g[32];
         tmem_ld32(T0 + 32 * grp, g);
 #pragma unroll
         for (int i = 0; i < 32; ++i) g[i] += PRM[6 * kF + 32 * grp + i];
+        float4* const stage = reinterpret_cast<float4*>(Y);
 #pragma unroll 1
         for (int xyz = 0; xyz < 3; ++xyz) {
-#pragma unroll 1
-          for (int kg = 0; kg < 4; kg += 2) {
-            float u0[8], u1[8];
-            tmem_ld8x2(lt + 128 * (1 + xyz), lt + 128 * (1 + xyz) + 8, 32 * grp + 8 * kg, u0, u1);
-            if (live) {
-              float* vp = p.v + (node * 3 + xyz) * kF + 32 * grp + 8 * kg;
-              const float4 v0 = *reinterpret_cast<const float4*>(vp), v1 = *reinterpret_cast<const float4*>(vp + 4);
-              const float4 v2 = *reinterpret_cast<const float4*>(vp + 8), v3 = *reinterpret_cast<const float4*>(vp + 12);
-              const float vo[16] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w, v2.x, v2.y, v2.z, v2.w, v3.x, v3.y, v3.z, v3.w};
-              float o[16];
+          float* const vplane = p.v + ((size_t)node0 * 3 + xyz) * kF;
+          // coalesced load: warp w, iteration it -> row 8*it' ... : 512 threads x 8 chunks = 128 rows x 32 chunks
 #pragma unroll
-              for (int i = 0; i < 8; ++i) {
-                o[i] = fmaf(u0[i], kg == 0 ? g[i] : g[16 + i], vo[i]);
-                o[8 + i] = fmaf(u1[i], kg == 0 ? g[8 + i] : g[24 + i], vo[8 + i]);
-              }
-              *reinterpret_cast<float4*>(vp) = make_float4(o[0], o[1], o[2], o[3]);
-              *reinterpret_cast<float4*>(vp + 4) = make_float4(o[4], o[5], o[6], o[7]);
-              *reinterpret_cast<float4*>(vp + 8) = make_float4(o[8], o[9], o[10], o[11]);
-              *reinterpret_cast<float4*>(vp + 12) = make_float4(o[12], o[13], o[14], o[15]);
-            }
+          for (int it = 0; it < 8; ++it) {
+            const int r = (tid >> 5) + 16 * it, c = tid & 31;         // one row (512 B) per warp instruction
+            if (r < rows) stage[r * 32 + (c ^ (r & 31))] = *reinterpret_cast<const float4*>(vplane + (size_t)r * 3 * kF + 4 * c);
           }
+          named_bar_sync(NB_ALL, kEpiThreads);
+          float u[32];
+          tmem_ld32(lt + 128 * (1 + xyz) + 32 * grp, u);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            float4* sp = stage + row * 32 + ((8 * grp + j) ^ (row & 31));
+            float4 t = *sp;
+            t.x = fmaf(u[4 * j + 0], g[4 * j + 0], t.x); t.y = fmaf(u[4 * j + 1], g[4 * j + 1], t.y);
+            t.z = fmaf(u[4 * j + 2], g[4 * j + 2], t.z); t.w = fmaf(u[4 * j + 3], g[4 * j + 3], t.w);
+            *sp = t;
+          }
+          named_bar_sync(NB_ALL, kEpiThreads);
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int r = (tid >> 5) + 16 * it, c = tid & 31;
+            if (r < rows) *reinterpret_cast<float4*>(vplane + (size_t)r * 3 * kF + 4 * c) = stage[r * 32 + (c ^ (r & 31))];
+          }
+          named_bar_sync(NB_ALL, kEpiThreads);                        // the stage is reused by the next plane
         }
       }
       ops_done();                                                     // T0..T3 drained: a, c may be written
       TIB_UPH(10);
       // step 8: s += q^2 * a + c                                                      (cpainn.py:371,373)
-      float so[32];
-      if (live) {
-        const float4* sp4 = reinterpret_cast<const float4*>(p.s + node * kF + 32 * grp);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { const float4 t = sp4[i]; so[4 * i] = t.x; so[4 * i + 1] = t.y; so[4 * i + 2] = t.z; so[4 * i + 3] = t.w; }
-      }
-      acc_ready();
-      TIB_UPH(11);
       {
-        float a[32];
+        float4* const stage = reinterpret_cast<float4*>(Y);
+        float* const srows = p.s + (size_t)node0 * kF;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int r = (tid >> 5) + 16 * it, c = tid & 31;
+          if (r < rows) stage[r * 32 + (c ^ (r & 31))] = *reinterpret_cast<const float4*>(srows + (size_t)r * kF + 4 * c);
+        }
+        acc_ready();
+        TIB_UPH(11);
+        named_bar_sync(NB_ALL, kEpiThreads);
+        float a[32], c[32];
         tmem_ld32(T0 + 32 * grp, a);
+        tmem_ld32(T1 + 32 * grp, c);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) so[i] = fmaf(q2[i], a[i] + PRM[7 * kF + 32 * grp + i], so[i]);
-        tmem_ld32(T1 + 32 * grp, a);
-        if (live) {
-          float4* sp4 = reinterpret_cast<float4*>(p.s + node * kF + 32 * grp);
+        for (int j = 0; j < 8; ++j) {
+          float4* sp = stage + row * 32 + ((8 * grp + j) ^ (row & 31));
+          float4 t = *sp;
+          const float* pa = PRM + 7 * kF + 32 * grp + 4 * j;
+          const float* pc = PRM + 8 * kF + 32 * grp + 4 * j;
+          t.x += fmaf(q2[4 * j + 0], a[4 * j + 0] + pa[0], c[4 * j + 0] + pc[0]);
+          t.y += fmaf(q2[4 * j + 1], a[4 * j + 1] + pa[1], c[4 * j + 1] + pc[1]);
+          t.z += fmaf(q2[4 * j + 2], a[4 * j + 2] + pa[2], c[4 * j + 2] + pc[2]);
+          t.w += fmaf(q2[4 * j + 3], a[4 * j + 3] + pa[3], c[4 * j + 3] + pc[3]);
+          *sp = t;
+        }
+        tc_fence_before();
+        named_bar_sync(NB_ALL, kEpiThreads);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            sp4[i] = make_float4(so[4 * i] + (a[4 * i] + PRM[8 * kF + 32 * grp + 4 * i]),
-                                 so[4 * i + 1] + (a[4 * i + 1] + PRM[8 * kF + 32 * grp + 4 * i + 1]),
-                                 so[4 * i + 2] + (a[4 * i + 2] + PRM[8 * kF + 32 * grp + 4 * i + 2]),
-                                 so[4 * i + 3] + (a[4 * i + 3] + PRM[8 * kF + 32 * grp + 4 * i + 3]));
+        for (int it = 0; it < 8; ++it) {
+          const int r = (tid >> 5) + 16 * it, c2 = tid & 31;
+          if (r < rows) *reinterpret_cast<float4*>(srows + (size_t)r * kF + 4 * c2) = stage[r * 32 + (c2 ^ (r & 31))];
         }
       }
       tc_fence_before();
