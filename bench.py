@@ -31,6 +31,7 @@ import sys
 import threading
 import time
 
+os.environ.setdefault("NCCL_DEBUG", "WARN")      # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
 REPO = os.path.dirname(os.path.abspath(__file__))
 if REPO not in sys.path:
     sys.path.insert(0, REPO)
@@ -324,7 +325,7 @@ def run_b200(args):
             rate, cores, steps, secs = cpu_oracle_rate(args, 128, budget_s=args.cpu_seconds, min_steps=2)
             line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port",
                                         sample=f"128 conformers x {steps} Euler steps of the same workload ({secs:.1f} s)")
-        print(json.dumps(line))
+        print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
