@@ -56,6 +56,7 @@ struct TcMsgP {
   float* s_new;
   float* v_new;
   float* e;                 // [E][F] (dst,src) order, updated in place
+  const float* edge_emb;    // first layer only: e0 = edge_emb[edge type] is formed on the fly, never read from e (embedding.py:89-103)
   const unsigned char* wblob;   // kChunksPerLayer chunks of this layer
   MsgParams prm;
   float length_scale;
@@ -65,7 +66,7 @@ struct TcMsgP {
   long long* dbg;           // optional [gridDim.x][8] stall-cycle counters (diagnostics), or NULL
 };
 
-struct RowA { int src; int dst; int slot_last; float dist; };   // slot | last << 8 | first << 9
+struct RowA { int src; int dst; int slot_last; float dist; };   // slot | last << 8 | first << 9 | edge type << 16
 struct RowB { float dx, dy, dz, pad; };
 
 struct MsgSmem {
@@ -129,7 +130,8 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
 }
 
 // rows [32*wq, +32) x column groups [4*grp, +4) of an operand image from row-major fp32 global rows
-// `base + row_index(r) * 128`, where row_index(r) = gather ? ROWA[r].src : row0 + r.
+// `base + row_index(r) * 128`, where row_index(r) = ROWA[r].src (gather 1), the edge type (gather 2: rows of
+// the edge-type embedding, first layer) or row0 + r (gather 0).
 __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int lane, int rows, const float* base,
                                         const RowA* rowa, int gather, int row0) {
 #pragma unroll
@@ -138,7 +140,8 @@ __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int 
     const int g = 4 * grp + (lane >> 3);
     float v[8];
     if (r < rows) {
-      const float* src = base + (size_t)(gather ? rowa[r].src : row0 + r) * kF + g * 8;
+      const size_t ri = gather == 1 ? (size_t)rowa[r].src : gather == 2 ? (size_t)((rowa[r].slot_last >> 16) & 0xFF) : (size_t)(row0 + r);
+      const float* src = base + ri * kF + g * 8;
       const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
     } else {
@@ -361,7 +364,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         // E4: e rows -> Y (after the s[src] half has been consumed)
         mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc, diag); pyf ^= 1;
-        build_rows(Y, wq, grp, lane, rows, p.e, ROWA, 0, row0);
+        if (p.first_layer) build_rows(Y, wq, grp, lane, rows, p.edge_emb, ROWA, 2, 0);
+        else build_rows(Y, wq, grp, lane, rows, p.e, ROWA, 0, row0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(2);   // E3 + E4
         // E5: w hidden 2 -> X (final: B operand of the output layer)
@@ -430,8 +434,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
             for (int q = 0; q < 32; ++q) acc_s[q >> 3] += P[q];
           } else if (sp == 3) {       // e += de                                       (cpainn.py:308)
             float* ep = p.e + (size_t)(row0 + c0) * kF + f;
+            if (p.first_layer) {
 #pragma unroll
-            for (int q = 0; q < 32; ++q) Q[q] = ep[(size_t)q * kF];
+              for (int q = 0; q < 32; ++q) Q[q] = __ldg(p.edge_emb + ((ROWA[c0 + q].slot_last >> 16) & 0xFF) * kF + f);
+            } else {
+#pragma unroll
+              for (int q = 0; q < 32; ++q) Q[q] = ep[(size_t)q * kF];
+            }
 #pragma unroll
             for (int q = 0; q < 32; ++q) ep[(size_t)q * kF] = Q[q] + P[q];
           } else {                    // cross_gates * (dir x v[dst]), linear in dir     (cpainn.py:296-300)
@@ -493,7 +502,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
               } else if (sp == 3) {     // e += de                                     (cpainn.py:308)
                 float* ep = p.e + (size_t)(row0 + r0) * kF + f;
 #pragma unroll
-                for (int q = 0; q < 8; ++q) Q[q] = (q >= qlo && q < qhi) ? ep[(size_t)q * kF] : 0.0f;
+                for (int q = 0; q < 8; ++q)
+                  Q[q] = !(q >= qlo && q < qhi) ? 0.0f
+                         : p.first_layer ? __ldg(p.edge_emb + ((ROWA[r0 + q].slot_last >> 16) & 0xFF) * kF + f)
+                                         : ep[(size_t)q * kF];
 #pragma unroll
                 for (int q = 0; q < 8; ++q)
                   if (q >= qlo && q < qhi) ep[(size_t)q * kF] = Q[q] + P[q];
@@ -554,11 +566,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
 
 // ---- small helpers of the tensor-core drift ---------------------------------------------------------
 // Per drift evaluation (geometry depends on x): node_in_ptr[j] = first (dst,src)-ordered edge row of node j
-// (node_in_ptr[N] = E) and, per edge row, RowA {src, dst, last << 8 | first << 9, dist} and RowB {dir, 0}:
+// (node_in_ptr[N] = E) and, per edge row, RowA {src, dst, last << 8 | first << 9 | edge type << 16, dist} and RowB {dir, 0}:
 // r = x[src] - x[dst], d = |r|, dir = r / (1 + d)                                       (graph.py:27-29)
 __global__ void k_edge_tables(const int* __restrict__ mol_ptr, const long long* __restrict__ edge_ptr, int n_mol,
-                              const float* __restrict__ x, int* __restrict__ node_in_ptr, uint4* __restrict__ rowa,
-                              uint4* __restrict__ rowb) {
+                              const float* __restrict__ x, const unsigned char* __restrict__ edge_type,
+                              int* __restrict__ node_in_ptr, uint4* __restrict__ rowa, uint4* __restrict__ rowb) {
   const int m = blockIdx.x;
   const int n0 = mol_ptr[m], n = mol_ptr[m + 1] - n0;
   const int e0 = (int)edge_ptr[m];
@@ -572,7 +584,9 @@ __global__ void k_edge_tables(const int* __restrict__ mol_ptr, const long long* 
     const float rz = x[3 * src + 2] - x[3 * dst + 2];
     const float dist = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(rx, rx), __fmul_rn(ry, ry)), __fmul_rn(rz, rz)));
     const float den = 1.0f + dist;
-    rowa[e0 + row] = make_uint4((uint32_t)src, (uint32_t)dst, (uint32_t)(((ip == n - 2) << 8) | ((ip == 0) << 9)),
+    // edge_type is given in the reference's (src,dst) order
+    const uint32_t et = edge_type[(size_t)e0 + il * (n - 1) + jl - (jl > il)];
+    rowa[e0 + row] = make_uint4((uint32_t)src, (uint32_t)dst, (uint32_t)(((ip == n - 2) << 8) | ((ip == 0) << 9)) | (et << 16),
                                 __float_as_uint(dist));
     rowb[e0 + row] = make_uint4(__float_as_uint(__fdiv_rn(rx, den)), __float_as_uint(__fdiv_rn(ry, den)),
                                 __float_as_uint(__fdiv_rn(rz, den)), 0u);

@@ -263,11 +263,10 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     }
     nodes_per_tile = std::min(tc::kTileNodes, 128 / (b->max_atoms - 1));
     n_tiles = (b->n_nodes + nodes_per_tile - 1) / nodes_per_tile;
-    tc::k_edge_tables<<<b->n_mol, 128, 0, st>>>(b->mol_ptr, (const long long*)b->edge_ptr, b->n_mol, x, ws.node_in_ptr,
-                                                ws.rowa, ws.rowb);
-    LAUNCH_CHECK();
+    // geometry + edge types per (dst,src)-ordered row; e0 = Emb(edge_type) is formed inside the first message layer
     ProfScope ps(TIB_K_EDGE_INIT, st);
-    tc::k_edge_init_dst<<<b->n_mol, 256, 0, st>>>(b->edge_type, m->edge_emb, b->mol_ptr, (const long long*)b->edge_ptr, ws.e, F);
+    tc::k_edge_tables<<<b->n_mol, 128, 0, st>>>(b->mol_ptr, (const long long*)b->edge_ptr, b->n_mol, x, b->edge_type,
+                                                ws.node_in_ptr, ws.rowa, ws.rowb);
     LAUNCH_CHECK();
   } else {
     const long long total = (long long)b->n_edges * (F / 4);
@@ -284,7 +283,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       tp.n_nodes = b->n_nodes; tp.n_tiles = n_tiles; tp.nodes_per_tile = nodes_per_tile;
       tp.node_in_ptr = ws.node_in_ptr; tp.rowa = ws.rowa; tp.rowb = ws.rowb;
       tp.s_old = ws.s[cur]; tp.v_old = ws.v[cur]; tp.s_new = ws.s[cur ^ 1]; tp.v_new = ws.v[cur ^ 1]; tp.e = ws.e;
-      tp.wblob = L.tc_msg;
+      tp.wblob = L.tc_msg; tp.edge_emb = m->edge_emb;
       tp.prm = tc::MsgParams{L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2, L.phi.b3,
                              L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2, L.w.b3};
       tp.length_scale = m->d.length_scale; tp.first_layer = (l == 0); tp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3;
