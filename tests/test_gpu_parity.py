@@ -362,5 +362,5 @@ def test_sampler_driver_writes_reference_file_format(tmp_path):
     assert s.shape == (10, 7, 9, 3) and np.array_equal(s, out["samples"])
     assert np.load(tmp_path / "latent_noises_t.npy").shape == (10, 9, 3)
     assert np.load(tmp_path / "latent_dlogps_t.npy").shape == (10,)
-    x0 = torch.cat([b.x0 for b in loader]).reshape(10, 9, 3).numpy()
+    x0 = torch.cat([b.x0.cpu() for b in loader]).reshape(10, 9, 3).numpy()
     np.testing.assert_array_equal(s[:, 0], x0)       # frame 0 is the start conformer, molecule by molecule
