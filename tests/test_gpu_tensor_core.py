@@ -16,7 +16,7 @@ def _rel(a, b):
     return float(np.abs(a - b).max() / np.abs(b).max())
 
 
-@pytest.mark.parametrize("transposed", [False, True])
+@pytest.mark.parametrize("transposed", [0, 1, 2])
 def test_selftest_gemm_split_f16(transposed):
     """One [128x128]x[128x128] product through the operand images, the bulk-copy weight ring, tcgen05.mma
     (3 split-f16 passes) and tcgen05.ld: fp32-faithful (error ~2^-21 per product)."""
@@ -25,7 +25,7 @@ def test_selftest_gemm_split_f16(transposed):
     A = torch.randn(128, 128, generator=gen)
     W = torch.randn(128, 128, generator=gen) * 0.2
     out = selftest_gemm(A.to(DEV), W, transposed).cpu().double()
-    ref = (W.double() @ A.double().T) if transposed else (A.double() @ W.double().T)
+    ref = (W.double() @ A.double().T) if transposed == 1 else (A.double() @ W.double().T)
     err = _rel(out.numpy(), ref.numpy())
     print(f"[tc] selftest transposed={transposed}: max rel err {err:.3e}")
     assert err < 2e-6

@@ -38,6 +38,7 @@ __device__ __forceinline__ void selftest_build(unsigned char* op, int warp, int 
 // Self test of the tensor-core plumbing (descriptors, operand image, ring, TMEM addressing):
 //   transposed = 0:  out[r][c] = sum_k A[r][k] * W[c][k]      (lane = row of A)
 //   transposed = 1:  out[r][c] = sum_k W[r][k] * A[c][k]      (lane = row of W)
+//   transposed = 2:  as 0, but the A operand is written to TMEM (tcgen05.st) and read from there
 // A is fp32 [128][128] row-major, wchunks = 4 packed chunks of W [128][128], out fp32 [128][128].
 __global__ void __launch_bounds__(kSelfThreads, 1) k_tc_selftest(const float* __restrict__ A, const unsigned char* __restrict__ wchunks,
                                                              float* __restrict__ out, int transposed, int* err_ptr) {
@@ -54,7 +55,7 @@ __global__ void __launch_bounds__(kSelfThreads, 1) k_tc_selftest(const float* __
     mbar_init(&bars[5], 1);     // accumulator full
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, 128);
+  if (warp == 4) tmem_alloc(tmem_slot, 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -73,14 +74,34 @@ __global__ void __launch_bounds__(kSelfThreads, 1) k_tc_selftest(const float* __
         mbar_wait(&bars[kb], 0, err);
         tc_fence_after();
         const uint32_t wst = smem_u32(RING) + kb * kChunkBytes, opk = smem_u32(X) + kb * (2 * kKStepBytes);
-        if (!transposed) mma_f16x3(tmem, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, kb > 0, 3);
-        else             mma_f16x3(tmem, wst, kChunkHalfBytes, opk, kOperandHalfBytes, 2, kb > 0, 3);
+        if (transposed == 0) mma_f16x3(tmem, opk, kOperandHalfBytes, wst, kChunkHalfBytes, 2, kb > 0, 3);
+        else if (transposed == 1) mma_f16x3(tmem, wst, kChunkHalfBytes, opk, kOperandHalfBytes, 2, kb > 0, 3);
+        else {
+          for (int ks = 0; ks < 2; ++ks) {
+            const uint32_t a_hi = tmem + 128 + 8 * (2 * kb + ks), a_lo = a_hi + 64;
+            const uint64_t bh = make_desc(wst + ks * kKStepBytes), bl = make_desc(wst + kChunkHalfBytes + ks * kKStepBytes);
+            tc_mma_f16_ts(tmem, a_hi, bh, kIdesc128x128, (kb | ks) ? 1u : 0u);
+            tc_mma_f16_ts(tmem, a_hi, bl, kIdesc128x128, 1u);
+            tc_mma_f16_ts(tmem, a_lo, bh, kIdesc128x128, 1u);
+          }
+        }
       }
       tc_commit(&bars[5]);
     }
   } else {
-    selftest_build(X, warp, lane, 128, [&](int r) { return A + (size_t)r * 128; });
-    fence_proxy_async();
+    const uint32_t lane_base = tmem + ((uint32_t)(warp * 32) << 16);
+    if (transposed == 2) {
+      for (int ks = 0; ks < 8; ++ks) {
+        float v[16];
+        for (int i = 0; i < 16; ++i) v[i] = A[(size_t)tid * 128 + 16 * ks + i];
+        tmem_store_kstep(lane_base + 128 + 8 * ks, lane_base + 192 + 8 * ks, v);
+      }
+      tmem_wait_st();
+      tc_fence_before();
+    } else {
+      selftest_build(X, warp, lane, 128, [&](int r) { return A + (size_t)r * 128; });
+      fence_proxy_async();
+    }
     mbar_arrive(&bars[4]);
     mbar_wait(&bars[5], 0, err);
     tc_fence_after();
@@ -93,7 +114,7 @@ __global__ void __launch_bounds__(kSelfThreads, 1) k_tc_selftest(const float* __
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) tmem_dealloc(tmem, 128);
+  if (warp == 4) tmem_dealloc(tmem, 256);
 }
 
 
