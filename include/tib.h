@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TIB_ABI_VERSION 2
+#define TIB_ABI_VERSION 3
 
 /* ---- model ------------------------------------------------------------------------------- */
 
@@ -102,6 +102,12 @@ typedef struct {
   const int32_t* embed_atom_id;/* [U] */
   const float*   embed_temp0;  /* [U] or NULL */
   const float*   embed_temp1;  /* [U] or NULL */
+  /* Optional tiling of the destination nodes for the tensor-core message kernel: tile t owns nodes
+   * [tile_node_ptr[t], tile_node_ptr[t+1]) - at most 16 nodes whose incoming edges total at most 128 rows.
+   * NULL (or n_tiles == 0) = uniform tiles of min(16, 128 / (max_atoms - 1)) nodes, which wastes rows when
+   * molecule sizes are mixed. */
+  int32_t        n_tiles;
+  const int32_t* tile_node_ptr;/* [n_tiles + 1] */
 } tib_batch;
 
 /* Scratch the caller must provide to tib_drift / tib_rollout_* for this batch shape. */

@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtib.so")
-ABI_VERSION = 2
+ABI_VERSION = 3
 
 VARIANT_AMBIENT, VARIANT_LATENT_MULTI_T, VARIANT_LATENT_SINGLE_T = 0, 1, 2
 MATH_FP32_SIMT, MATH_F16X3_TC, MATH_F16_TC = 0, 1, 2
@@ -30,7 +30,8 @@ class Batch(C.Structure):
                 ("mol_ptr", C.c_void_p), ("edge_ptr", C.c_void_p), ("atom_id", C.c_void_p),
                 ("edge_type", C.c_void_p), ("temp0", C.c_void_p), ("temp1", C.c_void_p),
                 ("n_embed_rows", C.c_int32), ("embed_index", C.c_void_p), ("embed_atom_id", C.c_void_p),
-                ("embed_temp0", C.c_void_p), ("embed_temp1", C.c_void_p)]
+                ("embed_temp0", C.c_void_p), ("embed_temp1", C.c_void_p),
+                ("n_tiles", C.c_int32), ("tile_node_ptr", C.c_void_p)]
 
 
 class FixedOpts(C.Structure):

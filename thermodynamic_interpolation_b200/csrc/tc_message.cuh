@@ -48,6 +48,7 @@ struct MsgParams {
 
 struct TcMsgP {
   int n_nodes, n_tiles, nodes_per_tile;
+  const int* tile_node_ptr; // [n_tiles+1] or NULL (uniform tiles of nodes_per_tile nodes)
   const int* node_in_ptr;   // [N+1] first (dst-major) edge row of each node
   const uint4* rowa;        // [E] RowA per (dst,src)-ordered edge row (k_edge_tables; slot filled per tile)
   const uint4* rowb;        // [E] RowB
@@ -317,8 +318,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
 #define TIB_PHASE(i) do { if (diag) { const long long _t = clock64(); phc[i] += _t - tlast; tlast = _t; } } while (0)
     const uint32_t lane_taddr = tmem + ((uint32_t)(wq * 32) << 16);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int node_lo = tile * p.nodes_per_tile;
-      const int node_hi = min(node_lo + p.nodes_per_tile, p.n_nodes);
+      const int node_lo = p.tile_node_ptr ? __ldg(p.tile_node_ptr + tile) : tile * p.nodes_per_tile;
+      const int node_hi = p.tile_node_ptr ? __ldg(p.tile_node_ptr + tile + 1) : min(node_lo + p.nodes_per_tile, p.n_nodes);
       const int row0 = __ldg(p.node_in_ptr + node_lo);
       const int rows = __ldg(p.node_in_ptr + node_hi) - row0;
       // ---- tile tables (the previous tile finished with an all-group barrier)

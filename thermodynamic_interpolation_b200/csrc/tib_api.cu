@@ -262,7 +262,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       m->tc_attrs_set = true;
     }
     nodes_per_tile = std::min(tc::kTileNodes, 128 / (b->max_atoms - 1));
-    n_tiles = (b->n_nodes + nodes_per_tile - 1) / nodes_per_tile;
+    n_tiles = (b->tile_node_ptr && b->n_tiles > 0) ? b->n_tiles : (b->n_nodes + nodes_per_tile - 1) / nodes_per_tile;
     // geometry + edge types per (dst,src)-ordered row; e0 = Emb(edge_type) is formed inside the first message layer
     ProfScope ps(TIB_K_EDGE_INIT, st);
     tc::k_edge_tables<<<b->n_mol, 128, 0, st>>>(b->mol_ptr, (const long long*)b->edge_ptr, b->n_mol, x, b->edge_type,
@@ -282,6 +282,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       tc::TcMsgP tp{};
       tp.n_nodes = b->n_nodes; tp.n_tiles = n_tiles; tp.nodes_per_tile = nodes_per_tile;
       tp.node_in_ptr = ws.node_in_ptr; tp.rowa = ws.rowa; tp.rowb = ws.rowb;
+      tp.tile_node_ptr = (b->tile_node_ptr && b->n_tiles > 0) ? b->tile_node_ptr : nullptr;
       tp.s_old = ws.s[cur]; tp.v_old = ws.v[cur]; tp.s_new = ws.s[cur ^ 1]; tp.v_new = ws.v[cur ^ 1]; tp.e = ws.e;
       tp.wblob = L.tc_msg; tp.edge_emb = m->edge_emb;
       tp.prm = tc::MsgParams{L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2, L.phi.b3,

@@ -88,6 +88,22 @@ def pack_state_dict(sd: Dict[str, torch.Tensor], hp: Hyper) -> np.ndarray:
     return np.ascontiguousarray(torch.cat(parts).numpy())
 
 
+def pack_node_tiles(n_atoms: np.ndarray, max_nodes: int = 16, max_rows: int = 128) -> np.ndarray:
+    """Greedy packing of consecutive destination nodes into tiles of at most `max_nodes` nodes and `max_rows`
+    incoming-edge rows (node j of a molecule with n atoms has n - 1 rows).  Returns tile_node_ptr (int32)."""
+    rows = np.repeat(n_atoms - 1, n_atoms).astype(np.int64)
+    cum = np.concatenate([[0], np.cumsum(rows)])
+    n = rows.shape[0]
+    ptr = [0]
+    j = 0
+    while j < n:
+        hi = int(np.searchsorted(cum, cum[j] + max_rows, side="right")) - 1      # last node index bound by rows
+        nxt = max(j + 1, min(hi, j + max_nodes, n))
+        ptr.append(nxt)
+        j = nxt
+    return np.asarray(ptr, dtype=np.int32)
+
+
 class PreparedBatch:
     """Device-side view of a batch in the layout `tib_batch` wants; keeps the tensors alive."""
 
@@ -145,6 +161,11 @@ class PreparedBatch:
         self.embed_temp0 = uniq[:, 1].to(torch.int32).view(torch.float32).contiguous() if self.temp0 is not None else None
         self.embed_temp1 = uniq[:, 2].to(torch.int32).view(torch.float32).contiguous() if self.temp1 is not None else None
         dedupe = self.n_embed_rows * 2 <= N
+        # destination-node tiles of the tensor-core message kernel (<= 16 nodes, <= 128 incoming-edge rows)
+        self.tile_node_ptr = None
+        cmin, cmax = int(counts.min().item()), self.max_atoms
+        if cmin != cmax:          # uniform batches tile perfectly with the library's default
+            self.tile_node_ptr = torch.from_numpy(pack_node_tiles(counts.cpu().numpy())).to(device)
         self.c = _lib.Batch(
             n_mol=n_mol, n_nodes=N, n_edges=self.n_edges, max_atoms=self.max_atoms,
             mol_ptr=self.mol_ptr.data_ptr(), edge_ptr=self.edge_ptr.data_ptr(),
@@ -155,7 +176,9 @@ class PreparedBatch:
             embed_index=self.embed_index.data_ptr() if dedupe else None,
             embed_atom_id=self.embed_atom_id.data_ptr() if dedupe else None,
             embed_temp0=self.embed_temp0.data_ptr() if (dedupe and self.embed_temp0 is not None) else None,
-            embed_temp1=self.embed_temp1.data_ptr() if (dedupe and self.embed_temp1 is not None) else None)
+            embed_temp1=self.embed_temp1.data_ptr() if (dedupe and self.embed_temp1 is not None) else None,
+            n_tiles=int(self.tile_node_ptr.numel() - 1) if self.tile_node_ptr is not None else 0,
+            tile_node_ptr=self.tile_node_ptr.data_ptr() if self.tile_node_ptr is not None else None)
 
 
 class DriftEngine:

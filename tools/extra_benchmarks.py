@@ -1,0 +1,78 @@
+"""Additional measurements next to bench.py's headline (BASELINE.json configs 2-4), one JSON line each:
+  * cfg 3: latent multi-T flow, 16 384 molecules with 9..25 atoms, F = 128, fixed-grid Euler
+  * cfg 2 with the reference's own solver: dopri5, rtol = atol = 1e-5, 100 saved frames (NFE-based throughput)
+  * 10506-shaped batch (25 atoms, F = 256): the fp32 SIMT path (tensor cores are built for F = 128)
+Run on a B200:  python tools/extra_benchmarks.py > gpurun_out/extra.jsonl"""
+import json
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tests._util import perturb_  # noqa: E402
+from thermodynamic_interpolation_b200 import _lib  # noqa: E402
+from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch, synthetic_latent_batch  # noqa: E402
+
+DEV = "cuda:0"
+
+
+def timed(fn, reps=1):
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(reps):
+        out = fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return out, e0.elapsed_time(e1) * 1e-3 / reps
+
+
+def euler_rate(model, mb, steps):
+    eng = model.engine()
+    pb = eng.prepare(mb)
+    grid = torch.linspace(0.0, 1.0, steps + 1)
+    eng.rollout_fixed(pb, mb.x0.contiguous(), grid[:4], method="euler", save_frames=False)      # warm-up
+    _, sec = timed(lambda: eng.rollout_fixed(pb, mb.x0.contiguous(), grid, method="euler", save_frames=False))
+    eng.status()
+    return pb.n_mol * steps / sec, sec / steps
+
+
+def main():
+    # ---- cfg 3
+    from thermodynamic_interpolation_b200.latent.models.cpainn import cPaiNN as Latent
+    torch.manual_seed(0)
+    model = perturb_(Latent(n_features=128, score_layers=5, temp_length=75), 1).eval().to(DEV)
+    gen = torch.Generator().manual_seed(2)
+    n_list = torch.randint(9, 26, (16384,), generator=gen).tolist()
+    mb = synthetic_latent_batch(len(n_list), n_list, T=800, seed=3).to(DEV)
+    rate, per = euler_rate(model, mb, 20)
+    print(json.dumps(dict(workload="cfg 3: latent multi-T, 16384 molecules with 9..25 atoms, F=128 L=5, Euler",
+                          math=_lib.MATH_NAMES[1], value=rate, unit="molecule*steps/s", ms_per_step=per * 1e3,
+                          n_nodes=int(mb.x0.shape[0]), n_edges=int(mb.edge_index.shape[1]))), flush=True)
+    del model, mb
+    # ---- cfg 2 under dopri5
+    from thermodynamic_interpolation_b200.ambient.integrators import MoleculeIntegrator
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN as Ambient
+    torch.manual_seed(0)
+    model = perturb_(Ambient(n_features=128, score_layers=5, temp_length=100), 1).eval().to(DEV)
+    mb = synthetic_ambient_batch(4096, 9, seed=100).to(DEV)
+    integ = MoleculeIntegrator(model, method="dopri5", n_step=100, atol=1e-5, rtol=1e-5)
+    integ.rollout(mb)
+    (xts, dlogp, nfe, _), sec = timed(lambda: integ.rollout(mb))
+    print(json.dumps(dict(workload="cfg 2 under the reference's solver: dopri5 rtol=atol=1e-5, 100 frames, 4096 x 9 atoms, F=128",
+                          math=_lib.MATH_NAMES[1], nfe=int(nfe), attempts=integ.last_stats["attempts"],
+                          accepted=integ.last_stats["accepted"], seconds=sec, value=4096 * nfe / sec,
+                          unit="molecule*drift-evals/s", finite=bool(torch.isfinite(xts).all()))), flush=True)
+    del model, mb, integ
+    # ---- 10506-shaped: 25 atoms, F = 256 (fp32 SIMT path)
+    torch.manual_seed(0)
+    model = perturb_(Ambient(n_features=256, score_layers=5, temp_length=100), 1).eval().to(DEV)
+    mb = synthetic_ambient_batch(512, 25, seed=100).to(DEV)
+    rate, per = euler_rate(model, mb, 5)
+    print(json.dumps(dict(workload="10506-shaped: 512 conformers x 25 atoms, F=256 L=5, Euler", math=_lib.MATH_NAMES[0],
+                          value=rate, unit="molecule*steps/s", ms_per_step=per * 1e3)), flush=True)
+
+
+if __name__ == "__main__":
+    main()
