@@ -34,7 +34,7 @@ struct EmbedP {
 // ---------------------------------------------------------------------------------------------
 // embed: s0 = MLP(cat[Emb(atom), PE(T0'), PE(T1'), PE(t)])          (embedding.py:68-86,249-261)
 // ---------------------------------------------------------------------------------------------
-template <int F, int RPT>
+template <int F, int RPT, int KU = 4>
 __global__ void __launch_bounds__(TIB_THREADS, 1) k_embed(EmbedP p) {
   using C = Cols<F>;
   constexpr int TR = 8 * RPT;
@@ -78,12 +78,12 @@ __global__ void __launch_bounds__(TIB_THREADS, 1) k_embed(EmbedP p) {
   }
   __syncthreads();
 
-  layer_ln_silu<F, RPT>(X0, kin, kin, p.mlp.W1t, p.mlp.b1, p.mlp.g1, p.mlp.be1, XA, F, warp, lane);
-  layer_ln_silu<F, RPT>(XA, F, F, p.mlp.W2t, p.mlp.b2, p.mlp.g2, p.mlp.be2, XB, F, warp, lane);
+  layer_ln_silu<F, RPT, KU>(X0, kin, kin, p.mlp.W1t, p.mlp.b1, p.mlp.g1, p.mlp.be1, XA, F, warp, lane);
+  layer_ln_silu<F, RPT, KU>(XA, F, F, p.mlp.W2t, p.mlp.b2, p.mlp.g2, p.mlp.be2, XB, F, warp, lane);
 #pragma unroll
   for (int ch = 0; ch < C::NCH; ++ch) {
     float acc[RPT][C::CPL];
-    out_chunk<F, RPT>(acc, XB, F, p.mlp.W3t, F, p.mlp.b3, ch * C::CW, warp, lane);
+    out_chunk<F, RPT, KU>(acc, XB, F, p.mlp.W3t, F, p.mlp.b3, ch * C::CW, warp, lane);
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
       const int node = node0 + q * 8 + warp;

@@ -14,38 +14,44 @@
 namespace tib {
 
 // acc[q][c] = sum_k A[(q*8+warp)*lda + k] * Wt[k*ldw + col + c]      (k ascending, fmaf chain)
-template <int RPT, int CPL>
+// KU weight rows are in flight per lane (double buffered); KU = 16 is for launches with a handful of
+// CTAs where the loop is bound by the latency of the weight loads, not by their throughput.
+template <int RPT, int CPL, int KU = 4>
 __device__ __forceinline__ void gemm_rows(float (&acc)[RPT][CPL], const float* A, int lda, int K,
                                           const float* __restrict__ Wt, int ldw, int col, int warp) {
+  static_assert(KU % 4 == 0, "KU must be a multiple of 4");
 #pragma unroll
   for (int q = 0; q < RPT; ++q)
 #pragma unroll
     for (int c = 0; c < CPL; ++c) acc[q][c] = 0.0f;
   const float* wp = Wt + col;
   const float* ap = A + warp * lda;
-  float w[4][CPL], wn[4][CPL];
+  float w[KU][CPL], wn[KU][CPL];
 #pragma unroll
-  for (int kk = 0; kk < 4; ++kk) ldg_vec<CPL>(w[kk], wp + (size_t)kk * ldw);
-  for (int k0 = 0; k0 < K; k0 += 4) {
-    if (k0 + 4 < K) {
+  for (int kk = 0; kk < KU; ++kk) ldg_vec<CPL>(w[kk], wp + (size_t)kk * ldw);
+  for (int k0 = 0; k0 < K; k0 += KU) {
+    if (k0 + KU < K) {
 #pragma unroll
-      for (int kk = 0; kk < 4; ++kk) ldg_vec<CPL>(wn[kk], wp + (size_t)(k0 + 4 + kk) * ldw);
+      for (int kk = 0; kk < KU; ++kk) ldg_vec<CPL>(wn[kk], wp + (size_t)(k0 + KU + kk) * ldw);
     }
 #pragma unroll
     for (int q = 0; q < RPT; ++q) {
-      const float4 a = *reinterpret_cast<const float4*>(ap + q * 8 * lda + k0);
 #pragma unroll
-      for (int c = 0; c < CPL; ++c) {
-        float t = acc[q][c];
-        t = fmaf(a.x, w[0][c], t);
-        t = fmaf(a.y, w[1][c], t);
-        t = fmaf(a.z, w[2][c], t);
-        t = fmaf(a.w, w[3][c], t);
-        acc[q][c] = t;
+      for (int k4 = 0; k4 < KU; k4 += 4) {
+        const float4 a = *reinterpret_cast<const float4*>(ap + q * 8 * lda + k0 + k4);
+#pragma unroll
+        for (int c = 0; c < CPL; ++c) {
+          float t = acc[q][c];
+          t = fmaf(a.x, w[k4 + 0][c], t);
+          t = fmaf(a.y, w[k4 + 1][c], t);
+          t = fmaf(a.z, w[k4 + 2][c], t);
+          t = fmaf(a.w, w[k4 + 3][c], t);
+          acc[q][c] = t;
+        }
       }
     }
 #pragma unroll
-    for (int kk = 0; kk < 4; ++kk)
+    for (int kk = 0; kk < KU; ++kk)
 #pragma unroll
       for (int c = 0; c < CPL; ++c) w[kk][c] = wn[kk][c];
   }
@@ -53,7 +59,7 @@ __device__ __forceinline__ void gemm_rows(float (&acc)[RPT][CPL], const float* A
 
 // Hidden layer: Xout[r][:] = SiLU(LayerNorm(A[r][:] @ Wt + b) * g + be) for the warp's rows.
 // LayerNorm (eps 1e-5, biased variance, two-pass) is done in registers across the warp.
-template <int F, int RPT>
+template <int F, int RPT, int KU = 4>
 __device__ __forceinline__ void layer_ln_silu(const float* A, int lda, int K, const float* __restrict__ Wt,
                                               const float* __restrict__ b, const float* __restrict__ g,
                                               const float* __restrict__ be, float* Xout, int ldo,
@@ -62,7 +68,7 @@ __device__ __forceinline__ void layer_ln_silu(const float* A, int lda, int K, co
   float acc[C::NCH][RPT][C::CPL];
 #pragma unroll
   for (int ch = 0; ch < C::NCH; ++ch)
-    gemm_rows<RPT, C::CPL>(acc[ch], A, lda, K, Wt, F, ch * C::CW + lane * C::CPL, warp);
+    gemm_rows<RPT, C::CPL, KU>(acc[ch], A, lda, K, Wt, F, ch * C::CW + lane * C::CPL, warp);
   float bb[C::NCH][C::CPL], gg[C::NCH][C::CPL], ee[C::NCH][C::CPL];
 #pragma unroll
   for (int ch = 0; ch < C::NCH; ++ch) {
@@ -108,12 +114,12 @@ __device__ __forceinline__ void layer_ln_silu(const float* A, int lda, int K, co
 
 // Output layer, one chunk of CW columns starting at column c0 of W3t [F][n_out]:
 // acc[q][c] = H[r][:] @ W3t[:, c0 + lane*CPL + c] + b3[...]
-template <int F, int RPT>
+template <int F, int RPT, int KU = 4>
 __device__ __forceinline__ void out_chunk(float (&acc)[RPT][Cols<F>::CPL], const float* H, int ldh,
                                           const float* __restrict__ W3t, int n_out,
                                           const float* __restrict__ b3, int c0, int warp, int lane) {
   using C = Cols<F>;
-  gemm_rows<RPT, C::CPL>(acc, H, ldh, F, W3t, n_out, c0 + lane * C::CPL, warp);
+  gemm_rows<RPT, C::CPL, KU>(acc, H, ldh, F, W3t, n_out, c0 + lane * C::CPL, warp);
   float bb[C::CPL];
   ldg_vec<C::CPL>(bb, b3 + c0 + lane * C::CPL);
 #pragma unroll

@@ -221,6 +221,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
   constexpr int RM = Tiles<F>::MSG, RN = Tiles<F>::NODE;
   if (!m->attrs_set) {
     if (set_smem(k_embed<F, RN>, smem_embed<F, RN>())) return -1;
+    if (set_smem(k_embed<F, 1, 16>, smem_embed<F, 1>())) return -1;
     if (set_smem(k_message<F, RM>, smem_message<F, RM>())) return -1;
     if (set_smem(k_update<F, RN>, smem_update<F, RN>())) return -1;
     if (set_smem(k_readout<F, RN>, smem_readout<F, RN>())) return -1;
@@ -239,7 +240,10 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     EmbedP ep{du, m->combine, m->atom_emb, m->n_temp, t, m->d.temp_mean, m->d.temp_range, m->d.temp_length,
               m->d.time_length, ws.s[1]};
     ProfScope ps(TIB_K_EMBED, st);
-    k_embed<F, RN><<<(b->n_embed_rows + 8 * RN - 1) / (8 * RN), TIB_THREADS, smem_embed<F, RN>(), st>>>(ep);
+    if (b->n_embed_rows <= 8 * 2 * 148)   // few rows: 8 per CTA and 16 weight rows in flight per lane (latency bound)
+      k_embed<F, 1, 16><<<(b->n_embed_rows + 7) / 8, TIB_THREADS, smem_embed<F, 1>(), st>>>(ep);
+    else
+      k_embed<F, RN><<<(b->n_embed_rows + 8 * RN - 1) / (8 * RN), TIB_THREADS, smem_embed<F, RN>(), st>>>(ep);
     LAUNCH_CHECK();
     const long long total = (long long)b->n_nodes * (F / 4);
     k_gather_rows<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(ws.s[1], b->embed_index, ws.s[0],
