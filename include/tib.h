@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TIB_ABI_VERSION 3
+#define TIB_ABI_VERSION 4
 
 /* ---- model ------------------------------------------------------------------------------- */
 
@@ -119,6 +119,20 @@ size_t tib_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, i
  *   x [N,3] fp32 (device), t scalar, out_b [N,3] fp32 (device). */
 int tib_drift(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b,
               void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- the drift with its exact divergence: ODEWrapper.forward with return_dlogp=True ---------
+ * Replaces  b(batch).output  plus  ODEWrapper.compute_divergence(b, batch)
+ * (mdqm9/thermo/ambient/models/ode_wrapper.py:39-49,59-91; latent/models/ode_wrapper.py:38-46,57-86):
+ *   out_div[mol] = sum over atoms a and coordinates c of d b[a][c] / d x[a][c], UNSCALED (the ambient
+ *   wrapper's x 1e-2 and the sign are applied by the caller), fp32 [n_mol] on the device.
+ * The reference runs 3n reverse passes; this runs 3 * max_atoms forward-mode tangent directions through
+ * dual-number fp32 kernels (always CUDA-core arithmetic, whatever tib_model_set_math says), D at a time,
+ * and - unlike the reference (ode_wrapper.py:75,79) - accepts molecules of different sizes.
+ * out_b is the TIB_MATH_FP32_SIMT drift up to the grouping of the per-node edge sums.  The workspace is larger than
+ * tib_workspace_bytes: use tib_div_workspace_bytes. */
+size_t tib_div_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges);
+int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div,
+                  void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- K1: fused integrator state updates ---------------------------------------------------
  * One explicit Euler / Euler-Maruyama update over a flat state of n floats:

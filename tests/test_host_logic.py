@@ -128,7 +128,7 @@ def test_no_cpu_fallback():
         m(b)
     with pytest.raises(RuntimeError, match="CUDA"):
         MoleculeIntegrator(m, method="euler", n_step=3).rollout(b)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError, match="CUDA"):
         MoleculeIntegrator(m, method="euler", n_step=3, return_dlogp=True).rollout(b)
 
 

@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtib.so")
-ABI_VERSION = 3
+ABI_VERSION = 4
 
 VARIANT_AMBIENT, VARIANT_LATENT_MULTI_T, VARIANT_LATENT_SINGLE_T = 0, 1, 2
 MATH_FP32_SIMT, MATH_F16X3_TC, MATH_F16_TC = 0, 1, 2
@@ -64,6 +64,8 @@ SYMBOLS = [
     ("tib_selftest_gemm", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("tib_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
     ("tib_drift", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("tib_div_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
+    ("tib_drift_div", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_step_euler", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_rollout_fixed", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(FixedOpts), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_rollout_dopri5", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(Dopri5Opts), C.c_void_p, C.POINTER(Dopri5Stats), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -6,12 +6,17 @@ from torch import nn
 
 
 class ODEWrapper(nn.Module):
-    """`forward(t, states, batch[, n_steps])` -> drift b(t, x) [N,3] (reference ode_wrapper.py:26-57).
+    """`forward(t, states, batch[, n_steps])` -> drift b(t, x) [N,3] (reference ode_wrapper.py:26-57), or with
+    `return_dlogp=True` the tuple `(b, -div * scale)` (`(-b, div * scale)` under `reverse_ode`) where div is the
+    exact per-molecule divergence (compute_divergence, ode_wrapper.py:59-91) and scale = 1e-2 for the ambient
+    variant (ode_wrapper.py:91).
 
     Unlike the reference it neither clones the batch nor re-stamps `batch.x` / `batch.t` per call
     (reset_batch, ode_wrapper.py:93-113): the prepared batch is cached and `x`, `t` go straight to
-    the kernel.  The exact-divergence branch (`return_dlogp=True`, ode_wrapper.py:39-49,59-91) is the
-    next scope row and raises here rather than silently returning zeros."""
+    the kernels.  The divergence comes from forward-mode tangents (csrc/simt_tangent.cuh) instead of 3n
+    autograd passes and also works for molecules of different sizes.  The reference's ambient
+    `reverse_ode` branch returns a 3-tuple torchdiffeq cannot integrate (ode_wrapper.py:49); here it
+    follows the latent wrapper's `(-b, divergence)` (latent ode_wrapper.py:46)."""
 
     variant_scale = 1e-2      # ambient multiplies the divergence by 1e-2 (ode_wrapper.py:91)
 
@@ -29,13 +34,14 @@ class ODEWrapper(nn.Module):
         return eng, self._prepared[1]
 
     def forward(self, integration_time, states, batch, n_steps: list = None):
-        if self.return_dlogp:
-            raise NotImplementedError(
-                "return_dlogp=True (exact divergence, ode_wrapper.py:59-91) is not built yet in the "
-                "B200 path; use return_dlogp=False")
-        x = states
         if n_steps is not None:
             n_steps.append(n_steps[-1] + 1)
         eng, pb = self.prepared(batch)
         t = float(integration_time) if not torch.is_tensor(integration_time) else float(integration_time.to(torch.float32))
+        if self.return_dlogp:
+            x, _ = states
+            b, div = eng.drift_div(pb, x.to(eng.device, torch.float32), t)
+            div = div * self.variant_scale
+            return (b, -div) if not self.reverse_ode else (-b, div)
+        x = states
         return eng.drift(pb, x.to(eng.device, torch.float32), t)

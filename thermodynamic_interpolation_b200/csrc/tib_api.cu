@@ -10,6 +10,7 @@
 
 #include "../../include/tib.h"
 #include "simt_drift.cuh"
+#include "simt_tangent.cuh"
 #include "steps.cuh"
 #include "adw.cuh"
 #include "tc_message.cuh"
@@ -98,6 +99,7 @@ struct tib_model {
   // tensor-core path (F = 128): per-layer streamed weight chunks in split-f16 operand images
   unsigned char* tc_blob = nullptr;
   bool tc_attrs_set = false;
+  bool jvp_attrs_set = false;
   int* dev_err = nullptr;     // device error word written by the bounded mbarrier waits
   int n_sms = 148;
   long long* dev_dbg = nullptr;   // optional stall counters of the last tensor-core message launch
@@ -215,22 +217,12 @@ struct Workspace {
   static size_t kstride(int n_nodes) { return align(sizeof(float) * (size_t)n_nodes * 3) / sizeof(float); }
 };
 
+// s0 = InvariantFeatures(atoms, T0, T1, t) into ws.s[0] (de-duplicated rows + gather when the batch has the tables)
 template <int F>
-int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float* out, Workspace& ws, cudaStream_t st) {
+int launch_embed(tib_model* m, const tib_batch* b, const tib::DriftBatch& db, float t, Workspace& ws, cudaStream_t st) {
   using namespace tib;
-  constexpr int RM = Tiles<F>::MSG, RN = Tiles<F>::NODE;
-  if (!m->attrs_set) {
-    if (set_smem(k_embed<F, RN>, smem_embed<F, RN>())) return -1;
-    if (set_smem(k_embed<F, 1, 16>, smem_embed<F, 1>())) return -1;
-    if (set_smem(k_message<F, RM>, smem_message<F, RM>())) return -1;
-    if (set_smem(k_update<F, RN>, smem_update<F, RN>())) return -1;
-    if (set_smem(k_readout<F, RN>, smem_readout<F, RN>())) return -1;
-    m->attrs_set = true;
-  }
-  DriftBatch db{b->n_mol, b->n_nodes, (long long)b->n_edges, b->mol_ptr, (const long long*)b->edge_ptr,
-                b->atom_id, b->edge_type, b->temp0, b->temp1};
+  constexpr int RN = Tiles<F>::NODE;
   const int node_tiles = (b->n_nodes + 8 * RN - 1) / (8 * RN);
-
   if (b->embed_index && b->n_embed_rows > 0 && b->n_embed_rows <= b->n_nodes) {
     // de-duplicated embedding: U distinct rows into ws.s[1] (free until the first message layer), then a gather
     if (!b->embed_atom_id || (m->n_temp >= 1 && !b->embed_temp0) || (m->n_temp >= 2 && !b->embed_temp1))
@@ -256,6 +248,26 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     k_embed<F, RN><<<node_tiles, TIB_THREADS, smem_embed<F, RN>(), st>>>(ep);
     LAUNCH_CHECK();
   }
+  return 0;
+}
+
+template <int F>
+int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float* out, Workspace& ws, cudaStream_t st) {
+  using namespace tib;
+  constexpr int RM = Tiles<F>::MSG, RN = Tiles<F>::NODE;
+  if (!m->attrs_set) {
+    if (set_smem(k_embed<F, RN>, smem_embed<F, RN>())) return -1;
+    if (set_smem(k_embed<F, 1, 16>, smem_embed<F, 1>())) return -1;
+    if (set_smem(k_message<F, RM>, smem_message<F, RM>())) return -1;
+    if (set_smem(k_update<F, RN>, smem_update<F, RN>())) return -1;
+    if (set_smem(k_readout<F, RN>, smem_readout<F, RN>())) return -1;
+    m->attrs_set = true;
+  }
+  DriftBatch db{b->n_mol, b->n_nodes, (long long)b->n_edges, b->mol_ptr, (const long long*)b->edge_ptr,
+                b->atom_id, b->edge_type, b->temp0, b->temp1};
+  const int node_tiles = (b->n_nodes + 8 * RN - 1) / (8 * RN);
+
+  if (launch_embed<F>(m, b, db, t, ws, st)) return -1;
   const bool use_tc = (F == 128) && m->math != TIB_MATH_FP32_SIMT;
   int nodes_per_tile = 0, n_tiles = 0;
   if (use_tc) {
@@ -323,6 +335,93 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
   ReadoutP rp{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], out};
   { ProfScope ps(TIB_K_READOUT, st); k_readout<F, RN><<<node_tiles, TIB_THREADS, smem_readout<F, RN>(), st>>>(rp); }
   LAUNCH_CHECK();
+  return 0;
+}
+
+
+// ---- exact divergence by forward-mode tangents (csrc/simt_tangent.cuh) ----------------------------
+// D tangent directions per pass and tile heights (rows per thread) of the dual-number kernels; the
+// budgets are the 227 KB of shared memory: (1 + D) copies of every activation buffer.
+template <int F> struct JvpTiles { static constexpr int D = 3, MSG = 2, NODE = 1; };
+template <> struct JvpTiles<256> { static constexpr int D = 1, MSG = 2, NODE = 1; };
+
+struct TangentWs {
+  float *ts[2], *tv[2], *te, *tout;
+  size_t st_s, st_v, st_e, st_o;   // floats between directions
+  static size_t align(size_t x) { return Workspace::align(x); }
+  static size_t bytes(int F, int D, int n_nodes, long long n_edges) {
+    return (size_t)D * (2 * align(sizeof(float) * (size_t)n_nodes * F) + 2 * align(sizeof(float) * (size_t)n_nodes * 3 * F) +
+                        align(sizeof(float) * (size_t)n_edges * F) + align(sizeof(float) * (size_t)n_nodes * 3));
+  }
+  void carve(void* base, int F, int D, int n_nodes, long long n_edges) {
+    char* p = (char*)base;
+    st_s = align(sizeof(float) * (size_t)n_nodes * F) / sizeof(float);
+    st_v = align(sizeof(float) * (size_t)n_nodes * 3 * F) / sizeof(float);
+    st_e = align(sizeof(float) * (size_t)n_edges * F) / sizeof(float);
+    st_o = align(sizeof(float) * (size_t)n_nodes * 3) / sizeof(float);
+    auto take = [&](size_t floats) { float* r = (float*)p; p += sizeof(float) * floats * D; return r; };
+    ts[0] = take(st_s); ts[1] = take(st_s);
+    tv[0] = take(st_v); tv[1] = take(st_v);
+    te = take(st_e);
+    tout = take(st_o);
+  }
+};
+
+int jvp_dirs(int F) { return F == 256 ? JvpTiles<256>::D : JvpTiles<128>::D; }
+
+template <int F>
+int drift_div_simt(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div,
+                   Workspace& ws, TangentWs& tw, cudaStream_t st) {
+  using namespace tib;
+  constexpr int D = JvpTiles<F>::D, RM = JvpTiles<F>::MSG, RN = JvpTiles<F>::NODE;
+  if (!m->jvp_attrs_set) {
+    if (set_smem(k_embed<F, Tiles<F>::NODE>, smem_embed<F, Tiles<F>::NODE>())) return -1;
+    if (set_smem(k_embed<F, 1, 16>, smem_embed<F, 1>())) return -1;
+    if (set_smem(k_message_jvp<F, RM, D>, smem_message_jvp<F, RM, D>())) return -1;
+    if (set_smem(k_update_jvp<F, RN, D>, smem_update_jvp<F, RN, D>())) return -1;
+    if (set_smem(k_readout_jvp<F, RN, D>, smem_readout_jvp<F, RN, D>())) return -1;
+    m->jvp_attrs_set = true;
+  }
+  DriftBatch db{b->n_mol, b->n_nodes, (long long)b->n_edges, b->mol_ptr, (const long long*)b->edge_ptr,
+                b->atom_id, b->edge_type, b->temp0, b->temp1};
+  const int node_tiles = (b->n_nodes + 8 * RN - 1) / (8 * RN);
+  const int n_dirs = 3 * b->max_atoms;
+  for (int dir0 = 0; dir0 < n_dirs; dir0 += D) {
+    // the primal state is rebuilt in every pass: e is updated in place by the message layers
+    if (launch_embed<F>(m, b, db, t, ws, st)) return -1;
+    {
+      const long long total = (long long)b->n_edges * (F / 4);
+      const int blocks = (int)std::min<long long>((total + 255) / 256, 148 * 16);
+      ProfScope ps(TIB_K_EDGE_INIT, st);
+      k_edge_init<<<blocks > 0 ? blocks : 1, 256, 0, st>>>(b->edge_type, m->edge_emb, ws.e, (long long)b->n_edges, F);
+      LAUNCH_CHECK();
+    }
+    int cur = 0;
+    for (int l = 0; l < m->d.n_layers; ++l) {
+      const tib_model::Layer& L = m->layers[l];
+      MessageJvpP mp{{db, L.phi, L.w, x, ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->d.length_scale, l == 0},
+                     tw.ts[cur], tw.tv[cur], tw.ts[cur ^ 1], tw.tv[cur ^ 1], tw.te, tw.st_s, tw.st_v, tw.st_e, dir0};
+      {
+        ProfScope ps(TIB_K_MESSAGE, st);
+        k_message_jvp<F, RM, D><<<b->n_mol, TIB_THREADS, smem_message_jvp<F, RM, D>(), st>>>(mp);
+        LAUNCH_CHECK();
+      }
+      cur ^= 1;
+      UpdateJvpP up{{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]}, tw.ts[cur], tw.tv[cur], tw.st_s, tw.st_v};
+      ProfScope ps(TIB_K_UPDATE, st);
+      k_update_jvp<F, RN, D><<<node_tiles, TIB_THREADS, smem_update_jvp<F, RN, D>(), st>>>(up);
+      LAUNCH_CHECK();
+    }
+    ReadoutJvpP rp{{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], dir0 == 0 ? out_b : nullptr},
+                   tw.ts[cur], tw.tv[cur], tw.tout, tw.st_s, tw.st_v, tw.st_o};
+    {
+      ProfScope ps(TIB_K_READOUT, st);
+      k_readout_jvp<F, RN, D><<<node_tiles, TIB_THREADS, smem_readout_jvp<F, RN, D>(), st>>>(rp);
+      LAUNCH_CHECK();
+    }
+    k_div_pick<<<(b->n_mol + 255) / 256, 256, 0, st>>>(b->mol_ptr, b->n_mol, tw.tout, tw.st_o, dir0, D, out_div);
+    LAUNCH_CHECK();
+  }
   return 0;
 }
 
@@ -596,6 +695,34 @@ int tib_drift(tib_model* m, const tib_batch* b, const float* x, float t, float* 
   Workspace ws;
   if (prep_ws(m, b, workspace, workspace_bytes, ws)) return -1;
   return drift_dispatch(m, b, x, t, out_b, ws, (cudaStream_t)stream);
+}
+
+size_t tib_div_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges) {
+  (void)n_mol;
+  if (!m) return 0;
+  const int F = m->d.n_features;
+  return Workspace::bytes(F, n_nodes, (long long)n_edges) + TangentWs::bytes(F, jvp_dirs(F), n_nodes, (long long)n_edges);
+}
+
+int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  if (check_batch(m, b)) return -1;
+  if (!x || !out_b || !out_div) return fail("tib_drift_div: null x/out");
+  const int F = m->d.n_features;
+  const size_t need = tib_div_workspace_bytes(m, b->n_mol, b->n_nodes, b->n_edges);
+  if (!workspace || workspace_bytes < need) return fail("divergence workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  Workspace ws;
+  if (prep_ws(m, b, workspace, workspace_bytes, ws)) return -1;
+  TangentWs tw;
+  tw.carve((char*)workspace + Workspace::bytes(F, b->n_nodes, (long long)b->n_edges), F, jvp_dirs(F), b->n_nodes, (long long)b->n_edges);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (F) {
+    case 32: return drift_div_simt<32>(m, b, x, t, out_b, out_div, ws, tw, st);
+    case 64: return drift_div_simt<64>(m, b, x, t, out_b, out_div, ws, tw, st);
+    case 128: return drift_div_simt<128>(m, b, x, t, out_b, out_div, ws, tw, st);
+    case 256: return drift_div_simt<256>(m, b, x, t, out_b, out_div, ws, tw, st);
+  }
+  return fail("unsupported n_features=%d", F);
 }
 
 int tib_step_euler(const float* x, const float* b, const float* score, const float* noise, float dt, float eps,

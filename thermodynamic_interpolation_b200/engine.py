@@ -208,6 +208,7 @@ class DriftEngine:
                                              packed.size, idx), "tib_model_create")
         self.handle = handle
         self._ws: Optional[torch.Tensor] = None
+        self._ws_div: Optional[torch.Tensor] = None
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -255,6 +256,22 @@ class DriftEngine:
             _lib.check(self.lib.tib_drift(self.handle, C.byref(pb.c), x.data_ptr(), float(t), out.data_ptr(),
                                           wp, wn, self._stream()), "tib_drift")
         return out
+
+    def drift_div(self, pb: PreparedBatch, x: torch.Tensor, t: float):
+        """(b [N,3], div [n_mol]): the drift and its exact divergence sum_ac d b[a][c] / d x[a][c] per molecule,
+        unscaled (reference ODEWrapper.compute_divergence, ode_wrapper.py:59-91, before its x 1e-2)."""
+        x = self._state(x, pb)
+        out = torch.empty_like(x)
+        div = torch.empty(pb.n_mol, dtype=torch.float32, device=self.device)
+        need = self.lib.tib_div_workspace_bytes(self.handle, pb.n_mol, pb.n_nodes, pb.n_edges)
+        if self._ws_div is None or self._ws_div.numel() < need + 256:
+            self._ws_div = None
+            self._ws_div = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        wp, wn = self._aligned(self._ws_div)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib.tib_drift_div(self.handle, C.byref(pb.c), x.data_ptr(), float(t), out.data_ptr(),
+                                              div.data_ptr(), wp, wn, self._stream()), "tib_drift_div")
+        return out, div
 
     def _state(self, x, pb):
         if x.device != self.device or x.dtype != torch.float32 or tuple(x.shape) != (pb.n_nodes, 3):

@@ -2,6 +2,8 @@
   * cfg 3: latent multi-T flow, 16 384 molecules with 9..25 atoms, F = 128, fixed-grid Euler
   * cfg 2 with the reference's own solver: dopri5, rtol = atol = 1e-5, 100 saved frames (NFE-based throughput)
   * 10506-shaped batch (25 atoms, F = 256): the fp32 SIMT path (tensor cores are built for F = 128)
+  * cfg 2 with return_dlogp=True: the drift plus its exact divergence (27 forward-mode tangent directions),
+    with the CPU oracle's autograd divergence timed on a 32-conformer sample beside it
 Run on a B200:  python tools/extra_benchmarks.py > gpurun_out/extra.jsonl"""
 import json
 import os
@@ -72,6 +74,32 @@ def main():
     rate, per = euler_rate(model, mb, 5)
     print(json.dumps(dict(workload="10506-shaped: 512 conformers x 25 atoms, F=256 L=5, Euler", math=_lib.MATH_NAMES[0],
                           value=rate, unit="molecule*steps/s", ms_per_step=per * 1e3)), flush=True)
+    del model, mb
+    # ---- cfg 2 with the exact divergence (return_dlogp=True right-hand side)
+    import time
+    from oracle import cpainn_oracle as co   # CPU baseline leg only
+    from tests._util import oracle_hp_sd, oracle_temps
+    torch.manual_seed(0)
+    model = perturb_(Ambient(n_features=128, score_layers=5, temp_length=100), 1).eval().to(DEV)
+    mb = synthetic_ambient_batch(4096, 9, seed=100).to(DEV)
+    eng = model.engine()
+    pb = eng.prepare(mb)
+    eng.drift_div(pb, mb.x0.contiguous(), 0.3)
+    (b, div), sec = timed(lambda: eng.drift_div(pb, mb.x0.contiguous(), 0.3), reps=2)
+    small = synthetic_ambient_batch(32, 9, seed=100)
+    hp, sd = oracle_hp_sd(model)
+    torch.set_num_threads(len(os.sched_getaffinity(0)))
+    t0 = time.perf_counter()
+    dref = co.divergence(sd, hp, small.x0, 0.3, small.atoms, small.edge_index, small.edge_type, small.ptr.tolist(),
+                         **oracle_temps(small, hp))
+    cpu_sec = time.perf_counter() - t0
+    err = float((div[:32].cpu() - dref).abs().max() / dref.abs().max())
+    print(json.dumps(dict(workload="cfg 2 right-hand side with return_dlogp=True: drift + exact divergence, 4096 x 9 atoms, F=128 L=5",
+                          math="fp32 dual-number kernels, 3 directions per pass", seconds_per_eval=sec,
+                          value=4096 / sec, unit="molecule*(drift+divergence) evals/s",
+                          cpu_oracle=dict(value=32 / cpu_sec, seconds=cpu_sec, sample="32 conformers, autograd, "
+                                          f"{torch.get_num_threads()} threads"),
+                          max_rel_diff_vs_oracle_on_sample=err)), flush=True)
 
 
 if __name__ == "__main__":
