@@ -169,3 +169,25 @@ def test_divergence_is_invariant_under_rigid_motion_at_cfg2_shape():
     assert torch.isfinite(d0).all() and float(d0.abs().max()) > 0
     _close(d1.cpu().numpy(), d0.cpu().numpy(), rtol=2e-3, atol_rel=2e-4, what="divergence under rotation+translation")
     _close(b1.cpu().numpy(), (b0 @ R.T).cpu().numpy(), rtol=1e-3, atol_rel=1e-4, what="drift equivariance")
+
+
+def test_sampler_driver_writes_dlogps_file(tmp_path):
+    """sample() with config.return_dlogp (mdqm9/sample_ambient.py:76-114): dlogps_<name>.npy holds the last-frame
+    dlogp of every molecule, next to the samples the analysis scripts read (results_00031.py:173-201)."""
+    import argparse
+    from thermodynamic_interpolation_b200.ambient.integrators import MoleculeIntegrator
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    from thermodynamic_interpolation_b200.sample_ambient import sample
+    torch.manual_seed(3)
+    model = perturb_(cPaiNN(n_features=32, score_layers=2, temp_length=100), 4).eval()
+    loader = [synthetic_ambient_batch(4, 9, seed=s) for s in (1, 2)]
+    cfg = argparse.Namespace(seed=0, data_save_path=str(tmp_path), data_save_name="d", rtol=1e-4, atol=1e-4, n_steps=4,
+                             return_dlogp=1)
+    out = sample(cfg, model, loader, method="euler", verbose=False)
+    dl = np.load(tmp_path / "dlogps_d.npy")
+    assert dl.shape == (8,) and np.isfinite(dl).all() and np.abs(dl).max() > 0
+    assert np.load(tmp_path / "samples_d.npy").shape == (8, 4, 9, 3)
+    _, ref, _, _ = MoleculeIntegrator(model, method="euler", n_step=4, return_dlogp=True).rollout(
+        synthetic_ambient_batch(4, 9, seed=2).to(DEV))
+    np.testing.assert_allclose(dl[4:], ref[-1].cpu().numpy(), rtol=1e-6)

@@ -189,3 +189,42 @@ def test_tc_cfg3_size_latent_mixed_batch():
     assert err < 1e-5                                # different tiles -> different summation partners, same values
     xts, dlogp, bvec = MoleculeIntegrator(model, method="euler", n_step=3, save_frames=False).rollout(sub)
     assert xts.shape == sub.x0.shape and torch.isfinite(xts).all()
+
+
+def test_tc_range_of_node_features():
+    """Split-f16 operands overflow at 65504; raw state enters the GEMMs scaled by 2^-4 (tc_common.cuh), so node
+    features of ~1e5 (reached with random weights, test_tc_cfg3_size...) are fine, and beyond ~1e6 the readout
+    flags the non-finite result instead of returning NaN silently."""
+    from thermodynamic_interpolation_b200 import _lib
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    torch.manual_seed(61)
+    model = perturb_(cPaiNN(n_features=128, score_layers=2, temp_length=100), 62).eval()
+    mb = synthetic_ambient_batch(40, 9, seed=63).to(DEV)
+
+    def run(gain):
+        sd = {k: v.clone() for k, v in model.state_dict().items()}
+        sd["net.8.layers.3.mlp.mlp.6.bias"][256:] += gain       # last update: s += q^2 * a + c, rows [2F, 3F) are c
+        m2 = cPaiNN(n_features=128, score_layers=2, temp_length=100)
+        m2.load_state_dict(sd)
+        m2 = m2.eval().to(DEV)
+        eng = m2.engine()
+        pb = eng.prepare(mb)
+        tc = eng.drift(pb, mb.x0, 0.5).clone()
+        try:
+            eng.status()
+            ok = True
+        except RuntimeError as e:
+            ok = False
+            assert "split-f16 range" in str(e)
+        m2.set_math(_lib.MATH_FP32_SIMT)
+        ref = m2.engine().drift(pb, mb.x0, 0.5)
+        return tc, ref, ok
+
+    tc, ref, ok = run(3.0e5)            # |s| ~ 3e5 > 65504: representable thanks to the 2^-4 scale
+    assert ok and torch.isfinite(tc).all()
+    err = float((tc - ref).abs().max() / ref.abs().max())
+    print(f"[tc] |s| ~ 3e5: tensor-core vs fp32 path {err:.3e}")
+    assert err < 2e-5
+    tc, ref, ok = run(5.0e6)            # beyond the range: flagged, and the fp32 path still answers
+    assert not ok and torch.isfinite(ref).all()

@@ -272,6 +272,14 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   hi = *reinterpret_cast<const uint32_t*>(&h);
   lo = *reinterpret_cast<const uint32_t*>(&l);
 }
+// Raw state (s, v, e) enters the GEMMs scaled by 2^-4 and the accumulators are scaled back in the epilogue (both
+// exact): a split-f16 operand overflows at |x| >= 65504, which the node features of a random-weight network reach
+// (|s| ~ 1e5 after q^2-scaled updates); with the scale the bound is 1.05e6 and values of O(1) still keep ~21 bits
+// (the f16 subnormal quantum 2^-24 becomes 2^-20 in true units).  Hidden activations (after LayerNorm + SiLU) and
+// positional encodings are O(1) and enter unscaled.
+constexpr float kStateScale = 0.0625f;
+constexpr float kStateUnscale = 16.0f;
+
 // z * sigmoid(z) with the two MUFU approximations (ex2, rcp): ~2 ulp
 __device__ __forceinline__ float silu_fast(float z) {
   float e, r;

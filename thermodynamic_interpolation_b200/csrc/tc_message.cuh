@@ -92,8 +92,8 @@ enum { NB_ALL = 1, NB_CHAIN_W = 2, NB_CHAIN_PHI = 3 };
 // version of this kernel was ~220 KB of SASS and ran instruction-fetch bound (16 warps streaming
 // through code far larger than the 32 KB instruction cache).
 __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, const float* b, const float* g, const float* be,
-                                             unsigned char* op, float* stat_f) {
-  // Accumulator row `row` (TMEM lane), columns [32*grp, +32): + bias -> LayerNorm over all 128 columns
+                                             unsigned char* op, float* stat_f, float ascale) {
+  // Accumulator row `row` (TMEM lane), columns [32*grp, +32): * ascale + bias -> LayerNorm over all 128 columns
   // (sum and sum of squares exchanged between the four threads of a row) -> SiLU -> operand image.
   float2* stat = reinterpret_cast<float2*>(stat_f);
   float v[32];
@@ -103,7 +103,8 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
 #pragma unroll
   for (int c = 0; c < 8; ++c) {
     const float4 bb = bp[c];
-    v[4 * c + 0] += bb.x; v[4 * c + 1] += bb.y; v[4 * c + 2] += bb.z; v[4 * c + 3] += bb.w;
+    v[4 * c + 0] = fmaf(v[4 * c + 0], ascale, bb.x); v[4 * c + 1] = fmaf(v[4 * c + 1], ascale, bb.y);
+    v[4 * c + 2] = fmaf(v[4 * c + 2], ascale, bb.z); v[4 * c + 3] = fmaf(v[4 * c + 3], ascale, bb.w);
     sum += (v[4 * c + 0] + v[4 * c + 1]) + (v[4 * c + 2] + v[4 * c + 3]);
     ss = fmaf(v[4 * c + 0], v[4 * c + 0], fmaf(v[4 * c + 1], v[4 * c + 1], fmaf(v[4 * c + 2], v[4 * c + 2], fmaf(v[4 * c + 3], v[4 * c + 3], ss))));
   }
@@ -132,7 +133,7 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
 
 // rows [32*wq, +32) x column groups [4*grp, +4) of an operand image from row-major fp32 global rows
 // `base + row_index(r) * 128`, where row_index(r) = ROWA[r].src (gather 1), the edge type (gather 2: rows of
-// the edge-type embedding, first layer) or row0 + r (gather 0).
+// the edge-type embedding, first layer) or row0 + r (gather 0).  These are raw state rows: scaled by kStateScale.
 __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int lane, int rows, const float* base,
                                         const RowA* rowa, int gather, int row0) {
 #pragma unroll
@@ -144,7 +145,8 @@ __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int 
       const size_t ri = gather == 1 ? (size_t)rowa[r].src : gather == 2 ? (size_t)((rowa[r].slot_last >> 16) & 0xFF) : (size_t)(row0 + r);
       const float* src = base + ri * kF + g * 8;
       const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      v[0] = a.x * kStateScale; v[1] = a.y * kStateScale; v[2] = a.z * kStateScale; v[3] = a.w * kStateScale;
+      v[4] = b.x * kStateScale; v[5] = b.y * kStateScale; v[6] = b.z * kStateScale; v[7] = b.w * kStateScale;
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = 0.0f;
@@ -361,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         TIB_PHASE(1);   // E1 + E2
         // E3: w hidden 1 -> X
         mbar_wait_timed(&bars[B_ACC0], pacc0, err, w_acc, diag); pacc0 ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr, grp, row, PRM + kPrmW, PRM + kPrmW + kF, PRM + kPrmW + 2 * kF, X, STAT);
+        hidden_epilogue(lane_taddr, grp, row, PRM + kPrmW, PRM + kPrmW + kF, PRM + kPrmW + 2 * kF, X, STAT, 1.0f);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         // E4: e rows -> Y (after the s[src] half has been consumed)
         mbar_wait_timed(&bars[B_YFREE], pyf, err, w_acc, diag); pyf ^= 1;
@@ -371,16 +373,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         TIB_PHASE(2);   // E3 + E4
         // E5: w hidden 2 -> X (final: B operand of the output layer)
         mbar_wait_timed(&bars[B_ACC0], pacc0, err, w_acc, diag); pacc0 ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr, grp, row, PRM + kPrmW + 3 * kF, PRM + kPrmW + 4 * kF, PRM + kPrmW + 5 * kF, X, STAT + 1024);
+        hidden_epilogue(lane_taddr, grp, row, PRM + kPrmW + 3 * kF, PRM + kPrmW + 4 * kF, PRM + kPrmW + 5 * kF, X, STAT + 1024, 1.0f);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         // E6: phi hidden 1 -> Y
         mbar_wait_timed(&bars[B_ACC1], pacc1, err, w_acc, diag); pacc1 ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi, PRM + kPrmPhi + kF, PRM + kPrmPhi + 2 * kF, Y, STAT);
+        hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi, PRM + kPrmPhi + kF, PRM + kPrmPhi + 2 * kF, Y, STAT, kStateUnscale);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(3);   // E5 + E6
         // E7: phi hidden 2 -> Y (final)
         mbar_wait_timed(&bars[B_ACC1], pacc1, err, w_acc, diag); pacc1 ^= 1; tc_fence_after();
-        hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi + 3 * kF, PRM + kPrmPhi + 4 * kF, PRM + kPrmPhi + 5 * kF, Y, STAT + 1024);
+        hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi + 3 * kF, PRM + kPrmPhi + 4 * kF, PRM + kPrmPhi + 5 * kF, Y, STAT + 1024, 1.0f);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
         TIB_PHASE(4);   // E7
       }

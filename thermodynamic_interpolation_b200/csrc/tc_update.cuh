@@ -53,6 +53,7 @@ struct UpdSmem {
 enum { U_FULL = 0, U_EMPTY = U_FULL + kStages, U_OPS = U_EMPTY + kStages, U_ACC, U_COUNT };
 
 // rows [32*wq, +32) x column groups [4*grp, +4) of an operand image from fp32 global rows base + r*stride
+// (raw state: scaled by kStateScale, see tc_common.cuh)
 __device__ __noinline__ void upd_build(unsigned char* op, int wq, int grp, int lane, int rows, const float* base, size_t stride) {
 #pragma unroll
   for (int oct = 0; oct < 4; ++oct) {
@@ -62,7 +63,8 @@ __device__ __noinline__ void upd_build(unsigned char* op, int wq, int grp, int l
     if (r < rows) {
       const float* src = base + (size_t)r * stride + g * 8;
       const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+      v[0] = a.x * kStateScale; v[1] = a.y * kStateScale; v[2] = a.z * kStateScale; v[3] = a.w * kStateScale;
+      v[4] = b.x * kStateScale; v[5] = b.y * kStateScale; v[6] = b.z * kStateScale; v[7] = b.w * kStateScale;
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) v[i] = 0.0f;
@@ -74,7 +76,7 @@ __device__ __noinline__ void upd_build(unsigned char* op, int wq, int grp, int l
 // accumulator row, columns [32*grp, +32): + bias -> LayerNorm over all 128 columns (4-way statistics
 // exchange) -> SiLU -> operand image
 __device__ __noinline__ void upd_hidden(uint32_t taddr, int grp, int row, const float* b, const float* g, const float* be,
-                                        unsigned char* op, float2* stat) {
+                                        unsigned char* op, float2* stat, float ascale) {
   const uint32_t t0 = taddr + 32 * grp;
   const float* bq = b + 32 * grp;
   float sum = 0.0f, ss = 0.0f;
@@ -87,7 +89,7 @@ __device__ __noinline__ void upd_hidden(uint32_t taddr, int grp, int row, const 
     const float bb[16] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w, b2.x, b2.y, b2.z, b2.w, b3.x, b3.y, b3.z, b3.w};
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
-      const float x0 = t[i] + bb[i], x1 = u[i] + bb[8 + i];
+      const float x0 = fmaf(t[i], ascale, bb[i]), x1 = fmaf(u[i], ascale, bb[8 + i]);
       sum += x0 + x1;
       ss = fmaf(x0, x0, fmaf(x1, x1, ss));
     }
@@ -112,7 +114,7 @@ __device__ __noinline__ void upd_hidden(uint32_t taddr, int grp, int row, const 
     const float ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
     float y[8];
 #pragma unroll
-    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(fmaf(t[i] + bb[i], rstd, nmr), gg[i], ee[i]));
+    for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(fmaf(fmaf(t[i], ascale, bb[i]), rstd, nmr), gg[i], ee[i]));
     store_group(op, kOperandHalfBytes, row, 4 * grp + kg, y);
   }
   named_bar_sync(NB_ALL, kEpiThreads);     // `stat` may be rewritten by the next call
@@ -229,7 +231,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
         if (xyz < 2) ops_done();                                      // next plane's operand ready, T0 drained
         TIB_UPH(2);
       }
-      // step 4: q -> X (X is free: the MMAs of plane 2 have completed)
+      // step 4: q -> X (X is free: the MMAs of plane 2 have completed).  q2 holds (kStateScale |V v|)^2, so its
+      // root is q already scaled like every other raw-state operand.
 #pragma unroll
       for (int kg = 0; kg < 4; ++kg) {
         float q[8];
@@ -242,13 +245,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
       // step 5
       acc_ready();
       TIB_UPH(5);
-      upd_hidden(T0, grp, row, PRM, PRM + kF, PRM + 2 * kF, X, STAT);
+      upd_hidden(T0, grp, row, PRM, PRM + kF, PRM + 2 * kF, X, STAT, kStateUnscale);
       ops_done();
       TIB_UPH(6);
       // step 6
       acc_ready();
       TIB_UPH(7);
-      upd_hidden(T0, grp, row, PRM + 3 * kF, PRM + 4 * kF, PRM + 5 * kF, X, STAT);
+      upd_hidden(T0, grp, row, PRM + 3 * kF, PRM + 4 * kF, PRM + 5 * kF, X, STAT, 1.0f);
       ops_done();
       TIB_UPH(8);
       // step 7: v += (U v) * g                                                        (cpainn.py:370,374)
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
         float g[32];
         tmem_ld32(T0 + 32 * grp, g);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) g[i] += PRM[6 * kF + 32 * grp + i];
+        for (int i = 0; i < 32; ++i) g[i] = (g[i] + PRM[6 * kF + 32 * grp + i]) * kStateUnscale;   // T1..T3 hold kStateScale * U v
         float4* const stage = reinterpret_cast<float4*>(Y);
 #pragma unroll 1
         for (int xyz = 0; xyz < 3; ++xyz) {
@@ -315,10 +318,11 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
           float4 t = *sp;
           const float* pa = PRM + 7 * kF + 32 * grp + 4 * j;
           const float* pc = PRM + 8 * kF + 32 * grp + 4 * j;
-          t.x += fmaf(q2[4 * j + 0], a[4 * j + 0] + pa[0], c[4 * j + 0] + pc[0]);
-          t.y += fmaf(q2[4 * j + 1], a[4 * j + 1] + pa[1], c[4 * j + 1] + pc[1]);
-          t.z += fmaf(q2[4 * j + 2], a[4 * j + 2] + pa[2], c[4 * j + 2] + pc[2]);
-          t.w += fmaf(q2[4 * j + 3], a[4 * j + 3] + pa[3], c[4 * j + 3] + pc[3]);
+          constexpr float kU2 = kStateUnscale * kStateUnscale;   // q2 is the square of the scaled norm
+          t.x += fmaf(q2[4 * j + 0] * kU2, a[4 * j + 0] + pa[0], c[4 * j + 0] + pc[0]);
+          t.y += fmaf(q2[4 * j + 1] * kU2, a[4 * j + 1] + pa[1], c[4 * j + 1] + pc[1]);
+          t.z += fmaf(q2[4 * j + 2] * kU2, a[4 * j + 2] + pa[2], c[4 * j + 2] + pc[2]);
+          t.w += fmaf(q2[4 * j + 3] * kU2, a[4 * j + 3] + pa[3], c[4 * j + 3] + pc[3]);
           *sp = t;
         }
         tc_fence_before();

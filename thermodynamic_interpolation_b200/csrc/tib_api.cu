@@ -16,6 +16,7 @@
 #include "tc_message.cuh"
 #include "tc_selftest.cuh"
 #include "tc_update.cuh"
+#include "tc_readout.cuh"
 
 namespace {
 
@@ -94,13 +95,14 @@ struct tib_model {
   struct Layer { tib::MlpW phi, w, upd; const float *Ut, *Vt; const unsigned char* tc_msg = nullptr; const unsigned char* tc_upd = nullptr; };
   std::vector<Layer> layers;
   tib::MlpW readout{};
+  const unsigned char* tc_ro = nullptr;   // readout W1 | W2 as tensor-core chunks (F = 128)
   const float* Vout = nullptr;
   bool attrs_set = false;
   // tensor-core path (F = 128): per-layer streamed weight chunks in split-f16 operand images
   unsigned char* tc_blob = nullptr;
   bool tc_attrs_set = false;
   bool jvp_attrs_set = false;
-  int* dev_err = nullptr;     // device error word written by the bounded mbarrier waits
+  int* dev_err = nullptr;     // device error words: [0] bounded mbarrier waits, [1] non-finite tensor-core readout
   int n_sms = 148;
   long long* dev_dbg = nullptr;   // optional stall counters of the last tensor-core message launch
 };
@@ -275,6 +277,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     if (!m->tc_attrs_set) {
       if (set_smem(tc::k_message_tc, tc::MsgSmem::TOTAL)) return -1;
       if (set_smem(tc::k_update_tc, tc::UpdSmem::TOTAL)) return -1;
+      if (set_smem(tc::k_readout_tc, tc::RoSmem::TOTAL)) return -1;
       m->tc_attrs_set = true;
     }
     nodes_per_tile = std::min(tc::kTileNodes, 128 / (b->max_atoms - 1));
@@ -332,8 +335,21 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       LAUNCH_CHECK();
     }
   }
-  ReadoutP rp{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], out};
-  { ProfScope ps(TIB_K_READOUT, st); k_readout<F, RN><<<node_tiles, TIB_THREADS, smem_readout<F, RN>(), st>>>(rp); }
+  if (use_tc) {
+    tc::TcRoP rp{};
+    rp.n_nodes = b->n_nodes; rp.n_tiles = (b->n_nodes + 127) / 128;
+    rp.s = ws.s[cur]; rp.v = ws.v[cur]; rp.out = out; rp.wblob = m->tc_ro;
+    rp.b1 = m->readout.b1; rp.g1 = m->readout.g1; rp.be1 = m->readout.be1;
+    rp.b2 = m->readout.b2; rp.g2 = m->readout.g2; rp.be2 = m->readout.be2;
+    rp.w3 = m->readout.W3t + F; rp.b3 = m->readout.b3 + 1; rp.vout = m->Vout;
+    rp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3; rp.err = m->dev_err;
+    ProfScope ps(TIB_K_READOUT, st);
+    tc::k_readout_tc<<<std::min(rp.n_tiles, m->n_sms), tc::kThreads, tc::RoSmem::TOTAL, st>>>(rp);
+  } else {
+    ReadoutP rp{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], out};
+    ProfScope ps(TIB_K_READOUT, st);
+    k_readout<F, RN><<<node_tiles, TIB_THREADS, smem_readout<F, RN>(), st>>>(rp);
+  }
   LAUNCH_CHECK();
   return 0;
 }
@@ -565,6 +581,7 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
     L.Vt = push_T(src, F, F); src += (size_t)F * F;
     src = repack_mlp(src, {2 * F, F, 3 * F}, stage, base, &L.upd, true);
   }
+  const float* ro_src = src;
   src = repack_mlp(src, {F, F, 2}, stage, base, &m->readout, false);
   m->Vout = push(src, F); src += F;
   if ((size_t)(src - w) != n_floats) { delete m; return fail("internal: weight walk consumed %zu of %zu", (size_t)(src - w), n_floats); }
@@ -583,8 +600,8 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
   {
     cudaDeviceProp prop;
     if (cudaGetDeviceProperties(&prop, device) == cudaSuccess) m->n_sms = prop.multiProcessorCount;
-    e = cudaMalloc(&m->dev_err, sizeof(int));
-    if (e == cudaSuccess) e = cudaMemset(m->dev_err, 0, sizeof(int));
+    e = cudaMalloc(&m->dev_err, 2 * sizeof(int));
+    if (e == cudaSuccess) e = cudaMemset(m->dev_err, 0, 2 * sizeof(int));
     if (e != cudaSuccess) { tib_model_destroy(m); return fail("cudaMalloc(error word): %s", cudaGetErrorString(e)); }
   }
   if (F == 128) {
@@ -592,7 +609,8 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
     const size_t per_msg = (size_t)tib::tc::kChunksPerLayer * tib::tc::kChunkBytes;
     const size_t per_upd = (size_t)32 * tib::tc::kChunkBytes;      // 8 matrices (tc_update.cuh)
     const size_t per_layer = per_msg + per_upd;
-    std::vector<uint16_t> blob(per_layer / 2 * d->n_layers);
+    const size_t per_ro = (size_t)tib::tc::kRoChunks * tib::tc::kChunkBytes;   // readout W1 | W2 (tc_readout.cuh)
+    std::vector<uint16_t> blob(per_layer / 2 * d->n_layers + per_ro / 2);
     for (int l = 0; l < d->n_layers; ++l) {
       uint16_t* out16 = blob.data() + per_layer / 2 * l;
       const float* pW1 = phi_src[l];                                   // [F][2F]
@@ -629,10 +647,18 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
       mat(uW3, F, 0, 0);
       mat(U, F, 0, 0);
     }
+    {
+      uint16_t* out16 = blob.data() + per_layer / 2 * d->n_layers;
+      const float* rW1 = ro_src;                                       // [F][F]
+      const float* rW2 = rW1 + (size_t)F * F + 3 * F;
+      for (const float* W : {rW1, rW2})
+        for (int kb = 0; kb < 4; ++kb) { pack_tc_chunk(out16, W, F, 0, 32 * kb); out16 += tib::tc::kChunkBytes / 2; }
+    }
     e = cudaMalloc(&m->tc_blob, blob.size() * 2);
     if (e == cudaSuccess) e = cudaMemcpy(m->tc_blob, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice);
     if (e != cudaSuccess) { tib_model_destroy(m); return fail("tensor-core weight upload: %s", cudaGetErrorString(e)); }
     for (int l = 0; l < d->n_layers; ++l) { m->layers[l].tc_msg = m->tc_blob + per_layer * l; m->layers[l].tc_upd = m->tc_blob + per_layer * l + per_msg; }
+    m->tc_ro = m->tc_blob + per_layer * d->n_layers;
   }
   *out = m;
   return 0;
@@ -650,11 +676,14 @@ void tib_model_destroy(tib_model* m) {
 int tib_model_status(tib_model* m, void* stream) {
   if (!m) return fail("null model");
   CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
-  int h = 0;
-  CUDA_TRY(cudaMemcpy(&h, m->dev_err, sizeof(int), cudaMemcpyDeviceToHost));
-  if (h != 0) {
-    CUDA_TRY(cudaMemset(m->dev_err, 0, sizeof(int)));
-    return fail("device pipeline error %d: an mbarrier wait timed out inside a tensor-core kernel (results are invalid)", h);
+  int h[2] = {0, 0};
+  CUDA_TRY(cudaMemcpy(h, m->dev_err, 2 * sizeof(int), cudaMemcpyDeviceToHost));
+  if (h[0] != 0 || h[1] != 0) {
+    CUDA_TRY(cudaMemset(m->dev_err, 0, 2 * sizeof(int)));
+    if (h[0] != 0)
+      return fail("device pipeline error %d: an mbarrier wait timed out inside a tensor-core kernel (results are invalid)", h[0]);
+    return fail("non-finite drift from the tensor-core path: node features beyond the split-f16 range (|x| >= 1.0e6) or "
+                "non-finite inputs; TIB_MATH_FP32_SIMT has the full fp32 range");
   }
   return 0;
 }
