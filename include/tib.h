@@ -134,6 +134,16 @@ size_t tib_div_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_node
 int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div,
                   void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- post-processing: internal coordinates of sampled conformers --------------------------------
+ * Replaces  z_matrix.construct_z_matrix_batch(X_batch, ref_atoms, placing_order)
+ * (mdqm9/analysis/utils/z_matrix.py:56-102; distances / angles / atan2 torsions of mol_geometry.py:25-81), the
+ * step that turns samples into the torsion features of the reference's analysis (results_00031.py:15-18,140-149).
+ *   x [n_conf][n_atoms][3] fp32 (device), order [n_atoms] int32 = placing_order, ref [n_atoms][3] int32 = the
+ *   reference triplets (distance, angle, torsion partner; rows 0..2 are only partly used, as in the reference),
+ *   z [n_conf][n_atoms-1][3] fp32 = (distance, angle, torsion), zero where the reference leaves zeros. */
+int tib_zmatrix(const float* x, int64_t n_conf, int32_t n_atoms, const int32_t* order, const int32_t* ref, float* z,
+                void* stream);
+
 /* ---- K1: fused integrator state updates ---------------------------------------------------
  * One explicit Euler / Euler-Maruyama update over a flat state of n floats:
  *     x_out = x + dt*b                       [+ dt*eps*score] [+ sqrt(2*eps*dt)*noise]

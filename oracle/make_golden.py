@@ -181,6 +181,29 @@ def stats_case(name="stats"):
     print(name, "ess", out["ess"], "dF", out["dF"])
 
 
+def zmatrix_case(name="zmatrix"):
+    """construct_z_matrix_batch of the unmodified reference on random conformers with a random valid
+    reference-triplet table (every atom refers to three distinct earlier atoms where they exist)."""
+    import importlib
+    if ref_loader.REFERENCE_ROOT not in sys.path:
+        sys.path.append(ref_loader.REFERENCE_ROOT)
+    zm = importlib.import_module("mdqm9.analysis.utils.z_matrix")
+    rng = np.random.default_rng(21)
+    out = {}
+    for tag, n_atoms, n_conf in (("a9", 9, 64), ("a25", 25, 16)):
+        X = rng.normal(0.0, 1.0, (n_conf, n_atoms, 3)).astype(np.float32)
+        order = rng.permutation(n_atoms).tolist()
+        ref = []
+        for a in range(n_atoms):
+            placed = [order[i] for i in rng.permutation(a)]            # earlier atoms, random order
+            filler = [o for o in order if o != order[a] and o not in placed]   # unused slots of rows 0..2
+            ref.append([int(v) for v in (placed + filler)[:3]])
+        z = zm.construct_z_matrix_batch(torch.tensor(X), ref, order).numpy()
+        out[f"{tag}::X"], out[f"{tag}::order"], out[f"{tag}::ref"], out[f"{tag}::z"] = X, np.array(order), np.array(ref), z
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, {k: v.shape for k, v in out.items()})
+
+
 def main():
     os.makedirs(GOLDEN, exist_ok=True)
     torch.set_num_threads(8)
@@ -194,6 +217,7 @@ def main():
     latent_case(ns, "latent_single_f32", F=32, L=2, n_list=[9, 9, 9], seed=4, temperatures=[800])
     adw_case()
     stats_case()
+    zmatrix_case()
 
 
 if __name__ == "__main__":

@@ -13,6 +13,7 @@
 #include "simt_tangent.cuh"
 #include "steps.cuh"
 #include "adw.cuh"
+#include "postproc.cuh"
 #include "tc_message.cuh"
 #include "tc_selftest.cuh"
 #include "tc_update.cuh"
@@ -752,6 +753,16 @@ int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, flo
     case 256: return drift_div_simt<256>(m, b, x, t, out_b, out_div, ws, tw, st);
   }
   return fail("unsupported n_features=%d", F);
+}
+
+int tib_zmatrix(const float* x, int64_t n_conf, int32_t n_atoms, const int32_t* order, const int32_t* ref, float* z, void* stream) {
+  if (!x || !order || !ref || !z) return fail("tib_zmatrix: null argument");
+  if (n_conf < 0 || n_atoms < 2) return fail("tib_zmatrix: need n_conf >= 0 and n_atoms >= 2 (got %lld, %d)", (long long)n_conf, n_atoms);
+  if (n_conf == 0) return 0;
+  const long long total = (long long)n_conf * (n_atoms - 1);
+  tib::k_zmatrix<<<grid_for((size_t)total), 256, 0, (cudaStream_t)stream>>>(x, (long long)n_conf, n_atoms, order, ref, z);
+  LAUNCH_CHECK();
+  return 0;
 }
 
 int tib_step_euler(const float* x, const float* b, const float* score, const float* noise, float dt, float eps,
