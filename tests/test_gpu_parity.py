@@ -364,3 +364,23 @@ def test_sampler_driver_writes_reference_file_format(tmp_path):
     assert np.load(tmp_path / "latent_dlogps_t.npy").shape == (10,)
     x0 = torch.cat([b.x0.cpu() for b in loader]).reshape(10, 9, 3).numpy()
     np.testing.assert_array_equal(s[:, 0], x0)       # frame 0 is the start conformer, molecule by molecule
+
+
+def test_latent_sampler_driver_writes_reference_file_format(tmp_path):
+    """sample() of mdqm9/sample_latent.py:18-100: `samples_<name>_forward.npy` [n_mol, T, n, 3], frame 0 = x0 (the
+    ambient dataset reads frames [:, 0] and [:, -1], mdqm9_ambient.py:173-199)."""
+    import argparse
+    from thermodynamic_interpolation_b200.batch import synthetic_latent_batch
+    from thermodynamic_interpolation_b200.latent.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.sample_latent import sample
+    torch.manual_seed(5)
+    model = perturb_(cPaiNN(n_features=32, score_layers=2, temp_length=75), 6).eval()
+    loader = [synthetic_latent_batch(4, 9, T=800, seed=s) for s in (1, 2, 3)]
+    cfg = argparse.Namespace(seed=0, data_save_path=str(tmp_path), data_save_name="lat", rtol=1e-4, atol=1e-4, n_steps=5,
+                             return_dlogp=0)
+    out = sample(cfg, model, loader, method="euler", verbose=False, save_every=2)
+    s = np.load(tmp_path / "samples_lat_forward.npy")
+    assert s.shape == (12, 5, 9, 3) and np.array_equal(s, out["samples"]) and np.isfinite(s).all()
+    x0 = torch.cat([b.x0.cpu() for b in loader]).reshape(12, 9, 3).numpy()
+    np.testing.assert_array_equal(s[:, 0], x0)
+    assert not (tmp_path / "dlogps_lat_forward.npy").exists()

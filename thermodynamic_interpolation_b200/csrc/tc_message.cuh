@@ -76,17 +76,18 @@ struct MsgSmem {
   static constexpr uint32_t Y = X + kOperandBytes;
   static constexpr uint32_t RING = Y + kOperandBytes;
   static constexpr uint32_t PRM = RING + kStages * kChunkBytes;                // layer parameters (fp32), see kPrm*
-  static constexpr uint32_t ROWA = PRM + kPrmFloats * 4;                       // RowA[128]
-  static constexpr uint32_t ROWB = ROWA + 128 * 16;                            // RowB[128]
-  static constexpr uint32_t STAT = ROWB + 128 * 16;                            // 2 x float2 [4 groups][128 rows] (alternating)
-  static constexpr uint32_t SLOTROW = STAT + 2 * 4 * 128 * 8;              // int[kTileNodes + 1] first row of each slot
-  static constexpr uint32_t BARS = SLOTROW + 128;
+  // tile tables, two sets: the next tile's set is filled while this tile waits for its last hidden-layer MMAs
+  static constexpr uint32_t ROWA = PRM + kPrmFloats * 4;                       // 2 x RowA[128]
+  static constexpr uint32_t ROWB = ROWA + 2 * 128 * 16;                        // 2 x RowB[128]
+  static constexpr uint32_t STAT = ROWB + 2 * 128 * 16;                        // 2 x float2 [4 groups][128 rows] (alternating)
+  static constexpr uint32_t SLOTROW = STAT + 2 * 4 * 128 * 8;              // 2 x int[32]: first row of each slot (kTileNodes + 1 used)
+  static constexpr uint32_t BARS = SLOTROW + 2 * 128;
   static constexpr uint32_t TOTAL = BARS + 256;
 };
 // barrier indices
 enum { B_FULL = 0, B_EMPTY = B_FULL + kStages /* one per PAIR of stages */, B_XFULL = B_EMPTY + kStages / 2, B_YFULL, B_YFREE, B_ACC0, B_ACC1,
        B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_COUNT };
-enum { NB_ALL = 1, NB_CHAIN_W = 2, NB_CHAIN_PHI = 3 };
+enum { NB_ALL = 1 };   // named barrier of the 512 epilogue threads
 
 // The hot loops below are deliberately ROLLED (small bodies, TMEM re-read per pass): the straight-line
 // version of this kernel was ~220 KB of SASS and ran instruction-fetch bound (16 warps streaming
@@ -136,21 +137,25 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
 // the edge-type embedding, first layer) or row0 + r (gather 0).  These are raw state rows: scaled by kStateScale.
 __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int lane, int rows, const float* base,
                                         const RowA* rowa, int gather, int row0) {
+  const int g = 4 * grp + (lane >> 3);
+  float4 a[4], b[4];
+  // all eight 16-byte loads are issued before the first conversion (the build is bound by their latency)
 #pragma unroll
   for (int oct = 0; oct < 4; ++oct) {
     const int r = 32 * wq + 8 * oct + (lane & 7);
-    const int g = 4 * grp + (lane >> 3);
-    float v[8];
+    a[oct] = b[oct] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < rows) {
       const size_t ri = gather == 1 ? (size_t)rowa[r].src : gather == 2 ? (size_t)((rowa[r].slot_last >> 16) & 0xFF) : (size_t)(row0 + r);
       const float* src = base + ri * kF + g * 8;
-      const float4 a = __ldg(reinterpret_cast<const float4*>(src)), b = __ldg(reinterpret_cast<const float4*>(src + 4));
-      v[0] = a.x * kStateScale; v[1] = a.y * kStateScale; v[2] = a.z * kStateScale; v[3] = a.w * kStateScale;
-      v[4] = b.x * kStateScale; v[5] = b.y * kStateScale; v[6] = b.z * kStateScale; v[7] = b.w * kStateScale;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+      a[oct] = __ldg(reinterpret_cast<const float4*>(src));
+      b[oct] = __ldg(reinterpret_cast<const float4*>(src + 4));
     }
+  }
+#pragma unroll
+  for (int oct = 0; oct < 4; ++oct) {
+    const int r = 32 * wq + 8 * oct + (lane & 7);
+    const float v[8] = {a[oct].x * kStateScale, a[oct].y * kStateScale, a[oct].z * kStateScale, a[oct].w * kStateScale,
+                        b[oct].x * kStateScale, b[oct].y * kStateScale, b[oct].z * kStateScale, b[oct].w * kStateScale};
     store_group(op, kOperandHalfBytes, r, g, v);
   }
 }
@@ -217,9 +222,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   unsigned char* const Y = smem + MsgSmem::Y;
   unsigned char* const RING = smem + MsgSmem::RING;
   float* const PRM = reinterpret_cast<float*>(smem + MsgSmem::PRM);
-  int* const SLOTROW = reinterpret_cast<int*>(smem + MsgSmem::SLOTROW);
-  RowA* const ROWA = reinterpret_cast<RowA*>(smem + MsgSmem::ROWA);
-  RowB* const ROWB = reinterpret_cast<RowB*>(smem + MsgSmem::ROWB);
+  int* const SLOTROW_b = reinterpret_cast<int*>(smem + MsgSmem::SLOTROW);
+  RowA* const ROWA_b = reinterpret_cast<RowA*>(smem + MsgSmem::ROWA);
+  RowB* const ROWB_b = reinterpret_cast<RowB*>(smem + MsgSmem::ROWB);
   float* const STAT = reinterpret_cast<float*>(smem + MsgSmem::STAT);
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + MsgSmem::BARS);
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + MsgSmem::BARS + 8 * B_COUNT);
@@ -319,25 +324,35 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     long long tlast = clock64();
 #define TIB_PHASE(i) do { if (diag) { const long long _t = clock64(); phc[i] += _t - tlast; tlast = _t; } } while (0)
     const uint32_t lane_taddr = tmem + ((uint32_t)(wq * 32) << 16);
-    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int node_lo = p.tile_node_ptr ? __ldg(p.tile_node_ptr + tile) : tile * p.nodes_per_tile;
-      const int node_hi = p.tile_node_ptr ? __ldg(p.tile_node_ptr + tile + 1) : min(node_lo + p.nodes_per_tile, p.n_nodes);
-      const int row0 = __ldg(p.node_in_ptr + node_lo);
-      const int rows = __ldg(p.node_in_ptr + node_hi) - row0;
-      // ---- tile tables (the previous tile finished with an all-group barrier)
+    // bounds of a tile and its tables (set `par`): RowA / RowB of its edge rows and the first row of every node slot
+    int nx_node_lo = 0, nx_node_hi = 0, nx_row0 = 0, nx_rows = 0;
+    auto load_tables = [&](int tile, int par) {
+      nx_node_lo = p.tile_node_ptr ? __ldg(p.tile_node_ptr + tile) : tile * p.nodes_per_tile;
+      nx_node_hi = p.tile_node_ptr ? __ldg(p.tile_node_ptr + tile + 1) : min(nx_node_lo + p.nodes_per_tile, p.n_nodes);
+      nx_row0 = __ldg(p.node_in_ptr + nx_node_lo);
+      nx_rows = __ldg(p.node_in_ptr + nx_node_hi) - nx_row0;
       if (tid < 128) {
-        uint4 ra = make_uint4(0u, (uint32_t)node_lo, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u);
-        if (tid < rows) {
-          ra = __ldg(p.rowa + row0 + tid);
-          rb = __ldg(p.rowb + row0 + tid);
-          ra.z |= (uint32_t)((int)ra.y - node_lo);           // slot of the destination node inside this tile
+        uint4 ra = make_uint4(0u, (uint32_t)nx_node_lo, 0u, 0u), rb = make_uint4(0u, 0u, 0u, 0u);
+        if (tid < nx_rows) {
+          ra = __ldg(p.rowa + nx_row0 + tid);
+          rb = __ldg(p.rowb + nx_row0 + tid);
+          ra.z |= (uint32_t)((int)ra.y - nx_node_lo);        // slot of the destination node inside this tile
         }
-        reinterpret_cast<uint4*>(ROWA)[tid] = ra;
-        reinterpret_cast<uint4*>(ROWB)[tid] = rb;
+        reinterpret_cast<uint4*>(ROWA_b + par * 128)[tid] = ra;
+        reinterpret_cast<uint4*>(ROWB_b + par * 128)[tid] = rb;
       }
-      if (tid >= 128 && tid <= 128 + kTileNodes && node_lo + (tid - 128) <= node_hi)
-        SLOTROW[tid - 128] = __ldg(p.node_in_ptr + node_lo + (tid - 128)) - row0;
-      named_bar_sync(NB_ALL, kEpiThreads);
+      if (tid >= 128 && tid <= 128 + kTileNodes && nx_node_lo + (tid - 128) <= nx_node_hi)
+        SLOTROW_b[par * 32 + tid - 128] = __ldg(p.node_in_ptr + nx_node_lo + (tid - 128)) - nx_row0;
+    };
+    if ((int)blockIdx.x < p.n_tiles) load_tables(blockIdx.x, 0);
+    named_bar_sync(NB_ALL, kEpiThreads);
+    int par = 0;
+    for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x, par ^= 1) {
+      // this tile's tables were filled during the previous tile (or above); the end-of-tile barrier ordered them
+      const int node_lo = nx_node_lo, node_hi = nx_node_hi, row0 = nx_row0, rows = nx_rows;
+      const RowA* const ROWA = ROWA_b + par * 128;
+      const RowB* const ROWB = ROWB_b + par * 128;
+      const int* const SLOTROW = SLOTROW_b + par * 32;
       TIB_PHASE(0);   // tile tables
 
       // ---- hidden phase: one sequence, every epilogue on all 16 warps (group g = feature columns
@@ -379,7 +394,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         mbar_wait_timed(&bars[B_ACC1], pacc1, err, w_acc, diag); pacc1 ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi, PRM + kPrmPhi + kF, PRM + kPrmPhi + 2 * kF, Y, STAT, kStateUnscale);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
-        TIB_PHASE(3);   // E5 + E6
+        if (tile + (int)gridDim.x < p.n_tiles) load_tables(tile + gridDim.x, par ^ 1);   // under the MMAs of phi layer 2
+        TIB_PHASE(3);   // E5 + E6 (+ the next tile's tables)
         // E7: phi hidden 2 -> Y (final)
         mbar_wait_timed(&bars[B_ACC1], pacc1, err, w_acc, diag); pacc1 ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi + 3 * kF, PRM + kPrmPhi + 4 * kF, PRM + kPrmPhi + 5 * kF, Y, STAT + 1024, 1.0f);
@@ -593,23 +609,6 @@ __global__ void k_edge_tables(const int* __restrict__ mol_ptr, const long long* 
                                 __float_as_uint(dist));
     rowb[e0 + row] = make_uint4(__float_as_uint(__fdiv_rn(rx, den)), __float_as_uint(__fdiv_rn(ry, den)),
                                 __float_as_uint(__fdiv_rn(rz, den)), 0u);
-  }
-}
-
-// e0 = Emb4(edge_type) written in (dst,src) order; edge_type is given in the reference's (src,dst) order
-__global__ void k_edge_init_dst(const unsigned char* __restrict__ edge_type, const float* __restrict__ edge_emb,
-                                const int* __restrict__ mol_ptr, const long long* __restrict__ edge_ptr,
-                                float* __restrict__ e, int F) {
-  const int m = blockIdx.x;
-  const int n = mol_ptr[m + 1] - mol_ptr[m];
-  const long long e0 = edge_ptr[m];
-  const int ne = n * (n - 1), f4n = F / 4;
-  for (int idx = threadIdx.x; idx < ne * f4n; idx += blockDim.x) {
-    const int row = idx / f4n, f4 = idx % f4n;
-    const int jl = row / (n - 1), ip = row % (n - 1), il = ip + (ip >= jl);
-    const int src_major = il * (n - 1) + jl - (jl > il);
-    const float4 val = __ldg(reinterpret_cast<const float4*>(edge_emb + (size_t)edge_type[e0 + src_major] * F) + f4);
-    reinterpret_cast<float4*>(e + (size_t)(e0 + row) * F)[f4] = val;
   }
 }
 

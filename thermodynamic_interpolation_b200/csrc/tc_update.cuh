@@ -55,20 +55,24 @@ enum { U_FULL = 0, U_EMPTY = U_FULL + kStages, U_OPS = U_EMPTY + kStages, U_ACC,
 // rows [32*wq, +32) x column groups [4*grp, +4) of an operand image from fp32 global rows base + r*stride
 // (raw state: scaled by kStateScale, see tc_common.cuh)
 __device__ __noinline__ void upd_build(unsigned char* op, int wq, int grp, int lane, int rows, const float* base, size_t stride) {
+  const int g = 4 * grp + (lane >> 3);
+  float4 a[4], b[4];
+  // all eight 16-byte loads are issued before the first conversion (the build is bound by their latency)
 #pragma unroll
   for (int oct = 0; oct < 4; ++oct) {
     const int r = 32 * wq + 8 * oct + (lane & 7);
-    const int g = 4 * grp + (lane >> 3);
-    float v[8];
+    a[oct] = b[oct] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < rows) {
       const float* src = base + (size_t)r * stride + g * 8;
-      const float4 a = *reinterpret_cast<const float4*>(src), b = *reinterpret_cast<const float4*>(src + 4);
-      v[0] = a.x * kStateScale; v[1] = a.y * kStateScale; v[2] = a.z * kStateScale; v[3] = a.w * kStateScale;
-      v[4] = b.x * kStateScale; v[5] = b.y * kStateScale; v[6] = b.z * kStateScale; v[7] = b.w * kStateScale;
-    } else {
-#pragma unroll
-      for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+      a[oct] = *reinterpret_cast<const float4*>(src);
+      b[oct] = *reinterpret_cast<const float4*>(src + 4);
     }
+  }
+#pragma unroll
+  for (int oct = 0; oct < 4; ++oct) {
+    const int r = 32 * wq + 8 * oct + (lane & 7);
+    const float v[8] = {a[oct].x * kStateScale, a[oct].y * kStateScale, a[oct].z * kStateScale, a[oct].w * kStateScale,
+                        b[oct].x * kStateScale, b[oct].y * kStateScale, b[oct].z * kStateScale, b[oct].w * kStateScale};
     store_group(op, kOperandHalfBytes, r, g, v);
   }
 }
@@ -237,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
       for (int kg = 0; kg < 4; ++kg) {
         float q[8];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) q[i] = __fsqrt_rn(q2[8 * kg + i]);
+        for (int i = 0; i < 8; ++i) q[i] = sqrt_fast(q2[8 * kg + i]);
         store_group(X, kOperandHalfBytes, row, 4 * grp + kg, q);
       }
       ops_done();
