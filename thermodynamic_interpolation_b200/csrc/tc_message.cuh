@@ -87,7 +87,9 @@ struct MsgSmem {
 // barrier indices
 enum { B_FULL = 0, B_EMPTY = B_FULL + kStages /* one per PAIR of stages */, B_XFULL = B_EMPTY + kStages / 2, B_YFULL, B_YFREE, B_ACC0, B_ACC1,
        B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_COUNT };
-enum { NB_ALL = 1 };   // named barrier of the 512 epilogue threads
+// named barriers: all 512 epilogue threads, or the 4 warps (one per column group) that share TMEM lane quarter wq
+enum { NB_ALL = 1, NB_QUARTER = 2 /* + wq */ };
+constexpr int kQuarterThreads = 128;
 
 // The hot loops below are deliberately ROLLED (small bodies, TMEM re-read per pass): the straight-line
 // version of this kernel was ~220 KB of SASS and ran instruction-fetch bound (16 warps streaming
@@ -110,7 +112,7 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
     ss = fmaf(v[4 * c + 0], v[4 * c + 0], fmaf(v[4 * c + 1], v[4 * c + 1], fmaf(v[4 * c + 2], v[4 * c + 2], fmaf(v[4 * c + 3], v[4 * c + 3], ss))));
   }
   stat[grp * 128 + row] = make_float2(sum, ss);
-  named_bar_sync(NB_ALL, kEpiThreads);
+  named_bar_sync(NB_QUARTER + (row >> 5), kQuarterThreads);   // only the four threads of a row exchange statistics
   const float2 s0 = stat[row], s1 = stat[128 + row], s2 = stat[256 + row], s3 = stat[384 + row];
   const float mean = ((s0.x + s1.x) + (s2.x + s3.x)) * (1.0f / 128.0f);
   const float var = fmaxf(((s0.y + s1.y) + (s2.y + s3.y)) * (1.0f / 128.0f) - mean * mean, 0.0f);
@@ -353,6 +355,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       const RowA* const ROWA = ROWA_b + par * 128;
       const RowB* const ROWB = ROWB_b + par * 128;
       const int* const SLOTROW = SLOTROW_b + par * 32;
+      // The e rows of this tile (one contiguous block, 4 lines per row) are read ~20 k cycles from now (E4) and again in
+      // the e += de split: start them towards L2 now, so that those loads do not pay the HBM latency.
+      if (!p.first_layer && tid < 4 * rows)
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.e + (size_t)row0 * kF + (size_t)tid * 32));
       TIB_PHASE(0);   // tile tables
 
       // ---- hidden phase: one sequence, every epilogue on all 16 warps (group g = feature columns

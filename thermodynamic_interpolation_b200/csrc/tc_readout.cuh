@@ -53,7 +53,7 @@ __device__ __noinline__ float ro_gate(uint32_t taddr, int grp, int row, const fl
     ss = fmaf(t[i], t[i], ss);
   }
   stat[grp * 128 + row] = make_float2(sum, ss);
-  named_bar_sync(NB_ALL, kEpiThreads);
+  named_bar_sync(NB_QUARTER + (row >> 5), kQuarterThreads);
   const float2 s0 = stat[row], s1 = stat[128 + row], s2 = stat[256 + row], s3 = stat[384 + row];
   const float mean = ((s0.x + s1.x) + (s2.x + s3.x)) * (1.0f / 128.0f);
   const float var = fmaxf(((s0.y + s1.y) + (s2.y + s3.y)) * (1.0f / 128.0f) - mean * mean, 0.0f);
@@ -63,9 +63,9 @@ __device__ __noinline__ float ro_gate(uint32_t taddr, int grp, int row, const fl
 #pragma unroll
   for (int i = 0; i < 32; ++i)
     dot = fmaf(silu_fast(fmaf(fmaf(t[i], rstd, nmr), g[32 * grp + i], be[32 * grp + i])), w3[32 * grp + i], dot);
-  named_bar_sync(NB_ALL, kEpiThreads);     // everyone has read the statistics
+  named_bar_sync(NB_QUARTER + (row >> 5), kQuarterThreads);     // the row's four threads have read the statistics
   stat[grp * 128 + row].x = dot;
-  named_bar_sync(NB_ALL, kEpiThreads);
+  named_bar_sync(NB_QUARTER + (row >> 5), kQuarterThreads);
   return (stat[row].x + stat[128 + row].x) + (stat[256 + row].x + stat[384 + row].x);
 }
 

@@ -99,7 +99,7 @@ __device__ __noinline__ void upd_hidden(uint32_t taddr, int grp, int row, const 
     }
   }
   stat[grp * 128 + row] = make_float2(sum, ss);
-  named_bar_sync(NB_ALL, kEpiThreads);
+  named_bar_sync(NB_QUARTER + (row >> 5), kQuarterThreads);
   const float2 s0 = stat[row], s1 = stat[128 + row], s2 = stat[256 + row], s3 = stat[384 + row];
   const float mean = ((s0.x + s1.x) + (s2.x + s3.x)) * (1.0f / 128.0f);
   const float var = fmaxf(((s0.y + s1.y) + (s2.y + s3.y)) * (1.0f / 128.0f) - mean * mean, 0.0f);
@@ -121,7 +121,7 @@ __device__ __noinline__ void upd_hidden(uint32_t taddr, int grp, int row, const 
     for (int i = 0; i < 8; ++i) y[i] = silu_fast(fmaf(fmaf(fmaf(t[i], ascale, bb[i]), rstd, nmr), gg[i], ee[i]));
     store_group(op, kOperandHalfBytes, row, 4 * grp + kg, y);
   }
-  named_bar_sync(NB_ALL, kEpiThreads);     // `stat` may be rewritten by the next call
+  named_bar_sync(NB_QUARTER + (row >> 5), kQuarterThreads);     // `stat` rows of this quarter may be rewritten by the next call
 }
 
 __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
@@ -214,6 +214,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
       const float* vbase = p.v + (size_t)node0 * 3 * kF;
       const bool live = row < rows;
       const size_t node = (size_t)(node0 + row);
+      // The next tile's v and s rows (two contiguous blocks, 2048 lines) start towards L2 now: its builds then pay
+      // the L2 latency, not the HBM latency.  (The first tile of a CTA is not prefetched.)
+      {
+        const int nt = tile + gridDim.x;
+        if (nt < p.n_tiles) {
+          const int nrows = min(128, p.n_nodes - nt * 128);
+          const char* vb = reinterpret_cast<const char*>(p.v + (size_t)nt * 128 * 3 * kF);
+          const char* sb = reinterpret_cast<const char*>(p.s + (size_t)nt * 128 * kF);
+          for (int i = tid; i < nrows * 12; i += kEpiThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (size_t)i * 128));
+          if (tid < nrows * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(sb + (size_t)tid * 128));
+        }
+      }
       // steps 1-3: planes of v; q2 = sum over xyz of (V v)^2                            (cpainn.py:358-361)
       float q2[32];
 #pragma unroll
