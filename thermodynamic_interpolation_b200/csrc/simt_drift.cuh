@@ -92,6 +92,40 @@ __global__ void __launch_bounds__(TIB_THREADS, 1) k_embed(EmbedP p) {
   }
 }
 
+// First message layer, phi's hidden layers per distinct input: s0 takes n_rows distinct values (the de-duplicated
+// embedding rows) and e0 = Emb(edge type) n_et values, so H[u * n_et + t] = SiLU(LN(W2 SiLU(LN(W1 cat[s0[u], e0[t]] + b1)) + b2))
+// is evaluated once per (u, t) instead of once per edge (cpainn.py:275-281 with embedding.py:26-34).
+struct PhiTabP {
+  MlpW phi;
+  const float* s0;        // [n_rows][F]
+  const float* edge_emb;  // [n_et][F]
+  int n_rows, n_et;
+  float* out;             // [n_rows * n_et][F]
+};
+
+template <int F, int KU>
+__global__ void __launch_bounds__(TIB_THREADS, 1) k_phi_table(PhiTabP p) {
+  constexpr int TR = 8;
+  extern __shared__ __align__(16) float smem[];
+  float* X0 = smem;                 // [TR][2F]
+  float* XA = X0 + TR * 2 * F;      // [TR][F]
+  float* XB = XA + TR * F;          // [TR][F]
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int r0 = blockIdx.x * TR, total = p.n_rows * p.n_et;
+  for (int idx = tid; idx < TR * 2 * F; idx += TIB_THREADS) {
+    const int row = idx / (2 * F), f = idx % (2 * F), r = r0 + row;
+    float val = 0.0f;
+    if (r < total) val = f < F ? __ldg(p.s0 + (size_t)(r / p.n_et) * F + f) : __ldg(p.edge_emb + (size_t)(r % p.n_et) * F + f - F);
+    X0[idx] = val;
+  }
+  __syncthreads();
+  layer_ln_silu<F, 1, KU>(X0, 2 * F, 2 * F, p.phi.W1t, p.phi.b1, p.phi.g1, p.phi.be1, XA, F, warp, lane);
+  layer_ln_silu<F, 1, KU>(XA, F, F, p.phi.W2t, p.phi.b2, p.phi.g2, p.phi.be2, XB, F, warp, lane);
+  const int r = r0 + warp;
+  if (r < total)
+    for (int f = lane; f < F; f += 32) p.out[(size_t)r * F + f] = XB[warp * F + f];
+}
+
 // out[r][:] = table[index[r]][:]   (de-duplicated node embedding -> per-node rows)
 __global__ void k_gather_rows(const float* __restrict__ table, const int* __restrict__ index, float* __restrict__ out,
                               int n_rows, int F) {

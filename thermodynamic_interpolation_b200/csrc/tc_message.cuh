@@ -57,6 +57,9 @@ struct TcMsgP {
   float* s_new;
   float* v_new;
   float* e;                 // [E][F] (dst,src) order, updated in place
+  const float* phi_tab;     // first layer, optional: phi's second hidden activation per (embedding row, edge type), [U * n_et][F]
+  const int* embed_index;   //   row of each node in the de-duplicated embedding table (with phi_tab)
+  int n_et;                 //   number of edge types (with phi_tab)
   const float* edge_emb;    // first layer only: e0 = edge_emb[edge type] is formed on the fly, never read from e (embedding.py:89-103)
   const unsigned char* wblob;   // kChunksPerLayer chunks of this layer
   MsgParams prm;
@@ -136,9 +139,11 @@ __device__ __noinline__ void hidden_epilogue(uint32_t taddr, int grp, int row, c
 
 // rows [32*wq, +32) x column groups [4*grp, +4) of an operand image from row-major fp32 global rows
 // `base + row_index(r) * 128`, where row_index(r) = ROWA[r].src (gather 1), the edge type (gather 2: rows of
-// the edge-type embedding, first layer) or row0 + r (gather 0).  These are raw state rows: scaled by kStateScale.
+// the edge-type embedding, first layer), embed_index[src] * n_et + edge type (gather 3: rows of the first layer's
+// phi table, scale 1) or row0 + r (gather 0).  Raw state rows are scaled by kStateScale.
 __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int lane, int rows, const float* base,
-                                        const RowA* rowa, int gather, int row0) {
+                                        const RowA* rowa, int gather, int row0, float scale = kStateScale,
+                                        const int* embed_index = nullptr, int n_et = 0) {
   const int g = 4 * grp + (lane >> 3);
   float4 a[4], b[4];
   // all eight 16-byte loads are issued before the first conversion (the build is bound by their latency)
@@ -147,7 +152,9 @@ __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int 
     const int r = 32 * wq + 8 * oct + (lane & 7);
     a[oct] = b[oct] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r < rows) {
-      const size_t ri = gather == 1 ? (size_t)rowa[r].src : gather == 2 ? (size_t)((rowa[r].slot_last >> 16) & 0xFF) : (size_t)(row0 + r);
+      const size_t et = (size_t)((rowa[r].slot_last >> 16) & 0xFF);
+      const size_t ri = gather == 1 ? (size_t)rowa[r].src : gather == 2 ? et
+                        : gather == 3 ? (size_t)__ldg(embed_index + rowa[r].src) * n_et + et : (size_t)(row0 + r);
       const float* src = base + ri * kF + g * 8;
       a[oct] = __ldg(reinterpret_cast<const float4*>(src));
       b[oct] = __ldg(reinterpret_cast<const float4*>(src + 4));
@@ -156,8 +163,8 @@ __device__ __noinline__ void build_rows(unsigned char* op, int wq, int grp, int 
 #pragma unroll
   for (int oct = 0; oct < 4; ++oct) {
     const int r = 32 * wq + 8 * oct + (lane & 7);
-    const float v[8] = {a[oct].x * kStateScale, a[oct].y * kStateScale, a[oct].z * kStateScale, a[oct].w * kStateScale,
-                        b[oct].x * kStateScale, b[oct].y * kStateScale, b[oct].z * kStateScale, b[oct].w * kStateScale};
+    const float v[8] = {a[oct].x * scale, a[oct].y * scale, a[oct].z * scale, a[oct].w * scale,
+                        b[oct].x * scale, b[oct].y * scale, b[oct].z * scale, b[oct].w * scale};
     store_group(op, kOperandHalfBytes, r, g, v);
   }
 }
@@ -256,6 +263,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const int n_splits = p.first_layer ? 3 : 5;
+  // First layer with a phi table: s0 and e0 take a handful of distinct values, so phi's hidden layers were evaluated
+  // once per (embedding row, edge type) (k_phi_table) and the phi chain of every tile is a gather.
+  const bool phi_tab = p.first_layer && p.phi_tab != nullptr;
 
   if (warp == 16) {
     // =========================== weight producer ===========================
@@ -265,6 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         for (int c = 0; c < kChunksPerLayer; ++c) {
           if (p.first_layer && ((c >= 20 && c < 28) || c >= 52)) continue;   // splits 0 and 4 multiply v = 0
+          if (phi_tab && ((c >= 4 && c < 8) || (c >= 12 && c < 20))) continue;  // phi W1a, W1b, W2
           if (!(stage & 1)) mbar_wait_timed(&bars[B_EMPTY + (stage >> 1)], ph ^ 1, err, w_empty, diag);
           mbar_arrive_expect_tx(&bars[B_FULL + stage], kChunkBytes);
           bulk_g2s(RING + stage * kChunkBytes, p.wblob + (size_t)c * kChunkBytes, kChunkBytes, &bars[B_FULL + stage]);
@@ -289,19 +300,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
         gemm(acc0, xa, false, false);                       // w layer 1   : PE(d)
         tc_commit(&bars[B_ACC0]);
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
-        gemm(acc1, ya, false, false);                       // phi layer 1 : s[src] half
-        tc_commit(&bars[B_YFREE]);
+        if (!phi_tab) {
+          mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
+          gemm(acc1, ya, false, false);                     // phi layer 1 : s[src] half
+          tc_commit(&bars[B_YFREE]);
+        }
         mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
         gemm(acc0, xa, false, false);                       // w layer 2
         tc_commit(&bars[B_ACC0]);
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
-        gemm(acc1, ya, false, true);                        // phi layer 1 : e half (accumulates)
-        tc_commit(&bars[B_ACC1]);
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
-        gemm(acc1, ya, false, false);                       // phi layer 2
-        tc_commit(&bars[B_ACC1]);
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1;
+        if (!phi_tab) {
+          mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
+          gemm(acc1, ya, false, true);                      // phi layer 1 : e half (accumulates)
+          tc_commit(&bars[B_ACC1]);
+          mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();
+          gemm(acc1, ya, false, false);                     // phi layer 2
+          tc_commit(&bars[B_ACC1]);
+        }
+        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1;   // final phi operand (computed or gathered)
         mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
         for (int it = 0; it < n_splits; ++it) {
           const int pb = it & 1;
@@ -378,6 +393,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
           store_group(X, kOperandHalfBytes, row, kg, v);
         }
         fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+        if (phi_tab) {
+          // E2': phi hidden 2 of every edge is a row of the table -> Y (final)
+          build_rows(Y, wq, grp, lane, rows, p.phi_tab, ROWA, 3, 0, 1.0f, p.embed_index, p.n_et);
+          fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+          TIB_PHASE(1);
+          // E3: w hidden 1 -> X
+          mbar_wait_timed(&bars[B_ACC0], pacc0, err, w_acc, diag); pacc0 ^= 1; tc_fence_after();
+          hidden_epilogue(lane_taddr, grp, row, PRM + kPrmW, PRM + kPrmW + kF, PRM + kPrmW + 2 * kF, X, STAT, 1.0f);
+          tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+          if (tile + (int)gridDim.x < p.n_tiles) load_tables(tile + gridDim.x, par ^ 1);   // under the MMAs of w layer 2
+          TIB_PHASE(2);
+          // E5: w hidden 2 -> X (final)
+          mbar_wait_timed(&bars[B_ACC0], pacc0, err, w_acc, diag); pacc0 ^= 1; tc_fence_after();
+          hidden_epilogue(lane_taddr, grp, row, PRM + kPrmW + 3 * kF, PRM + kPrmW + 4 * kF, PRM + kPrmW + 5 * kF, X, STAT + 1024, 1.0f);
+          tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
+          TIB_PHASE(3);
+        } else {
         // E2: s[src] -> Y                                                            (cpainn.py:275-281)
         build_rows(Y, wq, grp, lane, rows, p.s_old, ROWA, 1, 0);
         fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
@@ -406,6 +438,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         mbar_wait_timed(&bars[B_ACC1], pacc1, err, w_acc, diag); pacc1 ^= 1; tc_fence_after();
         hidden_epilogue(lane_taddr + 128, grp, row, PRM + kPrmPhi + 3 * kF, PRM + kPrmPhi + 4 * kF, PRM + kPrmPhi + 5 * kF, Y, STAT + 1024, 1.0f);
         tc_fence_before(); fence_proxy_async(); mbar_arrive(&bars[B_YFULL]);
+        }
         TIB_PHASE(4);   // E7
       }
 

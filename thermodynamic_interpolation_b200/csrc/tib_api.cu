@@ -183,6 +183,8 @@ struct Workspace {
   double *partial, *scalar;
   int *node_in_ptr;
   uint4 *rowa, *rowb;
+  float *phitab;     // [kPhiTabRows][F] first-layer phi table (tc_message.cuh)
+  static constexpr int kPhiTabRows = 4096;
   static constexpr int kPartials = 1024;
   static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
   static size_t bytes(int F, int n_nodes, long long n_edges) {
@@ -193,6 +195,7 @@ struct Workspace {
     b += 12 * align(sizeof(float) * (size_t)n_nodes * 3);   // drift, score, k[7], ytmp, ycur, ynew
     b += align(sizeof(double) * kPartials * 5) + align(sizeof(double) * 8);
     b += align(sizeof(int) * ((size_t)n_nodes + 1)) + 2 * align(sizeof(uint4) * (size_t)n_edges);
+    b += align(sizeof(float) * (size_t)kPhiTabRows * F);
     return b;
   }
   void carve(void* base, int F, int n_nodes, long long n_edges) {
@@ -216,6 +219,7 @@ struct Workspace {
     node_in_ptr = (int*)take(sizeof(int) * ((size_t)n_nodes + 1));
     rowa = (uint4*)take(sizeof(uint4) * (size_t)n_edges);
     rowb = (uint4*)take(sizeof(uint4) * (size_t)n_edges);
+    phitab = (float*)take(sizeof(float) * (size_t)kPhiTabRows * F);
   }
   static size_t kstride(int n_nodes) { return align(sizeof(float) * (size_t)n_nodes * 3) / sizeof(float); }
 };
@@ -273,16 +277,28 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
   if (launch_embed<F>(m, b, db, t, ws, st)) return -1;
   const bool use_tc = (F == 128) && m->math != TIB_MATH_FP32_SIMT;
   int nodes_per_tile = 0, n_tiles = 0;
+  bool use_phi_tab = false;
   if (use_tc) {
     if (b->n_edges >= (1ll << 31)) return fail("tensor-core path: n_edges=%lld exceeds int32 row indices", (long long)b->n_edges);
     if (!m->tc_attrs_set) {
       if (set_smem(tc::k_message_tc, tc::MsgSmem::TOTAL)) return -1;
       if (set_smem(tc::k_update_tc, tc::UpdSmem::TOTAL)) return -1;
       if (set_smem(tc::k_readout_tc, tc::RoSmem::TOTAL)) return -1;
+      if (set_smem(k_phi_table<F, 16>, sizeof(float) * 8 * 4 * F)) return -1;
       m->tc_attrs_set = true;
     }
     nodes_per_tile = std::min(tc::kTileNodes, 128 / (b->max_atoms - 1));
     n_tiles = (b->tile_node_ptr && b->n_tiles > 0) ? b->n_tiles : (b->n_nodes + nodes_per_tile - 1) / nodes_per_tile;
+    // first layer: phi's hidden layers once per (de-duplicated embedding row, edge type) instead of once per edge
+    use_phi_tab = b->embed_index && b->n_embed_rows > 0 && b->n_embed_rows <= b->n_nodes &&
+                  (long long)b->n_embed_rows * m->d.n_edge_types <= Workspace::kPhiTabRows;
+    if (use_phi_tab) {
+      PhiTabP pp{m->layers[0].phi, ws.s[1], m->edge_emb, b->n_embed_rows, m->d.n_edge_types, ws.phitab};
+      const int total = b->n_embed_rows * m->d.n_edge_types;
+      ProfScope ps(TIB_K_EMBED, st);
+      k_phi_table<F, 16><<<(total + 7) / 8, TIB_THREADS, sizeof(float) * 8 * 4 * F, st>>>(pp);
+      LAUNCH_CHECK();
+    }
     // geometry + edge types per (dst,src)-ordered row; e0 = Emb(edge_type) is formed inside the first message layer
     ProfScope ps(TIB_K_EDGE_INIT, st);
     tc::k_edge_tables<<<b->n_mol, 128, 0, st>>>(b->mol_ptr, (const long long*)b->edge_ptr, b->n_mol, x, b->edge_type,
@@ -305,6 +321,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       tp.tile_node_ptr = (b->tile_node_ptr && b->n_tiles > 0) ? b->tile_node_ptr : nullptr;
       tp.s_old = ws.s[cur]; tp.v_old = ws.v[cur]; tp.s_new = ws.s[cur ^ 1]; tp.v_new = ws.v[cur ^ 1]; tp.e = ws.e;
       tp.wblob = L.tc_msg; tp.edge_emb = m->edge_emb;
+      if (l == 0 && use_phi_tab) { tp.phi_tab = ws.phitab; tp.embed_index = b->embed_index; tp.n_et = m->d.n_edge_types; }
       tp.prm = tc::MsgParams{L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2, L.phi.b3,
                              L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2, L.w.b3};
       tp.length_scale = m->d.length_scale; tp.first_layer = (l == 0); tp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3;
