@@ -126,6 +126,112 @@ __global__ void __launch_bounds__(TIB_THREADS, 1) k_phi_table(PhiTabP p) {
     for (int f = lane; f < F; f += 32) p.out[(size_t)r * F + f] = XB[warp * F + f];
 }
 
+// ---------------------------------------------------------------------------------------------
+// One CTA per table row, K split over the 8 warps: for the few de-duplicated rows of a single-species batch the
+// row-per-warp kernels above are one long chain of dependent weight loads (42 + 30 us for 9 + 36 rows); here every
+// layer is 1/8 of that chain plus a shared-memory reduction.  The partial sums are added in a fixed order, which
+// is NOT the k-ascending fmaf chain of the fp32 path - used by the tensor-core modes only (F = 128).
+// ---------------------------------------------------------------------------------------------
+template <int F>
+__device__ __forceinline__ void splitk_linear(const float* x, int K, const float* __restrict__ Wt, int ldw, float* part,
+                                              int warp, int lane) {
+  // part[warp][c] = sum over this warp's slice of k of x[k] * Wt[k][c],  c = 4 * lane .. 4 * lane + 3
+  static_assert(F == 128, "split-K helpers are built for F = 128");
+  const int ks = K / TIB_WARPS, k0 = warp * ks;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+  for (int kb = 0; kb < ks; kb += 16) {
+    float4 w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = __ldg(reinterpret_cast<const float4*>(Wt + (size_t)(k0 + kb + i) * ldw) + lane);
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+      const float a = x[k0 + kb + i];
+      acc[0] = fmaf(a, w[i].x, acc[0]); acc[1] = fmaf(a, w[i].y, acc[1]);
+      acc[2] = fmaf(a, w[i].z, acc[2]); acc[3] = fmaf(a, w[i].w, acc[3]);
+    }
+  }
+  *reinterpret_cast<float4*>(part + warp * F + 4 * lane) = make_float4(acc[0], acc[1], acc[2], acc[3]);
+}
+
+// out[c] = SiLU(LN(x @ Wt + b)) (ln = true) or x @ Wt + b (ln = false); one row, all 256 threads
+template <int F>
+__device__ __forceinline__ void splitk_layer(const float* x, int K, const float* __restrict__ Wt, const float* __restrict__ b,
+                                             const float* __restrict__ g, const float* __restrict__ be, bool ln, float* out,
+                                             float* part, int warp, int lane) {
+  splitk_linear<F>(x, K, Wt, F, part, warp, lane);
+  __syncthreads();
+  if (warp == 0) {
+    float z[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float t = 0.0f;
+#pragma unroll
+      for (int w = 0; w < TIB_WARPS; ++w) t += part[w * F + 4 * lane + i];
+      z[i] = t + __ldg(b + 4 * lane + i);
+    }
+    if (ln) {
+      const float mean = warp_sum((z[0] + z[1]) + (z[2] + z[3])) * (1.0f / F);
+      float ss = 0.0f;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { z[i] -= mean; ss = fmaf(z[i], z[i], ss); }
+      const float rstd = __fdiv_rn(1.0f, __fsqrt_rn(warp_sum(ss) * (1.0f / F) + 1e-5f));
+#pragma unroll
+      for (int i = 0; i < 4; ++i) z[i] = silu(z[i] * rstd * __ldg(g + 4 * lane + i) + __ldg(be + 4 * lane + i));
+    }
+    *reinterpret_cast<float4*>(out + 4 * lane) = make_float4(z[0], z[1], z[2], z[3]);
+  }
+  __syncthreads();
+}
+
+struct EmbedTabP {
+  EmbedP e;               // e.b.n_nodes = number of table rows U; e.s_out = s0 table [U][F]
+  MlpW phi;               // first message layer's phi (hidden layers only)
+  const float* edge_emb;  // [n_et][F]
+  int n_et;
+  float* phitab;          // [U * n_et][F] or NULL (then the grid is U CTAs)
+};
+
+// CTA (u, t): s0[u] = InvariantFeatures MLP of table row u (written by t == 0), then the phi table row (u, t)
+template <int F>
+__global__ void __launch_bounds__(TIB_THREADS, 1) k_embed_tab(EmbedTabP pp) {
+  const EmbedP& p = pp.e;
+  __shared__ __align__(16) float X0[4 * F], XA[2 * F], XB[F], PART[TIB_WARPS * F];
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int n_et = pp.phitab ? pp.n_et : 1;
+  const int u = blockIdx.x / n_et, et = blockIdx.x % n_et;
+  const int nseg = 2 + p.n_temp, kin = nseg * F, npair = F / 2;
+  for (int f = tid; f < F; f += TIB_THREADS) X0[f] = __ldg(p.atom_emb + (size_t)__ldg(p.b.atom_id + u) * F + f);
+  for (int idx = tid; idx < (nseg - 1) * npair; idx += TIB_THREADS) {
+    const int seg = 1 + idx / npair, rank = 1 + idx % npair;
+    float val, len;
+    if (seg <= p.n_temp) {
+      const float T = __ldg((seg == 1 ? p.b.temp0 : p.b.temp1) + u);
+      val = __fdiv_rn(T - p.temp_mean, p.temp_range);
+      len = p.temp_length;
+    } else {
+      val = p.t;
+      len = p.time_length;
+    }
+    float sn, cs;
+    sincosf(pe_arg(val, len, rank), &sn, &cs);
+    X0[seg * F + 2 * (rank - 1)] = cs;
+    X0[seg * F + 2 * (rank - 1) + 1] = sn;
+  }
+  __syncthreads();
+  splitk_layer<F>(X0, kin, p.mlp.W1t, p.mlp.b1, p.mlp.g1, p.mlp.be1, true, XA, PART, warp, lane);
+  splitk_layer<F>(XA, F, p.mlp.W2t, p.mlp.b2, p.mlp.g2, p.mlp.be2, true, XB, PART, warp, lane);
+  splitk_layer<F>(XB, F, p.mlp.W3t, p.mlp.b3, nullptr, nullptr, false, XA, PART, warp, lane);   // s0[u] in XA[0:F]
+  if (et == 0)
+    for (int f = tid; f < F; f += TIB_THREADS) p.s_out[(size_t)u * F + f] = XA[f];
+  if (!pp.phitab) return;
+  for (int f = tid; f < F; f += TIB_THREADS) XA[F + f] = __ldg(pp.edge_emb + (size_t)et * F + f);
+  __syncthreads();
+  splitk_layer<F>(XA, 2 * F, pp.phi.W1t, pp.phi.b1, pp.phi.g1, pp.phi.be1, true, XB, PART, warp, lane);
+  splitk_layer<F>(XB, F, pp.phi.W2t, pp.phi.b2, pp.phi.g2, pp.phi.be2, true, X0, PART, warp, lane);
+  for (int f = tid; f < F; f += TIB_THREADS) pp.phitab[(size_t)blockIdx.x * F + f] = X0[f];
+}
+
 // out[r][:] = table[index[r]][:]   (de-duplicated node embedding -> per-node rows)
 __global__ void k_gather_rows(const float* __restrict__ table, const int* __restrict__ index, float* __restrict__ out,
                               int n_rows, int F) {

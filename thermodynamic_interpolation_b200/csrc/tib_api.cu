@@ -274,10 +274,32 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
                 b->atom_id, b->edge_type, b->temp0, b->temp1};
   const int node_tiles = (b->n_nodes + 8 * RN - 1) / (8 * RN);
 
-  if (launch_embed<F>(m, b, db, t, ws, st)) return -1;
   const bool use_tc = (F == 128) && m->math != TIB_MATH_FP32_SIMT;
   int nodes_per_tile = 0, n_tiles = 0;
-  bool use_phi_tab = false;
+  bool use_phi_tab = false, fused_tab = false;
+  if constexpr (F == 128) {
+    // few de-duplicated rows (single-species batches): one CTA per (embedding row, edge type) computes s0 and the first
+    // layer's phi table with K split over its warps; the summation order differs from the fp32 path, so tensor-core modes only
+    const bool dedupe = b->embed_index && b->n_embed_rows > 0 && b->n_embed_rows <= b->n_nodes;
+    if (use_tc && dedupe && (long long)b->n_embed_rows * m->d.n_edge_types <= 2 * m->n_sms) {
+      if (!b->embed_atom_id || (m->n_temp >= 1 && !b->embed_temp0) || (m->n_temp >= 2 && !b->embed_temp1))
+        return fail("embed_index given without the de-duplicated atom/temperature tables");
+      DriftBatch du = db;
+      du.n_nodes = b->n_embed_rows; du.atom_id = b->embed_atom_id; du.temp0 = b->embed_temp0; du.temp1 = b->embed_temp1;
+      EmbedTabP ep{{du, m->combine, m->atom_emb, m->n_temp, t, m->d.temp_mean, m->d.temp_range, m->d.temp_length,
+                    m->d.time_length, ws.s[1]},
+                   m->layers[0].phi, m->edge_emb, m->d.n_edge_types, ws.phitab};
+      ProfScope ps(TIB_K_EMBED, st);
+      k_embed_tab<128><<<b->n_embed_rows * m->d.n_edge_types, TIB_THREADS, 0, st>>>(ep);
+      LAUNCH_CHECK();
+      const long long total = (long long)b->n_nodes * (F / 4);
+      k_gather_rows<<<(int)std::min<long long>((total + 255) / 256, 148 * 16), 256, 0, st>>>(ws.s[1], b->embed_index, ws.s[0],
+                                                                                        b->n_nodes, F);
+      LAUNCH_CHECK();
+      fused_tab = use_phi_tab = true;
+    }
+  }
+  if (!fused_tab && launch_embed<F>(m, b, db, t, ws, st)) return -1;
   if (use_tc) {
     if (b->n_edges >= (1ll << 31)) return fail("tensor-core path: n_edges=%lld exceeds int32 row indices", (long long)b->n_edges);
     if (!m->tc_attrs_set) {
@@ -290,9 +312,10 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     nodes_per_tile = std::min(tc::kTileNodes, 128 / (b->max_atoms - 1));
     n_tiles = (b->tile_node_ptr && b->n_tiles > 0) ? b->n_tiles : (b->n_nodes + nodes_per_tile - 1) / nodes_per_tile;
     // first layer: phi's hidden layers once per (de-duplicated embedding row, edge type) instead of once per edge
-    use_phi_tab = b->embed_index && b->n_embed_rows > 0 && b->n_embed_rows <= b->n_nodes &&
-                  (long long)b->n_embed_rows * m->d.n_edge_types <= Workspace::kPhiTabRows;
-    if (use_phi_tab) {
+    if (!fused_tab)
+      use_phi_tab = b->embed_index && b->n_embed_rows > 0 && b->n_embed_rows <= b->n_nodes &&
+                    (long long)b->n_embed_rows * m->d.n_edge_types <= Workspace::kPhiTabRows;
+    if (use_phi_tab && !fused_tab) {
       PhiTabP pp{m->layers[0].phi, ws.s[1], m->edge_emb, b->n_embed_rows, m->d.n_edge_types, ws.phitab};
       const int total = b->n_embed_rows * m->d.n_edge_types;
       ProfScope ps(TIB_K_EMBED, st);
