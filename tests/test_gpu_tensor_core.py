@@ -228,3 +228,25 @@ def test_tc_range_of_node_features():
     assert err < 2e-5
     tc, ref, ok = run(5.0e6)            # beyond the range: flagged, and the fp32 path still answers
     assert not ok and torch.isfinite(ref).all()
+
+
+def test_tc_positional_encoding_cache_is_bit_identical_on_partial_tiles(monkeypatch):
+    """Layers 1.. take the positional-encoding operand image of a tile by bulk copy from the first layer's store instead
+    of recomputing it.  12 atoms per molecule give 121-row (partial) tiles and several tiles per CTA - the case in
+    which a hidden-layer MMA of the next tile could overtake the last TMEM reads of the previous one."""
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    torch.manual_seed(71)
+    model = perturb_(cPaiNN(n_features=128, score_layers=5, temp_length=100), 72).eval().to(DEV)
+    mb = synthetic_ambient_batch(2048, 12, seed=73).to(DEV)
+    eng = model.engine()
+    pb = eng.prepare(mb)
+    cached = [eng.drift(pb, mb.x0, 0.4).clone() for _ in range(3)]
+    eng.status()
+    monkeypatch.setenv("TIB_NO_PE_CACHE", "1")
+    plain = eng.drift(pb, mb.x0, 0.4).clone()
+    eng.status()
+    monkeypatch.delenv("TIB_NO_PE_CACHE")
+    assert torch.isfinite(plain).all()
+    for c in cached:
+        assert torch.equal(c, plain)

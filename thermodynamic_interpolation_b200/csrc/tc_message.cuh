@@ -57,6 +57,8 @@ struct TcMsgP {
   float* s_new;
   float* v_new;
   float* e;                 // [E][F] (dst,src) order, updated in place
+  unsigned char* pe_img;    // optional [n_tiles][64 KB]: operand images of PositionalEncoder(edge_dist), identical in every layer
+  int pe_mode;              //   0 compute per tile, 1 compute and store the image (first layer), 2 load the stored image
   const float* phi_tab;     // first layer, optional: phi's second hidden activation per (embedding row, edge type), [U * n_et][F]
   const int* embed_index;   //   row of each node in the de-duplicated embedding table (with phi_tab)
   int n_et;                 //   number of edge types (with phi_tab)
@@ -89,7 +91,7 @@ struct MsgSmem {
 };
 // barrier indices
 enum { B_FULL = 0, B_EMPTY = B_FULL + kStages /* one per PAIR of stages */, B_XFULL = B_EMPTY + kStages / 2, B_YFULL, B_YFREE, B_ACC0, B_ACC1,
-       B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_COUNT };
+       B_TFULL0, B_TFULL1, B_TEMPTY0, B_TEMPTY1, B_XFREE, B_PEFULL, B_COUNT };
 // named barriers: all 512 epilogue threads, or the 4 warps (one per column group) that share TMEM lane quarter wq
 enum { NB_ALL = 1, NB_QUARTER = 2 /* + wq */ };
 constexpr int kQuarterThreads = 128;
@@ -248,6 +250,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     mbar_init(&bars[B_YFREE], 1); mbar_init(&bars[B_ACC0], 1); mbar_init(&bars[B_ACC1], 1);
     mbar_init(&bars[B_TFULL0], 1); mbar_init(&bars[B_TFULL1], 1);
     mbar_init(&bars[B_TEMPTY0], kEpiThreads); mbar_init(&bars[B_TEMPTY1], kEpiThreads);
+    mbar_init(&bars[B_XFREE], 1); mbar_init(&bars[B_PEFULL], 1);
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, 512);
@@ -266,13 +269,24 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   // First layer with a phi table: s0 and e0 take a handful of distinct values, so phi's hidden layers were evaluated
   // once per (embedding row, edge type) (k_phi_table) and the phi chain of every tile is a gather.
   const bool phi_tab = p.first_layer && p.phi_tab != nullptr;
+  // The positional encoding of the edge distances is the same in all layers of one drift evaluation: the first layer
+  // stores its operand image per tile, the later layers have the bulk-copy unit drop it into X as soon as the previous
+  // tile's last output MMAs have released X - that is during the previous tile's last scatter, off the critical path.
+  const bool pe_load = p.pe_img != nullptr && p.pe_mode == 2;
+  const bool pe_store = p.pe_img != nullptr && p.pe_mode == 1;
 
   if (warp == 16) {
     // =========================== weight producer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0;
       long long w_empty = 0;
+      uint32_t pxf = 0;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        if (pe_load) {
+          if (tile != (int)blockIdx.x) { mbar_wait(&bars[B_XFREE], pxf, err); pxf ^= 1; }   // previous tile's output MMAs are done with X
+          mbar_arrive_expect_tx(&bars[B_PEFULL], kOperandBytes);
+          bulk_g2s(X, p.pe_img + (size_t)tile * kOperandBytes, kOperandBytes, &bars[B_PEFULL]);
+        }
         for (int c = 0; c < kChunksPerLayer; ++c) {
           if (p.first_layer && ((c >= 20 && c < 28) || c >= 52)) continue;   // splits 0 and 4 multiply v = 0
           if (phi_tab && ((c >= 4 && c < 8) || (c >= 12 && c < 20))) continue;  // phi W1a, W1b, W2
@@ -287,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   } else if (warp == 17) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
-      uint32_t px = 0, py = 0, pte[2] = {0, 0};
+      uint32_t px = 0, py = 0, ppe = 0, pte[2] = {0, 0};
       long long w_operands = 0, w_tempty = 0;
       const long long t_start = clock64();
       const uint32_t xa = smem_u32(X), ya = smem_u32(Y), ring = smem_u32(RING);
@@ -297,7 +311,15 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       };
       const uint32_t acc0 = tmem, acc1 = tmem + 128;
       for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-        mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
+        if (pe_load) {
+          // X arrives by bulk copy, so this wait says nothing about the epilogue of the previous tile: the hidden
+          // accumulators alias output slot 0, whose last readers (split n_splits - 2) must have drained it
+          mbar_wait_timed(&bars[B_PEFULL], ppe, err, w_operands, diag); ppe ^= 1;
+          mbar_wait_timed(&bars[B_TEMPTY0], pte[0] ^ 1, err, w_tempty, diag);
+        } else {
+          mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1;
+        }
+        tc_fence_after();
         gemm(acc0, xa, false, false);                       // w layer 1   : PE(d)
         tc_commit(&bars[B_ACC0]);
         if (!phi_tab) {
@@ -319,11 +341,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1;   // final phi operand (computed or gathered)
         mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
         for (int it = 0; it < n_splits; ++it) {
-          const int pb = it & 1;
+          const int pb = (it + 1) & 1;   // the LAST split uses slot 1: slot 0 (= the hidden accumulators) drains one split early
           mbar_wait_timed(&bars[B_TEMPTY0 + pb], pte[pb] ^ 1, err, w_tempty, diag); pte[pb] ^= 1; tc_fence_after();
           gemm_pair_job(bars, ring, rs, tmem + 256 * pb, ya, tmem + 256 * pb + 128, xa, p.passes, err, diag);
           tc_commit(&bars[B_TFULL0 + pb]);                  // phi and w layer 3 of this split (transposed)
         }
+        tc_commit(&bars[B_XFREE]);                          // X (and Y) may be overwritten for the next tile
       }
       if (p.dbg) {
         p.dbg[blockIdx.x * 8 + 0] = rs.w_weights; p.dbg[blockIdx.x * 8 + 1] = w_operands;
@@ -380,19 +403,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       // [32g, 32g+32) of every row); the MMAs of one chain run under the epilogue of the other.
       {
         // E1: PositionalEncoder(edge_dist) -> X                                     (cpainn.py:283)
-        const float dist = ROWA[row].dist;
+        if (!pe_load) {
+          const float dist = ROWA[row].dist;
+          unsigned char* const img = pe_store ? p.pe_img + (size_t)tile * kOperandBytes : nullptr;
 #pragma unroll 2
-        for (int kg = 4 * grp; kg < 4 * grp + 4; ++kg) {
-          float v[8];
+          for (int kg = 4 * grp; kg < 4 * grp + 4; ++kg) {
+            float v[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            float sn = 0.0f, cs = 0.0f;
-            if (row < rows) sincos_cw(pe_arg(dist, p.length_scale, 4 * kg + q + 1), sn, cs);
-            v[2 * q] = cs; v[2 * q + 1] = sn;
+            for (int q = 0; q < 4; ++q) {
+              float sn = 0.0f, cs = 0.0f;
+              if (row < rows) sincos_cw(pe_arg(dist, p.length_scale, 4 * kg + q + 1), sn, cs);
+              v[2 * q] = cs; v[2 * q + 1] = sn;
+            }
+            store_group(X, kOperandHalfBytes, row, kg, v);
+            if (img) store_group(img, kOperandHalfBytes, row, kg, v);
           }
-          store_group(X, kOperandHalfBytes, row, kg, v);
+          fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         }
-        fence_proxy_async(); mbar_arrive(&bars[B_XFULL]);
         if (phi_tab) {
           // E2': phi hidden 2 of every edge is a row of the table -> Y (final)
           build_rows(Y, wq, grp, lane, rows, p.phi_tab, ROWA, 3, 0, 1.0f, p.embed_index, p.n_et);
@@ -460,7 +487,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       for (int k = 0; k < 4; ++k) { acc_s[k] = 0.0f; acc_v[k][0] = acc_v[k][1] = acc_v[k][2] = 0.0f; }
       for (int it = 0; it < n_splits; ++it) {
         const int sp = p.first_layer ? it + 1 : it;
-        const int pb = it & 1;
+        const int pb = (it + 1) & 1;   // the LAST split uses slot 1: slot 0 (= the hidden accumulators) drains one split early
         const float bphi = PRM[kPrmB3 + sp * kF + f], bw = PRM[kPrmB3 + 5 * kF + sp * kF + f];
         mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull, diag); ptf[pb] ^= 1; tc_fence_after();
         const uint32_t tphi = lane_taddr + 256 * pb, tw = tphi + 128;

@@ -4,6 +4,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -184,6 +185,10 @@ struct Workspace {
   int *node_in_ptr;
   uint4 *rowa, *rowb;
   float *phitab;     // [kPhiTabRows][F] first-layer phi table (tc_message.cuh)
+  unsigned char *peimg; size_t peimg_bytes;   // positional-encoding operand images, 64 KB per message tile (tc_message.cuh)
+  static size_t pe_bytes(int n_nodes, long long n_edges) {   // tiles close at 16 nodes or at > 64 rows
+    return (size_t)65536 * ((size_t)n_nodes / 16 + (size_t)n_edges / 64 + 2);
+  }
   static constexpr int kPhiTabRows = 4096;
   static constexpr int kPartials = 1024;
   static size_t align(size_t x) { return (x + 255) & ~(size_t)255; }
@@ -196,6 +201,7 @@ struct Workspace {
     b += align(sizeof(double) * kPartials * 5) + align(sizeof(double) * 8);
     b += align(sizeof(int) * ((size_t)n_nodes + 1)) + 2 * align(sizeof(uint4) * (size_t)n_edges);
     b += align(sizeof(float) * (size_t)kPhiTabRows * F);
+    if (F == 128) b += align(pe_bytes(n_nodes, n_edges));
     return b;
   }
   void carve(void* base, int F, int n_nodes, long long n_edges) {
@@ -220,6 +226,8 @@ struct Workspace {
     rowa = (uint4*)take(sizeof(uint4) * (size_t)n_edges);
     rowb = (uint4*)take(sizeof(uint4) * (size_t)n_edges);
     phitab = (float*)take(sizeof(float) * (size_t)kPhiTabRows * F);
+    peimg_bytes = F == 128 ? pe_bytes(n_nodes, n_edges) : 0;
+    peimg = F == 128 ? (unsigned char*)take(peimg_bytes) : nullptr;
   }
   static size_t kstride(int n_nodes) { return align(sizeof(float) * (size_t)n_nodes * 3) / sizeof(float); }
 };
@@ -345,6 +353,9 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       tp.s_old = ws.s[cur]; tp.v_old = ws.v[cur]; tp.s_new = ws.s[cur ^ 1]; tp.v_new = ws.v[cur ^ 1]; tp.e = ws.e;
       tp.wblob = L.tc_msg; tp.edge_emb = m->edge_emb;
       if (l == 0 && use_phi_tab) { tp.phi_tab = ws.phitab; tp.embed_index = b->embed_index; tp.n_et = m->d.n_edge_types; }
+      if (ws.peimg && (size_t)n_tiles * tc::kOperandBytes <= ws.peimg_bytes && m->d.n_layers > 1 && !getenv("TIB_NO_PE_CACHE")) {
+        tp.pe_img = ws.peimg; tp.pe_mode = l == 0 ? 1 : 2;
+      }
       tp.prm = tc::MsgParams{L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2, L.phi.b3,
                              L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2, L.w.b3};
       tp.length_scale = m->d.length_scale; tp.first_layer = (l == 0); tp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3;
