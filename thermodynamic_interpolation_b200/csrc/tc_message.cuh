@@ -274,6 +274,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   // tile's last output MMAs have released X - that is during the previous tile's last scatter, off the critical path.
   const bool pe_load = p.pe_img != nullptr && p.pe_mode == 2;
   const bool pe_store = p.pe_img != nullptr && p.pe_mode == 1;
+  const int first_split_chunk = 20 + 8 * (p.first_layer ? 1 : 0);   // first chunk of the first output split in the blob
 
   if (warp == 16) {
     // =========================== weight producer ===========================
@@ -290,9 +291,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         for (int c = 0; c < kChunksPerLayer; ++c) {
           if (p.first_layer && ((c >= 20 && c < 28) || c >= 52)) continue;   // splits 0 and 4 multiply v = 0
           if (phi_tab && ((c >= 4 && c < 8) || (c >= 12 && c < 20))) continue;  // phi W1a, W1b, W2
+          // the first output split is issued as w k0..k3 then phi k0..k3 (its w half starts before phi's operand is final);
+          // the blob holds every split as (phi k, w k) pairs
+          int ci = c;
+          if (c >= first_split_chunk && c < first_split_chunk + 8) {
+            const int j = c - first_split_chunk;
+            ci = first_split_chunk + (j < 4 ? 2 * j + 1 : 2 * (j - 4));
+          }
           if (!(stage & 1)) mbar_wait_timed(&bars[B_EMPTY + (stage >> 1)], ph ^ 1, err, w_empty, diag);
           mbar_arrive_expect_tx(&bars[B_FULL + stage], kChunkBytes);
-          bulk_g2s(RING + stage * kChunkBytes, p.wblob + (size_t)c * kChunkBytes, kChunkBytes, &bars[B_FULL + stage]);
+          bulk_g2s(RING + stage * kChunkBytes, p.wblob + (size_t)ci * kChunkBytes, kChunkBytes, &bars[B_FULL + stage]);
           if (++stage == kStages) { stage = 0; ph ^= 1; }
         }
       }
@@ -338,9 +346,17 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
           gemm(acc1, ya, false, false);                     // phi layer 2
           tc_commit(&bars[B_ACC1]);
         }
-        mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1;   // final phi operand (computed or gathered)
+        // first output split: its w half needs only X (final since E5) and runs under the last phi epilogues
         mbar_wait_timed(&bars[B_XFULL], px, err, w_operands, diag); px ^= 1; tc_fence_after();
-        for (int it = 0; it < n_splits; ++it) {
+        {
+          const int pb = 1;
+          mbar_wait_timed(&bars[B_TEMPTY0 + pb], pte[pb] ^ 1, err, w_tempty, diag); pte[pb] ^= 1; tc_fence_after();
+          gemm(tmem + 256 * pb + 128, xa, true, false);     // w layer 3, transposed
+          mbar_wait_timed(&bars[B_YFULL], py, err, w_operands, diag); py ^= 1; tc_fence_after();   // final phi operand
+          gemm(tmem + 256 * pb, ya, true, false);           // phi layer 3, transposed
+          tc_commit(&bars[B_TFULL0 + pb]);
+        }
+        for (int it = 1; it < n_splits; ++it) {
           const int pb = (it + 1) & 1;   // the LAST split uses slot 1: slot 0 (= the hidden accumulators) drains one split early
           mbar_wait_timed(&bars[B_TEMPTY0 + pb], pte[pb] ^ 1, err, w_tempty, diag); pte[pb] ^= 1; tc_fence_after();
           gemm_pair_job(bars, ring, rs, tmem + 256 * pb, ya, tmem + 256 * pb + 128, xa, p.passes, err, diag);
