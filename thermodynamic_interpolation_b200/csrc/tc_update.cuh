@@ -11,7 +11,7 @@
 //   step 4: q = sqrt(q2) -> X,  s -> Y;   layer 1 = X*W1[:, :F]^T + Y*W1[:, F:]^T -> T0
 //   step 5: LN/SiLU(T0) -> X;             layer 2 -> T0
 //   step 6: LN/SiLU(T0) -> X;             g = X*W3g^T -> T0
-//   step 7: v_new[xyz] = v + uv_xyz * g  (T1..T3, T0);      a, c = X*W3{a,c}^T -> T0, T1
+//   step 7: v_new[xyz] = v + uv_xyz * g  (T1..T3, T0);      a = X*W3a^T -> T1 once plane 0 is updated, c -> T2 after plane 1
 //   step 8: s_new = s + q2 * a + c
 // The epilogue (512 threads) and the MMA issuer alternate through one operand-ready / accumulator-ready
 // barrier pair; weights stream through the same bulk-copy ring as the message kernel.
@@ -192,7 +192,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
         ops_ready(); gemm(T0, xa, 0, 0, false); gemm(T0, ya, 0, 0, true); tc_commit(&bars[U_ACC]);    // 4: layer 1 (q in X, s in Y)
         ops_ready(); gemm(T0, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                               // 5: layer 2
         ops_ready(); gemm(T0, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                               // 6: g
-        ops_ready(); gemm(T0, xa, 0, 0, false); gemm(T1, xa, 0, 0, false); tc_commit(&bars[U_ACC]);   // 7: a, c
+        ops_ready(); gemm(T1, xa, 0, 0, false);                                                        // 7a: a -> T1 (uv0 consumed)
+        ops_ready(); gemm(T2, xa, 0, 0, false); tc_commit(&bars[U_ACC]);                               // 7b: c -> T2 (uv1 consumed)
       }
     }
   } else {
@@ -238,13 +239,16 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
       for (int xyz = 0; xyz < 3; ++xyz) {
         acc_ready();                                                  // vv, uv_xyz of plane xyz
         TIB_UPH(1);
-        if (xyz == 0) upd_build(X, wq, grp, lane, rows, vbase + 2 * kF, 3 * kF);   // plane 2 (X is free again)
-        if (xyz == 1) upd_build(Y, wq, grp, lane, rows, p.s + (size_t)node0 * kF, kF);   // s (Y is free again)
-        float t[32];
-        tmem_ld32(T0 + 32 * grp, t);
+        {
+          float t[32];
+          tmem_ld32(T0 + 32 * grp, t);
 #pragma unroll
-        for (int i = 0; i < 32; ++i) q2[i] = fmaf(t[i], t[i], q2[i]);
-        if (xyz < 2) ops_done();                                      // next plane's operand ready, T0 drained
+          for (int i = 0; i < 32; ++i) q2[i] = fmaf(t[i], t[i], q2[i]);
+        }
+        if (xyz < 2) ops_done();                                      // T0 drained: the next plane's MMAs (operand built earlier) may start
+        // operands that are needed two steps from now, under the MMAs just released
+        if (xyz == 0) upd_build(X, wq, grp, lane, rows, vbase + 2 * kF, 3 * kF);   // plane 2 (X is free: plane 0 is done)
+        if (xyz == 1) upd_build(Y, wq, grp, lane, rows, p.s + (size_t)node0 * kF, kF);   // s (Y is free: plane 1 is done)
         TIB_UPH(2);
       }
       // step 4: q -> X (X is free: the MMAs of plane 2 have completed).  q2 holds (kStateScale |V v|)^2, so its
@@ -309,9 +313,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
             if (r < rows) *reinterpret_cast<float4*>(vplane + (size_t)r * 3 * kF + 4 * c) = stage[r * 32 + (c ^ (r & 31))];
           }
           named_bar_sync(NB_ALL, kEpiThreads);                        // the stage is reused by the next plane
+          if (xyz < 2) ops_done();      // uv_xyz (T1 / T2) has been read by everyone: a / c may be accumulated there now
         }
       }
-      ops_done();                                                     // T0..T3 drained: a, c may be written
       TIB_UPH(10);
       // step 8: s += q^2 * a + c                                                      (cpainn.py:371,373)
       {
@@ -326,8 +330,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
         TIB_UPH(11);
         named_bar_sync(NB_ALL, kEpiThreads);
         float a[32], c[32];
-        tmem_ld32(T0 + 32 * grp, a);
-        tmem_ld32(T1 + 32 * grp, c);
+        tmem_ld32(T1 + 32 * grp, a);
+        tmem_ld32(lt + 256 + 32 * grp, c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float4* sp = stage + row * 32 + ((8 * grp + j) ^ (row & 31));

@@ -42,8 +42,8 @@ for i, nm in enumerate(names):
 
 ph = buf_all[n:3 * n].reshape(n, 2, 8).mean(0)
 tiles = 4096 * 9 / 16 / n
-print("epilogue phases, mean cycles per tile (thread 0 = w chain | thread 256 = phi chain):")
-for i, nm in enumerate(["tile tables+barrier", "E1 PE | E2 s[src]", "E3 w hid1 | E4 e rows", "E5 w hid2 | E6 phi hid1", "-- | E7 phi hid2",
+print("epilogue phases, mean cycles per tile (every epilogue thread runs the same sequence; columns: thread 0 | thread 256):")
+for i, nm in enumerate(["tile tables+barrier", "E1 PE + E2 s[src]", "E3 w hid1 + E4 e rows", "E5 w hid2 + E6 phi hid1", "E7 phi hid2",
                         "output layer", "write-back"]):
     print(f"  {nm:28s} {ph[0, i] / tiles:10.0f} | {ph[1, i] / tiles:10.0f}")
 print("  total per tile               %10.0f | %10.0f" % (ph[0].sum() / tiles, ph[1].sum() / tiles))
