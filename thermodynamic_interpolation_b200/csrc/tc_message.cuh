@@ -14,6 +14,10 @@
 //       (gates, scale_edge_dir, ds, de, cross_gates) at a time, phi and w side by side, double-buffered
 //       in TMEM so the MMAs of split i+1 overlap the scatter of split i.
 // Weights stream from L2 through a ring of 16 KB chunks with cp.async.bulk (TMA unit).
+// Not recomputed per layer / per edge: the positional-encoding operand image of a tile (stored by the first layer,
+// bulk-copied into X by the others; the issuer then starts the next tile's first hidden GEMM while the epilogue still
+// scatters the previous tile's last split) and, in the first layer, phi's hidden activations (a table per
+// (embedding row, edge type), gathered per edge).
 //
 // Warp roles (576 threads): warps 0-15 = four epilogue groups (group g = warp / 4; a warp reads the
 // TMEM lane quarter warp % 4), warp 16 weight producer (+ TMEM allocation), warp 17 MMA issuer.
@@ -35,7 +39,7 @@ constexpr int kStages = 4;
 // fp32 layer parameters staged in shared memory once per CTA:
 //   [0,6F): w  {b1,g1,be1,b2,g2,be2}   [6F,12F): phi {b1,g1,be1,b2,g2,be2}   [12F,17F): phi b3   [17F,22F): w b3
 constexpr int kPrmW = 0, kPrmPhi = 6 * 128, kPrmB3 = 12 * 128, kPrmFloats = 22 * 128;
-constexpr int kTileNodes = 16;                 // destination nodes per tile (delta-s / delta-v windows in smem)
+constexpr int kTileNodes = 16;                 // destination nodes per tile (4 per epilogue group: delta-s / delta-v live in registers)
 constexpr int kChunksPerLayer = 60;
 
 // streamed chunk order of one message layer (every entry is 4 chunks = one [128 x 128] matrix):
