@@ -4,6 +4,8 @@
   * 10506-shaped batch (25 atoms, F = 256): the fp32 SIMT path (tensor cores are built for F = 128)
   * cfg 2 with return_dlogp=True: the drift plus its exact divergence (27 forward-mode tangent directions),
     with the CPU oracle's autograd divergence timed on a 32-conformer sample beside it
+  * cfg 1 (ADW): FCNetMultiBeta fp64, 10 000 samples, 100 Euler steps with the exact 1-D divergence, and the CPU
+    oracle (the reference's own loop restated) on the same workload
 Run on a B200:  python tools/extra_benchmarks.py > gpurun_out/extra.jsonl"""
 import json
 import os
@@ -100,6 +102,29 @@ def main():
                           cpu_oracle=dict(value=32 / cpu_sec, seconds=cpu_sec, sample="32 conformers, autograd, "
                                           f"{torch.get_num_threads()} threads"),
                           max_rel_diff_vs_oracle_on_sample=err)), flush=True)
+    del model, mb, eng, pb
+    # ---- cfg 1: asymmetric double well (the reference's CPU configuration)
+    from thermodynamic_interpolation_b200.adw.integrators import StandardIntegrator
+    from thermodynamic_interpolation_b200.adw.models.simple import FCNetMultiBeta
+    torch.manual_seed(5)
+    adw = perturb_(FCNetMultiBeta(1, 1, 256, 5).double(), 6).eval()
+    gen = torch.Generator().manual_seed(7)
+    x0 = torch.randn(10000, 1, generator=gen)
+    b0 = torch.full((10000, 1), 1.0, dtype=torch.float64)
+    b1 = torch.full((10000, 1), 1.25, dtype=torch.float64)
+    t0 = time.perf_counter()
+    xo, dlo = co.adw_rollout(adw.state_dict(), x0, b0, b1, method="euler", n_step=101)
+    cpu_sec = time.perf_counter() - t0
+    adw = adw.to(DEV)
+    integ = StandardIntegrator(adw, method="euler", n_step=101, return_dlogp=True)
+    args = (x0.to(DEV), b0.to(DEV), b1.to(DEV))
+    integ.rollout(*args)
+    (x, dl), sec = timed(lambda: integ.rollout(*args), reps=3)
+    err = float((x[-1].cpu().double() - xo[-1].double()).abs().max())
+    print(json.dumps(dict(workload="cfg 1: ADW FCNetMultiBeta fp64, 10000 samples x 100 Euler steps with exact divergence",
+                          seconds=sec, value=10000 * 100 / sec, unit="sample*steps/s",
+                          cpu_oracle=dict(value=10000 * 100 / cpu_sec, seconds=cpu_sec, threads=torch.get_num_threads()),
+                          max_abs_diff_final_x=err)), flush=True)
 
 
 if __name__ == "__main__":
