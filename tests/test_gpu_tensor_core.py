@@ -250,3 +250,26 @@ def test_tc_positional_encoding_cache_is_bit_identical_on_partial_tiles(monkeypa
     assert torch.isfinite(plain).all()
     for c in cached:
         assert torch.equal(c, plain)
+
+
+def test_tc_cfg4_shard_size():
+    """BASELINE cfg 4: one GPU's shard of the temperature sweep, 125 000 conformers x 9 atoms in ONE batch (1.1 M nodes,
+    9 M edges, 4.6 GB of edge features).  Size-independent properties: finite drift, and a slice of the batch gets the
+    same drift when it is evaluated on its own (molecules are independent; different tiles, different CTAs)."""
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    from thermodynamic_interpolation_b200.dist import shard_batch
+    torch.manual_seed(81)
+    model = perturb_(cPaiNN(n_features=128, score_layers=5, temp_length=100), 82).eval().to(DEV)
+    mb = synthetic_ambient_batch(125_000, 9, seed=83).to(DEV)
+    eng = model.engine()
+    full = eng.drift(eng.prepare(mb), mb.x0, 0.7).clone()
+    eng.status()
+    assert torch.isfinite(full).all()
+    sub = shard_batch(mb, 77, 125)                  # molecules [77000, 78000)
+    out = eng.drift(eng.prepare(sub), sub.x0.contiguous(), 0.7)
+    eng.status()
+    ref = full[77_000 * 9: 78_000 * 9]
+    err = float((out - ref).abs().max() / ref.abs().max())
+    print(f"[tc] cfg4 shard: slice vs full batch {err:.3e}")
+    assert err < 1e-5
