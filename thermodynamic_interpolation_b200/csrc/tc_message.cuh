@@ -46,8 +46,8 @@ constexpr int kChunksPerLayer = 60;
 //   0 w.W1 | 4 phi.W1[:, :F] | 8 w.W2 | 12 phi.W1[:, F:] | 16 phi.W2 | 20+8sp: phi.W3[sp] and w.W3[sp] interleaved
 //   chunk by chunk (phi k0, w k0, phi k1, w k1, ...) so the two independent accumulators alternate in the MMA queue
 struct MsgParams {
-  const float *phi_b1, *phi_g1, *phi_be1, *phi_b2, *phi_g2, *phi_be2, *phi_b3;
-  const float *w_b1, *w_g1, *w_be1, *w_b2, *w_g2, *w_be2, *w_b3;
+  const float* vec[12];   // w {b1,g1,be1,b2,g2,be2} then phi {b1,g1,be1,b2,g2,be2}: rows [0,12) of PRM
+  const float *phi_b3, *w_b3;
 };
 
 struct TcMsgP {
@@ -231,6 +231,8 @@ __device__ __forceinline__ void gemm_pair_job(uint64_t* bars, uint32_t ring, Mma
   }
 }
 
+// DIAG = the stall-cycle counters of tib_debug_counters; the production instantiation carries none of their registers.
+template <bool DIAG>
 __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* const X = smem + MsgSmem::X;
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + MsgSmem::BARS + 8 * B_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   volatile int* err = p.err;
-  const bool diag = p.dbg != nullptr;
+  constexpr bool diag = DIAG;
 
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) mbar_init(&bars[B_FULL + i], 1);
@@ -258,12 +260,12 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, 512);
-  {
-    const float* src[22] = {p.prm.w_b1, p.prm.w_g1, p.prm.w_be1, p.prm.w_b2, p.prm.w_g2, p.prm.w_be2,
-                            p.prm.phi_b1, p.prm.phi_g1, p.prm.phi_be1, p.prm.phi_b2, p.prm.phi_g2, p.prm.phi_be2,
-                            p.prm.phi_b3, p.prm.phi_b3 + kF, p.prm.phi_b3 + 2 * kF, p.prm.phi_b3 + 3 * kF, p.prm.phi_b3 + 4 * kF,
-                            p.prm.w_b3, p.prm.w_b3 + kF, p.prm.w_b3 + 2 * kF, p.prm.w_b3 + 3 * kF, p.prm.w_b3 + 4 * kF};
-    for (int i = tid; i < kPrmFloats; i += kThreads) PRM[i] = __ldg(src[i >> 7] + (i & 127));
+  // PRM rows [0,12) are the 12 vectors of MsgParams in kPrmRow order, rows [12,17) phi b3, rows [17,22) w b3; the pointer
+  // table is read from the kernel-parameter bank (a local array of pointers would live on the stack)
+  for (int i = tid; i < kPrmFloats; i += kThreads) {
+    const int r = i >> 7;
+    const float* src = r < 12 ? p.prm.vec[r] : (r < 17 ? p.prm.phi_b3 + (r - 12) * kF : p.prm.w_b3 + (r - 17) * kF);
+    PRM[i] = __ldg(src + (i & 127));
   }
   tc_fence_before();
   __syncthreads();
@@ -308,7 +310,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
           if (++stage == kStages) { stage = 0; ph ^= 1; }
         }
       }
-      if (p.dbg) p.dbg[blockIdx.x * 8 + 2] = w_empty;
+      if (diag) p.dbg[blockIdx.x * 8 + 2] = w_empty;
     }
   } else if (warp == 17) {
     // =========================== MMA issuer ===========================
@@ -368,7 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         }
         tc_commit(&bars[B_XFREE]);                          // X (and Y) may be overwritten for the next tile
       }
-      if (p.dbg) {
+      if (diag) {
         p.dbg[blockIdx.x * 8 + 0] = rs.w_weights; p.dbg[blockIdx.x * 8 + 1] = w_operands;
         p.dbg[blockIdx.x * 8 + 3] = w_tempty; p.dbg[blockIdx.x * 8 + 4] = clock64() - t_start;
         p.dbg[blockIdx.x * 8 + 5] = rs.t_issue; p.dbg[blockIdx.x * 8 + 6] = rs.t_commit;
@@ -658,7 +660,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
       named_bar_sync(NB_ALL, kEpiThreads);                  // every reader of this tile's tables is done
       TIB_PHASE(6);     // write-back + end-of-tile barrier
     }
-    if (p.dbg && (tid == 0 || tid == 256)) {
+    if (diag && (tid == 0 || tid == 256)) {
       if (tid == 0) p.dbg[blockIdx.x * 8 + 7] = w_tfull + w_acc;
       for (int i = 0; i < 8; ++i) p.dbg[(size_t)(gridDim.x + blockIdx.x * 2 + (tid ? 1 : 0)) * 8 + i] = phc[i];
     }

@@ -311,7 +311,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
   if (use_tc) {
     if (b->n_edges >= (1ll << 31)) return fail("tensor-core path: n_edges=%lld exceeds int32 row indices", (long long)b->n_edges);
     if (!m->tc_attrs_set) {
-      if (set_smem(tc::k_message_tc, tc::MsgSmem::TOTAL)) return -1;
+      if (set_smem(tc::k_message_tc<false>, tc::MsgSmem::TOTAL)) return -1;
+      if (set_smem(tc::k_message_tc<true>, tc::MsgSmem::TOTAL)) return -1;
       if (set_smem(tc::k_update_tc, tc::UpdSmem::TOTAL)) return -1;
       if (set_smem(tc::k_readout_tc, tc::RoSmem::TOTAL)) return -1;
       if (set_smem(k_phi_table<F, 16>, sizeof(float) * 8 * 4 * F)) return -1;
@@ -356,12 +357,13 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       if (ws.peimg && (size_t)n_tiles * tc::kOperandBytes <= ws.peimg_bytes && m->d.n_layers > 1 && !getenv("TIB_NO_PE_CACHE")) {
         tp.pe_img = ws.peimg; tp.pe_mode = l == 0 ? 1 : 2;
       }
-      tp.prm = tc::MsgParams{L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2, L.phi.b3,
-                             L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2, L.w.b3};
+      tp.prm = tc::MsgParams{{L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2,
+                              L.phi.b1, L.phi.g1, L.phi.be1, L.phi.b2, L.phi.g2, L.phi.be2}, L.phi.b3, L.w.b3};
       tp.length_scale = m->d.length_scale; tp.first_layer = (l == 0); tp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3;
       tp.err = m->dev_err; tp.dbg = m->dev_dbg;
       ProfScope ps(TIB_K_MESSAGE, st);
-      tc::k_message_tc<<<std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st>>>(tp);
+      if (tp.dbg) tc::k_message_tc<true><<<std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st>>>(tp);
+      else tc::k_message_tc<false><<<std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st>>>(tp);
       LAUNCH_CHECK();
     } else {
       MessageP mp{db, L.phi, L.w, x, ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->d.length_scale, l == 0};
