@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TIB_ABI_VERSION 4
+#define TIB_ABI_VERSION 5
 
 /* ---- model ------------------------------------------------------------------------------- */
 
@@ -35,8 +35,11 @@ enum { TIB_VARIANT_AMBIENT = 0,       /* T0 and T1 encoders   (mdqm9/thermo/ambi
 /* GEMM arithmetic of the MLP / equivariant-linear layers. */
 enum { TIB_MATH_FP32_SIMT = 0,        /* fp32 FMA on CUDA cores: rounds like the reference op by op          */
        TIB_MATH_F16X3_TC = 1,         /* tcgen05, operands split hi+lo f16 (22 bits), 3 MMAs, fp32 accumulate: */
-                                      /*   fp32-faithful (~2^-21 per product); n_features = 128 only          */
-       TIB_MATH_F16_TC = 2            /* tcgen05, single f16 pass (TF32-class, ~2^-11): opt-in only           */ };
+                                      /*   fp32-faithful (~2^-21 per product); n_features = 128 (fused message */
+                                      /*   / update / readout kernels) and 256 (layered MLP-chain kernels)     */
+       TIB_MATH_F16_TC = 2,           /* tcgen05, single f16 pass (TF32-class, ~2^-11): opt-in only           */
+       TIB_MATH_F16X3_LAYERED = 3     /* F16X3 arithmetic on the layered kernels also for n_features = 128     */
+                                      /*   (cross-check of the path the divergence and F = 256 use)            */ };
 
 typedef struct tib_model tib_model;
 
@@ -125,12 +128,14 @@ int tib_drift(tib_model* m, const tib_batch* b, const float* x, float t, float* 
  * (mdqm9/thermo/ambient/models/ode_wrapper.py:39-49,59-91; latent/models/ode_wrapper.py:38-46,57-86):
  *   out_div[mol] = sum over atoms a and coordinates c of d b[a][c] / d x[a][c], UNSCALED (the ambient
  *   wrapper's x 1e-2 and the sign are applied by the caller), fp32 [n_mol] on the device.
- * The reference runs 3n reverse passes; this runs 3 * max_atoms forward-mode tangent directions through
- * dual-number fp32 kernels (always CUDA-core arithmetic, whatever tib_model_set_math says), D at a time,
- * and - unlike the reference (ode_wrapper.py:75,79) - accepts molecules of different sizes.
- * out_b is the TIB_MATH_FP32_SIMT drift up to the grouping of the per-node edge sums.  The workspace is larger than
- * tib_workspace_bytes: use tib_div_workspace_bytes. */
-size_t tib_div_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges);
+ * The reference runs 3n reverse passes; this runs 3 * max_atoms forward-mode tangent directions and - unlike the
+ * reference (ode_wrapper.py:75,79) - accepts molecules of different sizes.  With a tensor-core math mode
+ * (n_features 128 / 256) the primal runs layer by layer on the MLP-chain kernels (csrc/tc_chain.cuh) keeping its
+ * LayerNorm intermediates, and the tangents go through the same weights on tcgen05: one tangent for the w MLP (it
+ * depends on x through the scalar distance), none for the first layer's phi MLP.  With TIB_MATH_FP32_SIMT (and for
+ * n_features 32 / 64) dual-number fp32 kernels carry D directions per pass.  The workspace is larger than
+ * tib_workspace_bytes: use tib_div_workspace_bytes (max_atoms = the batch's largest molecule). */
+size_t tib_div_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges, int32_t max_atoms);
 int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div,
                   void* workspace, size_t workspace_bytes, void* stream);
 

@@ -7,14 +7,14 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtib.so")
-ABI_VERSION = 4
+ABI_VERSION = 5
 
 VARIANT_AMBIENT, VARIANT_LATENT_MULTI_T, VARIANT_LATENT_SINGLE_T = 0, 1, 2
-MATH_FP32_SIMT, MATH_F16X3_TC, MATH_F16_TC = 0, 1, 2
+MATH_FP32_SIMT, MATH_F16X3_TC, MATH_F16_TC, MATH_F16X3_LAYERED = 0, 1, 2, 3
 METHOD_EULER, METHOD_MIDPOINT, METHOD_RK4 = 0, 1, 2
 KERNEL_KINDS = ("embed", "edge_init", "message", "update", "readout", "step")
 N_KERNEL_KINDS = len(KERNEL_KINDS)
-MATH_NAMES = {0: "fp32_simt", 1: "f16x3_tcgen05", 2: "f16_tcgen05"}
+MATH_NAMES = {0: "fp32_simt", 1: "f16x3_tcgen05", 2: "f16_tcgen05", 3: "f16x3_tcgen05_layered"}
 METHODS = {"euler": METHOD_EULER, "midpoint": METHOD_MIDPOINT, "rk4": METHOD_RK4}
 
 
@@ -64,7 +64,7 @@ SYMBOLS = [
     ("tib_selftest_gemm", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     ("tib_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
     ("tib_drift", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
-    ("tib_div_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64]),
+    ("tib_div_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     ("tib_drift_div", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_zmatrix", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("tib_step_euler", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -19,6 +19,8 @@
 #include "tc_selftest.cuh"
 #include "tc_update.cuh"
 #include "tc_readout.cuh"
+#include "tc_chain.cuh"
+#include "layered.cuh"
 
 namespace {
 
@@ -94,7 +96,12 @@ struct tib_model {
   const float* edge_emb = nullptr;
   const float* atom_emb = nullptr;
   tib::MlpW combine{};
-  struct Layer { tib::MlpW phi, w, upd; const float *Ut, *Vt; const unsigned char* tc_msg = nullptr; const unsigned char* tc_upd = nullptr; };
+  struct Layer {
+    tib::MlpW phi, w, upd; const float *Ut, *Vt; const unsigned char* tc_msg = nullptr; const unsigned char* tc_upd = nullptr;
+    // layered path (tc_chain.cuh): weight streams of the phi / w / update MLPs and of the [V; U] GEMM, max |LayerNorm gain|
+    const unsigned char *ch_phi = nullptr, *ch_w = nullptr, *ch_uv = nullptr, *ch_upd = nullptr;
+    float gmax_phi[2], gmax_w[2], gmax_upd[2];
+  };
   std::vector<Layer> layers;
   tib::MlpW readout{};
   const unsigned char* tc_ro = nullptr;   // readout W1 | W2 as tensor-core chunks (F = 128)
@@ -102,7 +109,9 @@ struct tib_model {
   bool attrs_set = false;
   // tensor-core path (F = 128): per-layer streamed weight chunks in split-f16 operand images
   unsigned char* tc_blob = nullptr;
+  unsigned char* ch_blob = nullptr;   // layered path (F = 128, 256)
   bool tc_attrs_set = false;
+  bool ch_attrs_set = false;
   bool jvp_attrs_set = false;
   int* dev_err = nullptr;     // device error words: [0] bounded mbarrier waits, [1] non-finite tensor-core readout
   int n_sms = 148;
@@ -185,7 +194,8 @@ struct Workspace {
   int *node_in_ptr;
   uint4 *rowa, *rowb;
   float *phitab;     // [kPhiTabRows][F] first-layer phi table (tc_message.cuh)
-  unsigned char *peimg; size_t peimg_bytes;   // positional-encoding operand images, 64 KB per message tile (tc_message.cuh)
+  unsigned char *peimg; size_t peimg_bytes;
+  char* end;         // first byte after the carved region (the layered path carves its arrays from here)   // positional-encoding operand images, 64 KB per message tile (tc_message.cuh)
   static size_t pe_bytes(int n_nodes, long long n_edges) {   // tiles close at 16 nodes or at > 64 rows
     return (size_t)65536 * ((size_t)n_nodes / 16 + (size_t)n_edges / 64 + 2);
   }
@@ -228,6 +238,7 @@ struct Workspace {
     phitab = (float*)take(sizeof(float) * (size_t)kPhiTabRows * F);
     peimg_bytes = F == 128 ? pe_bytes(n_nodes, n_edges) : 0;
     peimg = F == 128 ? (unsigned char*)take(peimg_bytes) : nullptr;
+    end = p;
   }
   static size_t kstride(int n_nodes) { return align(sizeof(float) * (size_t)n_nodes * 3) / sizeof(float); }
 };
@@ -495,6 +506,8 @@ int drift_div_simt(tib_model* m, const tib_batch* b, const float* x, float t, fl
   return 0;
 }
 
+#include "layered_api.inl"
+
 int check_batch(const tib_model* m, const tib_batch* b) {
   if (!m || !b) return fail("null model or batch");
   if (b->n_mol <= 0 || b->n_nodes <= 0) return fail("empty batch (n_mol=%d, n_nodes=%d)", b->n_mol, b->n_nodes);
@@ -506,16 +519,26 @@ int check_batch(const tib_model* m, const tib_batch* b) {
   return 0;
 }
 
+bool uses_layered(const tib_model* m) {
+  return (m->d.n_features == 256 && m->math != TIB_MATH_FP32_SIMT) || (m->d.n_features == 128 && m->math == TIB_MATH_F16X3_LAYERED);
+}
+
 int drift_dispatch(tib_model* m, const tib_batch* b, const float* x, float t, float* out, Workspace& ws, cudaStream_t st) {
-  if (m->math != TIB_MATH_FP32_SIMT && m->d.n_features != 128)
-    return fail("the tensor-core math modes are built for n_features = 128 (got %d); use TIB_MATH_FP32_SIMT", m->d.n_features);
-  switch (m->d.n_features) {
+  const int F = m->d.n_features;
+  if (m->math != TIB_MATH_FP32_SIMT && F != 128 && F != 256)
+    return fail("the tensor-core math modes are built for n_features = 128 and 256 (got %d); use TIB_MATH_FP32_SIMT", F);
+  if (uses_layered(m)) {
+    LayWs lw;
+    lw.layout((char*)ws.end, F, b->n_nodes, (long long)b->n_edges, b->max_atoms, false);
+    return F == 256 ? drift_layered<256>(m, b, x, t, out, ws, lw, st) : drift_layered<128>(m, b, x, t, out, ws, lw, st);
+  }
+  switch (F) {
     case 32: return drift_simt<32>(m, b, x, t, out, ws, st);
     case 64: return drift_simt<64>(m, b, x, t, out, ws, st);
     case 128: return drift_simt<128>(m, b, x, t, out, ws, st);
     case 256: return drift_simt<256>(m, b, x, t, out, ws, st);
   }
-  return fail("unsupported n_features=%d", m->d.n_features);
+  return fail("unsupported n_features=%d", F);
 }
 
 int grid_for(size_t n, int threads = 256) {
@@ -524,8 +547,14 @@ int grid_for(size_t n, int threads = 256) {
   return (int)(blocks < 1 ? 1 : (blocks > cap ? cap : blocks));
 }
 
+size_t drift_ws_bytes(const tib_model* m, int n_nodes, long long n_edges, int max_atoms) {
+  size_t need = Workspace::bytes(m->d.n_features, n_nodes, n_edges);
+  if (uses_layered(m)) need += LayWs::bytes(m->d.n_features, n_nodes, n_edges, max_atoms, false);
+  return need;
+}
+
 int prep_ws(const tib_model* m, const tib_batch* b, void* workspace, size_t workspace_bytes, Workspace& ws) {
-  const size_t need = Workspace::bytes(m->d.n_features, b->n_nodes, (long long)b->n_edges);
+  const size_t need = drift_ws_bytes(m, b->n_nodes, (long long)b->n_edges, b->max_atoms);
   if (!workspace || workspace_bytes < need) return fail("workspace too small: %zu < %zu bytes", workspace_bytes, need);
   if (((uintptr_t)workspace & 255) != 0) return fail("workspace must be 256-byte aligned");
   ws.carve(workspace, m->d.n_features, b->n_nodes, (long long)b->n_edges);
@@ -595,7 +624,7 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
   m->d = *d;
   m->device = device;
   m->n_temp = n_temp_of(d->variant);
-  m->math = (F == 128) ? TIB_MATH_F16X3_TC : TIB_MATH_FP32_SIMT;
+  m->math = (F == 128 || F == 256) ? TIB_MATH_F16X3_TC : TIB_MATH_FP32_SIMT;
   const int nt = m->n_temp;
 
   // upper bound of the staged size: every tensor padded to 4 floats
@@ -714,6 +743,31 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
     for (int l = 0; l < d->n_layers; ++l) { m->layers[l].tc_msg = m->tc_blob + per_layer * l; m->layers[l].tc_upd = m->tc_blob + per_layer * l + per_msg; }
     m->tc_ro = m->tc_blob + per_layer * d->n_layers;
   }
+  if (F == 128 || F == 256) {
+    // layered path (tc_chain.cuh): per layer the streams of phi, w, [V; U] and the update MLP
+    std::vector<uint16_t> blob;
+    std::vector<size_t> offs;
+    std::vector<float> vu((size_t)2 * F * F);
+    for (int l = 0; l < d->n_layers; ++l) {
+      auto& L = m->layers[l];
+      offs.push_back(blob.size()); pack_chain_mlp(blob, phi_src[l], F, 2 * F, 5 * F, L.gmax_phi);
+      offs.push_back(blob.size()); pack_chain_mlp(blob, w_src[l], F, F, 5 * F, L.gmax_w);
+      const float* U = uv_src[l];
+      const float* V = U + (size_t)F * F;
+      std::memcpy(vu.data(), V, sizeof(float) * F * F);
+      std::memcpy(vu.data() + (size_t)F * F, U, sizeof(float) * F * F);
+      offs.push_back(blob.size()); pack_chain_matrix(blob, vu.data(), F, 2 * F, 0, F);
+      offs.push_back(blob.size()); pack_chain_mlp(blob, V + (size_t)F * F, F, 2 * F, 3 * F, L.gmax_upd);
+    }
+    e = cudaMalloc(&m->ch_blob, blob.size() * 2);
+    if (e == cudaSuccess) e = cudaMemcpy(m->ch_blob, blob.data(), blob.size() * 2, cudaMemcpyHostToDevice);
+    if (e != cudaSuccess) { tib_model_destroy(m); return fail("layered weight upload: %s", cudaGetErrorString(e)); }
+    for (int l = 0; l < d->n_layers; ++l) {
+      auto& L = m->layers[l];
+      L.ch_phi = m->ch_blob + offs[4 * l] * 2; L.ch_w = m->ch_blob + offs[4 * l + 1] * 2;
+      L.ch_uv = m->ch_blob + offs[4 * l + 2] * 2; L.ch_upd = m->ch_blob + offs[4 * l + 3] * 2;
+    }
+  }
   *out = m;
   return 0;
 }
@@ -722,6 +776,7 @@ void tib_model_destroy(tib_model* m) {
   if (!m) return;
   if (m->dev) cudaFree(m->dev);
   if (m->tc_blob) cudaFree(m->tc_blob);
+  if (m->ch_blob) cudaFree(m->ch_blob);
   if (m->dev_err) cudaFree(m->dev_err);
   if (m->dev_dbg) cudaFree(m->dev_dbg);
   delete m;
@@ -758,9 +813,10 @@ int tib_debug_counters(tib_model* m, int enable, long long* out, int max_ctas) {
 
 int tib_model_set_math(tib_model* m, int math_mode) {
   if (!m) return fail("null model");
-  if (math_mode < TIB_MATH_FP32_SIMT || math_mode > TIB_MATH_F16_TC) return fail("unknown math mode %d", math_mode);
-  if (math_mode != TIB_MATH_FP32_SIMT && m->d.n_features != 128)
-    return fail("the tensor-core math modes are built for n_features = 128 (got %d)", m->d.n_features);
+  if (math_mode < TIB_MATH_FP32_SIMT || math_mode > TIB_MATH_F16X3_LAYERED) return fail("unknown math mode %d", math_mode);
+  const int F = m->d.n_features;
+  if (math_mode != TIB_MATH_FP32_SIMT && F != 128 && F != 256)
+    return fail("the tensor-core math modes are built for n_features = 128 and 256 (got %d)", F);
   m->math = math_mode;
   return 0;
 }
@@ -768,7 +824,7 @@ int tib_model_set_math(tib_model* m, int math_mode) {
 size_t tib_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges) {
   (void)n_mol;
   if (!m) return 0;
-  return Workspace::bytes(m->d.n_features, n_nodes, (long long)n_edges);
+  return drift_ws_bytes(m, n_nodes, (long long)n_edges, TIB_MAX_ATOMS);
 }
 
 int tib_drift(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, void* workspace,
@@ -780,11 +836,14 @@ int tib_drift(tib_model* m, const tib_batch* b, const float* x, float t, float* 
   return drift_dispatch(m, b, x, t, out_b, ws, (cudaStream_t)stream);
 }
 
-size_t tib_div_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges) {
+size_t tib_div_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges, int32_t max_atoms) {
   (void)n_mol;
   if (!m) return 0;
   const int F = m->d.n_features;
-  return Workspace::bytes(F, n_nodes, (long long)n_edges) + TangentWs::bytes(F, jvp_dirs(F), n_nodes, (long long)n_edges);
+  const size_t simt = TangentWs::bytes(F, jvp_dirs(F), n_nodes, (long long)n_edges);
+  const bool tc = m->math != TIB_MATH_FP32_SIMT && (F == 128 || F == 256);
+  const size_t lay = tc ? LayWs::bytes(F, n_nodes, (long long)n_edges, max_atoms, true) : 0;
+  return Workspace::bytes(F, n_nodes, (long long)n_edges) + std::max(simt, lay);
 }
 
 int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div, void* workspace,
@@ -792,13 +851,20 @@ int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, flo
   if (check_batch(m, b)) return -1;
   if (!x || !out_b || !out_div) return fail("tib_drift_div: null x/out");
   const int F = m->d.n_features;
-  const size_t need = tib_div_workspace_bytes(m, b->n_mol, b->n_nodes, b->n_edges);
+  const size_t need = tib_div_workspace_bytes(m, b->n_mol, b->n_nodes, b->n_edges, b->max_atoms);
   if (!workspace || workspace_bytes < need) return fail("divergence workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  if (((uintptr_t)workspace & 255) != 0) return fail("workspace must be 256-byte aligned");
   Workspace ws;
-  if (prep_ws(m, b, workspace, workspace_bytes, ws)) return -1;
-  TangentWs tw;
-  tw.carve((char*)workspace + Workspace::bytes(F, b->n_nodes, (long long)b->n_edges), F, jvp_dirs(F), b->n_nodes, (long long)b->n_edges);
+  ws.carve(workspace, F, b->n_nodes, (long long)b->n_edges);
   cudaStream_t st = (cudaStream_t)stream;
+  if (m->math != TIB_MATH_FP32_SIMT && (F == 128 || F == 256)) {
+    LayWs lw;
+    lw.layout(ws.end, F, b->n_nodes, (long long)b->n_edges, b->max_atoms, true);
+    return F == 128 ? drift_div_layered<128>(m, b, x, t, out_b, out_div, ws, lw, st)
+                    : drift_div_layered<256>(m, b, x, t, out_b, out_div, ws, lw, st);
+  }
+  TangentWs tw;
+  tw.carve(ws.end, F, jvp_dirs(F), b->n_nodes, (long long)b->n_edges);
   switch (F) {
     case 32: return drift_div_simt<32>(m, b, x, t, out_b, out_div, ws, tw, st);
     case 64: return drift_div_simt<64>(m, b, x, t, out_b, out_div, ws, tw, st);

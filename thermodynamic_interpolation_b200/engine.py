@@ -263,7 +263,7 @@ class DriftEngine:
         x = self._state(x, pb)
         out = torch.empty_like(x)
         div = torch.empty(pb.n_mol, dtype=torch.float32, device=self.device)
-        need = self.lib.tib_div_workspace_bytes(self.handle, pb.n_mol, pb.n_nodes, pb.n_edges)
+        need = self.lib.tib_div_workspace_bytes(self.handle, pb.n_mol, pb.n_nodes, pb.n_edges, pb.max_atoms)
         if self._ws_div is None or self._ws_div.numel() < need + 256:
             self._ws_div = None
             self._ws_div = torch.empty(need + 256, dtype=torch.uint8, device=self.device)

@@ -42,7 +42,38 @@ def euler_rate(model, mb, steps):
     return pb.n_mol * steps / sec, sec / steps
 
 
+def kernel_shares(fn):
+    """Per-kernel-class device time (tib_profile_begin/end) of one call of fn."""
+    import ctypes as C
+    lib = _lib.load()
+    ms = (C.c_double * _lib.N_KERNEL_KINDS)()
+    n = (C.c_uint64 * _lib.N_KERNEL_KINDS)()
+    lib.tib_profile_begin()
+    fn()
+    torch.cuda.synchronize()
+    lib.tib_profile_end(ms, n)
+    return {k: dict(ms=round(ms[i], 3), launches=int(n[i])) for i, k in enumerate(_lib.KERNEL_KINDS) if n[i]}
+
+
 def main():
+    import argparse
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--only", default="cfg3,dopri5,f256,div,adw")
+    ap.add_argument("--f256-mols", type=int, default=512)
+    only = set(ap.parse_args().only.split(","))
+    if "cfg3" in only:
+        bench_cfg3()
+    if "dopri5" in only:
+        bench_dopri5()
+    if "f256" in only:
+        bench_f256(ap.parse_args().f256_mols)
+    if "div" in only:
+        bench_div()
+    if "adw" in only:
+        bench_adw()
+
+
+def bench_cfg3():
     # ---- cfg 3
     from thermodynamic_interpolation_b200.latent.models.cpainn import cPaiNN as Latent
     torch.manual_seed(0)
@@ -54,7 +85,9 @@ def main():
     print(json.dumps(dict(workload="cfg 3: latent multi-T, 16384 molecules with 9..25 atoms, F=128 L=5, Euler",
                           math=_lib.MATH_NAMES[1], value=rate, unit="molecule*steps/s", ms_per_step=per * 1e3,
                           n_nodes=int(mb.x0.shape[0]), n_edges=int(mb.edge_index.shape[1]))), flush=True)
-    del model, mb
+
+
+def bench_dopri5():
     # ---- cfg 2 under dopri5
     from thermodynamic_interpolation_b200.ambient.integrators import MoleculeIntegrator
     from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN as Ambient
@@ -68,19 +101,32 @@ def main():
                           math=_lib.MATH_NAMES[1], nfe=int(nfe), attempts=integ.last_stats["attempts"],
                           accepted=integ.last_stats["accepted"], seconds=sec, value=4096 * nfe / sec,
                           unit="molecule*drift-evals/s", finite=bool(torch.isfinite(xts).all()))), flush=True)
-    del model, mb, integ
-    # ---- 10506-shaped: 25 atoms, F = 256 (fp32 SIMT path)
+
+
+def bench_f256(n_mol):
+    # ---- 10506-shaped: 25 atoms, F = 256 (config/ambient/10506_settings_no_900.json:14): layered tcgen05 path vs fp32 kernels
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN as Ambient
     torch.manual_seed(0)
     model = perturb_(Ambient(n_features=256, score_layers=5, temp_length=100), 1).eval().to(DEV)
-    mb = synthetic_ambient_batch(512, 25, seed=100).to(DEV)
-    rate, per = euler_rate(model, mb, 5)
-    print(json.dumps(dict(workload="10506-shaped: 512 conformers x 25 atoms, F=256 L=5, Euler", math=_lib.MATH_NAMES[0],
-                          value=rate, unit="molecule*steps/s", ms_per_step=per * 1e3)), flush=True)
-    del model, mb
+    mb = synthetic_ambient_batch(n_mol, 25, seed=100).to(DEV)
+    for math in (1, 0):
+        model.set_math(math)
+        rate, per = euler_rate(model, mb, 5)
+        eng = model.engine()
+        pb = eng.prepare(mb)
+        shares = kernel_shares(lambda: eng.drift(pb, mb.x0.contiguous(), 0.3))
+        flops = 25 * 12 * 256 ** 2 + 5 * (600 * 30 * 256 ** 2 + 25 * 24 * 256 ** 2) + 25 * (4 * 256 ** 2)
+        print(json.dumps(dict(workload=f"10506-shaped: {n_mol} conformers x 25 atoms, F=256 L=5, Euler", math=_lib.MATH_NAMES[math],
+                              value=rate, unit="molecule*steps/s", ms_per_step=per * 1e3, algorithmic_tflops=rate * flops / 1e12,
+                              kernel_ms_per_drift=shares)), flush=True)
+
+
+def bench_div():
     # ---- cfg 2 with the exact divergence (return_dlogp=True right-hand side)
     import time
     from oracle import cpainn_oracle as co   # CPU baseline leg only
     from tests._util import oracle_hp_sd, oracle_temps
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN as Ambient
     torch.manual_seed(0)
     model = perturb_(Ambient(n_features=128, score_layers=5, temp_length=100), 1).eval().to(DEV)
     mb = synthetic_ambient_batch(4096, 9, seed=100).to(DEV)
@@ -88,6 +134,8 @@ def main():
     pb = eng.prepare(mb)
     eng.drift_div(pb, mb.x0.contiguous(), 0.3)
     (b, div), sec = timed(lambda: eng.drift_div(pb, mb.x0.contiguous(), 0.3), reps=2)
+    shares = kernel_shares(lambda: eng.drift_div(pb, mb.x0.contiguous(), 0.3))
+    _, sec_drift = timed(lambda: eng.drift(pb, mb.x0.contiguous(), 0.3), reps=3)
     small = synthetic_ambient_batch(32, 9, seed=100)
     hp, sd = oracle_hp_sd(model)
     torch.set_num_threads(len(os.sched_getaffinity(0)))
@@ -97,13 +145,18 @@ def main():
     cpu_sec = time.perf_counter() - t0
     err = float((div[:32].cpu() - dref).abs().max() / dref.abs().max())
     print(json.dumps(dict(workload="cfg 2 right-hand side with return_dlogp=True: drift + exact divergence, 4096 x 9 atoms, F=128 L=5",
-                          math="fp32 dual-number kernels, 3 directions per pass", seconds_per_eval=sec,
+                          math="tangent GEMMs on tcgen05 (split-f16 x3), layered MLP-chain kernels", seconds_per_eval=sec,
+                          seconds_per_plain_drift=sec_drift, ratio_to_plain_drift=sec / sec_drift, kernel_ms=shares,
                           value=4096 / sec, unit="molecule*(drift+divergence) evals/s",
                           cpu_oracle=dict(value=32 / cpu_sec, seconds=cpu_sec, sample="32 conformers, autograd, "
                                           f"{torch.get_num_threads()} threads"),
                           max_rel_diff_vs_oracle_on_sample=err)), flush=True)
-    del model, mb, eng, pb
+
+
+def bench_adw():
     # ---- cfg 1: asymmetric double well (the reference's CPU configuration)
+    import time
+    from oracle import cpainn_oracle as co   # CPU baseline leg only
     from thermodynamic_interpolation_b200.adw.integrators import StandardIntegrator
     from thermodynamic_interpolation_b200.adw.models.simple import FCNetMultiBeta
     torch.manual_seed(5)
