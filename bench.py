@@ -1,29 +1,35 @@
 #!/usr/bin/env python
-"""bench.py - molecule*SDE-steps/sec of the MDQM9 ambient sampler hot path (BASELINE.json cfg 2).
+"""bench.py - molecule*SDE-steps/sec of the MDQM9 ambient sampler hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg4]
 
-One bench "step" = one integrator step of the sampler over the whole batch: one drift-network
-evaluation b(t, x, T0, T1) on every molecule plus the fused state update and frame write (the unit
-SURVEY.md section 8d defines).  Workload (configs[1]): 4096 conformers x 9 atoms per GPU, cPaiNN
-F=128, L=5, T0=1000 K -> T1=300 K, fixed-grid Euler on linspace(0, 1, K+1), random-init weights,
-synthetic centred coordinates.  Weak scaling: every rank integrates its own 4096 conformers; there
-is no collective on the data path (trajectories are independent) - the final statistics all-reduce
-is outside the per-step loop and is exercised once after the timed region.
+One bench "step" = one integrator step of the sampler over the whole batch: one drift-network evaluation
+b(t, x, T0, T1) on every molecule plus the fused state update (the unit SURVEY.md section 8d defines).
 
-`value`    : device-resident rollout (inputs already in HBM), CUDA events, max over ranks.
-`e2e`      : the same K steps through the public API `MoleculeIntegrator.rollout(batch)` with the
-             batch in pinned host memory (H2D inside the timed region) and all K+1 frames read back
-             to pinned host memory (D2H), as mdqm9/sample_ambient.py:74,88-91 does.
-`roofline` : dominant kernel (the per-molecule message kernel, 30 F^2 FLOP per edge per layer) from
-             CUDA event pairs recorded around each of its launches in the timed region.
-`cpu_baseline`: the CPU oracle (restatement of the reference, validated against the unmodified
-             reference's outputs in tests/golden) on the host cores, bounded sample.
+Workloads (BASELINE.json configs):
+  cfg2 (default, configs[1]): 4096 conformers x 9 atoms per GPU, cPaiNN F=128 L=5, T0=1000 K -> T1=300 K, fixed-grid Euler
+        on linspace(0, 1, K+1), all K+1 frames saved.  Weak scaling: every rank integrates its own 4096 conformers; no
+        collective on the data path.
+  cfg4 (configs[3]): the temperature sweep - 125 000 conformers per GPU (1 M on 8 GPUs) in chunks of 15 625, T1 cycling over
+        {300, ..., 900} K (mdqm9/config/ambient/00031_settings_no_{300..900}.json:32-33), K Euler steps per temperature, final
+        samples only; after every temperature the reweighting statistics (tib_reweight_stats -> ONE fp64 all-reduce of 5
+        numbers) and the IQR outlier mask from the all-gathered weights (mdqm9/analysis/utils/sensititvity.py:4-12, k = 100 as
+        at results_00031.py:248-268) - the collectives are INSIDE the timed region.
+
+`value`    : device-resident run (inputs already in HBM), CUDA events, max over ranks.
+`e2e`      : the same work through the public API `MoleculeIntegrator.rollout(batch)` with the batch in pinned host memory
+             (H2D inside the timed region) and the result read back to pinned host memory (D2H).
+`roofline` : dominant kernel (the fused message kernel, 30 F^2 FLOP per edge per layer) from CUDA event pairs recorded around
+             each of its launches in the timed region.
+`cpu_baseline` / `--impl reference`: the reference's OWN modules (staged under baseline/_ref by tools/stage_reference.py,
+             imported behind oracle/stubs) running MoleculeIntegrator(method='euler').rollout on the host cores, B_cpu = 256
+             (BASELINE.md section 5); when the staged files are absent, the oracle port (kind "port").
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import hashlib
 import json
 import os
 import subprocess
@@ -41,6 +47,7 @@ import torch  # noqa: E402
 
 METRIC = "molecule*SDE-steps/sec, MDQM9 ambient sampler"
 UNIT = "molecule*steps/s"
+SWEEP_T1 = [300.0, 400.0, 500.0, 600.0, 700.0, 800.0, 900.0]
 
 
 def flops_per_mol_step(n, F, L):
@@ -53,12 +60,23 @@ def message_flops_per_launch(n_mol, n, F):
     return n_mol * n * (n - 1) * 30 * F * F
 
 
+def kernel_source_sha():
+    h = hashlib.sha256()
+    for f in ("tc_message.cuh", "tc_common.cuh"):
+        with open(os.path.join(REPO, "thermodynamic_interpolation_b200", "csrc", f), "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()[:16]
+
+
 def load_traffic():
-    """Per-launch DRAM bytes of the dominant kernel from the committed ncu capture (None if absent)."""
-    p = os.path.join(REPO, "profiles", "r01_ncu_traffic.json")
+    """Per-launch DRAM bytes of the dominant kernel from the ncu capture of THIS build of the kernel
+    (profiles/r02_ncu_traffic.json carries the hash of the kernel sources it was taken from); None otherwise."""
+    p = os.path.join(REPO, "profiles", "r02_ncu_traffic.json")
     try:
         with open(p) as f:
             d = json.load(f)["k_message_tc"]
+        if d.get("src_sha") != kernel_source_sha():
+            return None
         return d["dram_bytes_read"] + d["dram_bytes_write"]
     except Exception:
         return None
@@ -124,24 +142,28 @@ class ClockSampler:
                     samples=len(sm), reasons=sorted(reasons))
 
 
-def build_model_and_batch(args, seed, n_mol):
-    from tests._util import perturb_
-    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+def build_model_and_batch(args, seed, n_mol, T1=300.0):
     from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
-    torch.manual_seed(0)
-    model = perturb_(cPaiNN(n_features=args.features, score_layers=args.layers, temp_length=100), 1).eval()
-    batch = synthetic_ambient_batch(n_mol, args.atoms, T0=1000.0, T1=300.0, sigma=0.3, seed=100 + seed)
+    from thermodynamic_interpolation_b200.synthetic import seeded_ambient_model
+    model = seeded_ambient_model(args.features, args.layers, 100, seed=0)
+    batch = synthetic_ambient_batch(n_mol, args.atoms, T0=1000.0, T1=T1, sigma=0.3, seed=100 + seed)
     return model, batch
 
 
 def workload_name(args):
+    if args.workload == "cfg4":
+        return (f"MDQM9 ambient temperature sweep, {args.mols} conformers x {args.atoms} atoms per GPU in chunks of {args.chunk}, "
+                f"T1 in {{300..900}} K, cPaiNN F={args.features} L={args.layers}, fixed-grid Euler, per-temperature reweighting "
+                f"all-reduce + IQR mask (BASELINE configs[3])")
     return (f"MDQM9 ambient sampling, {args.mols} conformers x {args.atoms} atoms per GPU, cPaiNN F={args.features} "
             f"L={args.layers}, fixed-grid Euler (BASELINE configs[1])")
 
 
 # ---------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(args, n_mol, budget_s, min_steps, fixed_steps=None, warmup=1):
-    """Oracle Euler steps on the host cores: returns (mol*steps/s, cores, steps, seconds)."""
+# CPU arms (oracle/ and baseline/_ref are used here and only here)
+# ---------------------------------------------------------------------------------------------------
+def cpu_port_rate(args, n_mol, budget_s, min_steps, fixed_steps=None, warmup=1):
+    """The oracle PORT (oracle/cpainn_oracle.py) Euler steps on the host cores: (mol*steps/s, cores, steps, seconds)."""
     from oracle import cpainn_oracle as co
     from tests._util import oracle_hp_sd
     cores = len(os.sched_getaffinity(0))
@@ -174,24 +196,79 @@ def cpu_oracle_rate(args, n_mol, budget_s, min_steps, fixed_steps=None, warmup=1
     return n_mol * done / el, cores, done, el
 
 
+def reference_root():
+    """The staged copy of the reference's own modules (GPU box) or the reference itself (build container)."""
+    for p in (os.path.join(REPO, "baseline", "_ref"), "/root/reference"):
+        if os.path.isdir(os.path.join(p, "mdqm9", "thermo")):
+            return p
+    return None
+
+
+def cpu_reference_rate(args, n_mol, steps, warmup):
+    """The UNMODIFIED reference: MoleculeIntegrator(b, method='euler', n_step=steps + 1).rollout(batch) on the host cores
+    (mdqm9/thermo/ambient/integrators.py:28-68), weights from the same seeded recipe as the B200 arm.
+    Returns (mol*steps/s, cores, seconds) or None when the reference files are not available."""
+    root = reference_root()
+    if root is None:
+        return None
+    os.environ["TI_REFERENCE_ROOT"] = root
+    from oracle import ref_loader
+    from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch
+    from thermodynamic_interpolation_b200.synthetic import perturb_
+    ref_loader.REFERENCE_ROOT = root
+    ns = ref_loader.load_mdqm9()
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = perturb_(ns.ambient_cpainn.cPaiNN(n_features=args.features, score_layers=args.layers, temp_length=100), 1).eval()
+    mb = synthetic_ambient_batch(n_mol, args.atoms, T0=1000.0, T1=300.0, sigma=0.3, seed=100)
+
+    def ref_batch():
+        b = ns.torch_geometric.data.Batch()
+        for k in mb.keys():
+            b[k] = mb[k].clone() if torch.is_tensor(mb[k]) else mb[k]
+        return b
+
+    if warmup > 0:
+        ns.ambient_integrators.MoleculeIntegrator(model, method="euler", n_step=warmup + 1).rollout(ref_batch())
+    integ = ns.ambient_integrators.MoleculeIntegrator(model, method="euler", n_step=steps + 1)
+    b = ref_batch()
+    t0 = time.perf_counter()
+    xts, dlogp, nfe, bvec = integ.rollout(b)
+    el = time.perf_counter() - t0
+    assert tuple(xts.shape) == (steps + 1, mb.x0.shape[0], 3) and torch.isfinite(xts).all()
+    return n_mol * steps / el, cores, el
+
+
 def run_reference(args):
-    """`--impl reference`: the reference algorithm's CPU implementation (oracle port - the reference
-    itself needs torch_geometric / torch_scatter / torchdiffeq, absent from this image and the GPU
-    box) on all host threads, same workload shape, each step a bounded sample of 128 conformers."""
+    """`--impl reference`: rank 0 only; the other ranks exit without work."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n_cpu = min(args.mols, 128)
-    rate, cores, steps, secs = cpu_oracle_rate(args, n_cpu, budget_s=0.0, min_steps=args.steps,
-                                               fixed_steps=args.steps, warmup=args.warmup)
-    sample = f"{n_cpu} conformers x {steps} Euler steps of the same workload ({secs:.1f} s)"
+    n_cpu = min(args.mols, 256)
+    ref = cpu_reference_rate(args, n_cpu, args.steps, args.warmup)
+    if ref is not None:
+        rate, cores, secs = ref
+        kind = "reference"
+        sample = (f"the reference's MoleculeIntegrator(method='euler', n_step={args.steps + 1}).rollout on {n_cpu} conformers "
+                  f"of the same workload ({secs:.1f} s, {cores} threads); the sweep / statistics part of cfg4 is not included")
+        port_rate, _, port_steps, port_secs = cpu_port_rate(args, 128, budget_s=4.0, min_steps=2)
+        port = dict(value=port_rate, unit=UNIT, kind="port", sample=f"oracle port, 128 conformers x {port_steps} Euler steps ({port_secs:.1f} s)")
+    else:
+        n_cpu = min(args.mols, 128)
+        rate, cores, steps, secs = cpu_port_rate(args, n_cpu, budget_s=0.0, min_steps=args.steps, fixed_steps=args.steps, warmup=args.warmup)
+        kind = "port"
+        sample = f"oracle port (reference files not staged): {n_cpu} conformers x {steps} Euler steps of the same workload ({secs:.1f} s)"
+        port = None
     line = dict(metric=METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                ms_per_step=1e3 * secs / steps, higher_is_better=True, scaling="weak", vs_baseline=None,
+                ms_per_step=1e3 * secs / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None,
                 dtype="f32", data="synthetic", impl="reference",
                 config=dict(workload=workload_name(args), sample=sample),
-                cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind="port", sample=sample),
+                cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind=kind, sample=sample),
                 e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0),
                 gpu_launches=0)
+    if port:
+        line["cpu_baseline_port"] = port
     print(json.dumps(line))
 
 
@@ -213,17 +290,27 @@ def run_b200(args):
         dist.init_process_group("nccl", device_id=dev)
     lib = _lib.load()
     K, W = args.steps, max(args.warmup, 0)
+    sweep = args.workload == "cfg4"
+    temps = SWEEP_T1 if sweep else [300.0]
+    chunk = min(args.chunk, args.mols) if sweep else args.mols
+    n_chunks = (args.mols + chunk - 1) // chunk
 
-    model, host_batch = build_model_and_batch(args, rank, args.mols)
-    host_batch.pin_memory()
+    model, _ = build_model_and_batch(args, rank, 1)
     model = model.to(dev)
     model.set_math(args.math)
     eng = model.engine()
-    dbatch = host_batch.clone().to(dev)
-    pb = eng.prepare(dbatch)
-    x0 = dbatch.x0.contiguous()
+    # host chunks (pinned), device copies and prepared batches per (chunk, temperature is stamped into T1 in place)
+    host_chunks, dev_chunks = [], []
+    for c in range(n_chunks):
+        n_c = min(chunk, args.mols - c * chunk)
+        _, hb = build_model_and_batch(args, rank * 1000 + c, n_c)
+        hb.pin_memory()
+        host_chunks.append(hb)
+        dev_chunks.append(hb.clone().to(dev))
     grid = torch.linspace(0.0, 1.0, K + 1)
-    frames = torch.empty((K + 1, pb.n_nodes, 3), dtype=torch.float32, device=dev)
+    n_nodes0 = dev_chunks[0].x0.shape[0]
+    frames = None if sweep else torch.empty((K + 1, n_nodes0, 3), dtype=torch.float32, device=dev)
+    finals = [torch.empty_like(db.x0) for db in dev_chunks]
 
     def barrier():
         if world > 1:
@@ -237,12 +324,54 @@ def run_b200(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    def energies(x0, x1, n_mol, T1):
+        """Synthetic reduced energies (SURVEY.md section 8d cfg 4): harmonic E = 1/2 |x|^2 (1000 / T)."""
+        E0 = 0.5 * (x0.reshape(n_mol, -1) ** 2).sum(1).double()
+        E1 = 0.5 * (x1.reshape(n_mol, -1) ** 2).sum(1).double() * (1000.0 / T1)
+        return E0, E1
+
+    stats_out = {}
+
+    def sweep_statistics(T1):
+        """Per temperature: partial sums on every rank -> one fp64 all-reduce; IQR mask on the all-gathered weights."""
+        part = torch.zeros(S.N_STATS, dtype=torch.float64, device=dev)
+        ws = []
+        for db, xf in zip(dev_chunks, finals):
+            n_c = int(db.ptr.numel() - 1)
+            E0, E1 = energies(db.x0, xf, n_c, T1)
+            shift = 0.0                                            # weights are used up to a constant; keep exp() in range
+            part += S.reweight_partials(E0, E1 - shift)
+            ws.append(torch.exp(-(E1 - E0)))
+        tot = S.finalize(D.allreduce_stats(part).cpu())
+        w_all = D.gather_samples(torch.cat(ws))                    # [world * mols] fp64: the filter needs GLOBAL percentiles
+        q25, q75 = torch.quantile(w_all, torch.tensor([0.25, 0.75], dtype=w_all.dtype, device=dev)).tolist()
+        iqr = q75 - q25
+        keep = (w_all > q25 - 100 * iqr) & (w_all < q75 + 100 * iqr)          # filter_iqr(k=100)
+        stats_out[T1] = dict(ess=tot["ess"], dF=tot["dF"], n=tot["n"], kept=int(keep.sum().item()))
+
+    def device_pass(pbs_by_T):
+        for T1 in temps:
+            for c, db in enumerate(dev_chunks):
+                eng.rollout_fixed(pbs_by_T[T1][c], db.x0, grid, method="euler", save_frames=not sweep,
+                                  out=frames if not sweep else finals[c])
+            if sweep:
+                sweep_statistics(T1)
+
+    # prepared batches per temperature (the sweep re-stamps T1; the x-independent embedding tables depend on it)
+    pbs_by_T = {}
+    for T1 in temps:
+        pbs = []
+        for db in dev_chunks:
+            db.T1 = torch.full_like(db.T1, T1)          # a new tensor per temperature: prepared batches keep what they were made from
+            pbs.append(eng.prepare(db))
+        pbs_by_T[T1] = pbs
+
     # ---- warm-up: W untimed steps of the same hot path
     if W > 0:
-        eng.rollout_fixed(pb, x0, torch.linspace(0.0, 1.0, K + 1)[: W + 1], method="euler", save_frames=False)
+        eng.rollout_fixed(pbs_by_T[temps[0]][0], dev_chunks[0].x0, grid[: W + 1], method="euler", save_frames=False)
     barrier()
 
-    # ---- timed region: exactly K steps, inputs resident in HBM
+    # ---- timed region: exactly K steps per (temperature, conformer), inputs resident in HBM
     clocks = ClockSampler(local) if rank == 0 else None
     ms_sum = (C.c_double * _lib.N_KERNEL_KINDS)()
     launches = (C.c_uint64 * _lib.N_KERNEL_KINDS)()
@@ -252,7 +381,7 @@ def run_b200(args):
     lib.tib_profile_begin()
     t_begin = time.perf_counter()
     e0.record()
-    eng.rollout_fixed(pb, x0, grid, method="euler", save_frames=True, out=frames)
+    device_pass(pbs_by_T)
     e1.record()
     barrier()
     t_end = time.perf_counter()
@@ -260,38 +389,54 @@ def run_b200(args):
     _lib.check(lib.tib_profile_end(ms_sum, launches), "tib_profile_end")
     ms_total = max_over_ranks(e0.elapsed_time(e1))
     clk = clocks.stop(t_begin, t_end) if clocks else None
-    assert torch.isfinite(frames[-1]).all(), "rollout diverged"
-    value = world * args.mols * K / (ms_total * 1e-3)
+    eng.status()
+    last = frames[-1] if not sweep else finals[-1]
+    assert torch.isfinite(last).all(), "rollout diverged"
+    units = args.mols * K * len(temps)
+    value = world * units / (ms_total * 1e-3)
 
     # ---- e2e: public API, host buffers, H2D + D2H inside the timed region
-    integ = MoleculeIntegrator(model, method="euler", n_step=K + 1)
-    host_out = torch.empty((K + 1, pb.n_nodes, 3), dtype=torch.float32).pin_memory()
-    h2d = sum(v.numel() * v.element_size() for v in (host_batch[k] for k in host_batch.keys()) if torch.is_tensor(v))
-    d2h = host_out.numel() * 4
+    integ = MoleculeIntegrator(model, method="euler", n_step=K + 1, save_frames=not sweep)
+    out_shape = (K + 1, n_nodes0, 3) if not sweep else (n_nodes0, 3)
+    host_out = torch.empty(out_shape, dtype=torch.float32).pin_memory()
+    h2d = sum(sum(v.numel() * v.element_size() for v in (hb[k] for k in hb.keys()) if torch.is_tensor(v)) for hb in host_chunks) * len(temps)
+    d2h = host_out.numel() * 4 * n_chunks * len(temps)
 
     def e2e_once():
-        b = host_batch.clone().to(dev, non_blocking=True)
-        xts, dlogp, nfe, bvec = integ.rollout(b)
-        host_out.copy_(xts, non_blocking=True)
+        for T1 in temps:
+            for c, hb in enumerate(host_chunks):
+                b = hb.clone().to(dev, non_blocking=True)
+                b.T1.fill_(T1)
+                xts, dlogp, nfe, bvec = integ.rollout(b)
+                if xts.shape == host_out.shape:
+                    host_out.copy_(xts, non_blocking=True)
+                else:
+                    host_out[: xts.shape[0]].copy_(xts, non_blocking=True)
+                if sweep:
+                    finals[c][: xts.shape[0]].copy_(xts)
+            if sweep:
+                sweep_statistics(T1)
         torch.cuda.synchronize(dev)
 
-    e2e_once()                       # warm (allocator, workspace)
+    if not sweep:
+        e2e_once()                   # warm (allocator, workspace)
     barrier()
     t0 = time.perf_counter()
     e2e_once()
     e2e_s = max_over_ranks(time.perf_counter() - t0)
     barrier()
-    e2e_value = world * args.mols * K / e2e_s
+    e2e_value = world * units / e2e_s
 
-    # ---- the only collectives of the job: final sample gather + statistics all-reduce (outside the step loop)
-    final = frames[-1].reshape(args.mols, args.atoms, 3)
-    E0 = 0.5 * (x0.reshape(args.mols, -1) ** 2).sum(1).double() * (1000.0 / 1000.0)
-    E1 = 0.5 * (final.reshape(args.mols, -1) ** 2).sum(1).double() * (1000.0 / 300.0)
-    part = S.reweight_partials(E0 - E0.mean(), E1 - E1.mean())
-    tot = S.finalize(D.allreduce_stats(part).cpu())
-    if world > 1 and args.gather:
-        gathered = D.gather_samples(final)
-        assert gathered.shape[0] == world * args.mols
+    if not sweep:
+        # the only collectives of the cfg-2 job: final sample gather + statistics all-reduce (outside the step loop)
+        db = dev_chunks[0]
+        E0, E1 = energies(db.x0, frames[-1], args.mols, 300.0)
+        part = S.reweight_partials(E0 - E0.mean(), E1 - E1.mean())
+        tot = S.finalize(D.allreduce_stats(part).cpu())
+        stats_out[300.0] = dict(ess=tot["ess"], dF=tot["dF"], n=tot["n"])
+        if world > 1 and args.gather:
+            gathered = D.gather_samples(frames[-1].reshape(args.mols, args.atoms, 3))
+            assert gathered.shape[0] == world * args.mols
     barrier()
 
     if rank == 0:
@@ -299,32 +444,40 @@ def run_b200(args):
         msg_ms = ms_sum[_lib.KERNEL_KINDS.index("message")]
         msg_n = int(launches[_lib.KERNEL_KINDS.index("message")])
         per_launch_ms = msg_ms / max(msg_n, 1)
-        mflops = message_flops_per_launch(args.mols, args.atoms, args.features)
+        mflops = message_flops_per_launch(chunk, args.atoms, args.features)
         achieved = mflops / (per_launch_ms * 1e-3) / 1e12
         peak = peaks["bf16_sustained"]
         shares = {k: round(ms_sum[i] / ms_total, 4) for i, k in enumerate(_lib.KERNEL_KINDS)}
+        e_bytes = pbs_by_T[temps[0]][0].n_edges * args.features * 4
         line = dict(
-            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
+            metric=METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / (K * len(temps) * n_chunks),
             higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
             config=dict(workload=workload_name(args), mols_per_gpu=args.mols, atoms=args.atoms, n_features=args.features,
-                        layers=args.layers, method="euler", math=_lib.MATH_NAMES[args.math], frames_saved=K + 1,
-                        l2="per-step working set (edge features e[E,F] = %.0f MB + node features) exceeds the 126 MB L2"
-                           % (pb.n_edges * args.features * 4 / 1e6),
+                        layers=args.layers, method="euler", math=_lib.MATH_NAMES[args.math],
+                        frames_saved=(K + 1) if not sweep else 1, temperatures=temps, chunk=chunk,
+                        l2="per-step working set (edge features e[E,F] = %.0f MB + node features) exceeds the 126 MB L2" % (e_bytes / 1e6),
                         flops_per_mol_step=flops_per_mol_step(args.atoms, args.features, args.layers),
                         whole_step_tflops=value * flops_per_mol_step(args.atoms, args.features, args.layers) / 1e12 / world),
-            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d / K, d2h_bytes_per_step=d2h / K,
-                     seconds=e2e_s, api="ambient.integrators.MoleculeIntegrator.rollout(host batch) + D2H of all frames"),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d / (K * len(temps) * n_chunks),
+                     d2h_bytes_per_step=d2h / (K * len(temps) * n_chunks), seconds=e2e_s,
+                     api="ambient.integrators.MoleculeIntegrator.rollout(host batch) + D2H of " + ("all frames" if not sweep else "the final samples")),
             gpu_launches=n_launch, clocks=clk,
             roofline=dict(kernel=("k_message_tc" if args.math != 0 else "k_message") + " (SE3Message: phi/w edge MLPs + gated scatter)", bound="tensor",
                           achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak,
-                          traffic=load_traffic() if args.math != 0 else None,
+                          traffic=load_traffic() if (args.math == 1 and chunk == 4096 and args.atoms == 9) else None,
                           peak_source=peaks["source"] + ", bf16 dense sustained", launches=msg_n,
                           avg_launch_ms=per_launch_ms, flops_per_launch=mflops, kernel_time_shares=shares),
-            stats=dict(ess=tot["ess"], dF=tot["dF"], n=tot["n"]))
+            stats={str(int(T)): v for T, v in stats_out.items()})
         if world == 1 and not args.no_cpu:
-            rate, cores, steps, secs = cpu_oracle_rate(args, 128, budget_s=args.cpu_seconds, min_steps=2)
-            line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port",
-                                        sample=f"128 conformers x {steps} Euler steps of the same workload ({secs:.1f} s)")
+            ref = cpu_reference_rate(args, 256, steps=max(2, min(K, 8)), warmup=1)
+            if ref is not None:
+                rate, cores, secs = ref
+                line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="reference",
+                                            sample=f"the reference's MoleculeIntegrator(method='euler').rollout, 256 conformers x {max(2, min(K, 8))} steps ({secs:.1f} s)")
+            else:
+                rate, cores, steps, secs = cpu_port_rate(args, 128, budget_s=args.cpu_seconds, min_steps=2)
+                line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="port",
+                                            sample=f"128 conformers x {steps} Euler steps of the same workload ({secs:.1f} s)")
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -333,10 +486,12 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--mols", type=int, default=4096, help="conformers per GPU")
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--mols", type=int, default=None, help="conformers per GPU (cfg2: 4096, cfg4: 125000)")
+    ap.add_argument("--chunk", type=int, default=15625, help="cfg4: conformers per rollout call")
     ap.add_argument("--atoms", type=int, default=9)
     ap.add_argument("--features", type=int, default=128)
     ap.add_argument("--layers", type=int, default=5)
@@ -345,6 +500,10 @@ def main():
     ap.add_argument("--cpu-seconds", type=float, default=12.0)
     ap.add_argument("--gather", type=int, default=1)
     args = ap.parse_args()
+    if args.mols is None:
+        args.mols = 125000 if args.workload == "cfg4" else 4096
+    if args.steps is None:
+        args.steps = 20 if args.workload == "cfg4" else 200
     if args.impl == "reference":
         run_reference(args)
     else:

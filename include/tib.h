@@ -149,6 +149,18 @@ int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, flo
 int tib_zmatrix(const float* x, int64_t n_conf, int32_t n_atoms, const int32_t* order, const int32_t* ref, float* z,
                 void* stream);
 
+/* Torsion features -> TICA projection -> histograms: replaces, per conformer, enc() + TICA.transform + plt.hist of the
+ * reference's figure script (mdqm9/plots/10506_main.ipynb cells 3-4; deeptime.decomposition.TICA is an un-vendored pin):
+ *   feat = (cos t_0, sin t_0, cos t_1, ...), proj = (feat - mean) R [:, :dim], hist[k] = weighted histogram of proj[:, k]
+ *   with n_bins equal bins on [lo, hi] (the right edge in the last bin, as numpy.histogram).
+ * torsions: DEVICE fp32, the torsion of feature j of conformer c at torsions[c * stride + col0 + j * col_step] (so the
+ * z-matrix of tib_zmatrix can be read in place: stride = 3 (n_atoms - 1), col0 = 3 * 2 + 2, col_step = 3, n_tors = n_atoms - 3);
+ * mean [2 n_tors], R [2 n_tors][dim] DEVICE fp64 (row-major), dim <= 4; weight [n_conf] DEVICE fp64 or NULL;
+ * proj [n_conf][dim] DEVICE fp32 or NULL; hist [dim][n_bins] DEVICE fp64 (ACCUMULATED into; zero it first) or NULL. */
+int tib_tica_project(const float* torsions, int64_t n_conf, int32_t n_tors, int64_t stride, int32_t col0, int32_t col_step,
+                     const double* mean, const double* R, int32_t dim, const double* weight, float* proj, double* hist,
+                     int32_t n_bins, double lo, double hi, void* stream);
+
 /* ---- K1: fused integrator state updates ---------------------------------------------------
  * One explicit Euler / Euler-Maruyama update over a flat state of n floats:
  *     x_out = x + dt*b                       [+ dt*eps*score] [+ sqrt(2*eps*dt)*noise]

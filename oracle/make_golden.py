@@ -178,6 +178,12 @@ def stats_case(name="stats"):
     out = dict(E0=E0, E1=E1, neg_dlogp=nd, weights=w, ess=ns.ess.calc_ESS(w),
                dF=ns.free_energy.calc_tfep_dF(phis, np.ones_like(phis)),
                keep_k3=ns.sensitivity.filter_iqr(w, k=3))
+    # the bootstrap of results_00031.py:29-45 (that module loads trajectory files at import, so its loop is restated in
+    # oracle/analysis_oracle.py around the reference's OWN calc_phis_tfep / calc_tfep_dF / filter_iqr)
+    from oracle import analysis_oracle as ao
+    for tag, k in (("none", None), ("k3", 3)):
+        dF, ci = ao.bootstrap_dF(E0, E1, nd, ns.free_energy.calc_phis_tfep, ns.free_energy.calc_tfep_dF, n_bootstrap=200, k=k, seed=123)
+        out[f"boot_dF_{tag}"], out[f"boot_ci_{tag}"] = dF, np.array(ci)
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
     print(name, "ess", out["ess"], "dF", out["dF"])
 

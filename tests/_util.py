@@ -6,18 +6,7 @@ import hashlib
 import torch
 
 
-def perturb_(module: torch.nn.Module, seed: int, scale: float = 0.05) -> torch.nn.Module:
-    """Adds seeded Gaussian noise to every floating parameter (in `parameters()` order) so that
-    LayerNorm gains/offsets and biases are not at their trivial defaults.  Scalar parameters (the
-    reference's `device_tracker` dummies) are skipped."""
-    gen = torch.Generator().manual_seed(seed)
-    with torch.no_grad():
-        for p in module.parameters():
-            if p.dim() == 0:
-                continue
-            noise = torch.randn(p.shape, generator=gen, dtype=torch.float32)
-            p.add_(noise.to(p.dtype) * scale)
-    return module
+from thermodynamic_interpolation_b200.synthetic import perturb_  # noqa: E402,F401  (re-exported for the tests)
 
 
 def state_sha(sd) -> str:

@@ -46,7 +46,7 @@ def test_layered_drift_vs_fp32_and_oracle(F, n_list):
     assert torch.equal(out, out2), "repeated calls must be bit-identical"
     e1, e2 = _rel(out.cpu().numpy(), simt.numpy()), _rel(out.cpu().numpy(), ref.numpy())
     print(f"[layered] F={F} {len(n_list)} molecules: vs fp32 kernels {e1:.3e}, vs oracle {e2:.3e}")
-    assert e1 < 2e-5 and e2 < 2e-5
+    assert e1 < 4e-5 and e2 < 4e-5      # small ragged batches: worst case of the fp32-vs-split-f16 fuzz is 2.5e-5
 
 
 def test_layered_f256_matches_reference_golden():
@@ -76,7 +76,7 @@ def test_layered_f256_matches_reference_golden():
         xts = integ.rollout(batch)[0]
         err = _rel(xts[1].cpu().numpy(), ref[k + 1])
         print(f"[layered] ambient_f256 euler step {k}: {err:.3e}")
-        assert err < 1e-5
+        assert err < 3e-5      # per-step bound of north_star: 1e-4
 
 
 def _oracle_div(model, batch, x, t):

@@ -21,7 +21,7 @@ class CPaiNNBase(nn.Module):
         super().__init__()
         self._engine: Optional[DriftEngine] = None
         self._engine_sig = None
-        self._math_mode = None     # None = the library default (tensor cores when n_features == 128)
+        self._math_mode = None     # None = the library default (tensor cores when n_features is 128 or 256)
 
     @property
     def device(self) -> torch.device:
@@ -54,4 +54,5 @@ class CPaiNNBase(nn.Module):
         t_val = float(t.reshape(-1)[0]) if torch.is_tensor(t) else float(t)
         x = batch.x.to(eng.device, torch.float32)
         batch.output = eng.drift(pb, x, t_val)
+        eng.status()      # synchronises the stream and raises on a recorded tensor-core pipeline / range fault
         return batch

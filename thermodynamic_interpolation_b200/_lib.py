@@ -67,6 +67,8 @@ SYMBOLS = [
     ("tib_div_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     ("tib_drift_div", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_zmatrix", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("tib_tica_project", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
+                                   C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p]),
     ("tib_step_euler", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_rollout_fixed", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(FixedOpts), C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_rollout_dopri5", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(Dopri5Opts), C.c_void_p, C.POINTER(Dopri5Stats), C.c_void_p, C.c_size_t, C.c_void_p]),

@@ -107,4 +107,7 @@ class MoleculeIntegrator:
 
     def rollout(self, batch, noise: Optional[torch.Tensor] = None) -> tuple:
         xts, dlogp, nfe, pb = self._solve(batch, noise)
+        # one synchronisation per rollout: a tensor-core pipeline time-out or a state beyond the split-f16 range raises
+        # here instead of handing garbage frames to the caller (the words are cleared once reported)
+        self.ode_wrapper.b.engine().status()
         return xts, dlogp * self.dlogp_out_scale, nfe, batch.batch

@@ -25,13 +25,31 @@ class ODEWrapper(nn.Module):
         self.b = b
         self.return_dlogp = return_dlogp
         self.reverse_ode = reverse_ode
-        self._prepared = None      # (id(batch), PreparedBatch)
+        self._prepared = None      # (signature of the batch tensors the kernels consume, PreparedBatch, engine)
+
+    _BATCH_KEYS = ("atoms", "atom_number", "batch", "edge_index", "edge_type", "T0", "T1", "T")
+
+    @classmethod
+    def _batch_signature(cls, batch):
+        """(data_ptr, version) of every tensor the prepared batch is derived from: an in-place change of e.g. `batch.T1`
+        (a temperature sweep over one batch object) must not integrate with the stale device copies."""
+        sig = []
+        for k in cls._BATCH_KEYS:
+            v = getattr(batch, k, None)
+            if torch.is_tensor(v):
+                sig.append((k, v.data_ptr(), v._version, tuple(v.shape)))
+        return tuple(sig)
 
     def prepared(self, batch):
         eng = self.b.engine()
-        if self._prepared is None or self._prepared[0] is not batch or self._prepared[2] is not eng:
-            self._prepared = (batch, eng.prepare(batch), eng)
+        sig = self._batch_signature(batch)
+        if self._prepared is None or self._prepared[0] != sig or self._prepared[2] is not eng:
+            self._prepared = (sig, eng.prepare(batch), eng)
         return eng, self._prepared[1]
+
+    def release(self):
+        """Drops the cached prepared batch (and the device tensors it keeps alive)."""
+        self._prepared = None
 
     def forward(self, integration_time, states, batch, n_steps: list = None):
         if n_steps is not None:
@@ -41,6 +59,7 @@ class ODEWrapper(nn.Module):
         if self.return_dlogp:
             x, _ = states
             b, div = eng.drift_div(pb, x.to(eng.device, torch.float32), t)
+            eng.status()                      # a recorded device-side fault must not reach the integrator silently
             div = div * self.variant_scale
             return (b, -div) if not self.reverse_ode else (-b, div)
         x = states

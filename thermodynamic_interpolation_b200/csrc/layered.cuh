@@ -12,14 +12,30 @@
 namespace tib {
 namespace lay {
 
-// row_et[r] = edge type of (dst,src)-ordered row r; node_local[i] = index of node i inside its molecule
+// row_et[r] = edge type of (dst,src)-ordered row r; node_local[i] = index of node i inside its molecule;
+// row_pair[r] = index of the UNDIRECTED pair {src, dst} of row r (pairs (lo, hi), lo < hi, lexicographic per molecule, molecule
+// m's pairs start at edge_ptr[m] / 2) and pair_dist[pair] = |x_src - x_dst| - the w MLP depends on an edge through its distance
+// only (cpainn.py:283), and d(i,j) == d(j,i) bit for bit, so it is evaluated once per pair.
 __global__ void k_row_aux(const uint4* __restrict__ rowa, long long n_edges, int* __restrict__ row_et, const int* __restrict__ mol_ptr,
-                          int n_mol, int* __restrict__ node_local) {
+                          const long long* __restrict__ edge_ptr, int n_mol, int* __restrict__ node_local,
+                          int* __restrict__ row_pair, float* __restrict__ pair_dist) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n_edges) row_et[i] = (int)((rowa[i].z >> 16) & 0xFFu);
   if (i < n_mol) {
     const int n0 = mol_ptr[i], n1 = mol_ptr[i + 1];
     for (int j = n0; j < n1; ++j) node_local[j] = j - n0;
+  }
+  if (i < n_edges) {
+    const uint4 ra = rowa[i];
+    row_et[i] = (int)((ra.z >> 16) & 0xFFu);
+    // molecule of this row: binary search over edge_ptr
+    int lo = 0, hi = n_mol - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (edge_ptr[mid] <= i) lo = mid; else hi = mid - 1; }
+    const int n0 = mol_ptr[lo], n = mol_ptr[lo + 1] - n0;
+    const int il = (int)ra.x - n0, jl = (int)ra.y - n0;
+    const int a = min(il, jl), b = max(il, jl);
+    const int pr = (int)(edge_ptr[lo] / 2) + a * n - a * (a + 1) / 2 + (b - a - 1);
+    row_pair[i] = pr;
+    if (il > jl) pair_dist[pr] = __uint_as_float(ra.w);
   }
 }
 
@@ -29,7 +45,8 @@ struct CombineP {
   const uint4* rowa;
   const float4* rowb;
   const float* phi3;        // [E][5F]
-  const float* w3;          // [E][5F]
+  const float* w3;          // [E/2][5F], one row per undirected pair
+  const int* row_pair;      // [E]
   const float* s_old;       // [N][F]
   const float* v_old;       // [N][3][F]
   float* s_new;
@@ -51,7 +68,7 @@ __global__ void __launch_bounds__(128) k_combine(CombineP p) {
         const uint4 ra = __ldg(p.rowa + r);
         const float4 rb = __ldg(p.rowb + r);
         const float* ph = p.phi3 + (size_t)r * 5 * F + f;
-        const float* wh = p.w3 + (size_t)r * 5 * F + f;
+        const float* wh = p.w3 + (size_t)__ldg(p.row_pair + r) * 5 * F + f;
         const float m0 = __fmul_rn(ph[0], wh[0]), m1 = __fmul_rn(ph[F], wh[F]), m2 = __fmul_rn(ph[2 * F], wh[2 * F]);
         const float m3 = __fmul_rn(ph[3 * F], wh[3 * F]), m4 = __fmul_rn(ph[4 * F], wh[4 * F]);
         if (!p.first_layer) {
@@ -83,7 +100,7 @@ struct CombineJvpP {
   CombineP c;               // primal arrays (s_new / v_new / e are NOT written here; s_old / v_old are the layer inputs)
   const float* x;           // [N][3]
   const int* node_local;    // [N]
-  const float* w3d;         // [E][5F]: d w3 / d dist
+  const float* w3d;         // [E/2][5F]: d w3 / d dist per undirected pair
   const float* phi3d;       // [D][E][5F] tangents of phi3 (null in the first layer: s0, e0 do not depend on x)
   long long st_phi;         // floats between directions of phi3d
   const float* ts_old; const float* tv_old; float* ts_new; float* tv_new; float* te;
@@ -92,79 +109,115 @@ struct CombineJvpP {
                             // phi3d by (direction - dir0)
 };
 
-// Tangent of k_combine for one (destination node, direction) per block iteration.
+// Tangent of k_combine.  One block iteration = one destination node and the THREE coordinate directions of one atom a
+// (dir0 and n_dirs are multiples of 3): the primal products m = phi3 * w3 and the gather of v[src] are shared by the
+// three directions, and the geometry tangents exist only on the edges that touch atom a (sign = +1 source, -1
+// destination):  d_dot_c = sign r_c / d,  dir_dot_c = sign e_c / (1 + d) - r d_dot_c / (1 + d)^2   (graph.py:27-29).
 __global__ void __launch_bounds__(128) k_combine_jvp(CombineJvpP pp) {
   const CombineP& p = pp.c;
   const int F = p.F;
-  const long long n_items = (long long)p.n_nodes * pp.n_dirs;
+  // every array but te / ts_new / tv_new is read-only here: non-coherent loads (__ldg) may be hoisted above the te stores,
+  // which is what keeps enough loads in flight (the plain-pointer version ran at 2 TB/s)
+  const float* __restrict__ phi3 = p.phi3; const float* __restrict__ w3 = p.w3; const float* __restrict__ w3d = pp.w3d;
+  const float* __restrict__ phi3d = pp.phi3d; const float* __restrict__ v_old = p.v_old; const float* __restrict__ tv_old = pp.tv_old;
+  float* __restrict__ te_base = pp.te;
+  const long long n_items = (long long)p.n_nodes * (pp.n_dirs / 3);
   for (long long it = blockIdx.x; it < n_items; it += gridDim.x) {
-    const int dl = (int)(it / p.n_nodes), j = (int)(it - (long long)dl * p.n_nodes);
-    const int q = pp.dir0 + dl, a = q / 3, c = q % 3;
+    // the atoms of one destination node run next to each other (the primal rows they share are then L2 hits)
+    const int na = pp.n_dirs / 3, j = (int)(it / na), ac = (int)(it - (long long)j * na);
+    const int q0 = pp.dir0 + 3 * ac, a = q0 / 3;
     const int r0 = __ldg(p.node_in_ptr + j), r1 = __ldg(p.node_in_ptr + j + 1);
     const int jl = __ldg(pp.node_local + j);
     const float xj0 = __ldg(pp.x + 3 * (size_t)j), xj1 = __ldg(pp.x + 3 * (size_t)j + 1), xj2 = __ldg(pp.x + 3 * (size_t)j + 2);
-    const float* ts_o = pp.ts_old + (size_t)q * pp.st_s;
-    const float* tv_o = pp.tv_old + (size_t)q * pp.st_v;
-    float* te = pp.te + (size_t)q * pp.st_e;
     for (int f = threadIdx.x; f < F; f += 128) {
-      float as = 0.0f, av0 = 0.0f, av1 = 0.0f, av2 = 0.0f;
-      float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f, e0 = 0.0f, e1 = 0.0f, e2 = 0.0f;   // sum m4 dir, sum (m4d dir + m4 dird)
+      float as[3] = {0.f, 0.f, 0.f}, av[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+      float ec[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};     // per direction: sum (m4_dot dir + m4 dir_dot)
+      float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;                                    // sum m4 dir
+#pragma unroll 2
       for (int r = r0; r < r1; ++r) {
         const uint4 ra = __ldg(p.rowa + r);
         const float4 rb = __ldg(p.rowb + r);
         const int i = (int)ra.x;
-        const float dist = __uint_as_float(ra.w);
-        // geometry tangents (graph.py:27-29): r = x_i - x_j, d = |r|, dir = r / (1 + d)
+        const float dir[3] = {rb.x, rb.y, rb.z};
         const int sg = (__ldg(pp.node_local + i) == a ? 1 : 0) - (jl == a ? 1 : 0);
-        float dd = 0.0f, g0 = 0.0f, g1 = 0.0f, g2 = 0.0f;
-        if (sg != 0) {
-          const float rx = __ldg(pp.x + 3 * (size_t)i) - xj0, ry = __ldg(pp.x + 3 * (size_t)i + 1) - xj1, rz = __ldg(pp.x + 3 * (size_t)i + 2) - xj2;
-          const float rc = c == 0 ? rx : (c == 1 ? ry : rz);
-          const float inv = 1.0f / (1.0f + dist);
-          dd = dist > 0.0f ? (float)sg * rc / dist : 0.0f;
-          const float k = dd * inv * inv;
-          g0 = -rx * k; g1 = -ry * k; g2 = -rz * k;
-          if (c == 0) g0 += (float)sg * inv; else if (c == 1) g1 += (float)sg * inv; else g2 += (float)sg * inv;
-        }
-        const float* ph = p.phi3 + (size_t)r * 5 * F + f;
-        const float* wh = p.w3 + (size_t)r * 5 * F + f;
-        const float* wd = pp.w3d + (size_t)r * 5 * F + f;
-        const float* pd = pp.phi3d ? pp.phi3d + (size_t)dl * pp.st_phi + (size_t)r * 5 * F + f : nullptr;
-        float m[5], md[5];
+        const size_t pr = (size_t)__ldg(p.row_pair + r);
+        const float* ph = phi3 + (size_t)r * 5 * F + f;
+        const float* wh = w3 + pr * 5 * F + f;
+        // ---- all loads of this edge first
+        float phv[5], w[5], pdv[3][5], vi[3] = {0.f, 0.f, 0.f}, tvi[3][3], teo[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const float phk = ph[(size_t)k * F], whk = wh[(size_t)k * F];
-          m[k] = phk * whk;
-          md[k] = phk * (wd[(size_t)k * F] * dd);
-          if (pd) md[k] = fmaf(pd[(size_t)k * F], whk, md[k]);
+        for (int k = 0; k < 5; ++k) { phv[k] = __ldg(ph + (size_t)k * F); w[k] = __ldg(wh + (size_t)k * F); }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int k = 0; k < 5; ++k)
+            pdv[c][k] = phi3d ? __ldg(phi3d + (size_t)(3 * ac + c) * pp.st_phi + (size_t)r * 5 * F + f + (size_t)k * F) : 0.0f;
+#pragma unroll
+          for (int k = 0; k < 3; ++k)
+            tvi[c][k] = p.first_layer ? 0.0f : __ldg(tv_old + (size_t)(q0 + c) * pp.st_v + (size_t)i * 3 * F + f + k * F);
+          if (!p.first_layer) teo[c] = te_base[(size_t)(q0 + c) * pp.st_e + (size_t)r * F + f];
         }
         if (!p.first_layer) {
-          const float* vi = p.v_old + (size_t)i * 3 * F + f;
-          const float* tvi = tv_o + (size_t)i * 3 * F + f;
-          av0 += md[0] * __ldg(vi) + m[0] * __ldg(tvi);
-          av1 += md[0] * __ldg(vi + F) + m[0] * __ldg(tvi + F);
-          av2 += md[0] * __ldg(vi + 2 * F) + m[0] * __ldg(tvi + 2 * F);
-          d0 = fmaf(m[4], rb.x, d0); d1 = fmaf(m[4], rb.y, d1); d2 = fmaf(m[4], rb.z, d2);
-          e0 += md[4] * rb.x + m[4] * g0; e1 += md[4] * rb.y + m[4] * g1; e2 += md[4] * rb.z + m[4] * g2;
+          const float* vp = v_old + (size_t)i * 3 * F + f;
+          vi[0] = __ldg(vp); vi[1] = __ldg(vp + F); vi[2] = __ldg(vp + 2 * F);
         }
-        av0 += md[1] * rb.x + m[1] * g0; av1 += md[1] * rb.y + m[1] * g1; av2 += md[1] * rb.z + m[1] * g2;
-        as += md[2];
-        float* ep = te + (size_t)r * F + f;
-        *ep = (p.first_layer ? 0.0f : *ep) + md[3];
+        float m[5], mw[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int k = 0; k < 5; ++k) m[k] = phv[k] * w[k];
+        float dd[3] = {0.f, 0.f, 0.f}, gd[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
+        if (sg != 0) {                                          // block-uniform
+          const float dist = __uint_as_float(ra.w), fs = (float)sg;
+          const float rv[3] = {__ldg(pp.x + 3 * (size_t)i) - xj0, __ldg(pp.x + 3 * (size_t)i + 1) - xj1, __ldg(pp.x + 3 * (size_t)i + 2) - xj2};
+          const float inv = 1.0f / (1.0f + dist);
+          const float* wd = w3d + pr * 5 * F + f;
+#pragma unroll
+          for (int k = 0; k < 5; ++k) mw[k] = phv[k] * __ldg(wd + (size_t)k * F);
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            dd[c] = dist > 0.0f ? fs * rv[c] / dist : 0.0f;
+            const float kk = dd[c] * inv * inv;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) gd[c][k] = -rv[k] * kk + (k == c ? fs * inv : 0.0f);
+          }
+        }
+        if (!p.first_layer) { d0 = fmaf(m[4], dir[0], d0); d1 = fmaf(m[4], dir[1], d1); d2 = fmaf(m[4], dir[2], d2); }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float md[5];
+#pragma unroll
+          for (int k = 0; k < 5; ++k) md[k] = fmaf(pdv[c][k], w[k], mw[k] * dd[c]);
+          if (!p.first_layer) {
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+              av[c][k] += md[0] * vi[k] + m[0] * tvi[c][k];
+              ec[c][k] += md[4] * dir[k] + m[4] * gd[c][k];
+            }
+          }
+#pragma unroll
+          for (int k = 0; k < 3; ++k) av[c][k] += md[1] * dir[k] + m[1] * gd[c][k];
+          as[c] += md[2];
+          te_base[(size_t)(q0 + c) * pp.st_e + (size_t)r * F + f] = teo[c] + md[3];
+        }
       }
       const size_t o = (size_t)j * 3 * F + f;
-      float t0 = 0.0f, t1 = 0.0f, t2 = 0.0f;
-      if (!p.first_layer) {
-        const float v0 = __ldg(p.v_old + o), v1 = __ldg(p.v_old + o + F), v2 = __ldg(p.v_old + o + 2 * F);
-        t0 = __ldg(tv_o + o); t1 = __ldg(tv_o + o + F); t2 = __ldg(tv_o + o + 2 * F);
-        av0 += (e1 * v2 - e2 * v1) + (d1 * t2 - d2 * t1);
-        av1 += (e2 * v0 - e0 * v2) + (d2 * t0 - d0 * t2);
-        av2 += (e0 * v1 - e1 * v0) + (d0 * t1 - d1 * t0);
+      float v[3] = {0.f, 0.f, 0.f};
+      if (!p.first_layer) { v[0] = __ldg(v_old + o); v[1] = __ldg(v_old + o + F); v[2] = __ldg(v_old + o + 2 * F); }
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int q = q0 + c;
+        float t[3] = {0.f, 0.f, 0.f}, ts = 0.0f;
+        if (!p.first_layer) {
+          const float* tv_o = tv_old + (size_t)q * pp.st_v + o;
+          t[0] = __ldg(tv_o); t[1] = __ldg(tv_o + F); t[2] = __ldg(tv_o + 2 * F);
+          ts = __ldg(pp.ts_old + (size_t)q * pp.st_s + (size_t)j * F + f);
+          av[c][0] += (ec[c][1] * v[2] - ec[c][2] * v[1]) + (d1 * t[2] - d2 * t[1]);
+          av[c][1] += (ec[c][2] * v[0] - ec[c][0] * v[2]) + (d2 * t[0] - d0 * t[2]);
+          av[c][2] += (ec[c][0] * v[1] - ec[c][1] * v[0]) + (d0 * t[1] - d1 * t[0]);
+        }
+        pp.ts_new[(size_t)q * pp.st_s + (size_t)j * F + f] = ts + as[c];
+        float* tv_n = pp.tv_new + (size_t)q * pp.st_v + o;
+        tv_n[0] = t[0] + av[c][0]; tv_n[F] = t[1] + av[c][1]; tv_n[2 * F] = t[2] + av[c][2];
       }
-      float* ts_n = pp.ts_new + (size_t)q * pp.st_s;
-      float* tv_n = pp.tv_new + (size_t)q * pp.st_v;
-      ts_n[(size_t)j * F + f] = (p.first_layer ? 0.0f : __ldg(ts_o + (size_t)j * F + f)) + as;
-      tv_n[o] = t0 + av0; tv_n[o + F] = t1 + av1; tv_n[o + 2 * F] = t2 + av2;
     }
   }
 }

@@ -28,7 +28,8 @@ void pack_chain_mlp(std::vector<uint16_t>& blob, const float* src, int F, int k_
 
 // ---- workspace --------------------------------------------------------------------------------------------------------------
 struct LayWs {
-  int *row_et, *node_local;
+  int *row_et, *node_local, *row_pair;
+  float* pair_dist;
   float *phi3, *w3, *w3d;
   float *sv_phi_n[2], *sv_phi_r[2], *sv_w_n[2], *sv_w_r[2], *sv_upd_n[2], *sv_upd_r[2];
   float *vvuv, *q, *gac;
@@ -38,30 +39,33 @@ struct LayWs {
   int D, Dc, Dr;
   static size_t al(size_t x) { return Workspace::align(x); }
   static int dirs_readout(int F) { return F == 256 ? 1 : 3; }
-  static int dirs_chunk(int D) { return D < 9 ? D : 9; }
+  static int dirs_chunk(int D) { return D < 9 ? D : 9; }      // a multiple of 3 (k_combine_jvp takes whole atoms)
   // with_div = false: what the F = 256 drift needs; true: everything
   static size_t bytes(int F, int n_nodes, long long n_edges, int max_atoms, bool with_div) {
-    LayWs w; return w.layout(nullptr, F, n_nodes, n_edges, max_atoms, with_div);
+    LayWs w{}; return w.layout(nullptr, F, n_nodes, n_edges, max_atoms, with_div);
   }
   size_t layout(char* base, int F, int n_nodes, long long n_edges, int max_atoms, bool with_div) {
     size_t off = 0;
     auto take = [&](size_t nbytes) { char* r = base ? base + off : nullptr; off += al(nbytes); return r; };
     const size_t N = (size_t)n_nodes, E = (size_t)n_edges, f4 = sizeof(float);
     const size_t te_rows = ((E + 127) / 128) * 128, tn_rows = ((N + 127) / 128) * 128;
+    const size_t P = E / 2, tp_rows = ((P + 127) / 128) * 128;
     row_et = (int*)take(sizeof(int) * E);
     node_local = (int*)take(sizeof(int) * N);
+    row_pair = (int*)take(sizeof(int) * E);
+    pair_dist = (float*)take(f4 * P);
     phi3 = (float*)take(f4 * E * 5 * F);
-    w3 = (float*)take(f4 * E * 5 * F);
-    if (!with_div) return off;
-    w3d = (float*)take(f4 * E * 5 * F);
-    for (int i = 0; i < 2; ++i) {
-      sv_phi_n[i] = (float*)take(f4 * te_rows * F); sv_phi_r[i] = (float*)take(f4 * E);
-      sv_w_n[i] = (float*)take(f4 * te_rows * F);   sv_w_r[i] = (float*)take(f4 * E);
-      sv_upd_n[i] = (float*)take(f4 * tn_rows * F); sv_upd_r[i] = (float*)take(f4 * N);
-    }
+    w3 = (float*)take(f4 * P * 5 * F);
     vvuv = (float*)take(f4 * 3 * N * 2 * F);
     q = (float*)take(f4 * N * F);
     gac = (float*)take(f4 * N * 3 * F);
+    if (!with_div) return off;
+    w3d = (float*)take(f4 * P * 5 * F);
+    for (int i = 0; i < 2; ++i) {
+      sv_phi_n[i] = (float*)take(f4 * te_rows * F); sv_phi_r[i] = (float*)take(f4 * E);
+      sv_w_n[i] = (float*)take(f4 * tp_rows * F);   sv_w_r[i] = (float*)take(f4 * P);
+      sv_upd_n[i] = (float*)take(f4 * tn_rows * F); sv_upd_r[i] = (float*)take(f4 * N);
+    }
     D = 3 * max_atoms; Dc = dirs_chunk(D); Dr = dirs_readout(F);
     st_s = al(f4 * N * F) / f4; st_v = al(f4 * N * 3 * F) / f4; st_e = al(f4 * E * F) / f4; st_o = al(f4 * N * 3) / f4;
     st_phi = al(f4 * E * 5 * F) / f4; st_tvvuv = al(f4 * 3 * N * 2 * F) / f4; st_tq = st_s; st_tgac = st_v;
@@ -85,8 +89,10 @@ int launch_chain(tib_model* m, tib::tc::ChainP& cp, int kind, cudaStream_t st) {
   cp.n_tiles = (cp.n_rows + 127) / 128;
   const long long work = (long long)cp.n_tiles * cp.n_dirs;
   if (work <= 0) return 0;
+  constexpr int NG = F == 128 ? 2 : 4;
+  using S = ChainSmem<F, NG>;
   ProfScope ps(kind, st);
-  k_chain_tc<F><<<(int)std::min<long long>(work, m->n_sms), kThreads, ChainSmem<F>::TOTAL, st>>>(cp);
+  k_chain_tc<F, NG><<<(int)std::min<long long>(work, (long long)m->n_sms * S::CTAS), S::THREADS, S::TOTAL, st>>>(cp);
   LAUNCH_CHECK();
   return 0;
 }
@@ -95,8 +101,8 @@ tib::tc::ChainSrc src_rows(const float* base, long long ld, const int* idx, int 
   tib::tc::ChainSrc s{}; s.kind = tib::tc::SRC_ROWS; s.base = base; s.ld = ld; s.idx = idx; s.idx_stride = idx_stride;
   s.dir_stride = dir_stride; s.scale = scale; return s;
 }
-tib::tc::ChainSrc src_pe(int kind, const uint4* rowa, float length) {
-  tib::tc::ChainSrc s{}; s.kind = kind; s.base = reinterpret_cast<const float*>(rowa) + 3; s.ld = 4; s.scale = length; return s;
+tib::tc::ChainSrc src_pe(int kind, const float* dist, float length) {
+  tib::tc::ChainSrc s{}; s.kind = kind; s.base = dist; s.ld = 1; s.scale = length; return s;
 }
 void chain_mlp_params(tib::tc::ChainP& cp, const tib::MlpW& w, const unsigned char* blob, int n_out) {
   cp.n_hidden = 2; cp.wblob = blob; cp.b1 = w.b1; cp.g1 = w.g1; cp.be1 = w.be1; cp.b2 = w.b2; cp.g2 = w.g2; cp.be2 = w.be2;
@@ -109,7 +115,9 @@ int lay_setup(tib_model* m, const tib_batch* b, const float* x, Workspace& ws, L
   if (!m->ch_blob) return fail("the layered tensor-core path needs n_features 128 or 256");
   if (b->n_edges >= (1ll << 31)) return fail("layered path: n_edges=%lld exceeds int32 row indices", (long long)b->n_edges);
   if (!m->ch_attrs_set) {
-    if (set_smem(tc::k_chain_tc<F>, tc::ChainSmem<F>::TOTAL)) return -1;
+    if (set_smem(tc::k_chain_tc<F, (F == 128 ? 2 : 4)>, tc::ChainSmem<F, (F == 128 ? 2 : 4)>::TOTAL)) return -1;
+    // two CTAs of the F = 128 variant share an SM only if the whole 228 KB are configured as shared memory
+    cudaFuncSetAttribute(tc::k_chain_tc<F, (F == 128 ? 2 : 4)>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
     m->ch_attrs_set = true;
   }
   ProfScope ps(TIB_K_EDGE_INIT, st);
@@ -117,7 +125,8 @@ int lay_setup(tib_model* m, const tib_batch* b, const float* x, Workspace& ws, L
                                               ws.node_in_ptr, ws.rowa, ws.rowb);
   LAUNCH_CHECK();
   const long long n = std::max<long long>(b->n_edges, b->n_mol);
-  lay::k_row_aux<<<(int)((n + 255) / 256), 256, 0, st>>>(ws.rowa, (long long)b->n_edges, lw.row_et, b->mol_ptr, b->n_mol, lw.node_local);
+  lay::k_row_aux<<<(int)((n + 255) / 256), 256, 0, st>>>(ws.rowa, (long long)b->n_edges, lw.row_et, b->mol_ptr,
+                                                         (const long long*)b->edge_ptr, b->n_mol, lw.node_local, lw.row_pair, lw.pair_dist);
   LAUNCH_CHECK();
   return 0;
 }
@@ -130,8 +139,8 @@ int lay_message(tib_model* m, const tib_batch* b, const tib_model::Layer& L, Wor
   const int E = (int)b->n_edges;
   {
     tc::ChainP cp{};
-    cp.n_rows = E; cp.n_dirs = 1; cp.n_halves = 1; cp.epi = tc::EPI_PRIMAL;
-    cp.src[0] = src_pe(tc::SRC_PE, ws.rowa, m->d.length_scale);
+    cp.n_rows = E / 2; cp.n_dirs = 1; cp.n_halves = 1; cp.epi = tc::EPI_PRIMAL;     // one row per undirected pair
+    cp.src[0] = src_pe(tc::SRC_PE, lw.pair_dist, m->d.length_scale);
     chain_mlp_params(cp, L.w, L.ch_w, 5 * F);
     cp.ascale1 = 1.0f; cp.out = lw.w3;
     if (save) { cp.save_n[0] = lw.sv_w_n[0]; cp.save_n[1] = lw.sv_w_n[1]; cp.save_r[0] = lw.sv_w_r[0]; cp.save_r[1] = lw.sv_w_r[1]; }
@@ -148,7 +157,7 @@ int lay_message(tib_model* m, const tib_batch* b, const tib_model::Layer& L, Wor
     if (launch_chain<F>(m, cp, TIB_K_MESSAGE, st)) return -1;
   }
   if (do_combine) {
-    lay::CombineP c{b->n_nodes, F, ws.node_in_ptr, ws.rowa, reinterpret_cast<const float4*>(ws.rowb), lw.phi3, lw.w3,
+    lay::CombineP c{b->n_nodes, F, ws.node_in_ptr, ws.rowa, reinterpret_cast<const float4*>(ws.rowb), lw.phi3, lw.w3, lw.row_pair,
                     ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->edge_emb, first ? 1 : 0};
     ProfScope ps(TIB_K_MESSAGE, st);
     lay::k_combine<<<std::min(b->n_nodes, m->n_sms * 16), 128, 0, st>>>(c);
@@ -157,7 +166,63 @@ int lay_message(tib_model* m, const tib_batch* b, const tib_model::Layer& L, Wor
   return 0;
 }
 
-// drift on the layered path (F = 256 default; also F = 128 for cross-checks): tensor-core message MLPs, fp32 update / readout
+// Update (cpainn.py:345-376): [V; U] v as one plain GEMM over the (node, xyz) rows, q = |V v|, MLP(cat[q, s]) -> (g, a, c),
+// then v += (U v) g, s += q^2 a + c; with D > 0 the same for every tangent direction (LayerNorm intermediates saved).
+template <int F>
+int lay_update(tib_model* m, const tib_batch* b, const tib_model::Layer& L, Workspace& ws, LayWs& lw, int cur, int D, cudaStream_t st) {
+  using namespace tib;
+  const int N = b->n_nodes, nblk = m->n_sms * 16;
+  {
+    tc::ChainP cp{};
+    cp.n_rows = 3 * N; cp.n_dirs = 1; cp.n_halves = 1; cp.epi = tc::EPI_PRIMAL; cp.n_hidden = 0;
+    cp.src[0] = src_rows(ws.v[cur], F, nullptr, 0, 0, tc::kStateScale);
+    cp.wblob = L.ch_uv; cp.n_out = 2 * F; cp.ld_out = 2 * F; cp.out = lw.vvuv; cp.out_scale = tc::kStateUnscale;
+    if (launch_chain<F>(m, cp, TIB_K_UPDATE, st)) return -1;
+    if (D > 0) {
+      tc::ChainP ct = cp;
+      ct.epi = tc::EPI_JVP; ct.n_dirs = D;
+      ct.src[0] = src_rows(lw.tv[cur], F, nullptr, 0, (long long)lw.st_v, 1.0f);
+      ct.out = lw.tvvuv; ct.out_dir_stride = (long long)lw.st_tvvuv;
+      if (launch_chain<F>(m, ct, TIB_K_UPDATE, st)) return -1;
+    }
+  }
+  {
+    lay::UpdQP qp{N, F, lw.vvuv, lw.q, D, lw.tvvuv, (long long)lw.st_tvvuv, lw.tq, (long long)lw.st_tq};
+    ProfScope ps(TIB_K_UPDATE, st);
+    lay::k_upd_q<<<std::min(N, nblk), 128, 0, st>>>(qp);
+    LAUNCH_CHECK();
+  }
+  {
+    tc::ChainP cp{};
+    cp.n_rows = N; cp.n_dirs = 1; cp.n_halves = 2; cp.epi = tc::EPI_PRIMAL;
+    cp.src[0] = src_rows(lw.q, F, nullptr, 0, 0, tc::kStateScale);
+    cp.src[1] = src_rows(ws.s[cur], F, nullptr, 0, 0, tc::kStateScale);
+    chain_mlp_params(cp, L.upd, L.ch_upd, 3 * F);
+    cp.ascale1 = tc::kStateUnscale; cp.out = lw.gac;
+    if (D > 0) { cp.save_n[0] = lw.sv_upd_n[0]; cp.save_n[1] = lw.sv_upd_n[1]; cp.save_r[0] = lw.sv_upd_r[0]; cp.save_r[1] = lw.sv_upd_r[1]; }
+    if (launch_chain<F>(m, cp, TIB_K_UPDATE, st)) return -1;
+    if (D > 0) {
+      tc::ChainP ct = cp;
+      ct.epi = tc::EPI_JVP; ct.n_dirs = D;
+      ct.src[0] = src_rows(lw.tq, F, nullptr, 0, (long long)lw.st_tq, 1.0f);
+      ct.src[1] = src_rows(lw.ts[cur], F, nullptr, 0, (long long)lw.st_s, 1.0f);
+      ct.gmax1 = L.gmax_upd[0]; ct.gmax2 = L.gmax_upd[1];
+      ct.out = lw.tgac; ct.out_dir_stride = (long long)lw.st_tgac;
+      if (launch_chain<F>(m, ct, TIB_K_UPDATE, st)) return -1;
+    }
+  }
+  {
+    lay::UpdApplyP ap{N, F, lw.vvuv, lw.q, lw.gac, ws.s[cur], ws.v[cur], D, lw.tvvuv, (long long)lw.st_tvvuv,
+                      lw.tq, (long long)lw.st_tq, lw.tgac, (long long)lw.st_tgac, lw.ts[cur], (long long)lw.st_s,
+                      lw.tv[cur], (long long)lw.st_v};
+    ProfScope ps(TIB_K_UPDATE, st);
+    lay::k_upd_apply<<<std::min(N, nblk), 128, 0, st>>>(ap);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+// drift on the layered path (F = 256 default; also F = 128 for cross-checks): tensor-core message and update MLPs, fp32 scatter / readout
 template <int F>
 int drift_layered(tib_model* m, const tib_batch* b, const float* x, float t, float* out, Workspace& ws, LayWs& lw, cudaStream_t st) {
   using namespace tib;
@@ -180,10 +245,7 @@ int drift_layered(tib_model* m, const tib_batch* b, const float* x, float t, flo
     const tib_model::Layer& L = m->layers[l];
     if (lay_message<F>(m, b, L, ws, lw, cur, l == 0, false, true, st)) return -1;
     cur ^= 1;
-    UpdateP up{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]};
-    ProfScope ps(TIB_K_UPDATE, st);
-    k_update<F, RN><<<node_tiles, TIB_THREADS, smem_update<F, RN>(), st>>>(up);
-    LAUNCH_CHECK();
+    if (lay_update<F>(m, b, L, ws, lw, cur, 0, st)) return -1;
   }
   ReadoutP rp{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], out};
   ProfScope ps(TIB_K_READOUT, st);
@@ -224,15 +286,15 @@ int drift_div_layered(tib_model* m, const tib_batch* b, const float* x, float t,
     if (lay_message<F>(m, b, L, ws, lw, cur, first, true, false, st)) return -1;
     {
       tc::ChainP cp{};
-      cp.n_rows = E; cp.n_dirs = 1; cp.n_halves = 1; cp.epi = tc::EPI_JVP;
-      cp.src[0] = src_pe(tc::SRC_PE_D, ws.rowa, m->d.length_scale);
+      cp.n_rows = E / 2; cp.n_dirs = 1; cp.n_halves = 1; cp.epi = tc::EPI_JVP;
+      cp.src[0] = src_pe(tc::SRC_PE_D, lw.pair_dist, m->d.length_scale);
       chain_mlp_params(cp, L.w, L.ch_w, 5 * F);
       cp.gmax1 = L.gmax_w[0]; cp.gmax2 = L.gmax_w[1];
       cp.save_n[0] = lw.sv_w_n[0]; cp.save_n[1] = lw.sv_w_n[1]; cp.save_r[0] = lw.sv_w_r[0]; cp.save_r[1] = lw.sv_w_r[1];
       cp.out = lw.w3d;
       if (launch_chain<F>(m, cp, TIB_K_MESSAGE, st)) return -1;
     }
-    lay::CombineP c{N, F, ws.node_in_ptr, ws.rowa, reinterpret_cast<const float4*>(ws.rowb), lw.phi3, lw.w3,
+    lay::CombineP c{N, F, ws.node_in_ptr, ws.rowa, reinterpret_cast<const float4*>(ws.rowb), lw.phi3, lw.w3, lw.row_pair,
                     ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->edge_emb, first ? 1 : 0};
     for (int d0 = 0; d0 < D; d0 += lw.Dc) {
       const int nd = std::min(lw.Dc, D - d0);
@@ -251,7 +313,7 @@ int drift_div_layered(tib_model* m, const tib_batch* b, const float* x, float t,
                           lw.ts[cur], lw.tv[cur], lw.ts[cur ^ 1], lw.tv[cur ^ 1], lw.te,
                           (long long)lw.st_s, (long long)lw.st_v, (long long)lw.st_e, d0, nd};
       ProfScope ps(TIB_K_MESSAGE, st);
-      lay::k_combine_jvp<<<(int)std::min<long long>((long long)N * nd, nblk), 128, 0, st>>>(cj);
+      lay::k_combine_jvp<<<(int)std::min<long long>((long long)N * (nd / 3), nblk), 128, 0, st>>>(cj);
       LAUNCH_CHECK();
     }
     {
@@ -260,50 +322,7 @@ int drift_div_layered(tib_model* m, const tib_batch* b, const float* x, float t,
       LAUNCH_CHECK();
     }
     cur ^= 1;
-    // ---- update: [V; U] v (plain GEMM), q, MLP(cat[q, s]) with saves; the same for every tangent direction; apply
-    {
-      tc::ChainP cp{};
-      cp.n_rows = 3 * N; cp.n_dirs = 1; cp.n_halves = 1; cp.epi = tc::EPI_PRIMAL; cp.n_hidden = 0;
-      cp.src[0] = src_rows(ws.v[cur], F, nullptr, 0, 0, tc::kStateScale);
-      cp.wblob = L.ch_uv; cp.n_out = 2 * F; cp.ld_out = 2 * F; cp.out = lw.vvuv; cp.out_scale = tc::kStateUnscale;
-      if (launch_chain<F>(m, cp, TIB_K_UPDATE, st)) return -1;
-      tc::ChainP ct = cp;
-      ct.epi = tc::EPI_JVP; ct.n_dirs = D;
-      ct.src[0] = src_rows(lw.tv[cur], F, nullptr, 0, (long long)lw.st_v, 1.0f);
-      ct.out = lw.tvvuv; ct.out_dir_stride = (long long)lw.st_tvvuv;
-      if (launch_chain<F>(m, ct, TIB_K_UPDATE, st)) return -1;
-    }
-    {
-      lay::UpdQP qp{N, F, lw.vvuv, lw.q, D, lw.tvvuv, (long long)lw.st_tvvuv, lw.tq, (long long)lw.st_tq};
-      ProfScope ps(TIB_K_UPDATE, st);
-      lay::k_upd_q<<<std::min(N, nblk), 128, 0, st>>>(qp);
-      LAUNCH_CHECK();
-    }
-    {
-      tc::ChainP cp{};
-      cp.n_rows = N; cp.n_dirs = 1; cp.n_halves = 2; cp.epi = tc::EPI_PRIMAL;
-      cp.src[0] = src_rows(lw.q, F, nullptr, 0, 0, tc::kStateScale);
-      cp.src[1] = src_rows(ws.s[cur], F, nullptr, 0, 0, tc::kStateScale);
-      chain_mlp_params(cp, L.upd, L.ch_upd, 3 * F);
-      cp.ascale1 = tc::kStateUnscale; cp.out = lw.gac;
-      cp.save_n[0] = lw.sv_upd_n[0]; cp.save_n[1] = lw.sv_upd_n[1]; cp.save_r[0] = lw.sv_upd_r[0]; cp.save_r[1] = lw.sv_upd_r[1];
-      if (launch_chain<F>(m, cp, TIB_K_UPDATE, st)) return -1;
-      tc::ChainP ct = cp;
-      ct.epi = tc::EPI_JVP; ct.n_dirs = D;
-      ct.src[0] = src_rows(lw.tq, F, nullptr, 0, (long long)lw.st_tq, 1.0f);
-      ct.src[1] = src_rows(lw.ts[cur], F, nullptr, 0, (long long)lw.st_s, 1.0f);
-      ct.gmax1 = L.gmax_upd[0]; ct.gmax2 = L.gmax_upd[1];
-      ct.out = lw.tgac; ct.out_dir_stride = (long long)lw.st_tgac;
-      if (launch_chain<F>(m, ct, TIB_K_UPDATE, st)) return -1;
-    }
-    {
-      lay::UpdApplyP ap{N, F, lw.vvuv, lw.q, lw.gac, ws.s[cur], ws.v[cur], D, lw.tvvuv, (long long)lw.st_tvvuv,
-                        lw.tq, (long long)lw.st_tq, lw.tgac, (long long)lw.st_tgac, lw.ts[cur], (long long)lw.st_s,
-                        lw.tv[cur], (long long)lw.st_v};
-      ProfScope ps(TIB_K_UPDATE, st);
-      lay::k_upd_apply<<<std::min(N, nblk), 128, 0, st>>>(ap);
-      LAUNCH_CHECK();
-    }
+    if (lay_update<F>(m, b, L, ws, lw, cur, D, st)) return -1;
   }
   // ---- readout with tangents (fp32, DR directions per pass) and the trace
   const int jtiles = (N + 8 * JRN - 1) / (8 * JRN);

@@ -58,4 +58,42 @@ __global__ void k_zmatrix(const float* __restrict__ x, long long n_conf, int n_a
   }
 }
 
+// Torsion features -> TICA projection -> histograms (plots/10506_main.ipynb cells 3-4): per conformer
+//   feat[2 j] = cos(torsion_j), feat[2 j + 1] = sin(torsion_j)              (enc(): np.stack((cos, sin), -1).reshape)
+//   proj[k]   = sum_i (feat[i] - mean[i]) R[i][k],  k < dim <= 4             (deeptime TICA.transform)
+//   hist[k][bin(proj[k])] += weight                                          (plt.hist(bins=linspace(lo, hi, n_bins + 1)))
+// torsions: [n_conf][stride] floats with the torsion of feature j at column col0 + j * col_step (a z-matrix row block, or a
+// plain [n_conf][n_tors] array).  HBM bound: 4 n_tors bytes read + 4 dim written per conformer; one thread per conformer,
+// histogram counts accumulated in shared memory per block, then added to global memory with one atomic per bin.
+__global__ void k_tica_project(const float* __restrict__ tors, long long n_conf, int n_tors, long long stride, int col0, int col_step,
+                               const double* __restrict__ mean, const double* __restrict__ R, int dim, const double* __restrict__ weight,
+                               float* __restrict__ proj, double* __restrict__ hist, int n_bins, double lo, double hi) {
+  extern __shared__ double sh_hist[];           // [dim][n_bins]
+  for (int i = threadIdx.x; i < dim * n_bins; i += blockDim.x) sh_hist[i] = 0.0;
+  __syncthreads();
+  for (long long c = blockIdx.x * (long long)blockDim.x + threadIdx.x; c < n_conf; c += (long long)gridDim.x * blockDim.x) {
+    double acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const float* t = tors + c * stride + col0;
+    for (int j = 0; j < n_tors; ++j) {
+      float sn, cs;
+      sincosf(t[(long long)j * col_step], &sn, &cs);
+      const double fc = (double)cs - mean[2 * j], fs = (double)sn - mean[2 * j + 1];
+      for (int k = 0; k < dim; ++k) acc[k] += fc * R[(2 * j) * dim + k] + fs * R[(2 * j + 1) * dim + k];
+    }
+    const double w = weight ? weight[c] : 1.0;
+    for (int k = 0; k < dim; ++k) {
+      if (proj) proj[c * dim + k] = (float)acc[k];
+      if (hist && acc[k] >= lo && acc[k] <= hi) {
+        int b = (int)((acc[k] - lo) / (hi - lo) * n_bins);
+        b = b >= n_bins ? n_bins - 1 : b;      // the right edge belongs to the last bin (numpy.histogram)
+        atomicAdd(&sh_hist[k * n_bins + b], w);
+      }
+    }
+  }
+  __syncthreads();
+  if (hist)
+    for (int i = threadIdx.x; i < dim * n_bins; i += blockDim.x)
+      if (sh_hist[i] != 0.0) atomicAdd(&hist[i], sh_hist[i]);
+}
+
 }  // namespace tib

@@ -56,23 +56,33 @@ struct ChainP {
   int* err;
 };
 
-template <int F>
+// NG = epilogue warp groups of 4 warps (one warp per TMEM lane quarter in each group).  NG = 4: 16 epilogue warps, one CTA
+// per SM (F = 256 needs 128 KB of operand image).  NG = 2 (F = 128): 8 epilogue warps, one 64 KB operand buffer, a two-stage
+// weight ring, 256 TMEM columns - TWO CTAs per SM, so that one CTA's MMAs run under the other's epilogue (a single chain is
+// strictly serial: build -> MMA -> LayerNorm -> MMA -> LayerNorm -> MMA).
+template <int F, int NG>
 struct ChainSmem {
   static constexpr uint32_t OP_HALF = 128u * F * 2u;            // hi (or lo) image of a [128 x F] operand
   static constexpr uint32_t OP_BYTES = 2u * OP_HALF;
-  static constexpr int NBUF = F == 128 ? 2 : 1;
+  static constexpr int NBUF = (F == 128 && NG == 4) ? 2 : 1;
+  static constexpr int STAGES = NG == 4 ? 4 : 2;
+  static constexpr int NSLOT = NG == 4 ? 2 : 1;                 // output accumulator slots of 128 columns
+  static constexpr int TMEM_COLS = NG == 4 ? 512 : 256;
+  static constexpr int EPI = NG * 128;                          // epilogue threads
+  static constexpr int THREADS = EPI + 64;
+  static constexpr int CTAS = NG == 4 ? 1 : 2;
   static constexpr uint32_t BUF = 0;
   static constexpr uint32_t RING = BUF + NBUF * OP_BYTES;
-  static constexpr uint32_t PRM = RING + kStages * kChunkBytes;  // b1 g1 be1 b2 g2 be2
-  static constexpr uint32_t STAT = PRM + 6 * F * 4;              // 2 x float4 [4 groups][128 rows]
-  static constexpr uint32_t INVS = STAT + 2 * 4 * 128 * 16;      // float [128]: un-scale factor of each output column
+  static constexpr uint32_t PRM = RING + STAGES * kChunkBytes;   // b1 g1 be1 b2 g2 be2
+  static constexpr uint32_t STAT = PRM + 6 * F * 4;              // 2 x float4 [NG groups][128 rows]
+  static constexpr uint32_t INVS = STAT + 2 * NG * 128 * 16;     // float [128]: un-scale factor of each output column
   static constexpr uint32_t RED = INVS + 512;                    // float [16]: per-warp maxima of the tile-scale pass
   static constexpr uint32_t BARS = RED + 128;
   static constexpr uint32_t TOTAL = BARS + 256;
 };
 // C_OPS1: the second K half of layer 1 is announced on its own barrier - a thread arrives for both halves without a wait in
 // between, and two arrivals of one thread must not complete a phase that another thread has not arrived on yet
-enum { C_FULL = 0, C_EMPTY = C_FULL + kStages, C_OPS = C_EMPTY + kStages, C_OPS1, C_ACC, C_FREE0, C_FREE1, C_TFULL0, C_TFULL1,
+enum { C_FULL = 0, C_EMPTY = C_FULL + 4, C_OPS = C_EMPTY + 4, C_OPS1, C_ACC, C_FREE0, C_FREE1, C_TFULL0, C_TFULL1,
        C_TEMPTY0, C_TEMPTY1, C_COUNT };
 
 // 2^k with k clamped so that the result is a normal float
@@ -86,20 +96,20 @@ __host__ __device__ constexpr int chain_chunks(int n_hidden, int n_halves, int n
 }
 
 // ---- input build: rows [32*wq, +32) x this thread's column groups of one K half -> operand image -------------------------
-// thread (wq, grp, lane): rows 32*wq + 8*oct + (lane & 7), column groups 4*grp + (lane >> 3) + 16*j
+// thread (wq, grp, lane): rows 32*wq + 8*oct + (lane & 7), column groups 4*grp + (lane >> 3) + 4*NG*j
 template <int F>
 __device__ __forceinline__ const float* chain_row_ptr(const ChainSrc& s, long long dir, long long row) {
   const long long r = s.idx ? (long long)__ldg(s.idx + row * s.idx_stride) : row;
   return s.base + dir * s.dir_stride + r * s.ld;
 }
 
-template <int F>
+template <int F, int NG>
 __device__ __noinline__ float chain_absmax(const ChainSrc& s, long long dir, long long row0, int rows, int wq, int grp, int lane) {
   float m = 0.0f;
   if (s.kind != SRC_ROWS) return m;
 #pragma unroll 1
-  for (int j = 0; j < F / 128; ++j) {
-    const int g = 4 * grp + (lane >> 3) + 16 * j;
+  for (int j = 0; j < F / (32 * NG); ++j) {
+    const int g = 4 * grp + (lane >> 3) + 4 * NG * j;
     float4 a[4], b[4];
 #pragma unroll
     for (int oct = 0; oct < 4; ++oct) {
@@ -120,13 +130,13 @@ __device__ __noinline__ float chain_absmax(const ChainSrc& s, long long dir, lon
   return m;
 }
 
-template <int F>
+template <int F, int NG>
 __device__ __noinline__ void chain_build(unsigned char* op, const ChainSrc& s, long long dir, long long row0, int rows, int wq,
                                          int grp, int lane, float scale) {
-  constexpr uint32_t LO = ChainSmem<F>::OP_HALF;
+  constexpr uint32_t LO = 128u * F * 2u;
 #pragma unroll 1
-  for (int j = 0; j < F / 128; ++j) {
-    const int g = 4 * grp + (lane >> 3) + 16 * j;
+  for (int j = 0; j < F / (32 * NG); ++j) {
+    const int g = 4 * grp + (lane >> 3) + 4 * NG * j;
     if (s.kind == SRC_ROWS) {
       float4 a[4], b[4];
 #pragma unroll
@@ -178,12 +188,12 @@ __device__ __noinline__ void chain_build(unsigned char* op, const ChainSrc& s, l
 //   PRIMAL: z = acc * ascale + b ; n = (z - mean) / std ; h = SiLU(n g + be)                       -> image (unscaled)
 //   JVP   : zd = acc * ainv ; nd = rstd (zd - mean zd - n mean(n zd)) ; hd = SiLU'(n g + be) g nd   -> image * 2^k(row)
 // returns the row's image scale (1 for PRIMAL)
-template <int F, int EPI>
+template <int F, int NG, int EPI>
 __device__ __noinline__ float chain_hidden(uint32_t taddr, int grp, int row, bool live, const float* b, const float* g,
                                            const float* be, unsigned char* op, float4* stat, float ascale, float gmax,
                                            float* save_n, float* save_r) {
-  constexpr int CPT = F / 4;                 // columns per thread
-  constexpr uint32_t LO = ChainSmem<F>::OP_HALF;
+  constexpr int CPT = F / NG;                // columns per thread
+  constexpr uint32_t LO = 128u * F * 2u;
   const int col0 = grp * CPT;
   float sum = 0.0f, ss = 0.0f, zmax = 0.0f;
 #pragma unroll 1
@@ -206,8 +216,9 @@ __device__ __noinline__ float chain_hidden(uint32_t taddr, int grp, int row, boo
     }
   }
   stat[grp * 128 + row] = make_float4(sum, ss, zmax, 0.0f);
-  named_bar_sync(NB_QUARTER + (row >> 5), kQuarterThreads);
-  const float4 s0 = stat[row], s1 = stat[128 + row], s2 = stat[256 + row], s3 = stat[384 + row];
+  named_bar_sync(NB_QUARTER + (row >> 5), 32 * NG);
+  float4 s0 = stat[row], s1 = stat[128 + row], s2 = make_float4(0.f, 0.f, 0.f, 0.f), s3 = s2;
+  if (NG == 4) { s2 = stat[256 + row]; s3 = stat[384 + row]; }
   const float m1 = ((s0.x + s1.x) + (s2.x + s3.x)) * (1.0f / F);
   const float m2 = ((s0.y + s1.y) + (s2.y + s3.y)) * (1.0f / F);
   float rstd, c0, c1, rowscale = 1.0f;
@@ -253,9 +264,9 @@ __device__ __noinline__ float chain_hidden(uint32_t taddr, int grp, int row, boo
   return rowscale;
 }
 
-template <int F>
-__global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
-  using S = ChainSmem<F>;
+template <int F, int NG>
+__global__ void __launch_bounds__(ChainSmem<F, NG>::THREADS, ChainSmem<F, NG>::CTAS) k_chain_tc(ChainP p) {
+  using S = ChainSmem<F, NG>;
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* const BUF = smem + S::BUF;
   unsigned char* const RING = smem + S::RING;
@@ -269,21 +280,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
   volatile int* err = p.err;
   constexpr int KC = F / 32;          // chunks per K = F
   constexpr int NBH = F / 128;        // 128-column blocks of a hidden layer
+  constexpr int EW = 4 * NG;          // epilogue warps; warp EW = weight producer, warp EW + 1 = MMA issuer
+  constexpr int OCOLS = 128 / NG;     // output columns (= rows of the tile) per epilogue thread
   const int n_work = p.n_tiles * p.n_dirs;
   const int n_ob = p.n_out / 128;
 
   if (tid == 0) {
-    for (int i = 0; i < kStages; ++i) { mbar_init(&bars[C_FULL + i], 1); mbar_init(&bars[C_EMPTY + i], 1); }
-    mbar_init(&bars[C_OPS], kEpiThreads); mbar_init(&bars[C_OPS1], kEpiThreads);
+    for (int i = 0; i < S::STAGES; ++i) { mbar_init(&bars[C_FULL + i], 1); mbar_init(&bars[C_EMPTY + i], 1); }
+    mbar_init(&bars[C_OPS], S::EPI); mbar_init(&bars[C_OPS1], S::EPI);
     mbar_init(&bars[C_ACC], 1);
     mbar_init(&bars[C_FREE0], 1); mbar_init(&bars[C_FREE1], 1);
     mbar_init(&bars[C_TFULL0], 1); mbar_init(&bars[C_TFULL1], 1);
-    mbar_init(&bars[C_TEMPTY0], kEpiThreads); mbar_init(&bars[C_TEMPTY1], kEpiThreads);
+    mbar_init(&bars[C_TEMPTY0], S::EPI); mbar_init(&bars[C_TEMPTY1], S::EPI);
     fence_mbar_init();
   }
-  if (warp == 16) tmem_alloc(tmem_slot, 512);
+  if (warp == EW) tmem_alloc(tmem_slot, S::TMEM_COLS);
   if (p.n_hidden) {
-    for (int i = tid; i < 6 * F; i += kThreads) {
+    for (int i = tid; i < 6 * F; i += S::THREADS) {
       const int r = i / F;
       const float* src = r == 0 ? p.b1 : r == 1 ? p.g1 : r == 2 ? p.be1 : r == 3 ? p.b2 : r == 4 ? p.g2 : p.be2;
       PRM[i] = __ldg(src + (i - r * F));
@@ -293,9 +306,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t t_hid = tmem, t_out = tmem + F;       // hidden accumulator | two output slots of 128 columns
+  const uint32_t t_hid = tmem, t_out = tmem + F;       // hidden accumulator | NSLOT output slots of 128 columns
 
-  if (warp == 16) {
+  if (warp == EW) {
     // =========================== weight producer ===========================
     if (lane == 0) {
       const int per_item = chain_chunks<F>(p.n_hidden, p.n_halves, p.n_out);
@@ -305,10 +318,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
           mbar_wait(&bars[C_EMPTY + stage], ph ^ 1, err);
           mbar_arrive_expect_tx(&bars[C_FULL + stage], kChunkBytes);
           bulk_g2s(RING + stage * kChunkBytes, p.wblob + (size_t)c * kChunkBytes, kChunkBytes, &bars[C_FULL + stage]);
-          if (++stage == kStages) { stage = 0; ph ^= 1; }
+          if (++stage == S::STAGES) { stage = 0; ph ^= 1; }
         }
     }
-  } else if (warp == 17) {
+  } else if (warp == EW + 1) {
     // =========================== MMA issuer ===========================
     if (lane == 0) {
       int stage = 0; uint32_t ph = 0, pops[2] = {0, 0}, pte[2] = {0, 0};
@@ -321,10 +334,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
         if (!transposed) mma_f16x3(d, opk, S::OP_HALF, wst, kChunkHalfBytes, 2, acc, p.passes);
         else             mma_f16x3(d, wst, kChunkHalfBytes, opk, S::OP_HALF, 2, acc, p.passes);
         tc_commit(&bars[C_EMPTY + stage]);
-        if (++stage == kStages) { stage = 0; ph ^= 1; }
+        if (++stage == S::STAGES) { stage = 0; ph ^= 1; }
       };
       auto ops_ready = [&](int h = 0) { mbar_wait(&bars[C_OPS + h], pops[h], err); pops[h] ^= 1; tc_fence_after(); };
-      int oc = 0;                                                  // running output-block counter (slot = oc & 1)
+      int oc = 0;                                                  // running output-block counter (slot = oc % NSLOT)
       for (int w = blockIdx.x; w < n_work; w += gridDim.x) {
         if (p.n_hidden) {
           for (int h = 0; h < p.n_halves; ++h) {                   // layer 1, one K half at a time
@@ -347,7 +360,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
         ops_ready();                                               // output layer (H2, or the plain input, in buffer 0)
 #pragma unroll 1
         for (int ob = 0; ob < n_ob; ++ob, ++oc) {
-          const int sl = oc & 1;
+          const int sl = oc % S::NSLOT;
           mbar_wait(&bars[C_TEMPTY0 + sl], pte[sl] ^ 1, err); pte[sl] ^= 1; tc_fence_after();
 #pragma unroll 1
           for (int kc = 0; kc < KC; ++kc) chunk(t_out + 128 * sl, buf, kc, true, kc > 0);
@@ -356,7 +369,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
       }
     }
   } else {
-    // =========================== builders / epilogue (512 threads) ===========================
+    // =========================== builders / epilogue (128 NG threads) ===========================
     const int grp = warp >> 2, wq = warp & 3;
     const int row = 32 * wq + lane;
     const uint32_t lt = tmem + ((uint32_t)(wq * 32) << 16);
@@ -373,14 +386,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
       float in_scale = 1.0f, in_inv = 1.0f;
       if (p.epi == EPI_JVP) {
         float m = 0.0f;
-        for (int h = 0; h < p.n_halves; ++h) m = fmaxf(m, chain_absmax<F>(p.src[h], dir, row0, rows, wq, grp, lane));
+        for (int h = 0; h < p.n_halves; ++h) m = fmaxf(m, chain_absmax<F, NG>(p.src[h], dir, row0, rows, wq, grp, lane));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-        named_bar_sync(NB_ALL, kEpiThreads);                        // RED of the previous item has been read
+        named_bar_sync(NB_ALL, S::EPI);                             // RED of the previous item has been read
         if (lane == 0) RED[warp] = m;
-        named_bar_sync(NB_ALL, kEpiThreads);
+        named_bar_sync(NB_ALL, S::EPI);
 #pragma unroll
-        for (int i = 0; i < 16; ++i) m = fmaxf(m, RED[i]);
+        for (int i = 0; i < EW; ++i) m = fmaxf(m, RED[i]);
         if (p.src[0].kind == SRC_PE_D) m = fmaxf(m, 64.0f);          // derivative of the encoder: at most F/2 * pi / length
         if (m > 0.0f && m < 3.0e38f) { const int e = floor_log2f(m); in_scale = pow2i(9 - e); in_inv = pow2i(e - 9); }
       }
@@ -389,57 +402,60 @@ __global__ void __launch_bounds__(kThreads, 1) k_chain_tc(ChainP p) {
         for (int h = 0; h < p.n_halves; ++h) {
           const int bi = h % S::NBUF;
           if (h >= S::NBUF) { mbar_wait(&bars[C_FREE0 + bi], pfree[bi], err); pfree[bi] ^= 1; }
-          chain_build<F>(BUF + bi * S::OP_BYTES, p.src[h], dir, row0, rows, wq, grp, lane,
-                         p.epi == EPI_JVP ? in_scale : p.src[h].scale);
+          chain_build<F, NG>(BUF + bi * S::OP_BYTES, p.src[h], dir, row0, rows, wq, grp, lane,
+                             p.epi == EPI_JVP ? in_scale : p.src[h].scale);
           ops_done(h);
         }
         const size_t so = (size_t)tile * F * 128;
+        float4* const st0 = STAT + statsel * (NG * 128);
+        float4* const st1 = STAT + (statsel ^ 1) * (NG * 128);
         acc_ready();
         if (p.epi == EPI_PRIMAL)
-          chain_hidden<F, EPI_PRIMAL>(lt, grp, row, live, PRM, PRM + F, PRM + 2 * F, BUF, STAT + statsel * 512, p.ascale1, 0.0f,
-                                      p.save_n[0] ? p.save_n[0] + so : nullptr, p.save_r[0] ? p.save_r[0] + row0 + row : nullptr);
+          chain_hidden<F, NG, EPI_PRIMAL>(lt, grp, row, live, PRM, PRM + F, PRM + 2 * F, BUF, st0, p.ascale1, 0.0f,
+                                          p.save_n[0] ? p.save_n[0] + so : nullptr, p.save_r[0] ? p.save_r[0] + row0 + row : nullptr);
         else
-          rowscale = chain_hidden<F, EPI_JVP>(lt, grp, row, live, PRM, PRM + F, PRM + 2 * F, BUF, STAT + statsel * 512, in_inv,
-                                              p.gmax1, p.save_n[0] + so, p.save_r[0] + row0 + row);
-        statsel ^= 1;
+          rowscale = chain_hidden<F, NG, EPI_JVP>(lt, grp, row, live, PRM, PRM + F, PRM + 2 * F, BUF, st0, in_inv, p.gmax1,
+                                                  p.save_n[0] + so, p.save_r[0] + row0 + row);
         ops_done();
         acc_ready();
         if (p.epi == EPI_PRIMAL)
-          chain_hidden<F, EPI_PRIMAL>(lt, grp, row, live, PRM + 3 * F, PRM + 4 * F, PRM + 5 * F, BUF, STAT + statsel * 512, 1.0f, 0.0f,
-                                      p.save_n[1] ? p.save_n[1] + so : nullptr, p.save_r[1] ? p.save_r[1] + row0 + row : nullptr);
+          chain_hidden<F, NG, EPI_PRIMAL>(lt, grp, row, live, PRM + 3 * F, PRM + 4 * F, PRM + 5 * F, BUF, st1, 1.0f, 0.0f,
+                                          p.save_n[1] ? p.save_n[1] + so : nullptr, p.save_r[1] ? p.save_r[1] + row0 + row : nullptr);
         else
-          rowscale = chain_hidden<F, EPI_JVP>(lt, grp, row, live, PRM + 3 * F, PRM + 4 * F, PRM + 5 * F, BUF, STAT + statsel * 512,
-                                              1.0f / rowscale, p.gmax2, p.save_n[1] + so, p.save_r[1] + row0 + row);
-        statsel ^= 1;
+          rowscale = chain_hidden<F, NG, EPI_JVP>(lt, grp, row, live, PRM + 3 * F, PRM + 4 * F, PRM + 5 * F, BUF, st1, 1.0f / rowscale,
+                                                  p.gmax2, p.save_n[1] + so, p.save_r[1] + row0 + row);
         if (grp == 0) INVS[row] = 1.0f / rowscale;
       } else {
-        chain_build<F>(BUF, p.src[0], dir, row0, rows, wq, grp, lane, p.epi == EPI_JVP ? in_scale : p.src[0].scale);
+        chain_build<F, NG>(BUF, p.src[0], dir, row0, rows, wq, grp, lane, p.epi == EPI_JVP ? in_scale : p.src[0].scale);
         if (grp == 0) INVS[row] = p.epi == EPI_JVP ? in_inv : p.out_scale;
       }
       ops_done();
-      named_bar_sync(NB_ALL, kEpiThreads);                          // INVS is complete
+      named_bar_sync(NB_ALL, S::EPI);                               // INVS is complete
       // ---- output layer, transposed: this thread owns feature f = TMEM lane of each 128-feature block; columns are rows
-      float* const obase = p.out + (long long)dir * p.out_dir_stride + (row0 + 32 * grp) * p.ld_out + row;
-      const int qn = min(32, rows - 32 * grp);
+      float* const obase = p.out + (long long)dir * p.out_dir_stride + (row0 + OCOLS * grp) * p.ld_out + row;
+      const int qn = min(OCOLS, rows - OCOLS * grp);
 #pragma unroll 1
       for (int ob = 0; ob < n_ob; ++ob, ++oc) {
-        const int sl = oc & 1;
+        const int sl = oc % S::NSLOT;
         const float bias = (p.epi == EPI_PRIMAL && p.b3) ? __ldg(p.b3 + 128 * ob + row) : 0.0f;
         mbar_wait(&bars[C_TFULL0 + sl], ptf[sl], err); ptf[sl] ^= 1; tc_fence_after();
-        float v[32];
-        tmem_ld32(lt + F + 128 * sl + 32 * grp, v);
-        tc_fence_before(); mbar_arrive(&bars[C_TEMPTY0 + sl]);      // the slot may be refilled while we store
         float* o = obase + 128 * ob;
+#pragma unroll 1
+        for (int pc = 0; pc < OCOLS / 32; ++pc) {
+          float v[32];
+          tmem_ld32(lt + F + 128 * sl + OCOLS * grp + 32 * pc, v);
+          if (pc == OCOLS / 32 - 1) { tc_fence_before(); mbar_arrive(&bars[C_TEMPTY0 + sl]); }   // the slot may be refilled while we store
 #pragma unroll
-        for (int q = 0; q < 32; ++q)
-          if (q < qn) o[(long long)q * p.ld_out] = fmaf(v[q], INVS[32 * grp + q], bias);
+          for (int q = 0; q < 32; ++q)
+            if (32 * pc + q < qn) o[(long long)(32 * pc + q) * p.ld_out] = fmaf(v[q], INVS[OCOLS * grp + 32 * pc + q], bias);
+        }
       }
-      named_bar_sync(NB_ALL, kEpiThreads);                          // INVS / STAT may be rewritten by the next item
+      named_bar_sync(NB_ALL, S::EPI);                               // INVS / STAT may be rewritten by the next item
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 16) tmem_dealloc(tmem, 512);
+  if (warp == EW) tmem_dealloc(tmem, S::TMEM_COLS);
 }
 
 }  // namespace tc

@@ -60,6 +60,12 @@ struct ProfScope {
   }
 };
 
+struct DeviceGuard {
+  int prev = -1; bool ok = false;
+  explicit DeviceGuard(int dev) { if (cudaGetDevice(&prev) != cudaSuccess) prev = -1; ok = cudaSetDevice(dev) == cudaSuccess; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
 #define CUDA_TRY(expr)                                                                        \
   do {                                                                                        \
     cudaError_t _e = (expr);                                                                  \
@@ -112,6 +118,7 @@ struct tib_model {
   unsigned char* ch_blob = nullptr;   // layered path (F = 128, 256)
   bool tc_attrs_set = false;
   bool ch_attrs_set = false;
+  bool pe_cache = true;       // TIB_NO_PE_CACHE (read once, at model creation) turns the positional-encoding image cache off
   bool jvp_attrs_set = false;
   int* dev_err = nullptr;     // device error words: [0] bounded mbarrier waits, [1] non-finite tensor-core readout
   int n_sms = 148;
@@ -365,7 +372,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       tp.s_old = ws.s[cur]; tp.v_old = ws.v[cur]; tp.s_new = ws.s[cur ^ 1]; tp.v_new = ws.v[cur ^ 1]; tp.e = ws.e;
       tp.wblob = L.tc_msg; tp.edge_emb = m->edge_emb;
       if (l == 0 && use_phi_tab) { tp.phi_tab = ws.phitab; tp.embed_index = b->embed_index; tp.n_et = m->d.n_edge_types; }
-      if (ws.peimg && (size_t)n_tiles * tc::kOperandBytes <= ws.peimg_bytes && m->d.n_layers > 1 && !getenv("TIB_NO_PE_CACHE")) {
+      if (ws.peimg && (size_t)n_tiles * tc::kOperandBytes <= ws.peimg_bytes && m->d.n_layers > 1 && m->pe_cache) {
         tp.pe_img = ws.peimg; tp.pe_mode = l == 0 ? 1 : 2;
       }
       tp.prm = tc::MsgParams{{L.w.b1, L.w.g1, L.w.be1, L.w.b2, L.w.g2, L.w.be2,
@@ -528,7 +535,7 @@ int drift_dispatch(tib_model* m, const tib_batch* b, const float* x, float t, fl
   if (m->math != TIB_MATH_FP32_SIMT && F != 128 && F != 256)
     return fail("the tensor-core math modes are built for n_features = 128 and 256 (got %d); use TIB_MATH_FP32_SIMT", F);
   if (uses_layered(m)) {
-    LayWs lw;
+    LayWs lw{};
     lw.layout((char*)ws.end, F, b->n_nodes, (long long)b->n_edges, b->max_atoms, false);
     return F == 256 ? drift_layered<256>(m, b, x, t, out, ws, lw, st) : drift_layered<128>(m, b, x, t, out, ws, lw, st);
   }
@@ -619,11 +626,13 @@ int tib_model_create(tib_model** out, const tib_model_desc* d, const float* w, s
   if (d->n_layers < 1 || d->n_types < 1 || d->n_edge_types < 1) return fail("bad layer/type counts");
   if (n_floats != tib_packed_weight_count(d))
     return fail("packed weight count mismatch: got %zu, descriptor needs %zu", n_floats, tib_packed_weight_count(d));
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);          // the caller's current device is restored on every return path
+  if (!guard.ok) return fail("cudaSetDevice(%d) failed", device);
   tib_model* m = new tib_model();
   m->d = *d;
   m->device = device;
   m->n_temp = n_temp_of(d->variant);
+  m->pe_cache = getenv("TIB_NO_PE_CACHE") == nullptr;
   m->math = (F == 128 || F == 256) ? TIB_MATH_F16X3_TC : TIB_MATH_FP32_SIMT;
   const int nt = m->n_temp;
 
@@ -858,7 +867,7 @@ int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, flo
   ws.carve(workspace, F, b->n_nodes, (long long)b->n_edges);
   cudaStream_t st = (cudaStream_t)stream;
   if (m->math != TIB_MATH_FP32_SIMT && (F == 128 || F == 256)) {
-    LayWs lw;
+    LayWs lw{};
     lw.layout(ws.end, F, b->n_nodes, (long long)b->n_edges, b->max_atoms, true);
     return F == 128 ? drift_div_layered<128>(m, b, x, t, out_b, out_div, ws, lw, st)
                     : drift_div_layered<256>(m, b, x, t, out_b, out_div, ws, lw, st);
@@ -880,6 +889,22 @@ int tib_zmatrix(const float* x, int64_t n_conf, int32_t n_atoms, const int32_t* 
   if (n_conf == 0) return 0;
   const long long total = (long long)n_conf * (n_atoms - 1);
   tib::k_zmatrix<<<grid_for((size_t)total), 256, 0, (cudaStream_t)stream>>>(x, (long long)n_conf, n_atoms, order, ref, z);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int tib_tica_project(const float* torsions, int64_t n_conf, int32_t n_tors, int64_t stride, int32_t col0, int32_t col_step,
+                     const double* mean, const double* R, int32_t dim, const double* weight, float* proj, double* hist,
+                     int32_t n_bins, double lo, double hi, void* stream) {
+  if (!torsions || !mean || !R) return fail("tib_tica_project: null argument");
+  if (dim < 1 || dim > 4) return fail("tib_tica_project: dim must be in [1,4] (got %d)", dim);
+  if (n_conf < 0 || n_tors < 1) return fail("tib_tica_project: need n_conf >= 0 and n_tors >= 1");
+  if (hist && (n_bins < 1 || n_bins > 1024 || !(hi > lo))) return fail("tib_tica_project: bad histogram range / bins");
+  if (n_conf == 0) return 0;
+  const size_t smem = sizeof(double) * (size_t)dim * (size_t)(hist ? n_bins : 1);
+  tib::k_tica_project<<<grid_for((size_t)n_conf), 256, smem, (cudaStream_t)stream>>>(torsions, (long long)n_conf, n_tors, (long long)stride,
+                                                                                  col0, col_step, mean, R, dim, weight, proj, hist,
+                                                                                  hist ? n_bins : 1, lo, hi);
   LAUNCH_CHECK();
   return 0;
 }
@@ -1098,9 +1123,12 @@ int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const 
     }
     (void)have_interp;
   }
+  // n_times == 1: no step is taken and the dense-output kernel never runs; the final state is the initial state
+  if (!o->save_frames && o->n_times == 1) CUDA_TRY(cudaMemcpyAsync(out_xts, y, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   if (stats) { stats->nfe = nfe; stats->attempts = attempts; stats->accepted = accepted; stats->last_dt = dt; }
   CUDA_TRY(cudaStreamSynchronize(st));
-  return 0;
+  // the stream is idle here anyway: report a device-side pipeline / range fault instead of returning bad frames
+  return tib_model_status(m, stream);
 }
 
 int tib_reweight_stats(const double* E0, const double* E1, const double* nd, const double* wt, size_t n, double* out,
@@ -1119,6 +1147,7 @@ int tib_reweight_stats(const double* E0, const double* E1, const double* nd, con
 // ---- ADW -----------------------------------------------------------------------------------------
 struct tib_adw_model {
   int hidden, num_layers, device;
+  bool attr_set = false;
   double* dev;
   tib::AdwW w;
 };
@@ -1130,7 +1159,8 @@ int tib_adw_create(tib_adw_model** out, int32_t hidden, int32_t num_layers, cons
   const size_t H = hidden;
   const size_t need = (3 * H + H) + (H * H + H) + (H + 1) + (3 * H + H) + (size_t)(num_layers - 1) * (H * H + H) + (H + 1);
   if (n_doubles != need) return fail("ADW packed weight count mismatch: got %zu, need %zu", n_doubles, need);
-  CUDA_TRY(cudaSetDevice(device));
+  DeviceGuard guard(device);
+  if (!guard.ok) return fail("cudaSetDevice(%d) failed", device);
   // device layout: hidden->hidden matrices transposed to [in][out]; everything else as given
   std::vector<double> stage;
   stage.reserve(n_doubles);
@@ -1177,10 +1207,9 @@ int tib_adw_drift_div(tib_adw_model* m, const double* x, const double* beta0, co
                       double* out_b, double* out_div, size_t n, void* stream) {
   if (!m || !x || !beta0 || !beta1 || !out_b) return fail("tib_adw_drift_div: null pointer");
   if (n == 0) return 0;
-  static bool attr = false;
-  if (!attr) {
+  if (!m->attr_set) {          // per model (= per device): the opt-in shared-memory size is a per-device function attribute
     if (set_smem(tib::k_adw<256>, tib::adw_smem<256>())) return -1;
-    attr = true;
+    m->attr_set = true;
   }
   const int blocks = (int)((n + tib::kAdwRows - 1) / tib::kAdwRows);
   tib::k_adw<256><<<blocks, 256, tib::adw_smem<256>(), (cudaStream_t)stream>>>(m->w, x, beta0, beta1, t, out_b, out_div, n);
@@ -1194,19 +1223,18 @@ int tib_selftest_gemm(const float* A, const float* W_host, float* out, int trans
   cudaStream_t st = (cudaStream_t)stream;
   std::vector<uint16_t> chunks(4 * tib::tc::kChunkBytes / 2);
   for (int kb = 0; kb < 4; ++kb) pack_tc_chunk(chunks.data() + (size_t)kb * tib::tc::kChunkBytes / 2, W_host, 128, 0, 32 * kb);
-  unsigned char* dW = nullptr; int* derr = nullptr;
-  CUDA_TRY(cudaMalloc(&dW, chunks.size() * 2));
-  CUDA_TRY(cudaMalloc(&derr, sizeof(int)));
-  CUDA_TRY(cudaMemset(derr, 0, sizeof(int)));
-  CUDA_TRY(cudaMemcpy(dW, chunks.data(), chunks.size() * 2, cudaMemcpyHostToDevice));
+  struct Tmp { unsigned char* dW = nullptr; int* derr = nullptr; ~Tmp() { cudaFree(dW); cudaFree(derr); } } tmp;   // freed on every return path
+  CUDA_TRY(cudaMalloc(&tmp.dW, chunks.size() * 2));
+  CUDA_TRY(cudaMalloc(&tmp.derr, sizeof(int)));
+  CUDA_TRY(cudaMemset(tmp.derr, 0, sizeof(int)));
+  CUDA_TRY(cudaMemcpy(tmp.dW, chunks.data(), chunks.size() * 2, cudaMemcpyHostToDevice));
   const size_t smem = tib::tc::kOperandBytes + tib::tc::kSelfStages * tib::tc::kChunkBytes + 256;
   if (set_smem(tib::tc::k_tc_selftest, smem)) return -1;
-  tib::tc::k_tc_selftest<<<1, tib::tc::kSelfThreads, smem, st>>>(A, dW, out, transposed, derr);
+  tib::tc::k_tc_selftest<<<1, tib::tc::kSelfThreads, smem, st>>>(A, tmp.dW, out, transposed, tmp.derr);
   LAUNCH_CHECK();
   CUDA_TRY(cudaStreamSynchronize(st));
   int h = 0;
-  CUDA_TRY(cudaMemcpy(&h, derr, sizeof(int), cudaMemcpyDeviceToHost));
-  cudaFree(dW); cudaFree(derr);
+  CUDA_TRY(cudaMemcpy(&h, tmp.derr, sizeof(int), cudaMemcpyDeviceToHost));
   if (h) return fail("tib_selftest_gemm: an mbarrier wait timed out (pipeline protocol error)");
   return 0;
 }

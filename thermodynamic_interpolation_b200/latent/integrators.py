@@ -14,4 +14,5 @@ class MoleculeIntegrator(_AmbientIntegrator):
 
     def rollout(self, batch, noise=None) -> tuple:
         xts, dlogp, _nfe, _pb = self._solve(batch, noise)
+        self.ode_wrapper.b.engine().status()       # see the ambient integrator
         return xts, dlogp, batch.batch

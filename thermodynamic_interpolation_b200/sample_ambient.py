@@ -40,7 +40,7 @@ def regroup_frames(xts: np.ndarray, batch_idx: np.ndarray) -> np.ndarray:
 
 
 def sample(config: argparse.Namespace, b: torch.nn.Module, loader: Iterable, *, method: str = "dopri5",
-           device: Optional[str] = None, save_every: int = 0, verbose: bool = True) -> dict:
+           device: Optional[str] = None, save_every: int = 1, verbose: bool = True) -> dict:
     """Runs every batch of `loader` through `MoleculeIntegrator.rollout` and writes the reference's files
     under config.data_save_path.  Reads from `config`: seed, data_save_path, data_save_name, rtol, atol,
     n_steps, return_dlogp.  Returns the arrays it wrote."""

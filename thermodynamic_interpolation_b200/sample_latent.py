@@ -23,7 +23,7 @@ from .sample_ambient import regroup_frames
 
 
 def sample(config: argparse.Namespace, b: torch.nn.Module, loader: Iterable, *, method: str = "dopri5",
-           device: Optional[str] = None, save_every: int = 0, also_cwd: bool = False, verbose: bool = True) -> dict:
+           device: Optional[str] = None, save_every: int = 1, also_cwd: bool = False, verbose: bool = True) -> dict:
     """Reads from `config`: seed, data_save_path, data_save_name, rtol, atol, n_steps, return_dlogp."""
     torch.manual_seed(config.seed)
     np.random.seed(config.seed)

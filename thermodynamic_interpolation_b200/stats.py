@@ -36,4 +36,8 @@ def finalize(partials) -> dict:
     """ESS = (sum w)^2 / sum w^2 (calc_ESS, ess.py:32-35); dF = -log(sum exp(-phi) g / sum g)
     (calc_tfep_dF, free_energy.py:41-46)."""
     s = [float(v) for v in partials]
-    return dict(ess=s[0] * s[0] / s[1], dF=-math.log(s[2] / s[3]), n=int(round(s[4])), sum_w=s[0], sum_w2=s[1])
+    n = int(round(s[4]))
+    # empty input, or every weight underflowed: the statistics are undefined, not an arithmetic error
+    ess = s[0] * s[0] / s[1] if s[1] > 0.0 else float("nan")
+    dF = -math.log(s[2] / s[3]) if (s[2] > 0.0 and s[3] > 0.0) else float("nan")
+    return dict(ess=ess, dF=dF, n=n, sum_w=s[0], sum_w2=s[1])
