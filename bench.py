@@ -221,6 +221,11 @@ def cpu_reference_rate(args, n_mol, steps, warmup):
     torch.set_num_threads(cores)
     torch.manual_seed(0)
     model = perturb_(ns.ambient_cpainn.cPaiNN(n_features=args.features, score_layers=args.layers, temp_length=100), 1).eval()
+    # TemperatureEncoder parks its `temperatures` attribute on cuda whenever a GPU is visible (embedding.py:204); this is the
+    # CPU arm, so the attribute follows the parameters (what `.to(device)` does for registered tensors)
+    for mod in model.modules():
+        if isinstance(getattr(mod, "temperatures", None), torch.Tensor):
+            mod.temperatures = mod.temperatures.cpu()
     mb = synthetic_ambient_batch(n_mol, args.atoms, T0=1000.0, T1=300.0, sigma=0.3, seed=100)
 
     def ref_batch():

@@ -26,7 +26,8 @@ class MoleculeIntegrator:
     Keyword-only extensions (not in the reference): `save_frames=False` keeps only the final state;
     `eps`, `noise`, `score` switch Euler to Euler-Maruyama with pre-drawn noise (BASELINE north_star;
     no reference oracle - with eps=0 the result is bit-identical to Euler); `norm_allreduce` lets
-    shards of one batch share dopri5's global error norm."""
+    shards of one batch share dopri5's global error norm; `cuda_graph=True` captures a fixed-grid rollout once per
+    batch shape and replays it (the returned frames then live in a buffer that the next rollout of that shape overwrites)."""
 
     ode_wrapper_cls = ODEWrapper
     dlogp_out_scale = 1e2
@@ -34,7 +35,7 @@ class MoleculeIntegrator:
     def __init__(self, b: torch.nn.Module, method: str = 'dopri5', n_step: int = 100, atol: float = 1e-4,
                  rtol: float = 1e-4, start: float = 0.0, end: float = 1.0, return_dlogp: bool = False,
                  reverse_ode: bool = False, *, save_frames: bool = True, eps: float = 0.0,
-                 score: Optional[torch.nn.Module] = None, norm_allreduce=None) -> None:
+                 score: Optional[torch.nn.Module] = None, norm_allreduce=None, cuda_graph: bool = False) -> None:
         self.ode_wrapper = self.ode_wrapper_cls(b=b, return_dlogp=return_dlogp, reverse_ode=reverse_ode)
         self.start, self.end = start, end
         self.rtol, self.atol = rtol, atol
@@ -46,6 +47,7 @@ class MoleculeIntegrator:
         self.eps = eps
         self.score = score
         self.norm_allreduce = norm_allreduce
+        self.cuda_graph = cuda_graph          # fixed-grid methods: replay the captured rollout (small batches are launch bound)
         self.last_stats = None
 
     def _solve(self, batch, noise=None):
@@ -59,7 +61,7 @@ class MoleculeIntegrator:
         if self.method in _FIXED_NFE:
             score_engine = self.score.engine() if (self.score is not None and self.eps != 0.0) else None
             xts = eng.rollout_fixed(pb, x0, times, method=self.method, save_frames=self.save_frames,
-                                    eps=self.eps, noise=noise, score_engine=score_engine)
+                                    eps=self.eps, noise=noise, score_engine=score_engine, graph=self.cuda_graph)
             nfe = (self.n_step - 1) * _FIXED_NFE[self.method]
             self.last_stats = dict(nfe=nfe)
         elif self.method == "dopri5":

@@ -209,6 +209,7 @@ class DriftEngine:
         self.handle = handle
         self._ws: Optional[torch.Tensor] = None
         self._ws_div: Optional[torch.Tensor] = None
+        self._graphs: Dict[tuple, tuple] = {}     # captured fixed-grid rollouts (rollout_fixed(graph=True))
 
     def __del__(self):
         h = getattr(self, "handle", None)
@@ -280,7 +281,14 @@ class DriftEngine:
 
     def rollout_fixed(self, pb: PreparedBatch, x0: torch.Tensor, t_grid: torch.Tensor, method: str = "euler",
                       save_frames: bool = True, eps: float = 0.0, noise: Optional[torch.Tensor] = None,
-                      score_engine: Optional["DriftEngine"] = None, out: Optional[torch.Tensor] = None):
+                      score_engine: Optional["DriftEngine"] = None, out: Optional[torch.Tensor] = None,
+                      graph: bool = False):
+        """`graph=True`: the whole rollout (every drift evaluation and state update of every step - tib_rollout_fixed has
+        no host synchronisation) is captured once into a CUDA graph per (prepared batch, grid, method, buffers) and replayed:
+        one graph launch instead of ~15 kernel launches per step, which is what bounds the reference's real batch sizes
+        (12 / 64 conformers: config/ambient/00031_settings_no_300.json:18, 10506_settings_no_900.json:18)."""
+        if graph:
+            return self._rollout_fixed_graph(pb, x0, t_grid, method, save_frames, eps, noise, score_engine, out)
         x0 = self._state(x0, pb)
         tg = np.ascontiguousarray(t_grid.detach().to("cpu", torch.float32).numpy())
         T = int(tg.shape[0])
@@ -300,6 +308,35 @@ class DriftEngine:
             _lib.check(self.lib.tib_rollout_fixed(self.handle, C.byref(pb.c), x0.data_ptr(), C.byref(opts),
                                                   out.data_ptr(), wp, wn, self._stream()), "tib_rollout_fixed")
         return out
+
+    def _rollout_fixed_graph(self, pb, x0, t_grid, method, save_frames, eps, noise, score_engine, out):
+        x0 = self._state(x0, pb)
+        tg = tuple(float(v) for v in t_grid.detach().to("cpu", torch.float32).tolist())
+        key = (id(pb), tg, method, bool(save_frames), float(eps), None if noise is None else noise.data_ptr(),
+               None if score_engine is None else id(score_engine), None if out is None else out.data_ptr())
+        hit = self._graphs.get(key)
+        if hit is None:
+            if len(self._graphs) >= 8:               # a handful of shapes per run; do not grow without bound
+                self._graphs.clear()
+            static_x0 = torch.empty_like(x0)
+            static_x0.copy_(x0)
+            kw = dict(method=method, save_frames=save_frames, eps=eps, noise=noise, score_engine=score_engine, out=out)
+            # warm-up on a side stream (function attributes, workspace allocation), then capture
+            side = torch.cuda.Stream(device=self.device)
+            side.wait_stream(torch.cuda.current_stream(self.device))
+            with torch.cuda.stream(side):
+                static_out = self.rollout_fixed(pb, static_x0, t_grid, **kw)
+            torch.cuda.current_stream(self.device).wait_stream(side)
+            kw["out"] = static_out
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.rollout_fixed(pb, static_x0, t_grid, **kw)
+            hit = (g, static_x0, static_out, pb, self._ws)      # kept alive: their device addresses are baked into the graph
+            self._graphs[key] = hit
+        g, static_x0, static_out = hit[:3]
+        static_x0.copy_(x0)
+        g.replay()
+        return static_out
 
     def rollout_dopri5(self, pb: PreparedBatch, x0: torch.Tensor, t_grid: torch.Tensor, rtol: float, atol: float,
                        save_frames: bool = True, norm_allreduce=None, max_attempts: int = 0,
