@@ -212,6 +212,22 @@ int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const 
                        float* out_xts, tib_dopri5_stats* stats,
                        void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- rollouts of the tuple state (x, dlogp): MoleculeIntegrator(return_dlogp=True) -----------------------------------
+ * Replaces rollout() with return_dlogp=True (mdqm9/thermo/ambient/integrators.py:36-53; latent :57-74): the state is the
+ * tuple (x [N,3], dlogp [B]) that torchdiffeq flattens to y = [x | dlogp] (n = 3N + B fp32), the right-hand side is
+ * (mult_b * b, mult_d * div) with div the exact divergence (tib_drift_div): mult_b = 1, mult_d = -1e-2 for the ambient
+ * wrapper (ode_wrapper.py:47,91), mult_d = -1 for the latent one, signs flipped under reverse_ode.
+ * y0 / out are flat: out [T][n] with save_frames, else [n].  The fixed-grid solver takes the grid as given (decreasing
+ * grids integrate backwards); dopri5 wants an increasing grid: a decreasing one is passed NEGATED with time_sign = -1
+ * (torchdiffeq solves (-t, -f)); its error ratio is the MAX of the RMS norms of the two components.
+ * Workspace: tib_div_rollout_workspace_bytes. */
+size_t tib_div_rollout_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges, int32_t max_atoms);
+int tib_rollout_fixed_dlogp(tib_model* m, const tib_batch* b, const float* y0, const tib_fixed_opts* o, float mult_b, float mult_d,
+                            float* out, void* workspace, size_t workspace_bytes, void* stream);
+int tib_rollout_dopri5_dlogp(tib_model* m, const tib_batch* b, const float* y0, const tib_dopri5_opts* o, float mult_b, float mult_d,
+                             float time_sign, float* out, tib_dopri5_stats* stats, void* workspace, size_t workspace_bytes,
+                             void* stream);
+
 /* ---- reweighting statistics ---------------------------------------------------------------
  * Partial sums behind calc_ti_weights / calc_ESS / calc_tfep_dF
  * (mdqm9/analysis/utils/ess.py:8-10,32-35; free_energy.py:41-46):

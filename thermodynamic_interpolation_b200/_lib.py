@@ -66,6 +66,11 @@ SYMBOLS = [
     ("tib_drift", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_div_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
     ("tib_drift_div", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("tib_div_rollout_workspace_bytes", C.c_size_t, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_int32]),
+    ("tib_rollout_fixed_dlogp", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(FixedOpts), C.c_float, C.c_float,
+                                          C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("tib_rollout_dopri5_dlogp", C.c_int, [C.c_void_p, C.POINTER(Batch), C.c_void_p, C.POINTER(Dopri5Opts), C.c_float, C.c_float,
+                                           C.c_float, C.c_void_p, C.POINTER(Dopri5Stats), C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_zmatrix", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("tib_tica_project", C.c_int, [C.c_void_p, C.c_int64, C.c_int32, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p,
                                    C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_double, C.c_double, C.c_void_p]),

@@ -5,7 +5,6 @@ from typing import Optional
 
 import torch
 
-from .._tuple_ode import solve_dopri5, solve_fixed
 from .models.ode_wrapper import ODEWrapper
 
 _FIXED_NFE = {"euler": 1, "midpoint": 2, "rk4": 4}
@@ -19,9 +18,8 @@ class MoleculeIntegrator:
 
     `method`: 'dopri5' (adaptive, torchdiffeq semantics) or the fixed-grid 'euler' / 'midpoint' /
     'rk4' on `linspace(start, end, n_step)`.  The whole rollout - every drift evaluation and every
-    state update - runs inside libtib.so on the current CUDA stream.  With `return_dlogp=True` every
-    right-hand side is one `tib_drift_div` call (the drift plus 3*max_atoms tangent directions) and the
-    tuple-state stepper is `_tuple_ode.py` (torchdiffeq's flattened-tuple semantics, max-of-RMS error norm).
+    state update - runs inside libtib.so on the current CUDA stream, also with `return_dlogp=True` (the tuple state
+    (x, dlogp), every right-hand side the drift plus its exact divergence by forward-mode tangents).
 
     Keyword-only extensions (not in the reference): `save_frames=False` keeps only the final state;
     `eps`, `noise`, `score` switch Euler to Euler-Maruyama with pre-drawn noise (BASELINE north_star;
@@ -79,33 +77,24 @@ class MoleculeIntegrator:
         return xts, dlogp, nfe, pb
 
     def _solve_dlogp(self, batch):
-        """State (x, dlogp) flattened to y = [x.reshape(-1) | dlogp]  (integrators.py:36-53)."""
+        """State (x, dlogp) flattened to y = [x.reshape(-1) | dlogp]  (integrators.py:36-53), integrated inside libtib.so
+        (tib_rollout_fixed_dlogp / tib_rollout_dopri5_dlogp: torchdiffeq's flattened-tuple semantics, max-of-RMS error norm,
+        decreasing grids for `reverse_ode`); every right-hand side is the drift plus its exact divergence."""
         eng, pb = self.ode_wrapper.prepared(batch)
         x0 = batch.x0.to(eng.device, torch.float32)
-        n3, n_mol = x0.numel(), pb.n_mol
-        y0 = torch.cat([x0.reshape(-1), torch.zeros(n_mol, dtype=torch.float32, device=eng.device)])
         a, b_ = (self.end, self.start) if self.reverse_ode else (self.start, self.end)
         times = torch.linspace(a, b_, self.n_step)                          # integrators.py:41-43
-        count = [0]
-
-        def rhs(t, y):
-            count[0] += 1
-            db, dl = self.ode_wrapper.forward(t, (y[:n3].reshape(-1, 3), y[n3:]), batch)
-            return torch.cat([db.reshape(-1), dl])
-
-        stats = {}
-        if self.method in _FIXED_NFE:
-            sol = solve_fixed(rhs, y0, times, self.method)
-        elif self.method == "dopri5":
-            sol = solve_dopri5(rhs, y0, times, self.rtol, self.atol, split=n3, stats=stats)
-        else:
+        scale = self.ode_wrapper.variant_scale
+        mult_b, mult_d = (-1.0, scale) if self.reverse_ode else (1.0, -scale)   # ode_wrapper.py:47-49
+        if self.method not in _FIXED_NFE and self.method != "dopri5":
             raise ValueError(f"unsupported method {self.method!r}: use 'dopri5', 'euler', 'midpoint' or 'rk4'")
-        self.last_stats = dict(stats, nfe=count[0])
-        xts = sol[:, :n3].reshape(self.n_step, -1, 3)
-        dlogp = sol[:, n3:]
+        xts, dlogp, stats = eng.rollout_dlogp(pb, x0, times, self.method, mult_b=mult_b, mult_d=mult_d, rtol=self.rtol,
+                                              atol=self.atol, save_frames=True, norm_allreduce=self.norm_allreduce)
+        nfe = stats["nfe"] if "nfe" in stats else (self.n_step - 1) * _FIXED_NFE[self.method]
+        self.last_stats = dict(stats, nfe=nfe)
         if not self.save_frames:
             xts = xts[-1]
-        return xts, dlogp, count[0], pb
+        return xts, dlogp, nfe, pb
 
     def rollout(self, batch, noise: Optional[torch.Tensor] = None) -> tuple:
         xts, dlogp, nfe, pb = self._solve(batch, noise)

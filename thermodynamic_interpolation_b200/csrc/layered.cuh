@@ -113,7 +113,7 @@ struct CombineJvpP {
 // (dir0 and n_dirs are multiples of 3): the primal products m = phi3 * w3 and the gather of v[src] are shared by the
 // three directions, and the geometry tangents exist only on the edges that touch atom a (sign = +1 source, -1
 // destination):  d_dot_c = sign r_c / d,  dir_dot_c = sign e_c / (1 + d) - r d_dot_c / (1 + d)^2   (graph.py:27-29).
-__global__ void __launch_bounds__(128) k_combine_jvp(CombineJvpP pp) {
+__global__ void __launch_bounds__(128, 4) k_combine_jvp(CombineJvpP pp) {
   const CombineP& p = pp.c;
   const int F = p.F;
   // every array but te / ts_new / tv_new is read-only here: non-coherent loads (__ldg) may be hoisted above the te stores,

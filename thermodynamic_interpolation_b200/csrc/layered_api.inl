@@ -66,7 +66,8 @@ struct LayWs {
       sv_w_n[i] = (float*)take(f4 * tp_rows * F);   sv_w_r[i] = (float*)take(f4 * P);
       sv_upd_n[i] = (float*)take(f4 * tn_rows * F); sv_upd_r[i] = (float*)take(f4 * N);
     }
-    D = 3 * max_atoms; Dc = dirs_chunk(D); Dr = dirs_readout(F);
+    // translation invariance: the three directions of the last atom index are reconstructed (k_div_pick), not propagated
+    D = max_atoms > 2 ? 3 * (max_atoms - 1) : 3 * max_atoms; Dc = dirs_chunk(D); Dr = dirs_readout(F);
     st_s = al(f4 * N * F) / f4; st_v = al(f4 * N * 3 * F) / f4; st_e = al(f4 * E * F) / f4; st_o = al(f4 * N * 3) / f4;
     st_phi = al(f4 * E * 5 * F) / f4; st_tvvuv = al(f4 * 3 * N * 2 * F) / f4; st_tq = st_s; st_tgac = st_v;
     for (int i = 0; i < 2; ++i) { ts[i] = (float*)take(f4 * st_s * D); tv[i] = (float*)take(f4 * st_v * D); }
@@ -257,7 +258,8 @@ int drift_layered(tib_model* m, const tib_batch* b, const float* x, float t, flo
 // drift + exact divergence (ode_wrapper.py:39-49,59-91): primal layer by layer with saved LayerNorm intermediates, then the
 // tangents of all 3 * max_atoms directions through the same weights.  Work per evaluation relative to one drift: the w MLP
 // has ONE tangent (it depends on x through the scalar distance only), the first layer's phi MLP has none (s0, e0 do not
-// depend on x), so the tangent GEMMs cost about (3 n (L - 1) 16 + 14 L) / (30 L) drifts instead of 3 n.
+// depend on x), and the directions of the last atom follow from translation invariance, so the tangent GEMMs cost about
+// (3 (n - 1) (L - 1) 16 + 14 L) / (30 L) drifts instead of 3 n.
 template <int F>
 int drift_div_layered(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div, Workspace& ws,
                       LayWs& lw, cudaStream_t st) {
@@ -334,7 +336,8 @@ int drift_div_layered(tib_model* m, const tib_batch* b, const float* x, float t,
       k_readout_jvp<F, JRN, DR><<<jtiles, TIB_THREADS, smem_readout_jvp<F, JRN, DR>(), st>>>(rp);
       LAUNCH_CHECK();
     }
-    k_div_pick<<<(b->n_mol + 255) / 256, 256, 0, st>>>(b->mol_ptr, b->n_mol, lw.tout, lw.st_o, d0, DR, out_div);
+    k_div_pick<<<(b->n_mol + 255) / 256, 256, 0, st>>>(b->mol_ptr, b->n_mol, lw.tout, lw.st_o, d0, DR, out_div,
+                                                         D < 3 * b->max_atoms ? b->max_atoms : 0);
     LAUNCH_CHECK();
   }
   return 0;

@@ -694,8 +694,12 @@ __global__ void __launch_bounds__(TIB_THREADS, 1) k_readout_jvp(ReadoutJvpP pp) 
 }
 
 // div[mol] (+)= sum_dd tout[dd][mol_ptr[mol] + a_dd][c_dd]; the pass with dir0 == 0 starts the sum.
+// skip_last_of = n_max > 0: the directions of atom index n_max - 1 are NOT propagated.  The drift depends on x through
+// differences only (graph.py:27), so sum_a d b / d x_{a,c} = 0 as a field and, for a molecule with n = n_max atoms,
+//   d b_{n-1,c} / d x_{n-1,c} = - sum_{a < n-1} d b_{n-1,c} / d x_{a,c}:
+// the missing diagonal entries come out of the other directions' tangents at the last atom.
 __global__ void k_div_pick(const int* __restrict__ mol_ptr, int n_mol, const float* __restrict__ tout, size_t st_o,
-                           int dir0, int D, float* __restrict__ div) {
+                           int dir0, int D, float* __restrict__ div, int skip_last_of = 0) {
   const int mol = blockIdx.x * blockDim.x + threadIdx.x;
   if (mol >= n_mol) return;
   const int n0 = __ldg(mol_ptr + mol), n = __ldg(mol_ptr + mol + 1) - n0;
@@ -703,6 +707,7 @@ __global__ void k_div_pick(const int* __restrict__ mol_ptr, int n_mol, const flo
   for (int dd = 0; dd < D; ++dd) {
     const int q = dir0 + dd, a = q / 3, c = q % 3;
     if (a < n) acc += tout[dd * st_o + (size_t)(n0 + a) * 3 + c];
+    if (skip_last_of > 0 && n == skip_last_of && a < n - 1) acc -= tout[dd * st_o + (size_t)(n0 + n - 1) * 3 + c];
   }
   div[mol] = acc;
 }

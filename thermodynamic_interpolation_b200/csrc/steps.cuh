@@ -72,6 +72,16 @@ __global__ void k_rk4_stage(int mode, const float* __restrict__ y, const float* 
 }
 
 // ---- dopri5 (torchdiffeq rk_common._runge_kutta_step) -----------------------------------------
+// right-hand side of the (x, dlogp) state: out[0, n3) *= mb (the drift, negated for reverse_ode), out[n3, n3 + n_mol) *= md
+// (the divergence times -scale, or +scale)                                          (ode_wrapper.py:39-49,91)
+__global__ void k_dlogp_rhs_finish(float* __restrict__ out, size_t n3, size_t n_mol, float mb, float md) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n3 + n_mol; i += stride) {
+    if (i < n3) { if (mb != 1.0f) out[i] = __fmul_rn(out[i], mb); }
+    else out[i] = __fmul_rn(out[i], md);
+  }
+}
+
 struct StageCoef { float c[7]; int n; };
 
 // out = y + sum_{s<n} k_s * c_s   with c_s = fp32(beta_s * dt) (k[..., :i+1].matmul(beta_i * dt))

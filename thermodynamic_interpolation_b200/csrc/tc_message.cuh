@@ -514,56 +514,62 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
         mbar_wait_timed(&bars[B_TFULL0 + pb], ptf[pb], err, w_tfull, diag); ptf[pb] ^= 1; tc_fence_after();
         const uint32_t tphi = lane_taddr + 256 * pb, tw = tphi + 128;
         if (regular) {
-          // ---- fast path: one TMEM round trip for the group's 4 nodes x 8 edges, all loads independent
+          // ---- fast path: the group's 4 nodes x 8 edges in two TMEM round trips of 2 nodes each (phi and w accumulators
+          // of 16 edges = 32 registers live at the product instead of 64: no spills at 96 registers)
           const int c0 = 32 * grp;
-          float P[32], Q[32];
-          tmem_ld32x2(tphi + c0, tw + c0, P, Q);
 #pragma unroll
-          for (int q = 0; q < 32; ++q) P[q] = __fmul_rn(P[q] + bphi, Q[q] + bw);
-          if (sp == 0) {              // gates * v[src]
+          for (int h = 0; h < 2; ++h) {
+            const int ch = c0 + 16 * h;
+            float P[16], Q[16];
+            tmem_ld16x2(tphi + ch, tw + ch, P, Q);
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const float* vi = p.v_old + (size_t)ROWA[c0 + q].src * 3 * kF + f;
-              acc_v[q >> 3][0] = fmaf(P[q], __ldg(vi), acc_v[q >> 3][0]);
-              acc_v[q >> 3][1] = fmaf(P[q], __ldg(vi + kF), acc_v[q >> 3][1]);
-              acc_v[q >> 3][2] = fmaf(P[q], __ldg(vi + 2 * kF), acc_v[q >> 3][2]);
-            }
-          } else if (sp == 1) {       // scale_edge_dir * dir
+            for (int q = 0; q < 16; ++q) P[q] = __fmul_rn(P[q] + bphi, Q[q] + bw);
+            if (sp == 0) {              // gates * v[src]
 #pragma unroll
-            for (int q = 0; q < 32; ++q) {
-              const RowB rb = ROWB[c0 + q];
-              acc_v[q >> 3][0] = fmaf(P[q], rb.dx, acc_v[q >> 3][0]);
-              acc_v[q >> 3][1] = fmaf(P[q], rb.dy, acc_v[q >> 3][1]);
-              acc_v[q >> 3][2] = fmaf(P[q], rb.dz, acc_v[q >> 3][2]);
-            }
-          } else if (sp == 2) {       // ds
-#pragma unroll
-            for (int q = 0; q < 32; ++q) acc_s[q >> 3] += P[q];
-          } else if (sp == 3) {       // e += de                                       (cpainn.py:308)
-            float* ep = p.e + (size_t)(row0 + c0) * kF + f;
-            if (p.first_layer) {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) Q[q] = __ldg(p.edge_emb + ((ROWA[c0 + q].slot_last >> 16) & 0xFF) * kF + f);
-            } else {
-#pragma unroll
-              for (int q = 0; q < 32; ++q) Q[q] = ep[(size_t)q * kF];
-            }
-#pragma unroll
-            for (int q = 0; q < 32; ++q) ep[(size_t)q * kF] = Q[q] + P[q];
-          } else {                    // cross_gates * (dir x v[dst]), linear in dir     (cpainn.py:296-300)
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-#pragma unroll
-              for (int q = 0; q < 8; ++q) {
-                const RowB rb = ROWB[c0 + 8 * k + q];
-                d0 = fmaf(P[8 * k + q], rb.dx, d0); d1 = fmaf(P[8 * k + q], rb.dy, d1); d2 = fmaf(P[8 * k + q], rb.dz, d2);
+              for (int q = 0; q < 16; ++q) {
+                const float* vi = p.v_old + (size_t)ROWA[ch + q].src * 3 * kF + f;
+                acc_v[2 * h + (q >> 3)][0] = fmaf(P[q], __ldg(vi), acc_v[2 * h + (q >> 3)][0]);
+                acc_v[2 * h + (q >> 3)][1] = fmaf(P[q], __ldg(vi + kF), acc_v[2 * h + (q >> 3)][1]);
+                acc_v[2 * h + (q >> 3)][2] = fmaf(P[q], __ldg(vi + 2 * kF), acc_v[2 * h + (q >> 3)][2]);
               }
-              const float* vj = p.v_old + (size_t)(node_lo + 4 * grp + k) * 3 * kF + f;
-              const float vj0 = __ldg(vj), vj1 = __ldg(vj + kF), vj2 = __ldg(vj + 2 * kF);
-              acc_v[k][0] += __fmul_rn(d1, vj2) - __fmul_rn(d2, vj1);
-              acc_v[k][1] += __fmul_rn(d2, vj0) - __fmul_rn(d0, vj2);
-              acc_v[k][2] += __fmul_rn(d0, vj1) - __fmul_rn(d1, vj0);
+            } else if (sp == 1) {       // scale_edge_dir * dir
+#pragma unroll
+              for (int q = 0; q < 16; ++q) {
+                const RowB rb = ROWB[ch + q];
+                acc_v[2 * h + (q >> 3)][0] = fmaf(P[q], rb.dx, acc_v[2 * h + (q >> 3)][0]);
+                acc_v[2 * h + (q >> 3)][1] = fmaf(P[q], rb.dy, acc_v[2 * h + (q >> 3)][1]);
+                acc_v[2 * h + (q >> 3)][2] = fmaf(P[q], rb.dz, acc_v[2 * h + (q >> 3)][2]);
+              }
+            } else if (sp == 2) {       // ds
+#pragma unroll
+              for (int q = 0; q < 16; ++q) acc_s[2 * h + (q >> 3)] += P[q];
+            } else if (sp == 3) {       // e += de                                       (cpainn.py:308)
+              float* ep = p.e + (size_t)(row0 + ch) * kF + f;
+              if (p.first_layer) {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) Q[q] = __ldg(p.edge_emb + ((ROWA[ch + q].slot_last >> 16) & 0xFF) * kF + f);
+              } else {
+#pragma unroll
+                for (int q = 0; q < 16; ++q) Q[q] = ep[(size_t)q * kF];
+              }
+#pragma unroll
+              for (int q = 0; q < 16; ++q) ep[(size_t)q * kF] = Q[q] + P[q];
+            } else {                    // cross_gates * (dir x v[dst]), linear in dir     (cpainn.py:296-300)
+#pragma unroll
+              for (int k2 = 0; k2 < 2; ++k2) {
+                const int k = 2 * h + k2;
+                float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                  const RowB rb = ROWB[ch + 8 * k2 + q];
+                  d0 = fmaf(P[8 * k2 + q], rb.dx, d0); d1 = fmaf(P[8 * k2 + q], rb.dy, d1); d2 = fmaf(P[8 * k2 + q], rb.dz, d2);
+                }
+                const float* vj = p.v_old + (size_t)(node_lo + 4 * grp + k) * 3 * kF + f;
+                const float vj0 = __ldg(vj), vj1 = __ldg(vj + kF), vj2 = __ldg(vj + 2 * kF);
+                acc_v[k][0] += __fmul_rn(d1, vj2) - __fmul_rn(d2, vj1);
+                acc_v[k][1] += __fmul_rn(d2, vj0) - __fmul_rn(d0, vj2);
+                acc_v[k][2] += __fmul_rn(d0, vj1) - __fmul_rn(d1, vj0);
+              }
             }
           }
           tc_fence_before(); mbar_arrive(&bars[B_TEMPTY0 + pb]);

@@ -124,6 +124,8 @@ __device__ __noinline__ void upd_hidden(uint32_t taddr, int grp, int row, const 
   named_bar_sync(NB_QUARTER + (row >> 5), kQuarterThreads);     // `stat` rows of this quarter may be rewritten by the next call
 }
 
+// DIAG = the phase counters of tib_debug_counters (sixteen 64-bit counters): a template flag, as in k_message_tc
+template <bool DIAG>
 __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
   extern __shared__ __align__(1024) unsigned char smem[];
   unsigned char* const X = smem + UpdSmem::X;
@@ -143,9 +145,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
     fence_mbar_init();
   }
   if (warp == 16) tmem_alloc(tmem_slot, 512);
-  {
-    const float* src[9] = {p.b1, p.g1, p.be1, p.b2, p.g2, p.be2, p.b3, p.b3 + kF, p.b3 + 2 * kF};
-    for (int i = tid; i < 9 * kF; i += kThreads) PRM[i] = __ldg(src[i >> 7] + (i & 127));
+  for (int i = tid; i < 9 * kF; i += kThreads) {
+    const int r = i >> 7;
+    const float* src = r == 0 ? p.b1 : r == 1 ? p.g1 : r == 2 ? p.be1 : r == 3 ? p.b2 : r == 4 ? p.g2 : r == 5 ? p.be2 : p.b3 + (r - 6) * kF;
+    PRM[i] = __ldg(src + (i & 127));
   }
   tc_fence_before();
   __syncthreads();
@@ -203,7 +206,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
     const uint32_t lt = tmem + ((uint32_t)(wq * 32) << 16);
     const uint32_t T0 = lt, T1 = lt + 128;
     uint32_t pacc = 0;
-    const bool diag = p.dbg != nullptr && tid == 0;
+    const bool diag = DIAG && tid == 0;
     long long phc[16] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
     long long tlast = diag ? clock64() : 0;
 #define TIB_UPH(i) do { if (diag) { const long long _t = clock64(); phc[i] += _t - tlast; tlast = _t; } } while (0)
@@ -281,10 +284,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
         // Row-per-thread global accesses would cost 32 wavefronts per instruction (rows are 1.5 KB apart), so
         // each plane goes through the (free) Y buffer: coalesced load -> swizzled fp32 tile -> row-local
         // update -> coalesced store.  16-byte chunk c of row r lives at chunk (c ^ (r & 31)).
-        float g[32];
-        tmem_ld32(T0 + 32 * grp, g);
-#pragma unroll
-        for (int i = 0; i < 32; ++i) g[i] = (g[i] + PRM[6 * kF + 32 * grp + i]) * kStateUnscale;   // T1..T3 hold kStateScale * U v
+        // two halves of 16 columns: g and (U v) of 16 columns are live next to q2[32], not 2 x 32 (no spills at 96 registers)
         float4* const stage = reinterpret_cast<float4*>(Y);
 #pragma unroll 1
         for (int xyz = 0; xyz < 3; ++xyz) {
@@ -296,15 +296,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
             if (r < rows) stage[r * 32 + (c ^ (r & 31))] = *reinterpret_cast<const float4*>(vplane + (size_t)r * 3 * kF + 4 * c);
           }
           named_bar_sync(NB_ALL, kEpiThreads);
-          float u[32];
-          tmem_ld32(lt + 128 * (1 + xyz) + 32 * grp, u);
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            float4* sp = stage + row * 32 + ((8 * grp + j) ^ (row & 31));
-            float4 t = *sp;
-            t.x = fmaf(u[4 * j + 0], g[4 * j + 0], t.x); t.y = fmaf(u[4 * j + 1], g[4 * j + 1], t.y);
-            t.z = fmaf(u[4 * j + 2], g[4 * j + 2], t.z); t.w = fmaf(u[4 * j + 3], g[4 * j + 3], t.w);
-            *sp = t;
+          for (int h = 0; h < 2; ++h) {
+            float g[16], u[16];
+            tmem_ld16x2(T0 + 32 * grp + 16 * h, lt + 128 * (1 + xyz) + 32 * grp + 16 * h, g, u);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) g[i] = (g[i] + PRM[6 * kF + 32 * grp + 16 * h + i]) * kStateUnscale;   // T1..T3 hold kStateScale * U v
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float4* sp = stage + row * 32 + ((8 * grp + 4 * h + j) ^ (row & 31));
+              float4 t = *sp;
+              t.x = fmaf(u[4 * j + 0], g[4 * j + 0], t.x); t.y = fmaf(u[4 * j + 1], g[4 * j + 1], t.y);
+              t.z = fmaf(u[4 * j + 2], g[4 * j + 2], t.z); t.w = fmaf(u[4 * j + 3], g[4 * j + 3], t.w);
+              *sp = t;
+            }
           }
           named_bar_sync(NB_ALL, kEpiThreads);
 #pragma unroll
@@ -329,21 +334,23 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
         acc_ready();
         TIB_UPH(11);
         named_bar_sync(NB_ALL, kEpiThreads);
-        float a[32], c[32];
-        tmem_ld32(T1 + 32 * grp, a);
-        tmem_ld32(lt + 256 + 32 * grp, c);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          float4* sp = stage + row * 32 + ((8 * grp + j) ^ (row & 31));
-          float4 t = *sp;
-          const float* pa = PRM + 7 * kF + 32 * grp + 4 * j;
-          const float* pc = PRM + 8 * kF + 32 * grp + 4 * j;
-          constexpr float kU2 = kStateUnscale * kStateUnscale;   // q2 is the square of the scaled norm
-          t.x += fmaf(q2[4 * j + 0] * kU2, a[4 * j + 0] + pa[0], c[4 * j + 0] + pc[0]);
-          t.y += fmaf(q2[4 * j + 1] * kU2, a[4 * j + 1] + pa[1], c[4 * j + 1] + pc[1]);
-          t.z += fmaf(q2[4 * j + 2] * kU2, a[4 * j + 2] + pa[2], c[4 * j + 2] + pc[2]);
-          t.w += fmaf(q2[4 * j + 3] * kU2, a[4 * j + 3] + pa[3], c[4 * j + 3] + pc[3]);
-          *sp = t;
+        for (int h = 0; h < 2; ++h) {
+          float a[16], c[16];
+          tmem_ld16x2(T1 + 32 * grp + 16 * h, lt + 256 + 32 * grp + 16 * h, a, c);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float4* sp = stage + row * 32 + ((8 * grp + 4 * h + j) ^ (row & 31));
+            float4 t = *sp;
+            const float* pa = PRM + 7 * kF + 32 * grp + 16 * h + 4 * j;
+            const float* pc = PRM + 8 * kF + 32 * grp + 16 * h + 4 * j;
+            constexpr float kU2 = kStateUnscale * kStateUnscale;   // q2 is the square of the scaled norm
+            t.x += fmaf(q2[16 * h + 4 * j + 0] * kU2, a[4 * j + 0] + pa[0], c[4 * j + 0] + pc[0]);
+            t.y += fmaf(q2[16 * h + 4 * j + 1] * kU2, a[4 * j + 1] + pa[1], c[4 * j + 1] + pc[1]);
+            t.z += fmaf(q2[16 * h + 4 * j + 2] * kU2, a[4 * j + 2] + pa[2], c[4 * j + 2] + pc[2]);
+            t.w += fmaf(q2[16 * h + 4 * j + 3] * kU2, a[4 * j + 3] + pa[3], c[4 * j + 3] + pc[3]);
+            *sp = t;
+          }
         }
         tc_fence_before();
         named_bar_sync(NB_ALL, kEpiThreads);

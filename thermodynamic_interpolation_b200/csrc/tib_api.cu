@@ -331,7 +331,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     if (!m->tc_attrs_set) {
       if (set_smem(tc::k_message_tc<false>, tc::MsgSmem::TOTAL)) return -1;
       if (set_smem(tc::k_message_tc<true>, tc::MsgSmem::TOTAL)) return -1;
-      if (set_smem(tc::k_update_tc, tc::UpdSmem::TOTAL)) return -1;
+      if (set_smem(tc::k_update_tc<false>, tc::UpdSmem::TOTAL)) return -1;
+      if (set_smem(tc::k_update_tc<true>, tc::UpdSmem::TOTAL)) return -1;
       if (set_smem(tc::k_readout_tc, tc::RoSmem::TOTAL)) return -1;
       if (set_smem(k_phi_table<F, 16>, sizeof(float) * 8 * 4 * F)) return -1;
       m->tc_attrs_set = true;
@@ -398,7 +399,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       up.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3; up.err = m->dev_err;
       up.dbg = m->dev_dbg ? m->dev_dbg + 8 * 1024 : nullptr;   // second half of the diagnostics buffer
       ProfScope ps(TIB_K_UPDATE, st);
-      tc::k_update_tc<<<std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st>>>(up);
+      if (up.dbg) tc::k_update_tc<true><<<std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st>>>(up);
+      else tc::k_update_tc<false><<<std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st>>>(up);
       LAUNCH_CHECK();
     } else {
       UpdateP up{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]};
@@ -855,17 +857,14 @@ size_t tib_div_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_node
   return Workspace::bytes(F, n_nodes, (long long)n_edges) + std::max(simt, lay);
 }
 
-int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div, void* workspace,
-                  size_t workspace_bytes, void* stream) {
-  if (check_batch(m, b)) return -1;
-  if (!x || !out_b || !out_div) return fail("tib_drift_div: null x/out");
+}  // extern "C"
+namespace {
+// drift + exact divergence with the workspace already validated (shared by tib_drift_div and the (x, dlogp) rollouts)
+int drift_div_dispatch(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div, void* workspace,
+                       cudaStream_t st) {
   const int F = m->d.n_features;
-  const size_t need = tib_div_workspace_bytes(m, b->n_mol, b->n_nodes, b->n_edges, b->max_atoms);
-  if (!workspace || workspace_bytes < need) return fail("divergence workspace too small: %zu < %zu bytes", workspace_bytes, need);
-  if (((uintptr_t)workspace & 255) != 0) return fail("workspace must be 256-byte aligned");
   Workspace ws;
   ws.carve(workspace, F, b->n_nodes, (long long)b->n_edges);
-  cudaStream_t st = (cudaStream_t)stream;
   if (m->math != TIB_MATH_FP32_SIMT && (F == 128 || F == 256)) {
     LayWs lw{};
     lw.layout(ws.end, F, b->n_nodes, (long long)b->n_edges, b->max_atoms, true);
@@ -881,6 +880,18 @@ int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, flo
     case 256: return drift_div_simt<256>(m, b, x, t, out_b, out_div, ws, tw, st);
   }
   return fail("unsupported n_features=%d", F);
+}
+}  // namespace
+extern "C" {
+
+int tib_drift_div(tib_model* m, const tib_batch* b, const float* x, float t, float* out_b, float* out_div, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  if (check_batch(m, b)) return -1;
+  if (!x || !out_b || !out_div) return fail("tib_drift_div: null x/out");
+  const size_t need = tib_div_workspace_bytes(m, b->n_mol, b->n_nodes, b->n_edges, b->max_atoms);
+  if (!workspace || workspace_bytes < need) return fail("divergence workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  if (((uintptr_t)workspace & 255) != 0) return fail("workspace must be 256-byte aligned");
+  return drift_div_dispatch(m, b, x, t, out_b, out_div, workspace, (cudaStream_t)stream);
 }
 
 int tib_zmatrix(const float* x, int64_t n_conf, int32_t n_atoms, const int32_t* order, const int32_t* ref, float* z, void* stream) {
@@ -978,6 +989,7 @@ int tib_rollout_fixed(tib_model* m, const tib_batch* b, const float* x0, const t
   return 0;
 }
 
+}  // extern "C"
 // ---- dopri5 (torchdiffeq 0.2.5 RKAdaptiveStepsizeODESolver; restated in oracle/ode_oracle.py) ----
 namespace {
 const double DP_ALPHA[6] = {1 / 5., 3 / 10., 4 / 5., 8 / 9., 1., 1.};
@@ -994,72 +1006,74 @@ const double DP_C_MID[7] = {6025192743. / 30085553152. / 2, 0, 51252292925. / 65
                             -2691868925. / 45128329728. / 2, 187940372067. / 1594534317056. / 2,
                             -1776094331. / 19743644256. / 2, 11237099. / 235043384. / 2};
 
+// state buffers of a solver over a flat fp32 state of n floats (x alone, or [x | dlogp])
+struct StateBufs { float *ycur, *ynew, *ytmp, *k; size_t ks; double *partial, *scalar; };
+
+// torchdiffeq's norm of the flattened state: RMS over everything (tensor state), or the MAX of the per-component RMS norms
+// when the state is the tuple (x, dlogp) flattened with `split` = x.numel() (rk_common / misc._mixed_norm)
 struct Reducer {
-  Workspace* ws; cudaStream_t st; size_t n; const tib_dopri5_opts* o;
-  // rms = sqrt(mean(partials)) over the (optionally all-reduced) batch
-  int finish(double* rms) {
-    tib::k_reduce_partials<<<1, 256, 0, st>>>(ws->partial, Workspace::kPartials, ws->scalar);
-    LAUNCH_CHECK();
-    double h[2];
-    CUDA_TRY(cudaMemcpyAsync(&h[0], ws->scalar, sizeof(double), cudaMemcpyDeviceToHost, st));
+  StateBufs* sb; cudaStream_t st; size_t n, split; const tib_dopri5_opts* o;
+  template <typename Launch>   // launch(offset, count) fills sb->partial for the elements [offset, offset + count)
+  int norm(Launch&& launch, double* out) {
+    const int parts = split ? 2 : 1;
+    for (int p = 0; p < parts; ++p) {
+      const size_t off = p == 0 ? 0 : split, cnt = split ? (p == 0 ? split : n - split) : n;
+      if (launch(off, cnt)) return -1;
+      tib::k_reduce_partials<<<1, 256, 0, st>>>(sb->partial, Workspace::kPartials, sb->scalar + p);
+      LAUNCH_CHECK();
+    }
+    double h[2] = {0.0, 0.0};
+    CUDA_TRY(cudaMemcpyAsync(h, sb->scalar, sizeof(double) * parts, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
-    h[1] = (double)n;
-    if (o->norm_allreduce) o->norm_allreduce(h, o->norm_user);
-    *rms = std::sqrt(h[0] / h[1]);
+    double best = 0.0;
+    for (int p = 0; p < parts; ++p) {
+      double v[2] = {h[p], (double)(split ? (p == 0 ? split : n - split) : n)};
+      if (o->norm_allreduce) o->norm_allreduce(v, o->norm_user);
+      best = std::max(best, std::sqrt(v[0] / v[1]));
+      if (!(v[0] == v[0])) best = v[0];      // NaN propagates
+    }
+    *out = best;
     return 0;
   }
 };
-}  // namespace
 
-int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const tib_dopri5_opts* o, float* out_xts,
-                       tib_dopri5_stats* stats, void* workspace, size_t workspace_bytes, void* stream) {
-  if (check_batch(m, b)) return -1;
-  if (!x0 || !o || !out_xts || !o->t_grid) return fail("tib_rollout_dopri5: null argument");
-  if (o->n_times < 1) return fail("n_times must be >= 1");
-  for (int i = 1; i < o->n_times; ++i)
-    if (!(o->t_grid[i] > o->t_grid[i - 1])) return fail("t_grid must be strictly increasing");
-  Workspace ws;
-  if (prep_ws(m, b, workspace, workspace_bytes, ws)) return -1;
-  cudaStream_t st = (cudaStream_t)stream;
-  const size_t n = (size_t)b->n_nodes * 3;
-  const size_t ks = Workspace::kstride(b->n_nodes);
+// torchdiffeq 0.2.5 RKAdaptiveStepsizeODESolver (dopri5) over a flat state; rhs(y, t, out) evaluates the right-hand side
+template <typename Rhs>
+int dopri5_impl(Rhs&& rhs, size_t n, size_t split, const float* y0, const tib_dopri5_opts* o, float* out, StateBufs& sb,
+                tib_dopri5_stats* stats, cudaStream_t st, void* stream) {
+  const size_t ks = sb.ks;
   const int g = grid_for(n);
   const int gp = Workspace::kPartials;   // reduction kernels use exactly kPartials blocks
   const double rtol = o->rtol, atol = o->atol;
   const int max_attempts = o->max_attempts > 0 ? o->max_attempts : 100000;
-  Reducer red{&ws, st, n, o};
+  Reducer red{&sb, st, n, split, o};
   int nfe = 0, attempts = 0, accepted = 0;
-
-  float* y = ws.ycur;
-  float* ynew = ws.ynew;
-  float* k = ws.k;   // k_s at k + s*ks
-  CUDA_TRY(cudaMemcpyAsync(y, x0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
-  if (o->save_frames) CUDA_TRY(cudaMemcpyAsync(out_xts, x0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  float* y = sb.ycur;
+  float* ynew = sb.ynew;
+  float* k = sb.k;   // k_s at k + s*ks
+  CUDA_TRY(cudaMemcpyAsync(y, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (o->save_frames) CUDA_TRY(cudaMemcpyAsync(out, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
 
   // --- _before_integrate: f0 and Hairer's initial step (misc._select_initial_step, order = 4)
   const double tstart = (double)o->t_grid[0];
-  if (drift_dispatch(m, b, y, (float)tstart, k, ws, st)) return -1;
+  if (rhs(y, (float)tstart, k)) return -1;
   ++nfe;
   double d0, d1, d2, h0, h1, dt;
-  tib::k_scaled_sq<<<gp, 256, 0, st>>>(y, nullptr, y, rtol, atol, ws.partial, n); LAUNCH_CHECK();
-  if (red.finish(&d0)) return -1;
-  tib::k_scaled_sq<<<gp, 256, 0, st>>>(k, nullptr, y, rtol, atol, ws.partial, n); LAUNCH_CHECK();
-  if (red.finish(&d1)) return -1;
+  if (red.norm([&](size_t off, size_t cnt) { tib::k_scaled_sq<<<gp, 256, 0, st>>>(y + off, nullptr, y + off, rtol, atol, sb.partial, cnt); LAUNCH_CHECK(); return 0; }, &d0)) return -1;
+  if (red.norm([&](size_t off, size_t cnt) { tib::k_scaled_sq<<<gp, 256, 0, st>>>(k + off, nullptr, y + off, rtol, atol, sb.partial, cnt); LAUNCH_CHECK(); return 0; }, &d1)) return -1;
   if (d0 < 1e-5 || d1 < 1e-5) h0 = (double)1e-6f; else h0 = 0.01 * d0 / d1;
   h0 = std::fabs(h0);
   // y1 = y0 + h0*f0 (h0 is a 0-dim fp64 tensor times an fp32 tensor -> fp32 arithmetic)
-  if (tib_step_euler(y, k, nullptr, nullptr, (float)h0, 0.f, ws.ytmp, nullptr, n, stream)) return -1;
-  if (drift_dispatch(m, b, ws.ytmp, (float)(tstart + h0), k + ks, ws, st)) return -1;
+  if (tib_step_euler(y, k, nullptr, nullptr, (float)h0, 0.f, sb.ytmp, nullptr, n, stream)) return -1;
+  if (rhs(sb.ytmp, (float)(tstart + h0), k + ks)) return -1;
   ++nfe;
-  tib::k_scaled_sq<<<gp, 256, 0, st>>>(k + ks, k, y, rtol, atol, ws.partial, n); LAUNCH_CHECK();
-  if (red.finish(&d2)) return -1;
+  if (red.norm([&](size_t off, size_t cnt) { tib::k_scaled_sq<<<gp, 256, 0, st>>>(k + ks + off, k + off, y + off, rtol, atol, sb.partial, cnt); LAUNCH_CHECK(); return 0; }, &d2)) return -1;
   d2 = std::fabs(d2 / h0);
   if (d1 <= 1e-15 && d2 <= 1e-15) h1 = std::max((double)1e-6f, h0 * 1e-3);
   else h1 = std::pow(0.01 / std::max(d1, d2), 1.0 / 5.0);
   dt = std::min(100 * h0, std::fabs(h1));
 
   double t0 = tstart, t1 = tstart;   // rk_state.t0, rk_state.t1
-  bool have_interp = false;
   float dt_step = 0.f;               // fp32 dt of the last accepted step (for the dense output)
   tib::StageCoef cmid{}; cmid.n = 7;
   for (int i = 1; i < o->n_times; ++i) {
@@ -1073,19 +1087,18 @@ int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const 
       for (int s = 0; s < 6; ++s) {
         tib::StageCoef c{}; c.n = s + 1;
         for (int q = 0; q <= s; ++q) c.c[q] = (float)DP_BETA[s][q] * dt_s;   // beta_i (fp32) * dt (fp32)
-        float* yi = (s == 5) ? ynew : ws.ytmp;
+        float* yi = (s == 5) ? ynew : sb.ytmp;
         tib::k_dopri_stage<<<g, 256, 0, st>>>(y, k, ks, c, yi, n); LAUNCH_CHECK();
         float ti;
         if (DP_ALPHA[s] == 1.0) ti = std::nextafterf(t1_s, t1_s - 1.0f);   // Perturb.PREV
         else ti = t0_s + (float)DP_ALPHA[s] * dt_s;
-        if (drift_dispatch(m, b, yi, ti, k + (size_t)(s + 1) * ks, ws, st)) return -1;
+        if (rhs(yi, ti, k + (size_t)(s + 1) * ks)) return -1;
         ++nfe;
       }
       tib::StageCoef ce{}; ce.n = 7;
       for (int q = 0; q < 7; ++q) ce.c[q] = dt_s * (float)DP_C_ERROR[q];
-      tib::k_dopri_error<<<gp, 256, 0, st>>>(y, ynew, k, ks, ce, rtol, atol, ws.partial, n); LAUNCH_CHECK();
       double ratio;
-      if (red.finish(&ratio)) return -1;
+      if (red.norm([&](size_t off, size_t cnt) { tib::k_dopri_error<<<gp, 256, 0, st>>>(y + off, ynew + off, k + off, ks, ce, rtol, atol, sb.partial, cnt); LAUNCH_CHECK(); return 0; }, &ratio)) return -1;
       ++attempts;
       if (!(ratio == ratio)) return fail("dopri5: non-finite error ratio (state diverged)");
       if (ratio <= 1.0) {
@@ -1095,7 +1108,6 @@ int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const 
         for (int q = 0; q < 7; ++q) cmid.c[q] = dt_s * (float)DP_C_MID[q];
         dt_step = dt_s;
         t0 = t1; t1 = t_new;
-        have_interp = true;
         // frames i.. with t_grid <= t1
         int j = i;
         while (j < o->n_times && (double)o->t_grid[j] <= t1) {
@@ -1103,7 +1115,7 @@ int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const 
           while (j < o->n_times && (double)o->t_grid[j] <= t1 && da.n < 8) {
             const double xx = ((double)o->t_grid[j] - t0) / (t1 - t0);
             da.xs[da.n] = (float)xx;
-            da.frames[da.n] = o->save_frames ? out_xts + (size_t)j * n : ((j == o->n_times - 1) ? out_xts : nullptr);
+            da.frames[da.n] = o->save_frames ? out + (size_t)j * n : ((j == o->n_times - 1) ? out : nullptr);
             if (da.frames[da.n]) ++da.n;
             ++j;
           }
@@ -1121,13 +1133,143 @@ int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const 
         dt = dt * factor;
       }
     }
-    (void)have_interp;
   }
   // n_times == 1: no step is taken and the dense-output kernel never runs; the final state is the initial state
-  if (!o->save_frames && o->n_times == 1) CUDA_TRY(cudaMemcpyAsync(out_xts, y, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (!o->save_frames && o->n_times == 1) CUDA_TRY(cudaMemcpyAsync(out, y, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
   if (stats) { stats->nfe = nfe; stats->attempts = attempts; stats->accepted = accepted; stats->last_dt = dt; }
   CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
+// torchdiffeq FixedGridODESolver (euler / midpoint / rk4 = 3/8 rule) over a flat state, the output grid is the step grid
+template <typename Rhs>
+int fixed_impl(Rhs&& rhs, size_t n, const float* y0, const tib_fixed_opts* o, float* out, StateBufs& sb, cudaStream_t st, void* stream) {
+  const size_t ks = sb.ks;
+  float* y = sb.ycur;
+  float* f = sb.k + 6 * ks;     // right-hand side scratch
+  CUDA_TRY(cudaMemcpyAsync(y, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  if (o->save_frames) CUDA_TRY(cudaMemcpyAsync(out, y0, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  for (int j = 1; j < o->n_times; ++j) {
+    const float t0 = o->t_grid[j - 1], t1 = o->t_grid[j];
+    const float dt = t1 - t0;   // fp32, as `dt = t1 - t0` on the fp32 grid tensor (negative on a decreasing grid)
+    float* frame = o->save_frames ? out + (size_t)j * n : nullptr;
+    if (o->method == TIB_METHOD_EULER) {
+      if (rhs(y, t0, f)) return -1;
+      if (tib_step_euler(y, f, nullptr, nullptr, dt, 0.f, y, frame, n, stream)) return -1;
+    } else if (o->method == TIB_METHOD_MIDPOINT) {
+      const float half_dt = 0.5f * dt;
+      if (rhs(y, t0, f)) return -1;
+      if (tib_step_euler(y, f, nullptr, nullptr, half_dt, 0.f, sb.ytmp, nullptr, n, stream)) return -1;
+      if (rhs(sb.ytmp, t0 + half_dt, f)) return -1;
+      if (tib_step_euler(y, f, nullptr, nullptr, dt, 0.f, y, frame, n, stream)) return -1;
+    } else if (o->method == TIB_METHOD_RK4) {
+      float* k1 = sb.k; float* k2 = sb.k + ks; float* k3 = sb.k + 2 * ks; float* k4 = sb.k + 3 * ks;
+      const float third = (float)(1.0 / 3.0), two_thirds = (float)(2.0 / 3.0);
+      const int g = grid_for(n);
+      if (rhs(y, t0, k1)) return -1;
+      tib::k_rk4_stage<<<g, 256, 0, st>>>(0, y, k1, k2, k3, k4, dt, sb.ytmp, nullptr, n); LAUNCH_CHECK();
+      if (rhs(sb.ytmp, t0 + dt * third, k2)) return -1;
+      tib::k_rk4_stage<<<g, 256, 0, st>>>(1, y, k1, k2, k3, k4, dt, sb.ytmp, nullptr, n); LAUNCH_CHECK();
+      if (rhs(sb.ytmp, t0 + dt * two_thirds, k3)) return -1;
+      tib::k_rk4_stage<<<g, 256, 0, st>>>(2, y, k1, k2, k3, k4, dt, sb.ytmp, nullptr, n); LAUNCH_CHECK();
+      if (rhs(sb.ytmp, t1, k4)) return -1;
+      tib::k_rk4_stage<<<g, 256, 0, st>>>(3, y, k1, k2, k3, k4, dt, y, frame, n); LAUNCH_CHECK();
+    } else {
+      return fail("unknown fixed-grid method %d", o->method);
+    }
+  }
+  if (!o->save_frames) CUDA_TRY(cudaMemcpyAsync(out, y, sizeof(float) * n, cudaMemcpyDeviceToDevice, st));
+  return 0;
+}
+
+// state buffers of the (x, dlogp) rollouts: carved after the divergence workspace
+size_t tuple_state_stride(size_t n) { return Workspace::align(sizeof(float) * n) / sizeof(float); }
+size_t tuple_state_bytes(size_t n) {
+  return 10 * tuple_state_stride(n) * sizeof(float) + Workspace::align(sizeof(double) * Workspace::kPartials * 5) + Workspace::align(sizeof(double) * 8);
+}
+void tuple_state_carve(char* base, size_t n, StateBufs& sb) {
+  sb.ks = tuple_state_stride(n);
+  float* f = (float*)base;
+  sb.ycur = f; sb.ynew = f + sb.ks; sb.ytmp = f + 2 * sb.ks; sb.k = f + 3 * sb.ks;      // k: 7 slots
+  char* p = base + 10 * sb.ks * sizeof(float);
+  sb.partial = (double*)p; p += Workspace::align(sizeof(double) * Workspace::kPartials * 5);
+  sb.scalar = (double*)p;
+}
+}  // namespace
+extern "C" {
+
+int tib_rollout_dopri5(tib_model* m, const tib_batch* b, const float* x0, const tib_dopri5_opts* o, float* out_xts,
+                       tib_dopri5_stats* stats, void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_batch(m, b)) return -1;
+  if (!x0 || !o || !out_xts || !o->t_grid) return fail("tib_rollout_dopri5: null argument");
+  if (o->n_times < 1) return fail("n_times must be >= 1");
+  for (int i = 1; i < o->n_times; ++i)
+    if (!(o->t_grid[i] > o->t_grid[i - 1])) return fail("t_grid must be strictly increasing");
+  Workspace ws;
+  if (prep_ws(m, b, workspace, workspace_bytes, ws)) return -1;
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n = (size_t)b->n_nodes * 3;
+  StateBufs sb{ws.ycur, ws.ynew, ws.ytmp, ws.k, Workspace::kstride(b->n_nodes), ws.partial, ws.scalar};
+  auto rhs = [&](const float* y, float t, float* out) { return drift_dispatch(m, b, y, t, out, ws, st); };
+  if (dopri5_impl(rhs, n, 0, x0, o, out_xts, sb, stats, st, stream)) return -1;
   // the stream is idle here anyway: report a device-side pipeline / range fault instead of returning bad frames
+  return tib_model_status(m, stream);
+}
+
+/* ---- (x, dlogp) rollouts: the state of MoleculeIntegrator(return_dlogp=True) -------------------------------------------- */
+namespace {
+// rhs over y = [x | dlogp]: out = [b | -div * scale]  (reverse: [-b | +div * scale]; ode_wrapper.py:39-49, latent :38-46)
+// mult_b / mult_d carry the wrapper's signs and scale; time_sign = -1 solves a decreasing grid as torchdiffeq does
+// (odeint on (-t, -f), _check_inputs): the solver sees the negated, increasing grid
+struct DlogpRhs {
+  tib_model* m; const tib_batch* b; void* workspace; cudaStream_t st; size_t n3; float mult_b, mult_d, time_sign;
+  int operator()(const float* y, float t, float* out) const {
+    if (drift_div_dispatch(m, b, y, time_sign * t, out, out + n3, workspace, st)) return -1;
+    tib::k_dlogp_rhs_finish<<<grid_for(n3 + (size_t)b->n_mol), 256, 0, st>>>(out, n3, (size_t)b->n_mol, mult_b * time_sign, mult_d * time_sign);
+    LAUNCH_CHECK();
+    return 0;
+  }
+};
+int check_dlogp_args(tib_model* m, const tib_batch* b, const float* y0, const void* o, const float* out, void* workspace, size_t workspace_bytes) {
+  if (check_batch(m, b)) return -1;
+  if (!y0 || !o || !out) return fail("dlogp rollout: null argument");
+  const size_t need = tib_div_rollout_workspace_bytes(m, b->n_mol, b->n_nodes, b->n_edges, b->max_atoms);
+  if (!workspace || workspace_bytes < need) return fail("dlogp rollout workspace too small: %zu < %zu bytes", workspace_bytes, need);
+  if (((uintptr_t)workspace & 255) != 0) return fail("workspace must be 256-byte aligned");
+  return 0;
+}
+}  // namespace
+
+size_t tib_div_rollout_workspace_bytes(const tib_model* m, int32_t n_mol, int32_t n_nodes, int64_t n_edges, int32_t max_atoms) {
+  if (!m) return 0;
+  return Workspace::align(tib_div_workspace_bytes(m, n_mol, n_nodes, n_edges, max_atoms)) + tuple_state_bytes((size_t)n_nodes * 3 + (size_t)n_mol);
+}
+
+int tib_rollout_fixed_dlogp(tib_model* m, const tib_batch* b, const float* y0, const tib_fixed_opts* o, float mult_b, float mult_d,
+                            float* out, void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_dlogp_args(m, b, y0, o, out, workspace, workspace_bytes)) return -1;
+  if (!o->t_grid || o->n_times < 1) return fail("tib_rollout_fixed_dlogp: bad time grid");
+  if (o->eps != 0.0f || o->noise || o->score_model) return fail("Euler-Maruyama terms and the dlogp state are mutually exclusive");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n3 = (size_t)b->n_nodes * 3, n = n3 + (size_t)b->n_mol;
+  StateBufs sb;
+  tuple_state_carve((char*)workspace + Workspace::align(tib_div_workspace_bytes(m, b->n_mol, b->n_nodes, b->n_edges, b->max_atoms)), n, sb);
+  DlogpRhs rhs{m, b, workspace, st, n3, mult_b, mult_d, 1.0f};
+  return fixed_impl(rhs, n, y0, o, out, sb, st, stream);
+}
+
+int tib_rollout_dopri5_dlogp(tib_model* m, const tib_batch* b, const float* y0, const tib_dopri5_opts* o, float mult_b, float mult_d,
+                             float time_sign, float* out, tib_dopri5_stats* stats, void* workspace, size_t workspace_bytes, void* stream) {
+  if (check_dlogp_args(m, b, y0, o, out, workspace, workspace_bytes)) return -1;
+  if (!o->t_grid || o->n_times < 1) return fail("tib_rollout_dopri5_dlogp: bad time grid");
+  for (int i = 1; i < o->n_times; ++i)
+    if (!(o->t_grid[i] > o->t_grid[i - 1])) return fail("t_grid must be strictly increasing (a decreasing grid is passed negated, with time_sign = -1)");
+  cudaStream_t st = (cudaStream_t)stream;
+  const size_t n3 = (size_t)b->n_nodes * 3, n = n3 + (size_t)b->n_mol;
+  StateBufs sb;
+  tuple_state_carve((char*)workspace + Workspace::align(tib_div_workspace_bytes(m, b->n_mol, b->n_nodes, b->n_edges, b->max_atoms)), n, sb);
+  DlogpRhs rhs{m, b, workspace, st, n3, mult_b, mult_d, time_sign < 0.0f ? -1.0f : 1.0f};
+  if (dopri5_impl(rhs, n, n3, y0, o, out, sb, stats, st, stream)) return -1;
   return tib_model_status(m, stream);
 }
 

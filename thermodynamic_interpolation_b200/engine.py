@@ -274,6 +274,51 @@ class DriftEngine:
                                               div.data_ptr(), wp, wn, self._stream()), "tib_drift_div")
         return out, div
 
+    def _div_rollout_ws(self, pb: PreparedBatch):
+        need = self.lib.tib_div_rollout_workspace_bytes(self.handle, pb.n_mol, pb.n_nodes, pb.n_edges, pb.max_atoms)
+        if self._ws_div is None or self._ws_div.numel() < need + 256:
+            self._ws_div = None
+            self._ws_div = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
+        return self._aligned(self._ws_div)
+
+    def rollout_dlogp(self, pb: PreparedBatch, x0: torch.Tensor, t_grid: torch.Tensor, method: str, *, mult_b: float,
+                      mult_d: float, rtol: float = 1e-4, atol: float = 1e-4, save_frames: bool = True, norm_allreduce=None):
+        """The tuple state (x, dlogp) of `return_dlogp=True` integrated inside libtib.so (tib_rollout_fixed_dlogp /
+        tib_rollout_dopri5_dlogp): right-hand side (mult_b * b, mult_d * div).  Returns (xts [T,N,3], dlogp [T,B], stats)
+        - or ([N,3], [B], stats) without frames."""
+        x0 = self._state(x0, pb)
+        n3, n_mol = x0.numel(), pb.n_mol
+        y0 = torch.cat([x0.reshape(-1), torch.zeros(n_mol, dtype=torch.float32, device=self.device)])
+        tg = t_grid.detach().to("cpu", torch.float32)
+        T = int(tg.shape[0])
+        out = torch.empty((T, n3 + n_mol) if save_frames else (n3 + n_mol,), dtype=torch.float32, device=self.device)
+        wp, wn = self._div_rollout_ws(pb)
+        stats = {}
+        with torch.cuda.device(self.device):
+            if method in _lib.METHODS:
+                tgn = np.ascontiguousarray(tg.numpy())
+                opts = _lib.FixedOpts(method=_lib.METHODS[method], n_times=T, t_grid=tgn.ctypes.data_as(C.POINTER(C.c_float)),
+                                      save_frames=int(save_frames), eps=0.0, noise=None, score_model=None)
+                _lib.check(self.lib.tib_rollout_fixed_dlogp(self.handle, C.byref(pb.c), y0.data_ptr(), C.byref(opts), float(mult_b),
+                                                            float(mult_d), out.data_ptr(), wp, wn, self._stream()),
+                           "tib_rollout_fixed_dlogp")
+            elif method == "dopri5":
+                decreasing = T > 1 and float(tg[-1]) < float(tg[0])
+                tgn = np.ascontiguousarray((-tg if decreasing else tg).numpy())
+                cb = _lib.NORM_ALLREDUCE(norm_allreduce) if norm_allreduce is not None else _lib.NORM_ALLREDUCE()
+                opts = _lib.Dopri5Opts(rtol=float(rtol), atol=float(atol), n_times=T, t_grid=tgn.ctypes.data_as(C.POINTER(C.c_float)),
+                                       save_frames=int(save_frames), max_attempts=0, norm_allreduce=cb, norm_user=None)
+                st = _lib.Dopri5Stats()
+                _lib.check(self.lib.tib_rollout_dopri5_dlogp(self.handle, C.byref(pb.c), y0.data_ptr(), C.byref(opts), float(mult_b),
+                                                             float(mult_d), -1.0 if decreasing else 1.0, out.data_ptr(), C.byref(st),
+                                                             wp, wn, self._stream()), "tib_rollout_dopri5_dlogp")
+                stats = dict(nfe=st.nfe, attempts=st.attempts, accepted=st.accepted, last_dt=st.last_dt)
+            else:
+                raise ValueError(f"unsupported method {method!r}")
+        if save_frames:
+            return out[:, :n3].reshape(T, -1, 3), out[:, n3:], stats
+        return out[:n3].reshape(-1, 3), out[n3:], stats
+
     def _state(self, x, pb):
         if x.device != self.device or x.dtype != torch.float32 or tuple(x.shape) != (pb.n_nodes, 3):
             raise ValueError(f"state must be a float32 [{pb.n_nodes},3] tensor on {self.device}")

@@ -58,7 +58,7 @@ def kernel_shares(fn):
 def main():
     import argparse
     ap = argparse.ArgumentParser()
-    ap.add_argument("--only", default="cfg3,dopri5,f256,div,adw")
+    ap.add_argument("--only", default="cfg3,dopri5,f256,div,divdopri5,adw")
     ap.add_argument("--f256-mols", type=int, default=512)
     only = set(ap.parse_args().only.split(","))
     if "cfg3" in only:
@@ -69,6 +69,8 @@ def main():
         bench_f256(ap.parse_args().f256_mols)
     if "div" in only:
         bench_div()
+    if "divdopri5" in only:
+        bench_div_dopri5()
     if "adw" in only:
         bench_adw()
 
@@ -151,6 +153,24 @@ def bench_div():
                           cpu_oracle=dict(value=32 / cpu_sec, seconds=cpu_sec, sample="32 conformers, autograd, "
                                           f"{torch.get_num_threads()} threads"),
                           max_rel_diff_vs_oracle_on_sample=err)), flush=True)
+
+
+def bench_div_dopri5():
+    # ---- the reference's production configuration: return_dlogp: 1 under dopri5, rtol = atol = 1e-5, 100 frames
+    #      (config/ambient/00031_settings_no_300.json:29,34-36) at cfg-2 size
+    from thermodynamic_interpolation_b200.ambient.integrators import MoleculeIntegrator
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN as Ambient
+    torch.manual_seed(0)
+    model = perturb_(Ambient(n_features=128, score_layers=5, temp_length=100), 1).eval().to(DEV)
+    mb = synthetic_ambient_batch(4096, 9, seed=100).to(DEV)
+    integ = MoleculeIntegrator(model, method="dopri5", n_step=100, atol=1e-5, rtol=1e-5, return_dlogp=True)
+    (xts, dlogp, nfe, _), sec = timed(lambda: integ.rollout(mb))
+    print(json.dumps(dict(workload="cfg 2 with return_dlogp=True under the reference's solver: dopri5 rtol=atol=1e-5, 100 frames, 4096 x 9 atoms, F=128 L=5",
+                          math="tensor-core tangents, tuple-state dopri5 inside libtib.so", nfe=int(nfe),
+                          attempts=integ.last_stats.get("attempts"), accepted=integ.last_stats.get("accepted"), seconds=sec,
+                          value=4096 * nfe / sec, unit="molecule*(drift+divergence) evals/s",
+                          finite=bool(torch.isfinite(xts).all() and torch.isfinite(dlogp).all()),
+                          dlogp_mean=float(dlogp[-1].mean()), dlogp_std=float(dlogp[-1].std()))), flush=True)
 
 
 def bench_adw():
