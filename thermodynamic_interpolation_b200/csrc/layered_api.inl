@@ -67,7 +67,8 @@ struct LayWs {
       sv_upd_n[i] = (float*)take(f4 * tn_rows * F); sv_upd_r[i] = (float*)take(f4 * N);
     }
     // translation invariance: the three directions of the last atom index are reconstructed (k_div_pick), not propagated
-    D = max_atoms > 2 ? 3 * (max_atoms - 1) : 3 * max_atoms; Dc = dirs_chunk(D); Dr = dirs_readout(F);
+    static const bool no_skip = getenv("TIB_DIV_ALL_DIRECTIONS") != nullptr;      // diagnostics: propagate all 3 n directions
+    D = (max_atoms > 2 && !no_skip) ? 3 * (max_atoms - 1) : 3 * max_atoms; Dc = dirs_chunk(D); Dr = dirs_readout(F);
     st_s = al(f4 * N * F) / f4; st_v = al(f4 * N * 3 * F) / f4; st_e = al(f4 * E * F) / f4; st_o = al(f4 * N * 3) / f4;
     st_phi = al(f4 * E * 5 * F) / f4; st_tvvuv = al(f4 * 3 * N * 2 * F) / f4; st_tq = st_s; st_tgac = st_v;
     for (int i = 0; i < 2; ++i) { ts[i] = (float*)take(f4 * st_s * D); tv[i] = (float*)take(f4 * st_v * D); }

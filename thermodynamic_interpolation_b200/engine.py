@@ -265,21 +265,27 @@ class DriftEngine:
         out = torch.empty_like(x)
         div = torch.empty(pb.n_mol, dtype=torch.float32, device=self.device)
         need = self.lib.tib_div_workspace_bytes(self.handle, pb.n_mol, pb.n_nodes, pb.n_edges, pb.max_atoms)
-        if self._ws_div is None or self._ws_div.numel() < need + 256:
-            self._ws_div = None
-            self._ws_div = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
-        wp, wn = self._aligned(self._ws_div)
+        wp, wn = self._alloc_div_ws(need, pb)
         with torch.cuda.device(self.device):
             _lib.check(self.lib.tib_drift_div(self.handle, C.byref(pb.c), x.data_ptr(), float(t), out.data_ptr(),
                                               div.data_ptr(), wp, wn, self._stream()), "tib_drift_div")
         return out, div
 
-    def _div_rollout_ws(self, pb: PreparedBatch):
-        need = self.lib.tib_div_rollout_workspace_bytes(self.handle, pb.n_mol, pb.n_nodes, pb.n_edges, pb.max_atoms)
+    def _alloc_div_ws(self, need: int, pb: PreparedBatch):
         if self._ws_div is None or self._ws_div.numel() < need + 256:
             self._ws_div = None
+            free, _total = torch.cuda.mem_get_info(self.device)
+            if need + 256 > free:
+                raise RuntimeError(
+                    f"the exact-divergence workspace for {pb.n_mol} molecules ({pb.n_nodes} atoms, up to {pb.max_atoms} per molecule) "
+                    f"is {need / 2**30:.1f} GiB (tangent state of {3 * max(pb.max_atoms - 1, 1)} directions) but only {free / 2**30:.1f} GiB "
+                    f"are free on {self.device}: evaluate the batch in molecule chunks (dist.shard_batch)")
             self._ws_div = torch.empty(need + 256, dtype=torch.uint8, device=self.device)
         return self._aligned(self._ws_div)
+
+    def _div_rollout_ws(self, pb: PreparedBatch):
+        need = self.lib.tib_div_rollout_workspace_bytes(self.handle, pb.n_mol, pb.n_nodes, pb.n_edges, pb.max_atoms)
+        return self._alloc_div_ws(need, pb)
 
     def rollout_dlogp(self, pb: PreparedBatch, x0: torch.Tensor, t_grid: torch.Tensor, method: str, *, mult_b: float,
                       mult_d: float, rtol: float = 1e-4, atol: float = 1e-4, save_frames: bool = True, norm_allreduce=None):
