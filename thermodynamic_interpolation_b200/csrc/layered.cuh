@@ -133,6 +133,15 @@ __global__ void __launch_bounds__(128, 4) k_combine_jvp(CombineJvpP pp) {
       float as[3] = {0.f, 0.f, 0.f}, av[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};
       float ec[3][3] = {{0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}, {0.f, 0.f, 0.f}};     // per direction: sum (m4_dot dir + m4 dir_dot)
       float d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;                                    // sum m4 dir
+      // per-direction base pointers once per item: the 64-bit address arithmetic of ~40 loads per edge was most of the
+      // instruction stream
+      const float* pd_c[3]; const float* tv_c[3]; float* te_c[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        pd_c[c] = phi3d ? phi3d + (size_t)(3 * ac + c) * pp.st_phi + f : nullptr;
+        tv_c[c] = tv_old + (size_t)(q0 + c) * pp.st_v + f;
+        te_c[c] = te_base + (size_t)(q0 + c) * pp.st_e + f;
+      }
 #pragma unroll 2
       for (int r = r0; r < r1; ++r) {
         const uint4 ra = __ldg(p.rowa + r);
@@ -151,11 +160,11 @@ __global__ void __launch_bounds__(128, 4) k_combine_jvp(CombineJvpP pp) {
         for (int c = 0; c < 3; ++c) {
 #pragma unroll
           for (int k = 0; k < 5; ++k)
-            pdv[c][k] = phi3d ? __ldg(phi3d + (size_t)(3 * ac + c) * pp.st_phi + (size_t)r * 5 * F + f + (size_t)k * F) : 0.0f;
+            pdv[c][k] = phi3d ? __ldg(pd_c[c] + (size_t)r * 5 * F + (size_t)k * F) : 0.0f;
 #pragma unroll
           for (int k = 0; k < 3; ++k)
-            tvi[c][k] = p.first_layer ? 0.0f : __ldg(tv_old + (size_t)(q0 + c) * pp.st_v + (size_t)i * 3 * F + f + k * F);
-          if (!p.first_layer) teo[c] = te_base[(size_t)(q0 + c) * pp.st_e + (size_t)r * F + f];
+            tvi[c][k] = p.first_layer ? 0.0f : __ldg(tv_c[c] + (size_t)i * 3 * F + k * F);
+          if (!p.first_layer) teo[c] = te_c[c][(size_t)r * F];
         }
         if (!p.first_layer) {
           const float* vp = v_old + (size_t)i * 3 * F + f;
@@ -196,7 +205,7 @@ __global__ void __launch_bounds__(128, 4) k_combine_jvp(CombineJvpP pp) {
 #pragma unroll
           for (int k = 0; k < 3; ++k) av[c][k] += md[1] * dir[k] + m[1] * gd[c][k];
           as[c] += md[2];
-          te_base[(size_t)(q0 + c) * pp.st_e + (size_t)r * F + f] = teo[c] + md[3];
+          te_c[c][(size_t)r * F] = teo[c] + md[3];
         }
       }
       const size_t o = (size_t)j * 3 * F + f;

@@ -98,13 +98,13 @@ __host__ __device__ constexpr int chain_chunks(int n_hidden, int n_halves, int n
 // ---- input build: rows [32*wq, +32) x this thread's column groups of one K half -> operand image -------------------------
 // thread (wq, grp, lane): rows 32*wq + 8*oct + (lane & 7), column groups 4*grp + (lane >> 3) + 4*NG*j
 template <int F>
-__device__ __forceinline__ const float* chain_row_ptr(const ChainSrc& s, long long dir, long long row) {
+__device__ __forceinline__ const float* chain_row_ptr(const ChainSrc s, long long dir, long long row) {
   const long long r = s.idx ? (long long)__ldg(s.idx + row * s.idx_stride) : row;
   return s.base + dir * s.dir_stride + r * s.ld;
 }
 
 template <int F, int NG>
-__device__ __noinline__ float chain_absmax(const ChainSrc& s, long long dir, long long row0, int rows, int wq, int grp, int lane) {
+__device__ __noinline__ float chain_absmax(const ChainSrc s, long long dir, long long row0, int rows, int wq, int grp, int lane) {
   float m = 0.0f;
   if (s.kind != SRC_ROWS) return m;
 #pragma unroll 1
@@ -131,7 +131,7 @@ __device__ __noinline__ float chain_absmax(const ChainSrc& s, long long dir, lon
 }
 
 template <int F, int NG>
-__device__ __noinline__ void chain_build(unsigned char* op, const ChainSrc& s, long long dir, long long row0, int rows, int wq,
+__device__ __noinline__ void chain_build(unsigned char* op, const ChainSrc s, long long dir, long long row0, int rows, int wq,
                                          int grp, int lane, float scale) {
   constexpr uint32_t LO = 128u * F * 2u;
 #pragma unroll 1
@@ -386,7 +386,8 @@ __global__ void __launch_bounds__(ChainSmem<F, NG>::THREADS, ChainSmem<F, NG>::C
       float in_scale = 1.0f, in_inv = 1.0f;
       if (p.epi == EPI_JVP) {
         float m = 0.0f;
-        for (int h = 0; h < p.n_halves; ++h) m = fmaxf(m, chain_absmax<F, NG>(p.src[h], dir, row0, rows, wq, grp, lane));
+        m = chain_absmax<F, NG>(p.src[0], dir, row0, rows, wq, grp, lane);
+        if (p.n_halves > 1) m = fmaxf(m, chain_absmax<F, NG>(p.src[1], dir, row0, rows, wq, grp, lane));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
         named_bar_sync(NB_ALL, S::EPI);                             // RED of the previous item has been read
@@ -402,8 +403,9 @@ __global__ void __launch_bounds__(ChainSmem<F, NG>::THREADS, ChainSmem<F, NG>::C
         for (int h = 0; h < p.n_halves; ++h) {
           const int bi = h % S::NBUF;
           if (h >= S::NBUF) { mbar_wait(&bars[C_FREE0 + bi], pfree[bi], err); pfree[bi] ^= 1; }
-          chain_build<F, NG>(BUF + bi * S::OP_BYTES, p.src[h], dir, row0, rows, wq, grp, lane,
-                             p.epi == EPI_JVP ? in_scale : p.src[h].scale);
+          // constant indices only: indexing the kernel parameter with h would make ptxas copy it to local memory
+          if (h == 0) chain_build<F, NG>(BUF + bi * S::OP_BYTES, p.src[0], dir, row0, rows, wq, grp, lane, p.epi == EPI_JVP ? in_scale : p.src[0].scale);
+          else        chain_build<F, NG>(BUF + bi * S::OP_BYTES, p.src[1], dir, row0, rows, wq, grp, lane, p.epi == EPI_JVP ? in_scale : p.src[1].scale);
           ops_done(h);
         }
         const size_t so = (size_t)tile * F * 128;
@@ -445,9 +447,18 @@ __global__ void __launch_bounds__(ChainSmem<F, NG>::THREADS, ChainSmem<F, NG>::C
           float v[32];
           tmem_ld32(lt + F + 128 * sl + OCOLS * grp + 32 * pc, v);
           if (pc == OCOLS / 32 - 1) { tc_fence_before(); mbar_arrive(&bars[C_TEMPTY0 + sl]); }   // the slot may be refilled while we store
+          const float4* inv4 = reinterpret_cast<const float4*>(INVS + OCOLS * grp + 32 * pc);
+          const int qv = qn - 32 * pc;       // valid columns of this piece
 #pragma unroll
-          for (int q = 0; q < 32; ++q)
-            if (32 * pc + q < qn) o[(long long)(32 * pc + q) * p.ld_out] = fmaf(v[q], INVS[OCOLS * grp + 32 * pc + q], bias);
+          for (int q4 = 0; q4 < 8; ++q4) {
+            const float4 iv = inv4[q4];
+            const float is[4] = {iv.x, iv.y, iv.z, iv.w};
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              if (4 * q4 + i < qv) *o = fmaf(v[4 * q4 + i], is[i], bias);
+              o += p.ld_out;
+            }
+          }
         }
       }
       named_bar_sync(NB_ALL, S::EPI);                               // INVS / STAT may be rewritten by the next item
