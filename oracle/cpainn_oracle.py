@@ -160,12 +160,13 @@ def layer_readout(sd, prefix, hp: Hyper, s, v):
 
 
 def drift(sd: Dict[str, torch.Tensor], hp: Hyper, x, t, atoms, edge_index, edge_type,
-          T0=None, T1=None, T=None) -> torch.Tensor:
+          T0=None, T1=None, T=None, detach: bool = True) -> torch.Tensor:
     """cPaiNN.forward (ambient cpainn.py:93-115; latent cpainn.py:94-108) -> `batch.output` [N,3].
 
     `t` is a python float / 0-dim tensor; it becomes the per-node feature `t * ones_like(atoms)`
     exactly as ODEWrapper.reset_batch does (ode_wrapper.py:112)."""
-    sd = {k: v.detach() for k, v in sd.items()}
+    if detach:       # detach=False: the training oracle (oracle/train_oracle.py) differentiates through the weights
+        sd = {k: v.detach() for k, v in sd.items()}
     k = key_layout(hp)
     Fn, L = hp.n_features, hp.score_layers
     t = torch.as_tensor(t, dtype=x.dtype)

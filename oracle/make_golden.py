@@ -136,6 +136,87 @@ def latent_case(ns, name, F, L, n_list, seed, temperatures, temp_length=75, stor
     print(name, "drift |mean|", float(np.abs(out["drift"]).mean()), "bytes", os.path.getsize(os.path.join(GOLDEN, name + ".npz")))
 
 
+def synthetic_train_batches(n_mol, n_atoms, seed, T0=1000.0, T1=300.0):
+    """Two batches in the training contract of MDQM9MultiTempDataset.process (mdqm9/data/mdqm9_ambient.py:87-107):
+    x [N,3] centred per molecule, T [N] (the temperature repeated per atom), atoms, the coalesced complete digraph."""
+    out = []
+    for i, T in enumerate((T0, T1)):
+        mb = synthetic_ambient_batch(n_mol, n_atoms, seed=seed + i)
+        fields = {k: mb[k] for k in ("x", "atoms", "edge_index", "edge_type", "batch", "ptr")}
+        fields["T"] = torch.full((mb.x.shape[0],), float(T))
+        from thermodynamic_interpolation_b200.batch import MolBatch
+        out.append(MolBatch(**fields))
+    return out
+
+
+GRAD_SAMPLES = 48
+
+
+def tensor_summary(t, gen):
+    """(2-norm, sum, GRAD_SAMPLES entries at seeded positions) of one tensor - what the large training fixtures keep."""
+    flat = t.detach().reshape(-1).to(torch.float64)
+    idx = torch.randint(0, flat.numel(), (GRAD_SAMPLES,), generator=gen)
+    return np.concatenate([[float(flat.norm()), float(flat.sum())], flat[idx].numpy()]), idx.numpy()
+
+
+def train_case(ns, name, F, L, n_mol, n_atoms, seed, gamma="sin2", n_steps=2, lr=1e-4, weight_decay=0.0, full=False):
+    """The reference's training step (mdqm9/train_ambient.py:124-148): StandardVelocityLoss(LinearInterpolant(a=1,
+    gamma)) -> backward -> clip_grad_norm_(1) -> torch.optim.Adam, `n_steps` times on the same two batches.  Stored:
+    the draws (t, z) of every step (re-drawn from the same generator state the loss consumed), the loss values, the
+    un-clipped gradients of step 1 (full tensors, or per-tensor summaries) and the parameters after the last step."""
+    tg = ns.torch_geometric
+    kw = dict(n_features=F, score_layers=L, temp_length=100)
+    model = make_model(ns.ambient_cpainn.cPaiNN, seed, **kw).train()
+    sha0 = state_sha(model.state_dict())
+    b0, b1 = synthetic_train_batches(n_mol, n_atoms, seed + 20)
+    n_list = [n_atoms] * n_mol if isinstance(n_atoms, int) else list(n_atoms)
+    interp = ns.ambient_interpolants.LinearInterpolant(a=1, gamma=gamma)
+    loss_fn = ns.ambient_losses.StandardVelocityLoss(interpolant=interp, t_distr="uniform")
+    optim = torch.optim.Adam(model.parameters(), lr=lr, weight_decay=weight_decay)
+    out = dict(kind="ambient", F=F, L=L, temp_length=100, seed=seed, perturb=PERTURB, n_mol=n_mol, gamma=gamma,
+               n_atoms=np.array(n_list), batch_seed=seed + 20, sha=sha0, lr=lr, weight_decay=weight_decay, n_steps=n_steps,
+               full=int(full))
+    for k in ("x", "T", "atoms", "edge_index", "edge_type", "batch", "ptr"):
+        out["in0::" + k] = b0[k].numpy()
+        out["in1::" + k] = b1[k].numpy()
+    from oracle import train_oracle
+    gen = torch.Generator().manual_seed(seed + 99)
+    names = [k for k, _ in model.named_parameters()]
+    losses, norms = [], []
+    for step in range(n_steps):
+        torch.manual_seed(1000 + seed + step)
+        state = torch.get_rng_state()
+        t, z = train_oracle.draw_t_z(n_list)          # what the reference is about to draw
+        torch.set_rng_state(state)
+        out[f"t{step}"], out[f"z{step}"] = t.numpy(), z.numpy()
+        optim.zero_grad()
+        loss = loss_fn(to_ref_batch(tg, b0), to_ref_batch(tg, b1), model)
+        loss.backward()
+        losses.append(float(loss))
+        if step == 0:
+            for k, p in model.named_parameters():
+                if p.grad is None:
+                    continue
+                if full:
+                    out["g::" + k] = p.grad.detach().numpy().copy()
+                else:
+                    out["gs::" + k], out["gi::" + k] = tensor_summary(p.grad, gen)
+        norms.append(float(torch.nn.utils.clip_grad_norm_(model.parameters(), 1)))
+        optim.step()
+    out["loss"] = np.array(losses)
+    out["grad_norm"] = np.array(norms)
+    for k, p in model.named_parameters():
+        if p.dim() == 0:
+            continue
+        if full:
+            out["p::" + k] = p.detach().numpy().copy()
+        else:
+            out["ps::" + k], out["pi::" + k] = tensor_summary(p, gen)
+    out["names"] = np.array(names)
+    np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
+    print(name, "loss", losses, "grad norms", norms, "bytes", os.path.getsize(os.path.join(GOLDEN, name + ".npz")))
+
+
 def adw_case(name="adw"):
     ns = ref_loader.load_adw()
     torch.manual_seed(5)
@@ -243,6 +324,13 @@ def main():
         latent_case(ns, "latent_multi_f128", F=128, L=3, n_list=[9, 12, 9, 16], seed=6, temperatures=T8, store_weights=False)
     if want("latent_multi_f256"):
         latent_case(ns, "latent_multi_f256", F=256, L=2, n_list=[25, 9], seed=7, temperatures=T8, store_weights=False)
+    # round 2: the training step: loss, gradients, clipping and Adam of the unmodified reference
+    if want("train_f32"):
+        train_case(ns, "train_f32", F=32, L=2, n_mol=3, n_atoms=9, seed=8, full=True)
+    if want("train_f128"):
+        train_case(ns, "train_f128", F=128, L=5, n_mol=12, n_atoms=9, seed=9)      # batch_size 12: 00031_settings_no_300.json:18
+    if want("train_f128_mixed"):
+        train_case(ns, "train_f128_mixed", F=128, L=2, n_mol=4, n_atoms=[9, 12, 7, 16], seed=10, gamma="brownian")
     if want("adw"):
         adw_case()
     if want("stats"):

@@ -56,6 +56,8 @@ def load_mdqm9():
     ns.latent_ode_wrapper = importlib.import_module("thermo.latent.models.ode_wrapper")
     ns.latent_integrators = importlib.import_module("thermo.latent.integrators")
     ns.utils = importlib.import_module("thermo.utils")
+    ns.ambient_losses = importlib.import_module("thermo.ambient.losses")
+    ns.ambient_interpolants = importlib.import_module("thermo.ambient.interpolants")
     import torch_geometric
     ns.torch_geometric = torch_geometric
     return ns
