@@ -24,7 +24,7 @@
 extern "C" {
 #endif
 
-#define TIB_ABI_VERSION 5
+#define TIB_ABI_VERSION 6
 
 /* ---- model ------------------------------------------------------------------------------- */
 
@@ -251,6 +251,61 @@ void tib_adw_destroy(tib_adw_model* m);
  * unscaled; may be NULL). */
 int  tib_adw_drift_div(tib_adw_model* m, const double* x, const double* beta0, const double* beta1, float t,
                        double* out_b, double* out_div, size_t n, void* stream);
+
+/* ---- training step: loss, gradients, optimiser ------------------------------------------------------------
+ * Replaces, for the ambient drift network,
+ *     loss = StandardVelocityLoss(LinearInterpolant(a, gamma))(batch0, batch1, model); loss.backward()
+ * (mdqm9/thermo/ambient/losses.py:30-85,126-133; interpolants.py:16-33,53-108; mdqm9/train_ambient.py:130,144) and
+ *     torch.nn.utils.clip_grad_norm_(model.parameters(), 1); optim.step()      (train_ambient.py:96,146-148).
+ * The weights are a DEVICE vector in the packing order of tib_packed_weight_count (they change every optimiser step,
+ * so there is no handle and nothing is repacked); the gradient comes back in the same order.  The random draws stay
+ * with the caller (the reference draws them from torch's CPU generator: one uniform t per molecule repeated over
+ * its atoms, losses.py:46-47, then z = randn(N, 3), interpolants.py:29), so the step is reproducible against the
+ * reference on identical draws.  Both antithetic drift evaluations (x_t^+, x_t^-) run as one batch of 2 n_mol
+ * molecules; every dense contraction (forward, data gradient, weight gradient) is a split-f16 x3 GEMM on tcgen05. */
+enum { TIB_GAMMA_BROWNIAN = 0,        /* gamma = sqrt(a t (1 - t))        (interpolants.py:71-76) */
+       TIB_GAMMA_SIN2 = 1             /* gamma = sin^2(pi t)              (interpolants.py:78-82) */ };
+typedef struct { int32_t gamma_kind; float a; } tib_interpolant;
+
+/* batch0 / batch1 of the training loop in the contract of MDQM9MultiTempDataset.process
+ * (mdqm9/data/mdqm9_ambient.py:87-107) + the draws.  All pointers are DEVICE pointers. */
+typedef struct {
+  int32_t        n_mol;
+  int32_t        n_nodes;      /* N */
+  int64_t        n_edges;      /* E = sum n_m (n_m - 1): the complete digraph in (src,dst) order, as tib_batch */
+  const int32_t* mol_ptr;      /* [n_mol+1] */
+  const int64_t* edge_ptr;     /* [n_mol+1] */
+  const int32_t* atom_id;      /* [N] batch0.atoms */
+  const uint8_t* edge_type;    /* [E] batch0.edge_type */
+  const float*   temp0;        /* [N] batch0.T */
+  const float*   temp1;        /* [N] batch1.T */
+  const float*   x0;           /* [N,3] batch0.x */
+  const float*   x1;           /* [N,3] batch1.x */
+  const float*   t;            /* [N]   the time of each atom's molecule */
+  const float*   z;            /* [N,3] the interpolant's Gaussian noise */
+} tib_train_batch;
+
+size_t tib_train_workspace_bytes(const tib_model_desc* desc, int32_t n_mol, int32_t n_nodes, int64_t n_edges);
+/* loss: DEVICE double (overwritten); grad: DEVICE [tib_packed_weight_count] (overwritten); out_b: DEVICE [2N,3] or NULL,
+ * the drift at x_t^+ (rows 0..N) and x_t^- (rows N..2N).  Asynchronous on `stream`. */
+int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const tib_train_batch* batch, const tib_interpolant* ip,
+                        double* loss, float* grad, float* out_b, void* workspace, size_t workspace_bytes, void* stream);
+/* Synchronises `stream` and reports (once) a bounded-wait time-out of the training GEMMs.  0 = healthy. */
+int tib_train_status(void* stream);
+/* g *= min(1, max_grad_norm / (|g|_2 + 1e-6))  (skipped when max_grad_norm <= 0), then torch.optim.Adam's update
+ * (L2 weight decay added to the gradient, bias corrections of step `step` >= 1) on flat DEVICE vectors of n floats.
+ * `grad` itself is left un-clipped; scratch: DEVICE double[1] (receives |g|_2^2 before clipping).  For data-parallel
+ * training all-reduce `grad` between tib_train_loss_grad and this call. */
+int tib_adam_step(float* weights, const float* grad, float* m, float* v, size_t n, int32_t step, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float max_grad_norm, double* scratch, void* stream);
+/* The general GEMM behind the training step (csrc/train_gemm.cuh), exposed for tests and benchmarks:
+ *   C[M][N] (mode 0: =, 1: atomic +=, 2: +=)  sum_k A(m,k) B(n,k) (+ bias[n]),  fp32 in / out, split-f16 x3 on tcgen05;
+ *   trans = 0: Op(r,k) = ptr[row(r) * ld + k], trans = 1: Op(r,k) = ptr[row(k) * ld + r]; idx (may be NULL) gathers source rows;
+ *   scale = power-of-two operand scale, or amax_a (DEVICE float, may be NULL) = |max| of A for a dynamic one;
+ *   c_idx (may be NULL, mode 1 only) scatters result rows; split_k != 0 cuts K over CTAs (mode 1 only). */
+int tib_gemm_f16x3(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, int32_t trans_a, const int32_t* idx_a, float scale_a,
+                   const float* amax_a, const float* B, int64_t ldb, int32_t trans_b, const int32_t* idx_b, float scale_b, float* C,
+                   int64_t ldc, const int32_t* c_idx, const float* bias, int32_t mode, int32_t split_k, void* stream);
 
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* tib_last_error(void);

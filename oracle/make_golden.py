@@ -23,7 +23,7 @@ sys.path.insert(0, REPO)
 
 from oracle import ref_loader  # noqa: E402
 from tests._util import perturb_, state_sha  # noqa: E402
-from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch, synthetic_latent_batch  # noqa: E402
+from thermodynamic_interpolation_b200.batch import synthetic_ambient_batch, synthetic_latent_batch, synthetic_train_batches  # noqa: E402
 
 GOLDEN = os.path.join(REPO, "tests", "golden")
 PERTURB = 0.05
@@ -134,19 +134,6 @@ def latent_case(ns, name, F, L, n_list, seed, temperatures, temp_length=75, stor
         out.update(sd_arrays(model.state_dict()))
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
     print(name, "drift |mean|", float(np.abs(out["drift"]).mean()), "bytes", os.path.getsize(os.path.join(GOLDEN, name + ".npz")))
-
-
-def synthetic_train_batches(n_mol, n_atoms, seed, T0=1000.0, T1=300.0):
-    """Two batches in the training contract of MDQM9MultiTempDataset.process (mdqm9/data/mdqm9_ambient.py:87-107):
-    x [N,3] centred per molecule, T [N] (the temperature repeated per atom), atoms, the coalesced complete digraph."""
-    out = []
-    for i, T in enumerate((T0, T1)):
-        mb = synthetic_ambient_batch(n_mol, n_atoms, seed=seed + i)
-        fields = {k: mb[k] for k in ("x", "atoms", "edge_index", "edge_type", "batch", "ptr")}
-        fields["T"] = torch.full((mb.x.shape[0],), float(T))
-        from thermodynamic_interpolation_b200.batch import MolBatch
-        out.append(MolBatch(**fields))
-    return out
 
 
 GRAD_SAMPLES = 48

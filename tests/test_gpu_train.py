@@ -1,0 +1,230 @@
+"""GPU: the training step of libtib.so (tib_train_loss_grad, tib_adam_step, tib_gemm_f16x3) against fixtures made by the
+UNMODIFIED reference training step (oracle/make_golden.py::train_case) and against the CPU oracle (oracle/train_oracle.py)."""
+import numpy as np
+import pytest
+import torch
+
+from tests._util import golden_model, load_golden, oracle_hp_sd
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _lib():
+    from thermodynamic_interpolation_b200 import _lib as L
+    return L
+
+
+# ---- the general split-f16 GEMM ------------------------------------------------------------------------------------------------
+def _rel(a, b):
+    return float((a.double() - b.double()).abs().max() / b.double().abs().max().clamp_min(1e-300))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 128, 128), (200, 160, 96), (1000, 640, 256), (37, 32, 32)])
+def test_gemm_forward_form_with_gather_and_bias(M, N, K):
+    from thermodynamic_interpolation_b200.train import gemm_f16x3
+    g = torch.Generator(device="cpu").manual_seed(M + N + K)
+    src = torch.randn(50, K, generator=g).to(DEV)
+    idx = torch.randint(0, 50, (M,), generator=g).to(DEV, torch.int32)
+    W = (torch.randn(N, K, generator=g) * 0.3).to(DEV)
+    bias = torch.randn(N, generator=g).to(DEV)
+    out = gemm_f16x3(src, W, idx_a=idx, bias=bias)
+    ref = src[idx.long()].double() @ W.double().T + bias.double()
+    assert _rel(out, ref) < 2e-6
+    # operand scales are exact (powers of two)
+    out2 = gemm_f16x3(src, W, idx_a=idx, bias=bias, scale_a=0.0625, scale_b=4.0)
+    assert _rel(out2, ref) < 2e-6
+
+
+def test_gemm_data_gradient_form_accumulate_and_row_scatter():
+    from thermodynamic_interpolation_b200.train import gemm_f16x3
+    L = _lib()
+    g = torch.Generator().manual_seed(1)
+    R, O, I = 300, 640, 128
+    dY = (torch.randn(R, O, generator=g) * 1e-6).to(DEV)            # gradient-sized values: needs the dynamic scale
+    W = (torch.randn(O, I, generator=g) * 0.2).to(DEV)
+    amax = dY.abs().max().reshape(1).clone()
+    ref = dY.double() @ W.double()
+    out = gemm_f16x3(dY, W, trans_b=True, amax_a=amax)
+    assert _rel(out, ref) < 5e-6
+    acc = torch.full((R, I), 1e-5, device=DEV)
+    gemm_f16x3(dY, W, trans_b=True, amax_a=amax, out=acc, mode=L.GEMM_ACCUM)
+    assert _rel(acc, ref + 1e-5) < 5e-6
+    # scatter-add of result rows (d s[src] += ...)
+    dst = torch.randint(0, 40, (R,), generator=g).to(DEV, torch.int32)
+    sc = torch.zeros(40, I, device=DEV)
+    gemm_f16x3(dY, W, trans_b=True, amax_a=amax, out=sc, c_idx=dst, mode=L.GEMM_ATOMIC)
+    ref_sc = torch.zeros(40, I, dtype=torch.float64, device=DEV).index_add_(0, dst.long(), ref)
+    assert _rel(sc, ref_sc) < 5e-6
+    # without the dynamic scale the same product loses its low bits (f16 subnormals): the scale matters
+    bad = gemm_f16x3(dY, W, trans_b=True)
+    assert _rel(bad, ref) > 1e-4
+
+
+@pytest.mark.parametrize("R", [64, 1000, 36864])
+def test_gemm_weight_gradient_form_split_k(R):
+    from thermodynamic_interpolation_b200.train import gemm_f16x3
+    L = _lib()
+    g = torch.Generator().manual_seed(R)
+    O, I = 384, 128
+    dY = (torch.randn(R, O, generator=g) * 1e-3).to(DEV)
+    X = torch.randn(77, I, generator=g).to(DEV)
+    idx = torch.randint(0, 77, (R,), generator=g).to(DEV, torch.int32)
+    amax = dY.abs().max().reshape(1).clone()
+    out = torch.zeros(O, 2 * I, device=DEV)                                   # a column block of a wider gradient matrix
+    gemm_f16x3(dY, X, trans_a=True, trans_b=True, idx_b=idx, amax_a=amax, out=out[:, I:], mode=L.GEMM_ATOMIC, split_k=True,
+               M=O, N=I, K=R)
+    ref = dY.double().T @ X[idx.long()].double()
+    assert _rel(out[:, I:], ref) < 3e-6
+    assert float(out[:, :I].abs().max()) == 0.0
+
+
+# ---- loss and gradients against the reference -----------------------------------------------------------------------------------
+def _fixture_batches(g):
+    from thermodynamic_interpolation_b200.batch import MolBatch
+    out = []
+    for i in (0, 1):
+        out.append(MolBatch(**{k: torch.from_numpy(g[f"in{i}::{k}"]) for k in ("x", "T", "atoms", "edge_index", "edge_type", "batch", "ptr")}))
+    return out
+
+
+def _grad_dict(model, flat):
+    from thermodynamic_interpolation_b200.engine import packed_keys
+    out, off = {}, 0
+    for k, shp in packed_keys(model.hyper):
+        n = int(np.prod(shp))
+        out[k] = flat[off:off + n].view(*shp).cpu()
+        off += n
+    assert off == flat.numel()
+    return out
+
+
+def _check_summary(name, tensor, summary, index, tol, scale=None):
+    flat = tensor.detach().reshape(-1).to(torch.float64)
+    ref_norm, ref_vals = float(summary[0]), summary[2:]
+    scale = scale if scale is not None else max(float(np.abs(ref_vals).max()), ref_norm / np.sqrt(flat.numel()), 1e-30)
+    assert abs(float(flat.norm()) - ref_norm) <= tol * max(ref_norm, 1e-30), (name, float(flat.norm()), ref_norm)
+    err = float(np.abs(flat[torch.from_numpy(index)].numpy() - ref_vals).max())
+    assert err <= tol * scale, (name, err, scale)
+
+
+@pytest.mark.parametrize("name", ["train_f32", "train_f128_mixed", "train_f128"])
+def test_loss_and_gradients_match_reference(name):
+    from thermodynamic_interpolation_b200.train import TrainEngine, flatten, packed_parameters
+    g = load_golden(name)
+    model = golden_model(g, DEV)
+    b0, b1 = _fixture_batches(g)
+    eng = TrainEngine(model.hyper, DEV)
+    tb = eng.prepare(b0, b1)
+    w = flatten(packed_parameters(model))
+    t, z = torch.from_numpy(g["t0"]), torch.from_numpy(g["z0"])
+    loss, grad, b = eng.loss_and_grad(w, tb, t, z, gamma=str(g["gamma"]), want_b=True)
+    eng.status()
+    ref_loss = float(g["loss"][0])
+    assert abs(float(loss) - ref_loss) < 5e-5 * max(1.0, abs(ref_loss)), (float(loss), ref_loss)
+    grads = _grad_dict(model, grad)
+    full = bool(int(g["full"]))
+    worst = 0.0
+    for k, gr in grads.items():
+        if full:
+            ref = torch.from_numpy(g["g::" + k])
+            e = float((gr - ref).abs().max()) / max(float(ref.abs().max()), 1e-30)
+            worst = max(worst, e)
+            assert e < 3e-4, (k, e)
+        else:
+            _check_summary(k, gr, g["gs::" + k], g["gi::" + k], 3e-4)
+    total = float(grad.double().norm())
+    assert abs(total - float(g["grad_norm"][0])) < 2e-4 * float(g["grad_norm"][0])
+    print(name, "loss", float(loss), "ref", ref_loss, "worst relative gradient error", worst)
+
+
+def test_forward_of_both_passes_matches_oracle():
+    from oracle import train_oracle as to
+    from thermodynamic_interpolation_b200.train import TrainEngine, flatten, packed_parameters
+    g = load_golden("train_f128")
+    model = golden_model(g, DEV)
+    hp, sd = oracle_hp_sd(model)
+    b0, b1 = _fixture_batches(g)
+    eng = TrainEngine(model.hyper, DEV)
+    t, z = torch.from_numpy(g["t0"]), torch.from_numpy(g["z0"])
+    _, _, b = eng.loss_and_grad(flatten(packed_parameters(model)), eng.prepare(b0, b1), t, z, gamma="sin2", want_b=True)
+    with torch.no_grad():
+        _, bp, bm = to.velocity_loss(sd, hp, b0.x, b1.x, t, z, b0.atoms, b0.edge_index, b0.edge_type, b0.T, b1.T, gamma="sin2", detach=True)
+    ref = torch.cat([bp, bm])
+    assert float((b.cpu() - ref).abs().max()) < 2e-5 * float(ref.abs().max())
+
+
+@pytest.mark.parametrize("name", ["train_f32", "train_f128"])
+def test_trainer_steps_match_reference_adam(name):
+    """Two optimisation steps on the reference's draws: losses, clipped gradient norms and final parameters."""
+    from thermodynamic_interpolation_b200.ambient.interpolants import LinearInterpolant
+    from thermodynamic_interpolation_b200.train_ambient import Trainer
+    g = load_golden(name)
+    model = golden_model(g, DEV)
+    b0, b1 = _fixture_batches(g)
+    tr = Trainer(model, LinearInterpolant(a=1, gamma=str(g["gamma"])), lr=float(g["lr"]), weight_decay=float(g["weight_decay"]))
+    for step in range(int(g["n_steps"])):
+        loss = tr.step(b0, b1, t=torch.from_numpy(g[f"t{step}"]), z=torch.from_numpy(g[f"z{step}"]))
+        assert abs(float(loss) - float(g["loss"][step])) < 1e-4 * max(1.0, abs(float(g["loss"][step]))), step
+        assert abs(float(tr.last_grad_sqnorm.sqrt()) - float(g["grad_norm"][step])) < 5e-4 * float(g["grad_norm"][step])
+    tr.sync_to_model()
+    full = bool(int(g["full"]))
+    for k, p in model.named_parameters():
+        if p.dim() == 0:
+            continue
+        if full:
+            assert float((p.cpu() - torch.from_numpy(g["p::" + k])).abs().max()) < 5e-6, k
+        else:
+            _check_summary(k, p.cpu(), g["ps::" + k], g["pi::" + k], 2e-5, scale=1.0)
+
+
+def test_reference_style_loop_with_torch_optimizer():
+    """optim.zero_grad(); loss = loss_fn(batch0, batch1, model); loss.backward(); clip_grad_norm_; optim.step()
+    (train_ambient.py:124-148) through the drop-in loss: same parameters as the reference after two steps."""
+    from thermodynamic_interpolation_b200.ambient.interpolants import LinearInterpolant
+    from thermodynamic_interpolation_b200.ambient.losses import StandardVelocityLoss
+    g = load_golden("train_f32")
+    model = golden_model(g, DEV).train()
+    b0, b1 = _fixture_batches(g)
+    loss_fn = StandardVelocityLoss(LinearInterpolant(a=1, gamma="sin2"), t_distr="uniform")
+    optim = torch.optim.Adam(model.parameters(), lr=float(g["lr"]), weight_decay=float(g["weight_decay"]))
+    for step in range(int(g["n_steps"])):
+        torch.manual_seed(1000 + int(g["seed"]) + step)          # the generator state the reference drew from
+        optim.zero_grad()
+        loss = loss_fn(b0, b1, model)
+        loss.backward()
+        assert abs(float(loss) - float(g["loss"][step])) < 1e-4
+        norm = torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
+        assert abs(float(norm) - float(g["grad_norm"][step])) < 5e-4 * float(g["grad_norm"][step])
+        optim.step()
+    for k, p in model.named_parameters():
+        if p.dim() > 0:
+            assert float((p.detach().cpu() - torch.from_numpy(g["p::" + k])).abs().max()) < 5e-6, k
+    assert all(p.grad is None for p in model.parameters() if p.dim() == 0)       # the device_tracker dummies, as in the reference
+
+
+def test_gradients_match_oracle_autograd_on_a_larger_batch():
+    """32 molecules x 9 atoms, F = 128, L = 3, brownian gamma: CUDA adjoints vs torch autograd through the oracle."""
+    from oracle import train_oracle as to
+    from thermodynamic_interpolation_b200.batch import synthetic_train_batches
+    from thermodynamic_interpolation_b200.synthetic import seeded_ambient_model
+    from thermodynamic_interpolation_b200.train import TrainEngine, flatten, packed_parameters
+    model = seeded_ambient_model(128, 3, seed=21).to(DEV)
+    hp, sd = oracle_hp_sd(model)
+    b0, b1 = synthetic_train_batches(32, 9, 5)
+    torch.manual_seed(3)
+    t, z = to.draw_t_z([9] * 32)
+    t = t.clamp(0.05, 0.95)                     # brownian gamma_dot is singular at the ends
+    eng = TrainEngine(model.hyper, DEV)
+    loss, grad, _ = eng.loss_and_grad(flatten(packed_parameters(model)), eng.prepare(b0, b1), t, z, gamma="brownian")
+    eng.status()
+    ref_loss, ref_grads, _, _ = to.loss_and_grads(sd, hp, b0.x, b1.x, t, z, b0.atoms, b0.edge_index, b0.edge_type, b0.T, b1.T, gamma="brownian")
+    assert abs(float(loss) - float(ref_loss)) < 5e-5 * max(1.0, abs(float(ref_loss)))
+    worst = 0.0
+    for k, gr in _grad_dict(model, grad).items():
+        ref = ref_grads[k]
+        e = float((gr - ref).abs().max()) / max(float(ref.abs().max()), 1e-30)
+        worst = max(worst, e)
+        assert e < 3e-4, (k, e)
+    print("worst relative gradient error vs oracle autograd", worst)

@@ -7,7 +7,7 @@ import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "libtib.so")
-ABI_VERSION = 5
+ABI_VERSION = 6
 
 VARIANT_AMBIENT, VARIANT_LATENT_MULTI_T, VARIANT_LATENT_SINGLE_T = 0, 1, 2
 MATH_FP32_SIMT, MATH_F16X3_TC, MATH_F16_TC, MATH_F16X3_LAYERED = 0, 1, 2, 3
@@ -15,6 +15,9 @@ METHOD_EULER, METHOD_MIDPOINT, METHOD_RK4 = 0, 1, 2
 KERNEL_KINDS = ("embed", "edge_init", "message", "update", "readout", "step")
 N_KERNEL_KINDS = len(KERNEL_KINDS)
 MATH_NAMES = {0: "fp32_simt", 1: "f16x3_tcgen05", 2: "f16_tcgen05", 3: "f16x3_tcgen05_layered"}
+GAMMA_BROWNIAN, GAMMA_SIN2 = 0, 1
+GAMMAS = {"brownian": GAMMA_BROWNIAN, "sin2": GAMMA_SIN2}
+GEMM_STORE, GEMM_ATOMIC, GEMM_ACCUM = 0, 1, 2
 METHODS = {"euler": METHOD_EULER, "midpoint": METHOD_MIDPOINT, "rk4": METHOD_RK4}
 
 
@@ -53,6 +56,17 @@ class Dopri5Stats(C.Structure):
     _fields_ = [("nfe", C.c_int32), ("attempts", C.c_int32), ("accepted", C.c_int32), ("last_dt", C.c_double)]
 
 
+class Interpolant(C.Structure):
+    _fields_ = [("gamma_kind", C.c_int32), ("a", C.c_float)]
+
+
+class TrainBatch(C.Structure):
+    _fields_ = [("n_mol", C.c_int32), ("n_nodes", C.c_int32), ("n_edges", C.c_int64),
+                ("mol_ptr", C.c_void_p), ("edge_ptr", C.c_void_p), ("atom_id", C.c_void_p), ("edge_type", C.c_void_p),
+                ("temp0", C.c_void_p), ("temp1", C.c_void_p), ("x0", C.c_void_p), ("x1", C.c_void_p),
+                ("t", C.c_void_p), ("z", C.c_void_p)]
+
+
 # every symbol include/tib.h declares: (name, restype, argtypes)
 SYMBOLS = [
     ("tib_packed_weight_count", C.c_size_t, [C.POINTER(ModelDesc)]),
@@ -81,6 +95,15 @@ SYMBOLS = [
     ("tib_adw_create", C.c_int, [C.POINTER(C.c_void_p), C.c_int32, C.c_int32, C.c_void_p, C.c_size_t, C.c_int]),
     ("tib_adw_destroy", None, [C.c_void_p]),
     ("tib_adw_drift_div", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("tib_train_workspace_bytes", C.c_size_t, [C.POINTER(ModelDesc), C.c_int32, C.c_int32, C.c_int64]),
+    ("tib_train_loss_grad", C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.POINTER(TrainBatch), C.POINTER(Interpolant), C.c_void_p,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
+    ("tib_train_status", C.c_int, [C.c_void_p]),
+    ("tib_adam_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_float, C.c_float,
+                                C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
+    ("tib_gemm_f16x3", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_float,
+                                 C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_float, C.c_void_p, C.c_int64,
+                                 C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]),
     ("tib_last_error", C.c_char_p, []),
     ("tib_abi_version", C.c_int, []),
     ("tib_launch_count", C.c_uint64, [C.c_int]),

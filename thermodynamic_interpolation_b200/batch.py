@@ -155,3 +155,15 @@ def synthetic_latent_batch(n_mol: int, n_atoms=9, *, T: Optional[int] = 800, see
     if T is not None:
         fields["T"] = torch.full((N,), int(T), dtype=torch.long)
     return MolBatch(**fields)
+
+
+def synthetic_train_batches(n_mol: int, n_atoms=9, seed: int = 0, T0: float = 1000.0, T1: float = 300.0):
+    """(batch0, batch1) in the training contract of MDQM9MultiTempDataset.process (mdqm9/data/mdqm9_ambient.py:87-107):
+    x [N,3] centred per molecule, T [N] (the temperature repeated per atom), atoms, the coalesced complete digraph."""
+    out = []
+    for i, T in enumerate((T0, T1)):
+        mb = synthetic_ambient_batch(n_mol, n_atoms, seed=seed + i)
+        fields = {k: mb[k] for k in ("x", "atoms", "edge_index", "edge_type", "batch", "ptr")}
+        fields["T"] = torch.full((mb.x.shape[0],), float(T))
+        out.append(MolBatch(**fields))
+    return out

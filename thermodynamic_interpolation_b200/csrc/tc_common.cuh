@@ -57,7 +57,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a protocol bug must not hang the GPU.  On time-out the error word is set and
 // every later wait returns at once, so the kernel drains (with garbage results) and the host
 // reports the failure.
-__device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, volatile int* err) {
+static __device__ __noinline__ void mbar_wait_slow(uint64_t* bar, uint32_t parity, volatile int* err) {
   if (*err) return;
   for (uint32_t spins = 0; spins < (1u << 22); ++spins) {
     if (mbar_try_wait(bar, parity)) return;       // try_wait itself suspends the thread for a bounded time

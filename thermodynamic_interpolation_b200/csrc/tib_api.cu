@@ -92,6 +92,11 @@ struct HostMlp { tib::MlpW w; };
 
 }  // namespace
 
+namespace tib_internal {      // shared with train_api.cu (the library's second translation unit)
+int set_error(const char* msg) { g_err = msg; return -1; }
+void count_launches(uint64_t n) { g_launches += n; }
+}  // namespace tib_internal
+
 struct tib_model {
   tib_model_desc d;
   int device = 0;

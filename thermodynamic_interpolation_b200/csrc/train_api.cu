@@ -1,0 +1,475 @@
+// train_api.cu - second translation unit of libtib.so: the training step of the ambient drift network
+// (mdqm9/train_ambient.py:124-148, mdqm9/thermo/ambient/losses.py:30-85,126-133):
+//   tib_train_loss_grad : interpolant + both antithetic drift evaluations + loss + hand-written adjoints of every stage
+//   tib_adam_step       : clip_grad_norm_ + torch.optim.Adam on the flat weight vector
+// Dense contractions run on tcgen05 (train_gemm.cuh, split-f16 x3), everything else in train.cuh.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <vector>
+
+#include "../../include/tib.h"
+#include "train.cuh"
+#include "train_gemm.cuh"
+
+namespace tib_internal {      // defined in tib_api.cu (thread-local error string and launch counter of the library)
+int set_error(const char* msg);
+void count_launches(uint64_t n);
+}  // namespace tib_internal
+
+namespace {
+
+using namespace tib::train;
+
+int fail(const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  return tib_internal::set_error(buf);
+}
+
+#define LAUNCH_CHECK()                                                                        \
+  do {                                                                                        \
+    tib_internal::count_launches(1);                                                          \
+    cudaError_t _e = cudaGetLastError();                                                      \
+    if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define CUDA_TRY(expr)                                                                        \
+  do {                                                                                        \
+    cudaError_t _e = (expr);                                                                  \
+    if (_e != cudaSuccess) return fail("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+#define TRY(expr) do { if ((expr) != 0) return -1; } while (0)
+
+constexpr float kStateScale = tib::tc::kStateScale;
+
+// ---- offsets into the flat weight / gradient vector (order of tib_packed_weight_count, include/tib.h) ------------------------
+struct MlpOff { size_t W1, b1, g1, be1, W2, b2, g2, be2, W3, b3; int k_in, n_out; };
+struct LayerOff { MlpOff phi, w, upd; size_t UV; };          // U [F][F] then V [F][F]: one [2F][F] matrix
+struct Offsets {
+  size_t edge_emb, atom_emb; MlpOff combine; std::vector<LayerOff> layers; MlpOff readout; size_t Vout; size_t total;
+};
+
+MlpOff take_mlp(size_t& off, int k_in, int F, int n_out) {
+  MlpOff m{};
+  m.k_in = k_in; m.n_out = n_out;
+  m.W1 = off; off += (size_t)F * k_in; m.b1 = off; off += F; m.g1 = off; off += F; m.be1 = off; off += F;
+  m.W2 = off; off += (size_t)F * F; m.b2 = off; off += F; m.g2 = off; off += F; m.be2 = off; off += F;
+  m.W3 = off; off += (size_t)n_out * F; m.b3 = off; off += n_out;
+  return m;
+}
+Offsets make_offsets(const tib_model_desc& d, int n_temp) {
+  Offsets o{};
+  const int F = d.n_features;
+  size_t off = 0;
+  o.edge_emb = off; off += (size_t)d.n_edge_types * F;
+  o.atom_emb = off; off += (size_t)d.n_types * F;
+  o.combine = take_mlp(off, (2 + n_temp) * F, F, F);
+  for (int l = 0; l < d.n_layers; ++l) {
+    LayerOff L{};
+    L.phi = take_mlp(off, 2 * F, F, 5 * F);
+    L.w = take_mlp(off, F, F, 5 * F);
+    L.UV = off; off += 2 * (size_t)F * F;
+    L.upd = take_mlp(off, 2 * F, F, 3 * F);
+    o.layers.push_back(L);
+  }
+  o.readout = take_mlp(off, F, F, 2);
+  o.Vout = off; off += F;
+  o.total = off;
+  return o;
+}
+
+// ---- workspace ------------------------------------------------------------------------------------------------------------------
+struct MlpAct { float *n1, *r1, *h1, *n2, *r2, *h2, *out; long long rows; };
+struct LayerAct {
+  MlpAct phi, w, upd;
+  float *s_in, *v_in, *e_in, *s_mid, *v_mid, *uvvv, *q;
+};
+struct Ws {
+  // graph
+  int *src, *dst, *pair, *etype, *in_ptr;
+  float4* dir;
+  float *pair_dist, *pe;
+  // inputs / loss
+  float *xt, *tgt, *colsum, *gate;
+  float* amax; int n_amax;
+  // embedding
+  float *X0, *s0; MlpAct emb;
+  std::vector<LayerAct> layers;
+  float *s_last, *v_last, *e_spare;
+  MlpAct ro;
+  // backward
+  float *ds, *dv, *de, *dv_src, *d_phi3, *d_w3, *d_gac, *d_uvvv, *dq, *dA, *dB, *ds0, *dX0;
+  size_t bytes;
+};
+
+size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+size_t layout(Ws& w, char* base, const tib_model_desc& d, int n_temp, long long N, long long E) {
+  const int F = d.n_features, L = d.n_layers;
+  const long long N2 = 2 * N, E2 = 2 * E, P2 = E;
+  size_t off = 0;
+  auto take = [&](size_t nbytes) { char* r = base ? base + off : nullptr; off += al256(nbytes); return r; };
+  auto tf = [&](long long n) { return (float*)take(sizeof(float) * (size_t)n); };
+  auto ti = [&](long long n) { return (int*)take(sizeof(int) * (size_t)n); };
+  auto mlp = [&](MlpAct& a, long long rows, int n_out) {
+    a.rows = rows;
+    a.n1 = tf(rows * F); a.r1 = tf(rows); a.h1 = tf(rows * F);
+    a.n2 = tf(rows * F); a.r2 = tf(rows); a.h2 = tf(rows * F);
+    a.out = n_out > 0 ? tf(rows * n_out) : nullptr;
+  };
+  w.src = ti(E2); w.dst = ti(E2); w.pair = ti(E2); w.etype = ti(E2); w.in_ptr = ti(N2 + 1);
+  w.dir = (float4*)take(sizeof(float4) * (size_t)E2);
+  w.pair_dist = tf(P2); w.pe = tf(P2 * F);
+  w.xt = tf(N2 * 3); w.tgt = tf(N2 * 3); w.colsum = tf(8); w.gate = tf(N2);
+  w.n_amax = 16 * (L + 3); w.amax = tf(w.n_amax);
+  w.X0 = tf(N * (2 + n_temp) * F); mlp(w.emb, N, F); w.s0 = w.emb.out;
+  w.layers.resize(L);
+  for (int l = 0; l < L; ++l) {
+    LayerAct& a = w.layers[l];
+    a.s_in = tf(N2 * F); a.v_in = tf(N2 * 3 * F); a.e_in = tf(E2 * F);
+    mlp(a.w, P2, 5 * F); mlp(a.phi, E2, 5 * F);
+    a.s_mid = tf(N2 * F); a.v_mid = tf(N2 * 3 * F);
+    a.uvvv = tf(N2 * 3 * 2 * F); a.q = tf(N2 * F);
+    mlp(a.upd, N2, 3 * F);
+  }
+  w.s_last = tf(N2 * F); w.v_last = tf(N2 * 3 * F); w.e_spare = tf(E2 * F);
+  mlp(w.ro, N2, 0);
+  w.ds = tf(N2 * F); w.dv = tf(N2 * 3 * F); w.de = tf(E2 * F); w.dv_src = tf(N2 * 3 * F);
+  w.d_phi3 = tf(E2 * 5 * F); w.d_w3 = tf(P2 * 5 * F); w.d_gac = tf(N2 * 3 * F); w.d_uvvv = tf(N2 * 3 * 2 * F); w.dq = tf(N2 * F);
+  w.dA = tf(E2 * F); w.dB = tf(E2 * F); w.ds0 = tf(N * F); w.dX0 = tf(N * F);
+  w.bytes = off;
+  return off;
+}
+
+// ---- launch helpers ---------------------------------------------------------------------------------------------------------------
+bool g_gemm_attr[64] = {};     // opt-in shared-memory size set, per device
+
+struct Ctx {
+  cudaStream_t st;
+  int n_sms;
+  int* err;          // device error word (bounded mbarrier waits)
+  float* amax; int n_amax, next_amax;
+  float* new_amax() { return next_amax < n_amax ? amax + next_amax++ : nullptr; }
+};
+
+GemmOperand op(const float* ptr, long long ld, int trans, float scale, const float* amax = nullptr, const int* idx = nullptr) {
+  GemmOperand o{};
+  o.ptr = ptr; o.ld = ld; o.idx = idx; o.trans = trans; o.amax = amax; o.scale = scale;
+  return o;
+}
+
+int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B, float* C, long long ldc, int mode,
+         const float* bias = nullptr, const int* c_idx = nullptr, bool split_k = false) {
+  if (M <= 0 || N <= 0 || K <= 0) return 0;
+  GemmP p{};
+  p.M = M; p.N = N; p.K = K; p.A = A; p.B = B; p.C = C; p.ldc = ldc; p.c_idx = c_idx; p.bias = bias; p.mode = mode;
+  p.alpha = 1.0f; p.passes = 3; p.err = c.err;
+  const int mt = (M + 127) / 128, nt = (N + 127) / 128, chunks = (K + kGemmKC - 1) / kGemmKC;
+  int splits = 1;
+  if (split_k) {
+    splits = std::max(1, std::min(chunks / 4 + 1, (3 * c.n_sms + mt * nt - 1) / (mt * nt)));
+    if (mode != GEMM_ATOMIC) return fail("internal: split-K GEMM must accumulate atomically");
+  }
+  p.k_splits = splits;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (dev >= 0 && dev < 64 && !g_gemm_attr[dev]) {
+    CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kGemmSmem));
+    CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
+    g_gemm_attr[dev] = true;
+  }
+  k_gemm_tc<<<dim3(nt, mt, splits), kGemmThreads, kGemmSmem, c.st>>>(p);
+  LAUNCH_CHECK();
+  return 0;
+}
+
+int blocks_for(long long n, int per_block) { return (int)std::min<long long>((n + per_block - 1) / per_block, 1 << 20); }
+
+// one input segment of an MLP's first Linear: X[:, seg] = rows of `ptr` (optionally gathered), F_seg columns
+struct Seg { const float* ptr; long long ld; const int* idx; int width; float scale; };
+
+// Linear -> LN -> SiLU -> Linear -> LN -> SiLU [-> Linear]   (embedding.py:26-34)
+int mlp_forward(Ctx& c, const float* W, const MlpOff& m, int F, const Seg* segs, int n_seg, MlpAct& a, bool with_out) {
+  const int R = (int)a.rows;
+  int k0 = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    TRY(gemm(c, R, F, segs[s].width, op(segs[s].ptr, segs[s].ld, 0, segs[s].scale, nullptr, segs[s].idx),
+             op(W + m.W1 + k0, m.k_in, 0, 1.0f), a.n1, F, s == 0 ? GEMM_STORE : GEMM_ACCUM, s == 0 ? W + m.b1 : nullptr));
+    k0 += segs[s].width;
+  }
+  const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 8);
+  k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1);
+  LAUNCH_CHECK();
+  TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2));
+  k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2);
+  LAUNCH_CHECK();
+  if (with_out) TRY(gemm(c, R, m.n_out, F, op(a.h2, F, 0, 1.0f), op(W + m.W3, F, 0, 1.0f), a.out, m.n_out, GEMM_STORE, W + m.b3));
+  return 0;
+}
+
+// where the gradient of one input segment goes
+struct SegGrad { float* ptr; long long ld; int mode; const int* c_idx; };   // ptr == nullptr: not needed
+
+// Adjoint of mlp_forward.  dY [R][n_out] with its |max| slot (dY == nullptr: start from dh2 already in `dA`, the readout case).
+int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const Seg* segs, const SegGrad* sg, int n_seg,
+                 const MlpAct& a, const float* dY, const float* amax_dY, float* dA, float* dB) {
+  const int R = (int)a.rows;
+  const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 4);
+  const size_t ln_smem = 3 * (size_t)F * sizeof(float);
+  if (dY) {
+    TRY(gemm(c, m.n_out, F, R, op(dY, m.n_out, 1, 1.0f, amax_dY), op(a.h2, F, 1, 1.0f), G + m.W3, F, GEMM_ATOMIC, nullptr, nullptr, true));
+    k_tr_colsum<<<dim3((m.n_out + kEW - 1) / kEW, std::min(blocks_for(R, 64), 256)), kEW, 0, c.st>>>(R, m.n_out, dY, G + m.b3, nullptr);
+    LAUNCH_CHECK();
+    TRY(gemm(c, R, F, m.n_out, op(dY, m.n_out, 0, 1.0f, amax_dY), op(W + m.W3, F, 1, 1.0f), dA, F, GEMM_STORE));
+  }
+  float* am2 = c.new_amax();
+  k_tr_ln_silu_bwd<<<ln_blocks, kEW, ln_smem, c.st>>>(R, F, dA, a.n2, a.r2, W + m.g2, W + m.be2, G + m.g2, G + m.be2, G + m.b2, am2);
+  LAUNCH_CHECK();
+  TRY(gemm(c, F, F, R, op(dA, F, 1, 1.0f, am2), op(a.h1, F, 1, 1.0f), G + m.W2, F, GEMM_ATOMIC, nullptr, nullptr, true));
+  TRY(gemm(c, R, F, F, op(dA, F, 0, 1.0f, am2), op(W + m.W2, F, 1, 1.0f), dB, F, GEMM_STORE));
+  float* am1 = c.new_amax();
+  k_tr_ln_silu_bwd<<<ln_blocks, kEW, ln_smem, c.st>>>(R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1);
+  LAUNCH_CHECK();
+  int k0 = 0;
+  for (int s = 0; s < n_seg; ++s) {
+    TRY(gemm(c, F, segs[s].width, R, op(dB, F, 1, 1.0f, am1), op(segs[s].ptr, segs[s].ld, 1, segs[s].scale, nullptr, segs[s].idx),
+             G + m.W1 + k0, m.k_in, GEMM_ATOMIC, nullptr, nullptr, true));
+    if (sg && sg[s].ptr)
+      TRY(gemm(c, R, segs[s].width, F, op(dB, F, 0, 1.0f, am1), op(W + m.W1 + k0, m.k_in, 1, 1.0f), sg[s].ptr, sg[s].ld, sg[s].mode,
+               nullptr, sg[s].c_idx));
+    k0 += segs[s].width;
+  }
+  return 0;
+}
+
+thread_local int* g_dev_err = nullptr;     // one device error word per host thread (never freed: 4 bytes)
+thread_local int g_dev_err_device = -1;
+
+}  // namespace
+
+extern "C" {
+
+size_t tib_train_workspace_bytes(const tib_model_desc* desc, int32_t n_mol, int32_t n_nodes, int64_t n_edges) {
+  (void)n_mol;
+  if (!desc) return 0;
+  Ws w{};
+  const int n_temp = desc->variant == TIB_VARIANT_AMBIENT ? 2 : (desc->variant == TIB_VARIANT_LATENT_MULTI_T ? 1 : 0);
+  return layout(w, nullptr, *desc, n_temp, n_nodes, n_edges);
+}
+
+int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const tib_train_batch* b, const tib_interpolant* ip,
+                        double* loss, float* grad, float* out_b, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!desc || !weights || !b || !ip || !loss || !grad || !workspace) return fail("tib_train_loss_grad: null argument");
+  if (desc->abi_version != TIB_ABI_VERSION) return fail("tib_train_loss_grad: ABI version %d, expected %d", desc->abi_version, TIB_ABI_VERSION);
+  if (desc->variant != TIB_VARIANT_AMBIENT) return fail("tib_train_loss_grad: only the ambient variant trains (train_ambient.py)");
+  const int F = desc->n_features, L = desc->n_layers;
+  if (F % 32 != 0 || F < 32 || F > 256) return fail("tib_train_loss_grad: n_features must be a multiple of 32 in [32, 256]");
+  if (b->n_mol < 1 || b->n_nodes < 2 || b->n_edges < 2) return fail("tib_train_loss_grad: empty batch");
+  if (2 * b->n_edges >= (1ll << 31) || 6ll * b->n_nodes >= (1ll << 31)) return fail("tib_train_loss_grad: batch exceeds int32 row indices");
+  if (ip->gamma_kind != TIB_GAMMA_BROWNIAN && ip->gamma_kind != TIB_GAMMA_SIN2) return fail("tib_train_loss_grad: unknown gamma");
+  const int n_temp = 2;
+  const long long N = b->n_nodes, E = b->n_edges, N2 = 2 * N, E2 = 2 * E, P2 = E;
+  Ws w{};
+  if (layout(w, (char*)workspace, *desc, n_temp, N, E) > workspace_bytes)
+    return fail("tib_train_loss_grad: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
+  const Offsets o = make_offsets(*desc, n_temp);
+  cudaStream_t st = (cudaStream_t)stream;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!g_dev_err || g_dev_err_device != dev) {
+    CUDA_TRY(cudaMalloc(&g_dev_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(g_dev_err, 0, sizeof(int)));
+    g_dev_err_device = dev;
+  }
+  Ctx c{};
+  c.st = st; c.err = g_dev_err; c.amax = w.amax; c.n_amax = w.n_amax; c.next_amax = 0;
+  CUDA_TRY(cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, dev));
+  const float* W = weights;
+  float* G = grad;
+
+  CUDA_TRY(cudaMemsetAsync(G, 0, o.total * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(w.amax, 0, w.n_amax * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(w.colsum, 0, 8 * sizeof(float), st));
+  CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), st));
+
+  // ---- interpolant, targets, graph (interpolants.py:16-33; losses.py:52-57; graph.py:27-29) -----------------------------------------
+  k_tr_interp<<<std::min(blocks_for(N, kEW), c.n_sms * 4), kEW, 0, st>>>((int)N, b->x0, b->x1, b->t, b->z, ip->gamma_kind, ip->a, w.xt, w.tgt, w.colsum);
+  LAUNCH_CHECK();
+  k_tr_center<<<blocks_for(6 * N, kEW), kEW, 0, st>>>((int)N, w.xt, w.colsum);
+  LAUNCH_CHECK();
+  GraphP gp{b->n_mol, (int)N, E, b->mol_ptr, (const long long*)b->edge_ptr, b->edge_type, w.xt, w.src, w.dst, w.pair, w.etype, w.in_ptr,
+            w.dir, w.pair_dist};
+  k_tr_graph<<<dim3(b->n_mol, 2), kEW, 0, st>>>(gp);
+  LAUNCH_CHECK();
+
+  // ---- embeddings (embedding.py:68-86,249-261; cpainn.py:70-71): x-independent, shared by both passes ------------------------------
+  k_tr_embed_in<<<(int)N, kEW, 0, st>>>((int)N, F, n_temp, b->atom_id, b->temp0, b->temp1, b->t, W + o.atom_emb, desc->temp_mean,
+                                        desc->temp_range, desc->temp_length, desc->time_length, w.X0);
+  LAUNCH_CHECK();
+  const Seg seg_emb[1] = {{w.X0, (2 + n_temp) * F, nullptr, (2 + n_temp) * F, 1.0f}};
+  TRY(mlp_forward(c, W, o.combine, F, seg_emb, 1, w.emb, true));
+  LayerAct& A0 = w.layers[0];
+  k_tr_gather_rows<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2, F, nullptr, (int)N, w.s0, A0.s_in);
+  LAUNCH_CHECK();
+  k_tr_gather_rows<<<blocks_for(E2 * F, kEW), kEW, 0, st>>>(E2, F, w.etype, 0, W + o.edge_emb, A0.e_in);
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaMemsetAsync(A0.v_in, 0, sizeof(float) * N2 * 3 * F, st));
+  k_tr_pair_pe<<<blocks_for(P2 * (F / 2), kEW), kEW, 0, st>>>(P2, F, w.pair_dist, desc->length_scale, w.pe);
+  LAUNCH_CHECK();
+
+  // ---- forward through the layers (cpainn.py:138-150) ----------------------------------------------------------------------------------
+  const int node_blocks = (int)std::min<long long>(N2, c.n_sms * 16);
+  for (int l = 0; l < L; ++l) {
+    LayerAct& a = w.layers[l];
+    const LayerOff& lo = o.layers[l];
+    float* s_next = l + 1 < L ? w.layers[l + 1].s_in : w.s_last;
+    float* v_next = l + 1 < L ? w.layers[l + 1].v_in : w.v_last;
+    float* e_next = l + 1 < L ? w.layers[l + 1].e_in : w.e_spare;
+    const Seg seg_w[1] = {{w.pe, F, nullptr, F, 1.0f}};
+    TRY(mlp_forward(c, W, lo.w, F, seg_w, 1, a.w, true));
+    const Seg seg_phi[2] = {{a.s_in, F, w.src, F, kStateScale}, {a.e_in, F, nullptr, F, kStateScale}};
+    TRY(mlp_forward(c, W, lo.phi, F, seg_phi, 2, a.phi, true));
+    CombineP cp{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next};
+    k_tr_combine_fwd<<<node_blocks, kEW, 0, st>>>(cp);
+    LAUNCH_CHECK();
+    TRY(gemm(c, (int)(3 * N2), 2 * F, F, op(a.v_mid, F, 0, kStateScale), op(W + lo.UV, F, 0, 1.0f), a.uvvv, 2 * F, GEMM_STORE));
+    k_tr_upd_q<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q);
+    LAUNCH_CHECK();
+    const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
+    TRY(mlp_forward(c, W, lo.upd, F, seg_upd, 2, a.upd, true));
+    k_tr_upd_apply<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, a.s_mid, a.v_mid, s_next, v_next);
+    LAUNCH_CHECK();
+  }
+
+  // ---- readout, loss and d loss / d b (cpainn.py:425-437; losses.py:126-133) -----------------------------------------------------------
+  const Seg seg_ro[1] = {{w.s_last, F, nullptr, F, kStateScale}};
+  TRY(mlp_forward(c, W, o.readout, F, seg_ro, 1, w.ro, false));
+  float* am_ro = c.new_amax();
+  float* bout = out_b ? out_b : w.dX0;      // dX0 is free until the very end ([N][F] >= [2N][3] for F >= 32)
+  ReadoutP rp{(int)N2, F, (int)N, w.ro.h2, w.v_last, W + o.readout.W3, W + o.readout.b3, W + o.Vout, w.tgt, bout, w.gate, loss,
+              w.dA, w.dv, G + o.readout.W3, G + o.readout.b3, G + o.Vout, am_ro};
+  k_tr_readout<<<std::min(blocks_for(N2, 4), c.n_sms * 4), kEW, 2 * F * sizeof(float), st>>>(rp);
+  LAUNCH_CHECK();
+
+  // ---- backward ------------------------------------------------------------------------------------------------------------------------------
+  {
+    const SegGrad sg[1] = {{w.ds, F, GEMM_STORE, nullptr}};
+    // dh2 of the readout MLP is in dA; the W3 / b3 / Vout gradients were accumulated by k_tr_readout
+    MlpAct ro = w.ro;
+    TRY(mlp_backward(c, W, G, o.readout, F, seg_ro, sg, 1, ro, nullptr, am_ro, w.dA, w.dB));
+  }
+  CUDA_TRY(cudaMemsetAsync(w.de, 0, sizeof(float) * E2 * F, st));      // nothing reads the last layer's e_out
+  for (int l = L - 1; l >= 0; --l) {
+    LayerAct& a = w.layers[l];
+    const LayerOff& lo = o.layers[l];
+    // Update (cpainn.py:345-376)
+    float* am_gac = c.new_amax();
+    k_tr_upd_bwd1<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, w.ds, w.dv, w.d_gac, w.d_uvvv, w.dq, am_gac);
+    LAUNCH_CHECK();
+    const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
+    const SegGrad sg_upd[2] = {{w.dq, F, GEMM_ACCUM, nullptr}, {w.ds, F, GEMM_ACCUM, nullptr}};
+    TRY(mlp_backward(c, W, G, lo.upd, F, seg_upd, sg_upd, 2, a.upd, w.d_gac, am_gac, w.dA, w.dB));
+    float* am_uv = c.new_amax();
+    k_tr_upd_bwd2<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, w.dq, w.d_uvvv, am_uv);
+    LAUNCH_CHECK();
+    TRY(gemm(c, 2 * F, F, (int)(3 * N2), op(w.d_uvvv, 2 * F, 1, 1.0f, am_uv), op(a.v_mid, F, 1, kStateScale), G + lo.UV, F, GEMM_ATOMIC,
+             nullptr, nullptr, true));
+    TRY(gemm(c, (int)(3 * N2), F, 2 * F, op(w.d_uvvv, 2 * F, 0, 1.0f, am_uv), op(W + lo.UV, F, 1, 1.0f), w.dv, F, GEMM_ACCUM));
+    // SE3Message (cpainn.py:263-310)
+    CUDA_TRY(cudaMemsetAsync(w.d_w3, 0, sizeof(float) * P2 * 5 * F, st));
+    CUDA_TRY(cudaMemsetAsync(w.dv_src, 0, sizeof(float) * N2 * 3 * F, st));
+    float* am_phi = c.new_amax();
+    float* am_w = c.new_amax();
+    float* e_next = l + 1 < L ? w.layers[l + 1].e_in : w.e_spare;
+    CombineBwdP cb{{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next},
+                   w.ds, w.dv, w.de, w.d_phi3, w.d_w3, w.dv_src, am_phi, am_w};
+    k_tr_combine_bwd<<<node_blocks, kEW, 0, st>>>(cb);
+    LAUNCH_CHECK();
+    k_tr_add<<<blocks_for(N2 * 3 * F, kEW), kEW, 0, st>>>(N2 * 3 * F, w.dv, w.dv_src);
+    LAUNCH_CHECK();
+    const Seg seg_phi[2] = {{a.s_in, F, w.src, F, kStateScale}, {a.e_in, F, nullptr, F, kStateScale}};
+    const SegGrad sg_phi[2] = {{w.ds, F, GEMM_ATOMIC, w.src}, {w.de, F, GEMM_ACCUM, nullptr}};
+    TRY(mlp_backward(c, W, G, lo.phi, F, seg_phi, sg_phi, 2, a.phi, w.d_phi3, am_phi, w.dA, w.dB));
+    const Seg seg_w[1] = {{w.pe, F, nullptr, F, 1.0f}};
+    TRY(mlp_backward(c, W, G, lo.w, F, seg_w, nullptr, 1, a.w, w.d_w3, am_w, w.dA, w.dB));
+  }
+  // embeddings: e0 = Emb4(edge_type), s0 = combine MLP (both passes share it), atom embedding
+  {
+    const int nb = std::min(blocks_for(E2, 256), c.n_sms * 2);
+    k_tr_scatter_rows<<<nb, kEW, sizeof(float) * desc->n_edge_types * F, st>>>(E2, F, desc->n_edge_types, w.etype, w.de, G + o.edge_emb);
+    LAUNCH_CHECK();
+    float* am_s0 = c.new_amax();
+    k_tr_fold_passes<<<blocks_for(N * F, kEW), kEW, 0, st>>>(N * F, w.ds, w.ds0, am_s0);
+    LAUNCH_CHECK();
+    // weight gradients over all input columns; the input gradient only for the first F (the atom embedding) - the
+    // positional-encoding columns carry no parameters
+    const int kin = (2 + n_temp) * F;
+    const Seg seg2[2] = {{w.X0, kin, nullptr, F, 1.0f}, {w.X0 + F, kin, nullptr, kin - F, 1.0f}};
+    const SegGrad sg2[2] = {{w.dX0, F, GEMM_STORE, nullptr}, {nullptr, 0, 0, nullptr}};
+    TRY(mlp_backward(c, W, G, o.combine, F, seg2, sg2, 2, w.emb, w.ds0, am_s0, w.dA, w.dB));
+    const int nb2 = std::min(blocks_for(N, 64), c.n_sms * 2);
+    k_tr_scatter_rows<<<nb2, kEW, sizeof(float) * desc->n_types * F, st>>>(N, F, desc->n_types, b->atom_id, w.dX0, G + o.atom_emb);
+    LAUNCH_CHECK();
+  }
+  return 0;
+}
+
+int tib_train_status(void* stream) {
+  if (!g_dev_err) return 0;
+  int h = 0;
+  CUDA_TRY(cudaStreamSynchronize((cudaStream_t)stream));
+  CUDA_TRY(cudaMemcpy(&h, g_dev_err, sizeof(int), cudaMemcpyDeviceToHost));
+  if (h) {
+    CUDA_TRY(cudaMemset(g_dev_err, 0, sizeof(int)));
+    return fail("tib_train: a tensor-core pipeline wait timed out (device error word %d)", h);
+  }
+  return 0;
+}
+
+int tib_adam_step(float* weights, const float* grad, float* m, float* v, size_t n, int32_t step, float lr, float beta1, float beta2,
+                  float eps, float weight_decay, float max_grad_norm, double* scratch, void* stream) {
+  if (!weights || !grad || !m || !v || !scratch) return fail("tib_adam_step: null argument");
+  if (step < 1) return fail("tib_adam_step: step counts from 1");
+  cudaStream_t st = (cudaStream_t)stream;
+  CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double), st));
+  const int nb = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  if (max_grad_norm > 0.0f) {
+    k_tr_sqnorm<<<nb, 256, 0, st>>>((long long)n, grad, scratch);
+    LAUNCH_CHECK();
+  }
+  const double bc1 = 1.0 - std::pow((double)beta1, step), bc2 = 1.0 - std::pow((double)beta2, step);
+  k_tr_adam<<<nb, 256, 0, st>>>((long long)n, weights, grad, m, v, scratch, max_grad_norm, lr, beta1, beta2, eps, weight_decay,
+                                (float)bc1, (float)std::sqrt(bc2));
+  LAUNCH_CHECK();
+  return 0;
+}
+
+/* General split-f16 GEMM on tcgen05 (train_gemm.cuh) exposed for tests and benchmarks:
+ *   C[M][N] (mode 0: =, 1: atomic +=, 2: +=)  sum_k A(m,k) B(n,k),   operand (ptr, ld, trans, idx) as in train_gemm.cuh. */
+int tib_gemm_f16x3(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda, int32_t trans_a, const int32_t* idx_a, float scale_a,
+                   const float* amax_a, const float* B, int64_t ldb, int32_t trans_b, const int32_t* idx_b, float scale_b, float* C,
+                   int64_t ldc, const int32_t* c_idx, const float* bias, int32_t mode, int32_t split_k, void* stream) {
+  if (!A || !B || !C) return fail("tib_gemm_f16x3: null argument");
+  if (!trans_a && (K % 8 || lda % 4)) return fail("tib_gemm_f16x3: a row-major A operand needs K %% 8 == 0 and lda %% 4 == 0");
+  if (!trans_b && (K % 8 || ldb % 4)) return fail("tib_gemm_f16x3: a row-major B operand needs K %% 8 == 0 and ldb %% 4 == 0");
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  if (!g_dev_err || g_dev_err_device != dev) {
+    CUDA_TRY(cudaMalloc(&g_dev_err, sizeof(int)));
+    CUDA_TRY(cudaMemset(g_dev_err, 0, sizeof(int)));
+    g_dev_err_device = dev;
+  }
+  Ctx c{};
+  c.st = (cudaStream_t)stream; c.err = g_dev_err;
+  CUDA_TRY(cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, dev));
+  return gemm(c, M, N, K, op(A, lda, trans_a, scale_a, amax_a, idx_a), op(B, ldb, trans_b, scale_b, nullptr, idx_b), C, ldc, mode, bias,
+              c_idx, split_k != 0);
+}
+
+}  // extern "C"

@@ -51,41 +51,56 @@ class Hyper:
         return dict(edge_emb="net.2", atom_emb="net.3", combine="net.5", base="net.6")
 
 
-def pack_state_dict(sd: Dict[str, torch.Tensor], hp: Hyper) -> np.ndarray:
-    """Flattens the reference `state_dict` into the order documented at tib_packed_weight_count
-    (include/tib.h).  Tensors stay in their [out,in] layout; the library transposes."""
+def packed_keys(hp: Hyper) -> List[tuple]:
+    """(state_dict key, shape) of every tensor in the order documented at tib_packed_weight_count (include/tib.h)."""
     k = hp.key_layout()
-    parts: List[torch.Tensor] = []
-
-    def take(name, shape=None):
-        t = sd[name].detach().to("cpu", torch.float32)
-        if shape is not None and tuple(t.shape) != tuple(shape):
-            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
-        parts.append(t.reshape(-1))
+    out: List[tuple] = []
+    F, L = hp.n_features, hp.score_layers
 
     def take_mlp(prefix, f_in, f_out):
-        F = hp.n_features
-        take(f"{prefix}.0.weight", (F, f_in)); take(f"{prefix}.0.bias", (F,))
-        take(f"{prefix}.1.weight", (F,)); take(f"{prefix}.1.bias", (F,))
-        take(f"{prefix}.3.weight", (F, F)); take(f"{prefix}.3.bias", (F,))
-        take(f"{prefix}.4.weight", (F,)); take(f"{prefix}.4.bias", (F,))
-        take(f"{prefix}.6.weight", (f_out, F)); take(f"{prefix}.6.bias", (f_out,))
+        out.extend([(f"{prefix}.0.weight", (F, f_in)), (f"{prefix}.0.bias", (F,)),
+                    (f"{prefix}.1.weight", (F,)), (f"{prefix}.1.bias", (F,)),
+                    (f"{prefix}.3.weight", (F, F)), (f"{prefix}.3.bias", (F,)),
+                    (f"{prefix}.4.weight", (F,)), (f"{prefix}.4.bias", (F,)),
+                    (f"{prefix}.6.weight", (f_out, F)), (f"{prefix}.6.bias", (f_out,))])
 
-    F, L = hp.n_features, hp.score_layers
-    take(f"{k['edge_emb']}.embedding.weight", (hp.n_edge_types, F))
-    take(f"{k['atom_emb']}.embedding.weight", (hp.n_types, F))
+    out.append((f"{k['edge_emb']}.embedding.weight", (hp.n_edge_types, F)))
+    out.append((f"{k['atom_emb']}.embedding.weight", (hp.n_types, F)))
     take_mlp(f"{k['combine']}.mlp.mlp", (2 + hp.n_temp_encoders) * F, F)
     for l in range(L):
         msg, upd = f"{k['base']}.layers.{2 * l}", f"{k['base']}.layers.{2 * l + 1}"
         take_mlp(f"{msg}.phi.mlp", 2 * F, 5 * F)
         take_mlp(f"{msg}.w.mlp", F, 5 * F)
-        take(f"{upd}.u.linear.weight", (F, F))
-        take(f"{upd}.v.linear.weight", (F, F))
+        out.append((f"{upd}.u.linear.weight", (F, F)))
+        out.append((f"{upd}.v.linear.weight", (F, F)))
         take_mlp(f"{upd}.mlp.mlp", 2 * F, 3 * F)
     ro = f"{k['base']}.layers.{2 * L}"
     take_mlp(f"{ro}.mlp.mlp", F, 2)
-    take(f"{ro}.V.linear.weight", (1, F))
+    out.append((f"{ro}.V.linear.weight", (1, F)))
+    return out
+
+
+def pack_state_dict(sd: Dict[str, torch.Tensor], hp: Hyper) -> np.ndarray:
+    """Flattens the reference `state_dict` into the order documented at tib_packed_weight_count
+    (include/tib.h).  Tensors stay in their [out,in] layout; the library transposes."""
+    parts: List[torch.Tensor] = []
+    for name, shape in packed_keys(hp):
+        t = sd[name].detach().to("cpu", torch.float32)
+        if tuple(t.shape) != tuple(shape):
+            raise ValueError(f"{name}: expected shape {tuple(shape)}, got {tuple(t.shape)}")
+        parts.append(t.reshape(-1))
     return np.ascontiguousarray(torch.cat(parts).numpy())
+
+
+def model_desc(hp: Hyper) -> "_lib.ModelDesc":
+    """tib_model_desc of a reference constructor call (include/tib.h)."""
+    temps = torch.tensor(list(hp.temperatures), dtype=torch.float32)
+    return _lib.ModelDesc(
+        abi_version=_lib.ABI_VERSION, variant=hp.c_variant, n_features=hp.n_features,
+        n_layers=hp.score_layers, n_types=hp.n_types, n_edge_types=hp.n_edge_types,
+        temp_length=float(hp.temp_length), time_length=float(hp.time_length),
+        length_scale=float(hp.length_scale), temp_mean=float(temps.mean()),
+        temp_range=float(temps.max() - temps.min()))
 
 
 def pack_node_tiles(n_atoms: np.ndarray, max_nodes: int = 16, max_rows: int = 128) -> np.ndarray:
@@ -191,13 +206,7 @@ class DriftEngine:
         if self.device.type != "cuda":
             raise RuntimeError("thermodynamic_interpolation_b200 runs on CUDA devices only (no CPU fallback); "
                                f"got device {self.device}")
-        temps = torch.tensor(list(hp.temperatures), dtype=torch.float32)
-        desc = _lib.ModelDesc(
-            abi_version=_lib.ABI_VERSION, variant=hp.c_variant, n_features=hp.n_features,
-            n_layers=hp.score_layers, n_types=hp.n_types, n_edge_types=hp.n_edge_types,
-            temp_length=float(hp.temp_length), time_length=float(hp.time_length),
-            length_scale=float(hp.length_scale), temp_mean=float(temps.mean()),
-            temp_range=float(temps.max() - temps.min()))
+        desc = model_desc(hp)
         packed = pack_state_dict(state_dict, hp)
         need = self.lib.tib_packed_weight_count(C.byref(desc))
         if packed.size != need:
