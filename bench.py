@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py - molecule*SDE-steps/sec of the MDQM9 ambient sampler hot path.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg4]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload cfg2|cfg4|cfg5]
 
 One bench "step" = one integrator step of the sampler over the whole batch: one drift-network evaluation
 b(t, x, T0, T1) on every molecule plus the fused state update (the unit SURVEY.md section 8d defines).
@@ -15,6 +15,11 @@ Workloads (BASELINE.json configs):
         samples only; after every temperature the reweighting statistics (tib_reweight_stats -> ONE fp64 all-reduce of 5
         numbers) and the IQR outlier mask from the all-gathered weights (mdqm9/analysis/utils/sensititvity.py:4-12, k = 100 as
         at results_00031.py:248-268) - the collectives are INSIDE the timed region.
+
+  cfg5 (configs[4]): the training step of train_ambient.py - per GPU 256 molecules x 9 atoms (two batches at T0 / T1), loss =
+        StandardVelocityLoss(LinearInterpolant(a=1, gamma='sin2')) with both antithetic drift evaluations, backward, one NCCL
+        all-reduce of the gradient vector (data parallel, averaged over ranks), clip_grad_norm_(1), Adam(lr=1e-4).  One bench
+        step = one optimisation step; the unit is molecule*training-steps/s (molecules of batch0 per second).
 
 `value`    : device-resident run (inputs already in HBM), CUDA events, max over ranks.
 `e2e`      : the same work through the public API `MoleculeIntegrator.rollout(batch)` with the batch in pinned host memory
@@ -278,6 +283,232 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------------
+# cfg5: the training step (BASELINE configs[4])
+# ---------------------------------------------------------------------------------------------------
+TRAIN_METRIC = "molecule*training-steps/sec, MDQM9 ambient drift network (loss fwd+bwd, clip, Adam)"
+
+
+def train_workload_name(args):
+    return (f"MDQM9 ambient training step, {args.mols} molecules x {args.atoms} atoms per GPU (batch0 at 1000 K, batch1 at 300 K), "
+            f"cPaiNN F={args.features} L={args.layers}, StandardVelocityLoss(LinearInterpolant(a=1, gamma='sin2')), antithetic "
+            f"pair, clip_grad_norm_(1), Adam(lr=1e-4), data-parallel gradient all-reduce (BASELINE configs[4])")
+
+
+def train_flops_per_mol(n, F, L):
+    """Algorithmic FLOPs of one training step per molecule: two antithetic drift evaluations, each forward + data gradient +
+    weight gradient (3 x the forward contractions of SURVEY.md section 8d)."""
+    return 2 * 3 * flops_per_mol_step(n, F, L)
+
+
+def cpu_reference_train_rate(args, n_mol, steps, warmup):
+    """The UNMODIFIED reference training step on the host cores (mdqm9/train_ambient.py:124-148): loss_fn(batch0, batch1, model),
+    backward, clip_grad_norm_(1), Adam.  Returns (mol*steps/s, cores, seconds) or None."""
+    root = reference_root()
+    if root is None:
+        return None
+    os.environ["TI_REFERENCE_ROOT"] = root
+    from oracle import ref_loader
+    from thermodynamic_interpolation_b200.batch import synthetic_train_batches
+    from thermodynamic_interpolation_b200.synthetic import perturb_
+    ref_loader.REFERENCE_ROOT = root
+    ns = ref_loader.load_mdqm9()
+    cores = len(os.sched_getaffinity(0))
+    torch.set_num_threads(cores)
+    torch.manual_seed(0)
+    model = perturb_(ns.ambient_cpainn.cPaiNN(n_features=args.features, score_layers=args.layers, temp_length=100), 1).train()
+    for mod in model.modules():
+        if isinstance(getattr(mod, "temperatures", None), torch.Tensor):
+            mod.temperatures = mod.temperatures.cpu()
+    b0, b1 = synthetic_train_batches(n_mol, args.atoms, seed=100)
+
+    def ref_batch(mb):
+        b = ns.torch_geometric.data.Batch()
+        for k in mb.keys():
+            b[k] = mb[k].clone() if torch.is_tensor(mb[k]) else mb[k]
+        return b
+
+    loss_fn = ns.ambient_losses.StandardVelocityLoss(interpolant=ns.ambient_interpolants.LinearInterpolant(a=1, gamma="sin2"),
+                                                     t_distr="uniform")
+    optim = torch.optim.Adam(model.parameters(), lr=1e-4, weight_decay=0)
+
+    def one():
+        optim.zero_grad()
+        loss = loss_fn(ref_batch(b0), ref_batch(b1), model)
+        loss.backward()
+        torch.nn.utils.clip_grad_norm_(model.parameters(), 1)
+        optim.step()
+        return float(loss)
+
+    for _ in range(warmup):
+        one()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        last = one()
+    el = time.perf_counter() - t0
+    assert np.isfinite(last)
+    return n_mol * steps / el, cores, el
+
+
+def run_reference_train(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_cpu = min(args.mols, 64)
+    steps = max(1, min(args.steps, 5))
+    ref = cpu_reference_train_rate(args, n_cpu, steps, min(args.warmup, 1))
+    if ref is None:
+        print(json.dumps(dict(impl="reference", unavailable="the reference's training modules are not staged under baseline/_ref")))
+        return
+    rate, cores, secs = ref
+    sample = (f"the reference's own training step (StandardVelocityLoss -> backward -> clip_grad_norm_ -> Adam) on {n_cpu} molecules, "
+              f"{steps} steps ({secs:.1f} s, {cores} threads)")
+    print(json.dumps(dict(metric=TRAIN_METRIC, value=rate, unit=UNIT, n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                          ms_per_step=1e3 * secs / steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                          data="synthetic", impl="reference", config=dict(workload=train_workload_name(args), sample=sample),
+                          cpu_baseline=dict(value=rate, unit=UNIT, cores=cores, kind="reference", sample=sample),
+                          e2e=dict(value=rate, unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)))
+
+
+def run_train(args):
+    import torch.distributed as dist
+    from thermodynamic_interpolation_b200 import _lib
+    from thermodynamic_interpolation_b200.ambient.interpolants import LinearInterpolant
+    from thermodynamic_interpolation_b200.batch import synthetic_train_batches
+    from thermodynamic_interpolation_b200.synthetic import seeded_ambient_model
+    from thermodynamic_interpolation_b200.train_ambient import Trainer
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device (no CPU fallback); use --impl reference for the CPU arm")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = _lib.load()
+    K, W = args.steps, max(args.warmup, 0)
+    model = seeded_ambient_model(args.features, args.layers, 100, seed=0).to(dev)
+    trainer = Trainer(model, LinearInterpolant(a=1, gamma="sin2"), lr=1e-4, weight_decay=0.0, max_grad_norm=1.0,
+                      data_parallel=world > 1)
+    n_host = 4                                        # distinct host batches cycled through (each rank its own data)
+    host = []
+    gen = torch.Generator().manual_seed(1234 + rank)
+    for i in range(n_host):
+        b0, b1 = synthetic_train_batches(args.mols, args.atoms, seed=1000 * rank + 10 * i)
+        N = b0.x.shape[0]
+        t = torch.rand(args.mols, generator=gen).repeat_interleave(args.atoms).reshape(N, 1)
+        z = torch.randn(N, 3, generator=gen)
+        host.append((b0.pin_memory(), b1.pin_memory(), t.pin_memory(), z.pin_memory()))
+    devb = [(b0.clone().to(dev), b1.clone().to(dev), t.to(dev), z.to(dev)) for b0, b1, t, z in host]
+    tbs = [trainer.engine.prepare(b0, b1) for b0, b1, _, _ in devb]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize(dev)
+
+    def max_over_ranks(v):
+        if world == 1:
+            return v
+        tt = torch.tensor([v], dtype=torch.float64, device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    losses = torch.zeros(K + W + 8, dtype=torch.float64, device=dev)
+
+    def resident_step(i):
+        tb, (_, _, t, z) = tbs[i % n_host], devb[i % n_host]
+        loss, grad, _ = trainer.engine.loss_and_grad(trainer.weights, tb, t, z, gamma="sin2", a=1.0)
+        trainer.apply(grad)
+        losses[i] = loss[0]
+
+    for i in range(W):
+        resident_step(i)
+    barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms_sum = (C.c_double * _lib.N_KERNEL_KINDS)()
+    launches = (C.c_uint64 * _lib.N_KERNEL_KINDS)()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    lib.tib_launch_count(1)
+    lib.tib_train_gemm_flops(1)
+    lib.tib_profile_begin()
+    t_begin = time.perf_counter()
+    e0.record()
+    for i in range(K):
+        resident_step(W + i)
+    e1.record()
+    barrier()
+    t_end = time.perf_counter()
+    n_launch = int(lib.tib_launch_count(0))
+    gemm_flops = float(lib.tib_train_gemm_flops(0))
+    _lib.check(lib.tib_profile_end(ms_sum, launches), "tib_profile_end")
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    clk = clocks.stop(t_begin, t_end) if clocks else None
+    trainer.engine.status()
+    lh = losses[: W + K].cpu()
+    assert torch.isfinite(lh).all(), "training diverged"
+    value = world * args.mols * K / (ms_total * 1e-3)
+
+    # ---- e2e: host batches (pinned) -> H2D, prepare, step, loss read back - every step
+    host_loss = torch.zeros(1, dtype=torch.float64).pin_memory()
+    h2d = sum(v.numel() * v.element_size() for b in host[0][:2] for v in (b[k] for k in b.keys()) if torch.is_tensor(v))
+    h2d += host[0][2].numel() * 4 + host[0][3].numel() * 4
+
+    def e2e_step(i):
+        b0, b1, t, z = host[i % n_host]
+        loss = trainer.step(b0.clone().to(dev, non_blocking=True), b1.clone().to(dev, non_blocking=True),
+                            t=t.to(dev, non_blocking=True), z=z.to(dev, non_blocking=True))
+        host_loss.copy_(loss, non_blocking=True)
+
+    e2e_step(0)
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+        e2e_step(i)
+    torch.cuda.synchronize(dev)
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    barrier()
+    e2e_value = world * args.mols * K / e2e_s
+
+    if rank == 0:
+        peaks = load_peaks()
+        gi = _lib.KERNEL_KINDS.index("train_gemm")
+        gemm_ms, gemm_n = ms_sum[gi], int(launches[gi])
+        other_ms = ms_sum[_lib.KERNEL_KINDS.index("train_other")]
+        achieved = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+        peak = peaks["bf16_sustained"]
+        fl = train_flops_per_mol(args.atoms, args.features, args.layers)
+        line = dict(
+            metric=TRAIN_METRIC, value=value, unit=UNIT, n_gpus=world, steps=K, warmup=W, ms_per_step=ms_total / K,
+            higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+            config=dict(workload=train_workload_name(args), mols_per_gpu=args.mols, atoms=args.atoms, n_features=args.features,
+                        layers=args.layers, math="f16x3_tcgen05", optimizer="Adam(lr=1e-4), clip_grad_norm_(1)",
+                        l2="activations saved for the backward pass (%.0f MB per step) exceed the 126 MB L2" %
+                           (lib.tib_train_workspace_bytes(C.byref(trainer.engine.desc), tbs[0].pb.n_mol, tbs[0].pb.n_nodes, tbs[0].pb.n_edges) / 1e6),
+                        flops_per_mol_step=fl, whole_step_tflops=value * fl / 1e12 / world,
+                        loss_first=float(lh[0]), loss_last=float(lh[-1])),
+            e2e=dict(value=e2e_value, unit=UNIT, h2d_bytes_per_step=h2d, d2h_bytes_per_step=8, seconds=e2e_s,
+                     api="train_ambient.Trainer.step(host batch0, host batch1) + D2H of the loss"),
+            gpu_launches=n_launch, clocks=clk,
+            roofline=dict(kernel="k_gemm_tc (every Linear of the step: forward, data gradient, weight gradient)", bound="tensor",
+                          achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                          peak_source=peaks["source"] + ", bf16 dense sustained", launches=gemm_n,
+                          avg_launch_ms=gemm_ms / max(gemm_n, 1), flops_per_step=gemm_flops / K,
+                          kernel_time_shares=dict(train_gemm=round(gemm_ms / ms_total, 4), train_other=round(other_ms / ms_total, 4))))
+        if world == 1 and not args.no_cpu:
+            ref = cpu_reference_train_rate(args, min(args.mols, 64), steps=2, warmup=1)
+            if ref is not None:
+                rate, cores, secs = ref
+                line["cpu_baseline"] = dict(value=rate, unit=UNIT, cores=cores, kind="reference",
+                                            sample=f"the reference's own training step, {min(args.mols, 64)} molecules x 2 steps ({secs:.1f} s)")
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ---------------------------------------------------------------------------------------------------
 def run_b200(args):
     import torch.distributed as dist
     from thermodynamic_interpolation_b200 import _lib
@@ -494,7 +725,7 @@ def main():
     ap.add_argument("--steps", type=int, default=None)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4"])
+    ap.add_argument("--workload", default="cfg2", choices=["cfg2", "cfg4", "cfg5"])
     ap.add_argument("--mols", type=int, default=None, help="conformers per GPU (cfg2: 4096, cfg4: 125000)")
     ap.add_argument("--chunk", type=int, default=15625, help="cfg4: conformers per rollout call")
     ap.add_argument("--atoms", type=int, default=9)
@@ -506,10 +737,12 @@ def main():
     ap.add_argument("--gather", type=int, default=1)
     args = ap.parse_args()
     if args.mols is None:
-        args.mols = 125000 if args.workload == "cfg4" else 4096
+        args.mols = {"cfg4": 125000, "cfg5": 256}.get(args.workload, 4096)
     if args.steps is None:
-        args.steps = 20 if args.workload == "cfg4" else 200
-    if args.impl == "reference":
+        args.steps = {"cfg4": 20, "cfg5": 20}.get(args.workload, 200)
+    if args.workload == "cfg5":
+        (run_reference_train if args.impl == "reference" else run_train)(args)
+    elif args.impl == "reference":
         run_reference(args)
     else:
         run_b200(args)

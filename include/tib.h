@@ -307,6 +307,14 @@ int tib_gemm_f16x3(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
                    const float* amax_a, const float* B, int64_t ldb, int32_t trans_b, const int32_t* idx_b, float scale_b, float* C,
                    int64_t ldc, const int32_t* c_idx, const float* bias, int32_t mode, int32_t split_k, void* stream);
 
+/* Pipeline diagnostics of the training GEMM: enable = 1 makes every later k_gemm_tc launch of this thread record clock64()
+ * stamps of its CTA (0,0,0): start, TMEM allocated, per K chunk (operands built, barrier passed), all chunks issued,
+ * accumulator complete, epilogue done, end.  out (HOST int64[64], may be NULL) receives the stamps of the last launch,
+ * out[63] = their count.  Synchronises the device. */
+int tib_gemm_debug(int enable, long long* out);
+/* Algorithmic FLOPs (2 M N K) of the k_gemm_tc launches issued by this thread since the last reset. */
+double tib_train_gemm_flops(int reset);
+
 /* ---- misc -------------------------------------------------------------------------------- */
 const char* tib_last_error(void);
 int         tib_abi_version(void);
@@ -317,7 +325,8 @@ uint64_t    tib_launch_count(int reset);
 /* Per-kernel-class device time (CUDA event pairs around each launch on the launching stream) between
  * begin and end, for bench.py's roofline line.  ms_sum / launches are HOST arrays [TIB_K_COUNT]. */
 enum { TIB_K_EMBED = 0, TIB_K_EDGE_INIT = 1, TIB_K_MESSAGE = 2, TIB_K_UPDATE = 3, TIB_K_READOUT = 4,
-       TIB_K_STEP = 5, TIB_K_COUNT = 6 };
+       TIB_K_STEP = 5, TIB_K_TRAIN_GEMM = 6 /* k_gemm_tc launches of the training step */,
+       TIB_K_TRAIN_OTHER = 7 /* its element-wise / scatter kernels */, TIB_K_COUNT = 8 };
 /* Tensor-core plumbing self test: out = A * W^T (transposed = 0) or W * A^T (transposed = 1) through the
  * same operand images, weight ring and TMEM addressing the drift kernels use.  A, out: DEVICE fp32
  * [128][128]; W: HOST fp32 [128][128].  Synchronous. */

@@ -228,3 +228,49 @@ def test_gradients_match_oracle_autograd_on_a_larger_batch():
         worst = max(worst, e)
         assert e < 3e-4, (k, e)
     print("worst relative gradient error vs oracle autograd", worst)
+
+
+def test_f256_gradients_match_oracle_autograd():
+    """The reference's second production width (10506_settings_no_900.json:14): 2 molecules x 25 atoms, F = 256, L = 2."""
+    from oracle import train_oracle as to
+    from thermodynamic_interpolation_b200.batch import synthetic_train_batches
+    from thermodynamic_interpolation_b200.synthetic import seeded_ambient_model
+    from thermodynamic_interpolation_b200.train import TrainEngine, flatten, packed_parameters
+    model = seeded_ambient_model(256, 2, seed=31).to(DEV)
+    hp, sd = oracle_hp_sd(model)
+    b0, b1 = synthetic_train_batches(2, 25, 7)
+    torch.manual_seed(4)
+    t, z = to.draw_t_z([25, 25])
+    eng = TrainEngine(model.hyper, DEV)
+    loss, grad, _ = eng.loss_and_grad(flatten(packed_parameters(model)), eng.prepare(b0, b1), t, z, gamma="sin2")
+    eng.status()
+    ref_loss, ref_grads, _, _ = to.loss_and_grads(sd, hp, b0.x, b1.x, t, z, b0.atoms, b0.edge_index, b0.edge_type, b0.T, b1.T, gamma="sin2")
+    assert abs(float(loss) - float(ref_loss)) < 5e-5 * max(1.0, abs(float(ref_loss)))
+    for k, gr in _grad_dict(model, grad).items():
+        ref = ref_grads[k]
+        assert float((gr - ref).abs().max()) <= 3e-4 * max(float(ref.abs().max()), 1e-30), k
+
+
+def test_training_reduces_the_loss_and_rejects_bad_arguments():
+    from thermodynamic_interpolation_b200.ambient.interpolants import LinearInterpolant
+    from thermodynamic_interpolation_b200.batch import synthetic_train_batches
+    from thermodynamic_interpolation_b200.synthetic import seeded_ambient_model
+    from thermodynamic_interpolation_b200.train_ambient import Trainer
+    model = seeded_ambient_model(64, 2, seed=5).to(DEV)
+    tr = Trainer(model, LinearInterpolant(a=1, gamma="sin2"), lr=1e-3)
+    b0, b1 = synthetic_train_batches(24, 9, 11)
+    g = torch.Generator().manual_seed(0)
+    t = torch.rand(24, generator=g).repeat_interleave(9).reshape(-1, 1)
+    z = torch.randn(24 * 9, 3, generator=g)
+    losses = [float(tr.step(b0, b1, t=t, z=z)) for _ in range(30)]
+    assert losses[-1] < losses[0] - 0.5 and all(np.isfinite(losses))
+    before = [p.detach().clone() for p in model.parameters()]
+    tr.sync_to_model()
+    assert any(not torch.equal(a, b) for a, b in zip(before, model.parameters()))
+    with pytest.raises(ValueError):
+        tr.engine.loss_and_grad(tr.weights[:-1], tr.engine.prepare(b0, b1), t, z)
+    with pytest.raises(NotImplementedError):
+        Trainer(model, LinearInterpolant(a=1, gamma="sig_sum"))
+    with pytest.raises(RuntimeError):
+        from thermodynamic_interpolation_b200.train import TrainEngine
+        TrainEngine(model.hyper, "cpu")

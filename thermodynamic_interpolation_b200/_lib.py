@@ -12,7 +12,7 @@ ABI_VERSION = 6
 VARIANT_AMBIENT, VARIANT_LATENT_MULTI_T, VARIANT_LATENT_SINGLE_T = 0, 1, 2
 MATH_FP32_SIMT, MATH_F16X3_TC, MATH_F16_TC, MATH_F16X3_LAYERED = 0, 1, 2, 3
 METHOD_EULER, METHOD_MIDPOINT, METHOD_RK4 = 0, 1, 2
-KERNEL_KINDS = ("embed", "edge_init", "message", "update", "readout", "step")
+KERNEL_KINDS = ("embed", "edge_init", "message", "update", "readout", "step", "train_gemm", "train_other")
 N_KERNEL_KINDS = len(KERNEL_KINDS)
 MATH_NAMES = {0: "fp32_simt", 1: "f16x3_tcgen05", 2: "f16_tcgen05", 3: "f16x3_tcgen05_layered"}
 GAMMA_BROWNIAN, GAMMA_SIN2 = 0, 1
@@ -99,6 +99,8 @@ SYMBOLS = [
     ("tib_train_loss_grad", C.c_int, [C.POINTER(ModelDesc), C.c_void_p, C.POINTER(TrainBatch), C.POINTER(Interpolant), C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     ("tib_train_status", C.c_int, [C.c_void_p]),
+    ("tib_train_gemm_flops", C.c_double, [C.c_int]),
+    ("tib_gemm_debug", C.c_int, [C.c_int, C.c_void_p]),
     ("tib_adam_step", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int32, C.c_float, C.c_float,
                                 C.c_float, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p]),
     ("tib_gemm_f16x3", C.c_int, [C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p, C.c_float,

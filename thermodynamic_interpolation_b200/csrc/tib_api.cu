@@ -95,6 +95,9 @@ struct HostMlp { tib::MlpW w; };
 namespace tib_internal {      // shared with train_api.cu (the library's second translation unit)
 int set_error(const char* msg) { g_err = msg; return -1; }
 void count_launches(uint64_t n) { g_launches += n; }
+// event pair around a launch of the other translation unit, when tib_profile_begin is active
+void* prof_open(int kind, void* stream) { return g_prof.on ? new ProfScope(kind, (cudaStream_t)stream) : nullptr; }
+void prof_close(void* h) { delete static_cast<ProfScope*>(h); }
 }  // namespace tib_internal
 
 struct tib_model {

@@ -9,6 +9,8 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
+#include <cstdint>
 #include <vector>
 
 #include "../../include/tib.h"
@@ -18,6 +20,8 @@
 namespace tib_internal {      // defined in tib_api.cu (thread-local error string and launch counter of the library)
 int set_error(const char* msg);
 void count_launches(uint64_t n);
+void* prof_open(int kind, void* stream);
+void prof_close(void* h);
 }  // namespace tib_internal
 
 namespace {
@@ -32,6 +36,14 @@ int fail(const char* fmt, ...) {
   va_end(ap);
   return tib_internal::set_error(buf);
 }
+
+struct Prof {      // tib_profile_begin / tib_profile_end: device time per kernel class
+  void* h;
+  Prof(int kind, cudaStream_t st) : h(tib_internal::prof_open(kind, st)) {}
+  ~Prof() { if (h) tib_internal::prof_close(h); }
+};
+thread_local double g_gemm_flops = 0.0;
+thread_local long long* g_gemm_dbg = nullptr;      // device buffer [64] when tib_gemm_debug is on
 
 #define LAUNCH_CHECK()                                                                        \
   do {                                                                                        \
@@ -169,11 +181,11 @@ int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   GemmP p{};
   p.M = M; p.N = N; p.K = K; p.A = A; p.B = B; p.C = C; p.ldc = ldc; p.c_idx = c_idx; p.bias = bias; p.mode = mode;
-  p.alpha = 1.0f; p.passes = 3; p.err = c.err;
+  p.alpha = 1.0f; p.passes = 3; p.err = c.err; p.dbg = g_gemm_dbg;
   const int mt = (M + 127) / 128, nt = (N + 127) / 128, chunks = (K + kGemmKC - 1) / kGemmKC;
   int splits = 1;
   if (split_k) {
-    splits = std::max(1, std::min(chunks / 4 + 1, (3 * c.n_sms + mt * nt - 1) / (mt * nt)));
+    splits = std::max(1, std::min(chunks / 4 + 1, (2 * c.n_sms + mt * nt - 1) / (mt * nt)));
     if (mode != GEMM_ATOMIC) return fail("internal: split-K GEMM must accumulate atomically");
   }
   p.k_splits = splits;
@@ -184,8 +196,22 @@ int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B
     CUDA_TRY(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributePreferredSharedMemoryCarveout, 100));
     g_gemm_attr[dev] = true;
   }
-  k_gemm_tc<<<dim3(nt, mt, splits), kGemmThreads, kGemmSmem, c.st>>>(p);
-  LAUNCH_CHECK();
+  g_gemm_flops += 2.0 * M * (double)N * K;
+  static const bool trace = getenv("TIB_TRAIN_TRACE") != nullptr;      // diagnostics: synchronous per-launch timing on stderr
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (trace) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(c.st); cudaEventRecord(e0, c.st); }
+  {
+    Prof pf(TIB_K_TRAIN_GEMM, c.st);
+    k_gemm_tc<<<dim3(nt, mt, splits), kGemmThreads, kGemmSmem, c.st>>>(p);
+    LAUNCH_CHECK();
+  }
+  if (trace) {
+    float ms = 0.0f;
+    cudaEventRecord(e1, c.st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+    fprintf(stderr, "[gemm] M=%d N=%d K=%d tA=%d tB=%d idxA=%d idxB=%d mode=%d splits=%d ctas=%d  %.1f us  %.1f TFLOP/s\n", M, N, K, A.trans,
+            B.trans, A.idx != nullptr, B.idx != nullptr, mode, splits, nt * mt * splits, ms * 1e3, 2.0 * M * N * K / (ms * 1e-3) / 1e12);
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+  }
   return 0;
 }
 
@@ -203,12 +229,14 @@ int mlp_forward(Ctx& c, const float* W, const MlpOff& m, int F, const Seg* segs,
              op(W + m.W1 + k0, m.k_in, 0, 1.0f), a.n1, F, s == 0 ? GEMM_STORE : GEMM_ACCUM, s == 0 ? W + m.b1 : nullptr));
     k0 += segs[s].width;
   }
-  const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 8);
+  const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 16);
+  { Prof pf(TIB_K_TRAIN_OTHER, c.st);
   k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
   TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2));
+  { Prof pf(TIB_K_TRAIN_OTHER, c.st);
   k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
   if (with_out) TRY(gemm(c, R, m.n_out, F, op(a.h2, F, 0, 1.0f), op(W + m.W3, F, 0, 1.0f), a.out, m.n_out, GEMM_STORE, W + m.b3));
   return 0;
 }
@@ -220,22 +248,25 @@ struct SegGrad { float* ptr; long long ld; int mode; const int* c_idx; };   // p
 int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const Seg* segs, const SegGrad* sg, int n_seg,
                  const MlpAct& a, const float* dY, const float* amax_dY, float* dA, float* dB) {
   const int R = (int)a.rows;
-  const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 4);
+  const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 8);
   const size_t ln_smem = 3 * (size_t)F * sizeof(float);
   if (dY) {
     TRY(gemm(c, m.n_out, F, R, op(dY, m.n_out, 1, 1.0f, amax_dY), op(a.h2, F, 1, 1.0f), G + m.W3, F, GEMM_ATOMIC, nullptr, nullptr, true));
+    { Prof pf(TIB_K_TRAIN_OTHER, c.st);
     k_tr_colsum<<<dim3((m.n_out + kEW - 1) / kEW, std::min(blocks_for(R, 64), 256)), kEW, 0, c.st>>>(R, m.n_out, dY, G + m.b3, nullptr);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
     TRY(gemm(c, R, F, m.n_out, op(dY, m.n_out, 0, 1.0f, amax_dY), op(W + m.W3, F, 1, 1.0f), dA, F, GEMM_STORE));
   }
   float* am2 = c.new_amax();
+  { Prof pf(TIB_K_TRAIN_OTHER, c.st);
   k_tr_ln_silu_bwd<<<ln_blocks, kEW, ln_smem, c.st>>>(R, F, dA, a.n2, a.r2, W + m.g2, W + m.be2, G + m.g2, G + m.be2, G + m.b2, am2);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
   TRY(gemm(c, F, F, R, op(dA, F, 1, 1.0f, am2), op(a.h1, F, 1, 1.0f), G + m.W2, F, GEMM_ATOMIC, nullptr, nullptr, true));
   TRY(gemm(c, R, F, F, op(dA, F, 0, 1.0f, am2), op(W + m.W2, F, 1, 1.0f), dB, F, GEMM_STORE));
   float* am1 = c.new_amax();
+  { Prof pf(TIB_K_TRAIN_OTHER, c.st);
   k_tr_ln_silu_bwd<<<ln_blocks, kEW, ln_smem, c.st>>>(R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
   int k0 = 0;
   for (int s = 0; s < n_seg; ++s) {
     TRY(gemm(c, F, segs[s].width, R, op(dB, F, 1, 1.0f, am1), op(segs[s].ptr, segs[s].ld, 1, segs[s].scale, nullptr, segs[s].idx),
@@ -299,29 +330,36 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), st));
 
   // ---- interpolant, targets, graph (interpolants.py:16-33; losses.py:52-57; graph.py:27-29) -----------------------------------------
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_interp<<<std::min(blocks_for(N, kEW), c.n_sms * 4), kEW, 0, st>>>((int)N, b->x0, b->x1, b->t, b->z, ip->gamma_kind, ip->a, w.xt, w.tgt, w.colsum);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_center<<<blocks_for(6 * N, kEW), kEW, 0, st>>>((int)N, w.xt, w.colsum);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
   GraphP gp{b->n_mol, (int)N, E, b->mol_ptr, (const long long*)b->edge_ptr, b->edge_type, w.xt, w.src, w.dst, w.pair, w.etype, w.in_ptr,
             w.dir, w.pair_dist};
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_graph<<<dim3(b->n_mol, 2), kEW, 0, st>>>(gp);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
 
   // ---- embeddings (embedding.py:68-86,249-261; cpainn.py:70-71): x-independent, shared by both passes ------------------------------
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_embed_in<<<(int)N, kEW, 0, st>>>((int)N, F, n_temp, b->atom_id, b->temp0, b->temp1, b->t, W + o.atom_emb, desc->temp_mean,
                                         desc->temp_range, desc->temp_length, desc->time_length, w.X0);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
   const Seg seg_emb[1] = {{w.X0, (2 + n_temp) * F, nullptr, (2 + n_temp) * F, 1.0f}};
   TRY(mlp_forward(c, W, o.combine, F, seg_emb, 1, w.emb, true));
   LayerAct& A0 = w.layers[0];
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_gather_rows<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2, F, nullptr, (int)N, w.s0, A0.s_in);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_gather_rows<<<blocks_for(E2 * F, kEW), kEW, 0, st>>>(E2, F, w.etype, 0, W + o.edge_emb, A0.e_in);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
   CUDA_TRY(cudaMemsetAsync(A0.v_in, 0, sizeof(float) * N2 * 3 * F, st));
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_pair_pe<<<blocks_for(P2 * (F / 2), kEW), kEW, 0, st>>>(P2, F, w.pair_dist, desc->length_scale, w.pe);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
 
   // ---- forward through the layers (cpainn.py:138-150) ----------------------------------------------------------------------------------
   const int node_blocks = (int)std::min<long long>(N2, c.n_sms * 16);
@@ -336,15 +374,18 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     const Seg seg_phi[2] = {{a.s_in, F, w.src, F, kStateScale}, {a.e_in, F, nullptr, F, kStateScale}};
     TRY(mlp_forward(c, W, lo.phi, F, seg_phi, 2, a.phi, true));
     CombineP cp{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next};
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_combine_fwd<<<node_blocks, kEW, 0, st>>>(cp);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
     TRY(gemm(c, (int)(3 * N2), 2 * F, F, op(a.v_mid, F, 0, kStateScale), op(W + lo.UV, F, 0, 1.0f), a.uvvv, 2 * F, GEMM_STORE));
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_upd_q<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
     const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
     TRY(mlp_forward(c, W, lo.upd, F, seg_upd, 2, a.upd, true));
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_upd_apply<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, a.s_mid, a.v_mid, s_next, v_next);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
   }
 
   // ---- readout, loss and d loss / d b (cpainn.py:425-437; losses.py:126-133) -----------------------------------------------------------
@@ -354,8 +395,9 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   float* bout = out_b ? out_b : w.dX0;      // dX0 is free until the very end ([N][F] >= [2N][3] for F >= 32)
   ReadoutP rp{(int)N2, F, (int)N, w.ro.h2, w.v_last, W + o.readout.W3, W + o.readout.b3, W + o.Vout, w.tgt, bout, w.gate, loss,
               w.dA, w.dv, G + o.readout.W3, G + o.readout.b3, G + o.Vout, am_ro};
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_readout<<<std::min(blocks_for(N2, 4), c.n_sms * 4), kEW, 2 * F * sizeof(float), st>>>(rp);
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
 
   // ---- backward ------------------------------------------------------------------------------------------------------------------------------
   {
@@ -370,14 +412,16 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     const LayerOff& lo = o.layers[l];
     // Update (cpainn.py:345-376)
     float* am_gac = c.new_amax();
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_upd_bwd1<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, w.ds, w.dv, w.d_gac, w.d_uvvv, w.dq, am_gac);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
     const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
     const SegGrad sg_upd[2] = {{w.dq, F, GEMM_ACCUM, nullptr}, {w.ds, F, GEMM_ACCUM, nullptr}};
     TRY(mlp_backward(c, W, G, lo.upd, F, seg_upd, sg_upd, 2, a.upd, w.d_gac, am_gac, w.dA, w.dB));
     float* am_uv = c.new_amax();
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_upd_bwd2<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, w.dq, w.d_uvvv, am_uv);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
     TRY(gemm(c, 2 * F, F, (int)(3 * N2), op(w.d_uvvv, 2 * F, 1, 1.0f, am_uv), op(a.v_mid, F, 1, kStateScale), G + lo.UV, F, GEMM_ATOMIC,
              nullptr, nullptr, true));
     TRY(gemm(c, (int)(3 * N2), F, 2 * F, op(w.d_uvvv, 2 * F, 0, 1.0f, am_uv), op(W + lo.UV, F, 1, 1.0f), w.dv, F, GEMM_ACCUM));
@@ -389,10 +433,12 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     float* e_next = l + 1 < L ? w.layers[l + 1].e_in : w.e_spare;
     CombineBwdP cb{{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next},
                    w.ds, w.dv, w.de, w.d_phi3, w.d_w3, w.dv_src, am_phi, am_w};
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_combine_bwd<<<node_blocks, kEW, 0, st>>>(cb);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_add<<<blocks_for(N2 * 3 * F, kEW), kEW, 0, st>>>(N2 * 3 * F, w.dv, w.dv_src);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
     const Seg seg_phi[2] = {{a.s_in, F, w.src, F, kStateScale}, {a.e_in, F, nullptr, F, kStateScale}};
     const SegGrad sg_phi[2] = {{w.ds, F, GEMM_ATOMIC, w.src}, {w.de, F, GEMM_ACCUM, nullptr}};
     TRY(mlp_backward(c, W, G, lo.phi, F, seg_phi, sg_phi, 2, a.phi, w.d_phi3, am_phi, w.dA, w.dB));
@@ -401,12 +447,14 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   }
   // embeddings: e0 = Emb4(edge_type), s0 = combine MLP (both passes share it), atom embedding
   {
-    const int nb = std::min(blocks_for(E2, 256), c.n_sms * 2);
+    const int nb = std::min(blocks_for(E2, 32), c.n_sms * 8);
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_scatter_rows<<<nb, kEW, sizeof(float) * desc->n_edge_types * F, st>>>(E2, F, desc->n_edge_types, w.etype, w.de, G + o.edge_emb);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
     float* am_s0 = c.new_amax();
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_fold_passes<<<blocks_for(N * F, kEW), kEW, 0, st>>>(N * F, w.ds, w.ds0, am_s0);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
     // weight gradients over all input columns; the input gradient only for the first F (the atom embedding) - the
     // positional-encoding columns carry no parameters
     const int kin = (2 + n_temp) * F;
@@ -414,10 +462,31 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     const SegGrad sg2[2] = {{w.dX0, F, GEMM_STORE, nullptr}, {nullptr, 0, 0, nullptr}};
     TRY(mlp_backward(c, W, G, o.combine, F, seg2, sg2, 2, w.emb, w.ds0, am_s0, w.dA, w.dB));
     const int nb2 = std::min(blocks_for(N, 64), c.n_sms * 2);
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_scatter_rows<<<nb2, kEW, sizeof(float) * desc->n_types * F, st>>>(N, F, desc->n_types, b->atom_id, w.dX0, G + o.atom_emb);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
   }
   return 0;
+}
+
+/* Pipeline diagnostics of k_gemm_tc: enable = 1 makes every later launch of this thread record clock64() stamps of its CTA
+ * (0,0,0) (start, TMEM allocated, then per K chunk: built, barrier passed; all issued, accumulator complete, epilogue done,
+ * end); out (HOST [64], may be NULL) receives the stamps of the last launch, out[63] = their count.  Synchronises the device. */
+int tib_gemm_debug(int enable, long long* out) {
+  CUDA_TRY(cudaDeviceSynchronize());
+  if (out && g_gemm_dbg) CUDA_TRY(cudaMemcpy(out, g_gemm_dbg, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
+  if (enable && !g_gemm_dbg) {
+    CUDA_TRY(cudaMalloc(&g_gemm_dbg, 64 * sizeof(long long)));
+    CUDA_TRY(cudaMemset(g_gemm_dbg, 0, 64 * sizeof(long long)));
+  }
+  if (!enable && g_gemm_dbg) { cudaFree(g_gemm_dbg); g_gemm_dbg = nullptr; }
+  return 0;
+}
+
+double tib_train_gemm_flops(int reset) {
+  const double v = g_gemm_flops;
+  if (reset) g_gemm_flops = 0.0;
+  return v;
 }
 
 int tib_train_status(void* stream) {
@@ -440,13 +509,15 @@ int tib_adam_step(float* weights, const float* grad, float* m, float* v, size_t 
   CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double), st));
   const int nb = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
   if (max_grad_norm > 0.0f) {
+    { Prof pf(TIB_K_TRAIN_OTHER, st);
     k_tr_sqnorm<<<nb, 256, 0, st>>>((long long)n, grad, scratch);
-    LAUNCH_CHECK();
+    LAUNCH_CHECK(); }
   }
   const double bc1 = 1.0 - std::pow((double)beta1, step), bc2 = 1.0 - std::pow((double)beta2, step);
+  { Prof pf(TIB_K_TRAIN_OTHER, st);
   k_tr_adam<<<nb, 256, 0, st>>>((long long)n, weights, grad, m, v, scratch, max_grad_norm, lr, beta1, beta2, eps, weight_decay,
                                 (float)bc1, (float)std::sqrt(bc2));
-  LAUNCH_CHECK();
+  LAUNCH_CHECK(); }
   return 0;
 }
 
@@ -458,6 +529,8 @@ int tib_gemm_f16x3(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
   if (!A || !B || !C) return fail("tib_gemm_f16x3: null argument");
   if (!trans_a && (K % 8 || lda % 4)) return fail("tib_gemm_f16x3: a row-major A operand needs K %% 8 == 0 and lda %% 4 == 0");
   if (!trans_b && (K % 8 || ldb % 4)) return fail("tib_gemm_f16x3: a row-major B operand needs K %% 8 == 0 and ldb %% 4 == 0");
+  if (N % 4 || ldc % 4 || ((uintptr_t)C & 15) || ((uintptr_t)bias & 15)) return fail("tib_gemm_f16x3: N, ldc must be multiples of 4 and C, bias 16-byte aligned");
+  if ((!trans_a && ((uintptr_t)A & 15)) || (!trans_b && ((uintptr_t)B & 15))) return fail("tib_gemm_f16x3: row-major operands must be 16-byte aligned");
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
   if (!g_dev_err || g_dev_err_device != dev) {

@@ -19,9 +19,12 @@
 // from the tensor's |max| (tracked by the producing kernel with atomicMax), mapping it into [2^12, 2^13).  The scale is
 // undone on the accumulators (exact).
 //
-// Pipeline: 256 threads build K chunks of 32 into a 2-stage ring (32 KB per stage); thread 0 issues the three MMA
-// passes of a chunk and commits them to the stage's mbarrier; the next chunk is built while they run.  64 KB of shared
-// memory and 128 TMEM columns per CTA, so three CTAs share an SM and cover each other's build / issue gaps.
+// Pipeline: 256 threads build K chunks of 32 into a 2-stage ring (32 KB per stage): the global loads of chunk c + 1 are
+// issued into registers before chunk c's barrier, thread 0 issues the three MMA passes of a chunk and commits them to
+// the stage's mbarrier, and the next chunk is converted and stored while they run.  The accumulator tile leaves through
+// warp-private pieces of the idle ring (coalesced 256-byte row segments; float4 atomics for the split-K weight
+// gradients).  64 KB of shared memory and 128 TMEM columns per CTA, so three CTAs share an SM.  N, ldc, the bias and C
+// must be multiples of 4 floats / 16-byte aligned (every Linear of the network is).
 #pragma once
 #include "tc_common.cuh"
 
@@ -51,6 +54,7 @@ struct GemmP {
   float alpha;
   int passes;           // 3 = split-f16 x3, 1 = single f16 pass
   int* err;
+  long long* dbg;       // optional: clock64() stamps of CTA (0,0,0) thread 0 (pipeline diagnostics), else nullptr
 };
 
 constexpr int kGemmThreads = 256;
@@ -71,51 +75,81 @@ __device__ __forceinline__ float pow2_scale_for(float amax) {
 }
 __device__ __forceinline__ float operand_scale(const GemmOperand& o) { return o.amax ? pow2_scale_for(__ldg(o.amax)) : o.scale; }
 
-// One [128 x 32] operand tile (rows r0.., columns k0..) -> hi / lo images at `img` / `img + kGemmHalf`.
-__device__ __forceinline__ void build_tile(unsigned char* img, const GemmOperand& o, int r0, int r_end, int k0, int k_end,
-                                           float scale, int warp, int lane) {
+// One [128 x 32] operand tile (rows r0.., columns k0..) in two steps, so that the global loads of the NEXT chunk are in
+// flight while the current one is converted, stored and multiplied:
+//   load_tile : 16 floats per thread into registers (trans 0: 2 x 32 B of two rows; trans 1: 2 column groups x 8 source rows)
+//   store_tile: scale, split into hi / lo f16 and write the images at `img` / `img + kGemmHalf`
+struct TileRows { long long off[2]; bool ok[2]; };          // trans 0: the thread's two source rows (fixed over the K loop)
+
+__device__ __forceinline__ TileRows tile_rows(const GemmOperand& o, int r0, int r_end, int warp, int lane) {
+  TileRows t;
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int r = r0 + 16 * warp + 8 * half + (lane & 7);
+    t.ok[half] = o.trans == 0 && r < r_end;
+    t.off[half] = t.ok[half] ? (o.idx ? (long long)__ldg(o.idx + r) : (long long)r) * o.ld : 0;
+  }
+  return t;
+}
+
+__device__ __forceinline__ void load_tile(float (&v)[16], const GemmOperand& o, const TileRows& tr, int r0, int r_end, int k0,
+                                          int k_end, int warp, int lane) {
   if (o.trans == 0) {
-    // lane = (row & 7, column group): a warp covers 8 rows x 32 columns per step; two steps per warp cover its 16 rows
+    const int k = k0 + 8 * (lane >> 3);
 #pragma unroll
     for (int half = 0; half < 2; ++half) {
-      const int rl = 16 * warp + 8 * half + (lane & 7), g = lane >> 3;
-      const int r = r0 + rl, k = k0 + 8 * g;
-      float v[8];
-      if (r < r_end && k < k_end) {
-        const long long row = o.idx ? (long long)__ldg(o.idx + r) : (long long)r;
-        const float4* src = reinterpret_cast<const float4*>(o.ptr + row * o.ld + k);
-        const float4 a = __ldg(src), b = __ldg(src + 1);
-        v[0] = a.x * scale; v[1] = a.y * scale; v[2] = a.z * scale; v[3] = a.w * scale;
-        v[4] = b.x * scale; v[5] = b.y * scale; v[6] = b.z * scale; v[7] = b.w * scale;
-      } else {
-#pragma unroll
-        for (int i = 0; i < 8; ++i) v[i] = 0.0f;
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+      if (tr.ok[half] && k < k_end) {
+        const float4* src = reinterpret_cast<const float4*>(o.ptr + tr.off[half] + k);
+        a = __ldg(src);
+        b = __ldg(src + 1);
       }
-      tc::store_group(img, kGemmHalf, rl, g, v);
+      v[8 * half + 0] = a.x; v[8 * half + 1] = a.y; v[8 * half + 2] = a.z; v[8 * half + 3] = a.w;
+      v[8 * half + 4] = b.x; v[8 * half + 5] = b.y; v[8 * half + 6] = b.z; v[8 * half + 7] = b.w;
     }
   } else {
-    // lanes along r: warp w covers rows 32 (w & 3) .. +31 and the column groups 2 (w >> 2), 2 (w >> 2) + 1
-    const int rl = 32 * (warp & 3) + lane, r = r0 + rl;
+    // lanes along r; rows beyond the tile are clamped (their values are zeroed by store_tile's caller via `rok`), full
+    // chunks take a branch-free path with one IMAD.WIDE per address
+    const int r = min(r0 + 32 * (warp & 3) + lane, r_end - 1);
+    const int kb = k0 + 16 * (warp >> 2);
+    const char* const base = reinterpret_cast<const char*>(o.ptr + r);
+    const long long ldb = o.ld * 4;
+    if (k0 + kGemmKC <= k_end) {
+      if (o.idx) {
+        int rows[16];
 #pragma unroll
-    for (int gg = 0; gg < 2; ++gg) {
-      const int g = 2 * (warp >> 2) + gg;
-      float v[8];
+        for (int i = 0; i < 16; ++i) rows[i] = __ldg(o.idx + kb + i);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int k = k0 + 8 * g + i;
-        float x = 0.0f;
-        if (r < r_end && k < k_end) {
-          const long long row = o.idx ? (long long)__ldg(o.idx + k) : (long long)k;
-          x = __ldg(o.ptr + row * o.ld + r) * scale;
-        }
-        v[i] = x;
+        for (int i = 0; i < 16; ++i) v[i] = __ldg(reinterpret_cast<const float*>(base + rows[i] * ldb));
+      } else {
+        const char* q = base + kb * ldb;
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __ldg(reinterpret_cast<const float*>(q + i * ldb));
       }
-      tc::store_group(img, kGemmHalf, rl, g, v);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const int k = kb + i;
+        v[i] = 0.0f;
+        if (k < k_end) v[i] = __ldg(reinterpret_cast<const float*>(base + (o.idx ? (long long)__ldg(o.idx + k) : (long long)k) * ldb));
+      }
     }
   }
 }
 
-__global__ void __launch_bounds__(kGemmThreads, 2) k_gemm_tc(const GemmP p) {
+__device__ __forceinline__ void store_tile(unsigned char* img, int trans, float scale, int warp, int lane, const float (&v)[16]) {
+  // scale == 0 marks a thread whose trans-1 row lies beyond the tile (its clamped loads are discarded)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    float w[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) w[i] = v[8 * h + i] * scale;
+    if (trans == 0) tc::store_group(img, kGemmHalf, 16 * warp + 8 * h + (lane & 7), lane >> 3, w);
+    else tc::store_group(img, kGemmHalf, 32 * (warp & 3) + lane, 2 * (warp >> 2) + h, w);
+  }
+}
+
+__global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
   using namespace tc;
   extern __shared__ __align__(1024) unsigned char smem[];
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);   // [0..1] stage free, [2] done
@@ -129,26 +163,43 @@ __global__ void __launch_bounds__(kGemmThreads, 2) k_gemm_tc(const GemmP p) {
   const int c_begin = blockIdx.z * cps, c_end = min(chunks_total, c_begin + cps);
   if (c_begin >= c_end) return;                                   // uniform over the CTA
 
+  const bool dbg = p.dbg != nullptr && tid == 0 && blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0;
+  int di = 0;
+  if (dbg) p.dbg[di++] = clock64();
   if (tid == 0) {
     mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 128);
+  // the first chunk's operands are requested before the allocation barrier
+  const TileRows ra = tile_rows(p.A, m0, p.M, warp, lane), rb = tile_rows(p.B, n0, p.N, warp, lane);
+  float va[16], vb[16];
+  load_tile(va, p.A, ra, m0, p.M, c_begin * kGemmKC, p.K, warp, lane);
+  load_tile(vb, p.B, rb, n0, p.N, c_begin * kGemmKC, p.K, warp, lane);
+  const float sa = operand_scale(p.A), sb = operand_scale(p.B);
+  // a trans-1 thread whose row lies beyond the tile loads a clamped row and stores zeros
+  const float sa_t = (p.A.trans && m0 + 32 * (warp & 3) + lane >= p.M) ? 0.0f : sa;
+  const float sb_t = (p.B.trans && n0 + 32 * (warp & 3) + lane >= p.N) ? 0.0f : sb;
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const float sa = operand_scale(p.A), sb = operand_scale(p.B);
+  if (dbg) p.dbg[di++] = clock64();            // [1] after TMEM allocation
 
   for (int c = c_begin; c < c_end; ++c) {
     const int it = c - c_begin, st = it & 1;
     if (it >= kGemmStages) mbar_wait(&bars[st], ((it >> 1) - 1) & 1, err);      // the MMAs that read this stage are done
     unsigned char* const stage = smem + st * kGemmStageBytes;
-    const int k0 = c * kGemmKC;
-    build_tile(stage, p.A, m0, p.M, k0, p.K, sa, warp, lane);
-    build_tile(stage + 2 * kGemmHalf, p.B, n0, p.N, k0, p.K, sb, warp, lane);
+    store_tile(stage, p.A.trans, sa_t, warp, lane, va);
+    store_tile(stage + 2 * kGemmHalf, p.B.trans, sb_t, warp, lane, vb);
+    if (c + 1 < c_end) {                       // next chunk's loads fly under the barrier, the MMAs and the next wait
+      load_tile(va, p.A, ra, m0, p.M, (c + 1) * kGemmKC, p.K, warp, lane);
+      load_tile(vb, p.B, rb, n0, p.N, (c + 1) * kGemmKC, p.K, warp, lane);
+    }
+    if (dbg && di < 40) p.dbg[di++] = clock64();          // after the build of this chunk (thread 0's part)
     fence_proxy_async();
     __syncthreads();
+    if (dbg && di < 40) p.dbg[di++] = clock64();          // after the barrier
     if (tid == 0) {
       tc_fence_after();
       const uint32_t a = smem_u32(stage), b = a + 2 * kGemmHalf;
@@ -157,37 +208,51 @@ __global__ void __launch_bounds__(kGemmThreads, 2) k_gemm_tc(const GemmP p) {
       if (c + 1 == c_end) tc_commit(&bars[2]);
     }
   }
+  if (dbg) p.dbg[di++] = clock64();            // all chunks issued
   mbar_wait(&bars[2], 0, err);
   tc_fence_after();
+  if (dbg) p.dbg[di++] = clock64();            // accumulator complete
 
-  // ---- epilogue: warp w reads TMEM lanes 32 (w & 3) .. +31 (rows) and columns 64 (w >> 2) .. +63
-  const int m = m0 + 32 * (warp & 3) + lane;
-  const float unscale = p.alpha / (sa * sb);
-  const bool add_bias = p.bias != nullptr && blockIdx.z == 0;
-  const long long crow = (m < p.M) ? (p.c_idx ? (long long)__ldg(p.c_idx + m) : (long long)m) : 0;
+  // ---- epilogue.  Warp w owns TMEM lanes 32 (w & 3) .. +31 (rows) and columns 64 (w >> 2) .. +63; its [32 x 64] block goes
+  // through a warp-private 8 KB piece of the (now idle) operand ring so that global rows are written 256 contiguous bytes at
+  // a time: element (row r, float4 slot j) sits at r * 256 + ((j ^ (r & 15)) * 16) - conflict-free both ways.
+  {
+    float4* const tile = reinterpret_cast<float4*>(smem + warp * 8192);
+    const float unscale = p.alpha / (sa * sb);
 #pragma unroll 1
-  for (int blk = 0; blk < 2; ++blk) {
-    const int cn = 64 * (warp >> 2) + 32 * blk;
-    float v[32];
-    tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + cn, v);
-    if (m < p.M) {
-      float* dst = p.C + crow * p.ldc + n0 + cn;
+    for (int blk = 0; blk < 2; ++blk) {
+      float v[32];
+      tmem_ld32(tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 64 * (warp >> 2) + 32 * blk, v);
 #pragma unroll
-      for (int i = 0; i < 32; ++i) {
-        const int n = n0 + cn + i;
-        if (n < p.N) {
-          float r = v[i] * unscale;
-          if (add_bias) r += __ldg(p.bias + n);
-          if (p.mode == GEMM_STORE) dst[i] = r;
-          else if (p.mode == GEMM_ACCUM) dst[i] += r;
-          else atomicAdd(dst + i, r);
-        }
+      for (int q = 0; q < 8; ++q)
+        tile[lane * 16 + ((8 * blk + q) ^ (lane & 15))] =
+            make_float4(v[4 * q] * unscale, v[4 * q + 1] * unscale, v[4 * q + 2] * unscale, v[4 * q + 3] * unscale);
+    }
+    __syncwarp();
+    const int j = lane & 15;
+    const int n = n0 + 64 * (warp >> 2) + 4 * j;
+    float4 bias = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (p.bias != nullptr && blockIdx.z == 0 && n < p.N) bias = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+#pragma unroll 4
+    for (int i = 0; i < 16; ++i) {
+      const int r = 2 * i + (lane >> 4);
+      const int m = m0 + 32 * (warp & 3) + r;
+      if (m < p.M && n < p.N) {
+        float4 x = tile[r * 16 + (j ^ (r & 15))];
+        x.x += bias.x; x.y += bias.y; x.z += bias.z; x.w += bias.w;
+        const long long crow = p.c_idx ? (long long)__ldg(p.c_idx + m) : (long long)m;
+        float4* dst = reinterpret_cast<float4*>(p.C + crow * p.ldc + n);
+        if (p.mode == GEMM_STORE) *dst = x;
+        else if (p.mode == GEMM_ACCUM) { const float4 o = *dst; *dst = make_float4(o.x + x.x, o.y + x.y, o.z + x.z, o.w + x.w); }
+        else atomicAdd(dst, x);
       }
     }
   }
+  if (dbg) p.dbg[di++] = clock64();            // epilogue done
   tc_fence_before();
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128);
+  if (dbg) { p.dbg[di++] = clock64(); p.dbg[63] = di; }
 }
 
 }  // namespace train

@@ -7,6 +7,9 @@
     frames of its molecules (torchdiffeq's RMS norm couples the whole batch).
  2. reweighting partial sums + one fp64 all-reduce == the unsharded statistics; all-gather of the final samples.
  3. the IQR outlier mask from GLOBAL percentiles (sensititvity.py:4-12) == the mask computed on the gathered vector.
+ 4. data-parallel training (train_ambient.Trainer(data_parallel=True)): every rank computes the gradient of its own batch,
+    ONE NCCL all-reduce averages the flat gradient vector, every rank applies the same clipped Adam step - the weights after
+    two steps equal (a) each other on all ranks and (b) a single-process run that averages the per-rank gradients itself.
 Exit code 0 = all checks passed on every rank."""
 import os
 import sys
@@ -64,6 +67,40 @@ def main():
     q25, q75 = torch.quantile(w, torch.tensor([0.25, 0.75], dtype=torch.float64)).tolist()
     keep_ref = (w > q25 - 3 * (q75 - q25)) & (w < q75 + 3 * (q75 - q25))
     ok &= torch.equal(keep_local.cpu(), keep_ref[lo:hi]) and not bool(keep_ref[3])
+    # ---- 4. data-parallel training step
+    from thermodynamic_interpolation_b200.ambient.interpolants import LinearInterpolant
+    from thermodynamic_interpolation_b200.batch import synthetic_train_batches
+    from thermodynamic_interpolation_b200.train_ambient import Trainer
+    ip = LinearInterpolant(a=1, gamma="sin2")
+
+    def draws(r, step, n_mol=16):
+        g = torch.Generator().manual_seed(100 * r + step)
+        return torch.rand(n_mol, generator=g).repeat_interleave(9).reshape(-1, 1), torch.randn(n_mol * 9, 3, generator=g)
+
+    batches = [synthetic_train_batches(16, 9, seed=50 + r) for r in range(world)]
+    dp = Trainer(seeded_ambient_model(128, 2, 100, seed=3).to(dev), ip, data_parallel=True)
+    solo = Trainer(seeded_ambient_model(128, 2, 100, seed=3).to(dev), ip)
+    err_g = 0.0
+    for step in range(2):
+        t, z = draws(rank, step)
+        dp.step(*batches[rank], t=t, z=z)
+        grads = []
+        for r in range(world):                       # the same thing without NCCL: every rank's gradient, averaged by hand
+            t, z = draws(r, step)
+            grads.append(solo.loss_and_grad(*batches[r], t=t, z=z)[1])
+        mean_g = torch.stack(grads).mean(0)
+        if step == 0:                                # identical weights so far: the all-reduced gradient must equal the hand average
+            err_g = float((dp.last_grad - mean_g).abs().max() / mean_g.abs().max())
+        solo.apply(mean_g)
+    gathered_w = [torch.empty_like(dp.weights) for _ in range(world)]
+    dist.all_gather(gathered_w, dp.weights)
+    same_w = all(torch.equal(gathered_w[0], w_) for w_ in gathered_w)
+    err_w = float((dp.weights - solo.weights).abs().max())
+    print(f"[nccl rank {rank}] data-parallel training: replicas identical {same_w}, all-reduced gradient vs hand average {err_g:.2e}, "
+          f"weights after 2 steps {err_w:.2e}", flush=True)
+    # Adam normalises every element by its own magnitude, so elements whose gradient is at rounding level (the split-K sums are
+    # atomic: their order differs from run to run) may move by up to lr per step in either run: the weight bound is 2 lr + slack
+    ok &= same_w and err_g < 1e-5 and err_w < 2.5e-4
     flag = torch.tensor([1 if ok else 0], device=dev)
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
