@@ -175,16 +175,20 @@ __global__ void k_tr_gather_rows(long long rows, int F, const int* __restrict__ 
   out[i] = table[sr * F + f];
 }
 // grad_table[idx[r]] += d[r]  for a table with few rows (edge / atom embeddings): block-local sums in shared memory first
+// (shared-memory atomics: several rows of the block may hit the same table row), then one global atomic per entry and block
 __global__ void k_tr_scatter_rows(long long rows, int F, int table_rows, const int* __restrict__ idx, const float* __restrict__ d,
                                   float* __restrict__ grad_table) {
   extern __shared__ float acc[];                      // [table_rows][F]
   for (int i = threadIdx.x; i < table_rows * F; i += blockDim.x) acc[i] = 0.0f;
   __syncthreads();
+  const int lanes_per_row = F < (int)blockDim.x ? F : (int)blockDim.x, rows_per_it = blockDim.x / lanes_per_row;
+  const int f0 = threadIdx.x % lanes_per_row, rsub = threadIdx.x / lanes_per_row;
   const long long per = (rows + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = min(rows, r0 + per);
-  for (long long r = r0; r < r1; ++r) {
-    const int tr = idx[r];
-    for (int f = threadIdx.x; f < F; f += blockDim.x) acc[tr * F + f] += d[r * F + f];      // one thread per column: no race
-  }
+  if (rsub < rows_per_it)
+    for (long long r = r0 + rsub; r < r1; r += rows_per_it) {
+      const int tr = idx[r];
+      for (int f = f0; f < F; f += lanes_per_row) atomicAdd(&acc[tr * F + f], d[r * F + f]);
+    }
   __syncthreads();
   for (int i = threadIdx.x; i < table_rows * F; i += blockDim.x)
     if (acc[i] != 0.0f) atomicAdd(&grad_table[i], acc[i]);
@@ -221,10 +225,11 @@ __global__ void k_tr_ln_silu_fwd(long long R, int F, float* __restrict__ zn, flo
 
 // dh [R][F] (gradient wrt h) -> dz in place (gradient wrt the Linear output); accumulates d gamma, d beta, d bias
 // (= column sums of dz) with one atomic per column and block; records |max| of dz.
-__global__ void k_tr_ln_silu_bwd(long long R, int F, float* __restrict__ dh, const float* __restrict__ nrm, const float* __restrict__ rstd,
-                                 const float* __restrict__ gamma, const float* __restrict__ beta, float* __restrict__ g_gamma,
-                                 float* __restrict__ g_beta, float* __restrict__ g_bias, float* amax) {
-  constexpr int KM = 8;                                 // columns per lane: F <= 256
+template <int KM>                                       // columns per lane: F <= 32 KM
+__global__ void __launch_bounds__(256, 4) k_tr_ln_silu_bwd(long long R, int F, float* __restrict__ dh, const float* __restrict__ nrm,
+                                                           const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                                           const float* __restrict__ beta, float* __restrict__ g_gamma,
+                                                           float* __restrict__ g_beta, float* __restrict__ g_bias, float* amax) {
   extern __shared__ float sacc[];                       // [3][F]
   for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) sacc[i] = 0.0f;
   __syncthreads();
@@ -287,14 +292,21 @@ __global__ void k_tr_ln_silu_bwd(long long R, int F, float* __restrict__ dh, con
   }
 }
 
-// out[c] += sum_r d[r][c]   (bias gradient of an output Linear); also records |max| of d
+// out[c] += sum_r d[r][c]   (bias gradient of an output Linear); also records |max| of d.  grid = (column blocks, row slabs)
 __global__ void k_tr_colsum(long long R, int C, const float* __restrict__ d, float* __restrict__ out, float* amax) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const long long per = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(R, r0 + per);
-  float acc = 0.0f, mx = 0.0f;
-  if (c < C)
-    for (long long r = r0; r < r1; ++r) { const float v = d[r * C + c]; acc += v; mx = fmaxf(mx, fabsf(v)); }
-  if (c < C && acc != 0.0f) atomicAdd(&out[c], acc);
+  float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mx = 0.0f;
+  if (c < C) {
+    long long r = r0;
+    for (; r + 4 <= r1; r += 4) {                        // four independent loads in flight per thread
+#pragma unroll
+      for (int u = 0; u < 4; ++u) { const float v = __ldg(d + (r + u) * C + c); acc[u] += v; mx = fmaxf(mx, fabsf(v)); }
+    }
+    for (; r < r1; ++r) { const float v = __ldg(d + r * C + c); acc[0] += v; mx = fmaxf(mx, fabsf(v)); }
+    const float tot = (acc[0] + acc[1]) + (acc[2] + acc[3]);
+    if (tot != 0.0f) atomicAdd(&out[c], tot);
+  }
   warp_amax(amax, mx);
 }
 

@@ -37,10 +37,23 @@ int fail(const char* fmt, ...) {
   return tib_internal::set_error(buf);
 }
 
-struct Prof {      // tib_profile_begin / tib_profile_end: device time per kernel class
+thread_local long long g_trace_rows = 0;      // row count of the MLP being processed (trace labels only)
+struct Prof {      // tib_profile_begin / tib_profile_end: device time per kernel class; TIB_TRAIN_TRACE: per-launch times on stderr
   void* h;
-  Prof(int kind, cudaStream_t st) : h(tib_internal::prof_open(kind, st)) {}
-  ~Prof() { if (h) tib_internal::prof_close(h); }
+  const char* name; cudaStream_t st; cudaEvent_t e0 = nullptr, e1 = nullptr;
+  static bool tracing() { static const bool t = getenv("TIB_TRAIN_TRACE") != nullptr; return t; }
+  Prof(int kind, cudaStream_t s, const char* nm = nullptr) : h(tib_internal::prof_open(kind, s)), name(nm), st(s) {
+    if (name && tracing()) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(st); cudaEventRecord(e0, st); }
+  }
+  ~Prof() {
+    if (h) tib_internal::prof_close(h);
+    if (e0) {
+      float ms = 0.0f;
+      cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
+      fprintf(stderr, "[kern] %s_rows%lld  %.1f us\n", name, g_trace_rows, ms * 1e3);
+      cudaEventDestroy(e0); cudaEventDestroy(e1);
+    }
+  }
 };
 thread_local double g_gemm_flops = 0.0;
 thread_local long long* g_gemm_dbg = nullptr;      // device buffer [64] when tib_gemm_debug is on
@@ -116,7 +129,7 @@ struct Ws {
   float *s_last, *v_last, *e_spare;
   MlpAct ro;
   // backward
-  float *ds, *dv, *de, *dv_src, *d_phi3, *d_w3, *d_gac, *d_uvvv, *dq, *dA, *dB, *ds0, *dX0;
+  float *ds, *dv, *de, *dv_src, *d_phi3, *d_w3, *d_gac, *d_uvvv, *dq, *dA, *dB, *dAw, *dBw, *ds0, *dX0;
   size_t bytes;
 };
 
@@ -154,7 +167,7 @@ size_t layout(Ws& w, char* base, const tib_model_desc& d, int n_temp, long long 
   mlp(w.ro, N2, 0);
   w.ds = tf(N2 * F); w.dv = tf(N2 * 3 * F); w.de = tf(E2 * F); w.dv_src = tf(N2 * 3 * F);
   w.d_phi3 = tf(E2 * 5 * F); w.d_w3 = tf(P2 * 5 * F); w.d_gac = tf(N2 * 3 * F); w.d_uvvv = tf(N2 * 3 * 2 * F); w.dq = tf(N2 * F);
-  w.dA = tf(E2 * F); w.dB = tf(E2 * F); w.ds0 = tf(N * F); w.dX0 = tf(N * F);
+  w.dA = tf(E2 * F); w.dB = tf(E2 * F); w.dAw = tf(P2 * F); w.dBw = tf(P2 * F); w.ds0 = tf(N * F); w.dX0 = tf(N * F);
   w.bytes = off;
   return off;
 }
@@ -162,13 +175,88 @@ size_t layout(Ws& w, char* base, const tib_model_desc& d, int n_temp, long long 
 // ---- launch helpers ---------------------------------------------------------------------------------------------------------------
 bool g_gemm_attr[64] = {};     // opt-in shared-memory size set, per device
 
+thread_local std::vector<cudaEvent_t> g_events;     // reused by every call of this thread (no timing)
+thread_local cudaStream_t g_side[64] = {};          // the side stream of each device
+
+// Launch context.  `st` is the stream the helpers launch on: the caller's stream, or - between to_side() and to_main() -
+// the library's side stream, where everything that is off the critical path of the backward pass runs (weight-gradient
+// GEMMs, bias column sums, the whole w MLP): at 256 molecules most kernels of the main chain fill a fraction of the GPU.
+// Buffers the side stream still reads are tracked, and the main stream waits before it overwrites one.
 struct Ctx {
-  cudaStream_t st;
+  cudaStream_t st, main, side;
+  int depth;         // nesting of to_side()
   int n_sms;
   int* err;          // device error word (bounded mbarrier waits)
   float* amax; int n_amax, next_amax;
+  size_t next_ev;
+  struct Pending { const void* ptr; cudaEvent_t ev; } pend[16];
+  int n_pend;
   float* new_amax() { return next_amax < n_amax ? amax + next_amax++ : nullptr; }
+  bool two_streams() const { return side != main; }
+  cudaEvent_t new_event() {
+    if (next_ev == g_events.size()) {
+      cudaEvent_t e = nullptr;
+      if (cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) return nullptr;
+      g_events.push_back(e);
+    }
+    return g_events[next_ev++];
+  }
+  // order `to` after everything enqueued on `from` so far
+  int order(cudaStream_t from, cudaStream_t to) {
+    cudaEvent_t e = new_event();
+    if (!e) return fail("cudaEventCreate failed");
+    CUDA_TRY(cudaEventRecord(e, from));
+    CUDA_TRY(cudaStreamWaitEvent(to, e, 0));
+    return 0;
+  }
+  int to_side() {
+    if (!two_streams()) return 0;
+    if (depth++ == 0) { TRY(order(main, side)); st = side; }
+    return 0;
+  }
+  void to_main() {
+    if (!two_streams()) return;
+    if (--depth == 0) st = main;
+  }
+  // the side stream has enqueued its last read of `ptr`
+  int side_done(const void* ptr) {
+    if (!two_streams()) return 0;
+    cudaEvent_t e = new_event();
+    if (!e) return fail("cudaEventCreate failed");
+    CUDA_TRY(cudaEventRecord(e, side));
+    for (int i = 0; i < n_pend; ++i)
+      if (pend[i].ptr == ptr) { pend[i].ev = e; return 0; }
+    if (n_pend == 16) return fail("internal: too many buffers pending on the side stream");
+    pend[n_pend++] = {ptr, e};
+    return 0;
+  }
+  // the main stream is about to overwrite `ptr`
+  int before_write(const void* ptr) {
+    if (!two_streams() || st != main) return 0;
+    for (int i = 0; i < n_pend; ++i)
+      if (pend[i].ptr == ptr) {
+        CUDA_TRY(cudaStreamWaitEvent(main, pend[i].ev, 0));
+        pend[i] = pend[--n_pend];
+        return 0;
+      }
+    return 0;
+  }
+  int join() { return two_streams() ? order(side, main) : 0; }
 };
+
+int make_ctx(Ctx& c, cudaStream_t st, int* err, float* amax, int n_amax) {
+  c = Ctx{};
+  c.st = c.main = c.side = st; c.err = err; c.amax = amax; c.n_amax = n_amax;
+  int dev = 0;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, dev));
+  static const bool one_stream = getenv("TIB_TRAIN_NO_SIDE_STREAM") != nullptr || getenv("TIB_TRAIN_TRACE") != nullptr;
+  if (!one_stream && dev >= 0 && dev < 64) {
+    if (!g_side[dev]) CUDA_TRY(cudaStreamCreateWithFlags(&g_side[dev], cudaStreamNonBlocking));
+    c.side = g_side[dev];
+  }
+  return 0;
+}
 
 GemmOperand op(const float* ptr, long long ld, int trans, float scale, const float* amax = nullptr, const int* idx = nullptr) {
   GemmOperand o{};
@@ -223,6 +311,7 @@ struct Seg { const float* ptr; long long ld; const int* idx; int width; float sc
 // Linear -> LN -> SiLU -> Linear -> LN -> SiLU [-> Linear]   (embedding.py:26-34)
 int mlp_forward(Ctx& c, const float* W, const MlpOff& m, int F, const Seg* segs, int n_seg, MlpAct& a, bool with_out) {
   const int R = (int)a.rows;
+  g_trace_rows = R;
   int k0 = 0;
   for (int s = 0; s < n_seg; ++s) {
     TRY(gemm(c, R, F, segs[s].width, op(segs[s].ptr, segs[s].ld, 0, segs[s].scale, nullptr, segs[s].idx),
@@ -230,11 +319,11 @@ int mlp_forward(Ctx& c, const float* W, const MlpOff& m, int F, const Seg* segs,
     k0 += segs[s].width;
   }
   const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 16);
-  { Prof pf(TIB_K_TRAIN_OTHER, c.st);
+  { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
   k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1);
   LAUNCH_CHECK(); }
   TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2));
-  { Prof pf(TIB_K_TRAIN_OTHER, c.st);
+  { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
   k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2);
   LAUNCH_CHECK(); }
   if (with_out) TRY(gemm(c, R, m.n_out, F, op(a.h2, F, 0, 1.0f), op(W + m.W3, F, 0, 1.0f), a.out, m.n_out, GEMM_STORE, W + m.b3));
@@ -248,29 +337,47 @@ struct SegGrad { float* ptr; long long ld; int mode; const int* c_idx; };   // p
 int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const Seg* segs, const SegGrad* sg, int n_seg,
                  const MlpAct& a, const float* dY, const float* amax_dY, float* dA, float* dB) {
   const int R = (int)a.rows;
-  const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 8);
+  g_trace_rows = R;
+  constexpr int kLnBwdThreads = 256;
+  const int ln_blocks = std::min(blocks_for(R, kLnBwdThreads / 32), 4 * c.n_sms);
+  auto ln_bwd = F <= 128 ? k_tr_ln_silu_bwd<4> : k_tr_ln_silu_bwd<8>;      // <= 64 registers: 32 warps per SM
   const size_t ln_smem = 3 * (size_t)F * sizeof(float);
   if (dY) {
+    TRY(c.to_side());
     TRY(gemm(c, m.n_out, F, R, op(dY, m.n_out, 1, 1.0f, amax_dY), op(a.h2, F, 1, 1.0f), G + m.W3, F, GEMM_ATOMIC, nullptr, nullptr, true));
-    { Prof pf(TIB_K_TRAIN_OTHER, c.st);
-    k_tr_colsum<<<dim3((m.n_out + kEW - 1) / kEW, std::min(blocks_for(R, 64), 256)), kEW, 0, c.st>>>(R, m.n_out, dY, G + m.b3, nullptr);
+    { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_colsum");
+    k_tr_colsum<<<dim3((m.n_out + kEW - 1) / kEW, std::min(blocks_for(R, 32), 512)), kEW, 0, c.st>>>(R, m.n_out, dY, G + m.b3, nullptr);
     LAUNCH_CHECK(); }
+    TRY(c.side_done(dY));
+    c.to_main();
+    TRY(c.before_write(dA));
     TRY(gemm(c, R, F, m.n_out, op(dY, m.n_out, 0, 1.0f, amax_dY), op(W + m.W3, F, 1, 1.0f), dA, F, GEMM_STORE));
   }
   float* am2 = c.new_amax();
-  { Prof pf(TIB_K_TRAIN_OTHER, c.st);
-  k_tr_ln_silu_bwd<<<ln_blocks, kEW, ln_smem, c.st>>>(R, F, dA, a.n2, a.r2, W + m.g2, W + m.be2, G + m.g2, G + m.be2, G + m.b2, am2);
+  { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_bwd");
+  ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dA, a.n2, a.r2, W + m.g2, W + m.be2, G + m.g2, G + m.be2, G + m.b2, am2);
   LAUNCH_CHECK(); }
+  TRY(c.to_side());
   TRY(gemm(c, F, F, R, op(dA, F, 1, 1.0f, am2), op(a.h1, F, 1, 1.0f), G + m.W2, F, GEMM_ATOMIC, nullptr, nullptr, true));
+  TRY(c.side_done(dA));
+  c.to_main();
+  TRY(c.before_write(dB));
   TRY(gemm(c, R, F, F, op(dA, F, 0, 1.0f, am2), op(W + m.W2, F, 1, 1.0f), dB, F, GEMM_STORE));
   float* am1 = c.new_amax();
-  { Prof pf(TIB_K_TRAIN_OTHER, c.st);
-  k_tr_ln_silu_bwd<<<ln_blocks, kEW, ln_smem, c.st>>>(R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1);
+  { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_bwd");
+  ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1);
   LAUNCH_CHECK(); }
+  TRY(c.to_side());
   int k0 = 0;
   for (int s = 0; s < n_seg; ++s) {
     TRY(gemm(c, F, segs[s].width, R, op(dB, F, 1, 1.0f, am1), op(segs[s].ptr, segs[s].ld, 1, segs[s].scale, nullptr, segs[s].idx),
              G + m.W1 + k0, m.k_in, GEMM_ATOMIC, nullptr, nullptr, true));
+    k0 += segs[s].width;
+  }
+  TRY(c.side_done(dB));
+  c.to_main();
+  k0 = 0;
+  for (int s = 0; s < n_seg; ++s) {
     if (sg && sg[s].ptr)
       TRY(gemm(c, R, segs[s].width, F, op(dB, F, 0, 1.0f, am1), op(W + m.W1 + k0, m.k_in, 1, 1.0f), sg[s].ptr, sg[s].ld, sg[s].mode,
                nullptr, sg[s].c_idx));
@@ -319,8 +426,7 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     g_dev_err_device = dev;
   }
   Ctx c{};
-  c.st = st; c.err = g_dev_err; c.amax = w.amax; c.n_amax = w.n_amax; c.next_amax = 0;
-  CUDA_TRY(cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, dev));
+  TRY(make_ctx(c, st, g_dev_err, w.amax, w.n_amax));
   const float* W = weights;
   float* G = grad;
 
@@ -330,34 +436,34 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), st));
 
   // ---- interpolant, targets, graph (interpolants.py:16-33; losses.py:52-57; graph.py:27-29) -----------------------------------------
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_interp");
   k_tr_interp<<<std::min(blocks_for(N, kEW), c.n_sms * 4), kEW, 0, st>>>((int)N, b->x0, b->x1, b->t, b->z, ip->gamma_kind, ip->a, w.xt, w.tgt, w.colsum);
   LAUNCH_CHECK(); }
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_center");
   k_tr_center<<<blocks_for(6 * N, kEW), kEW, 0, st>>>((int)N, w.xt, w.colsum);
   LAUNCH_CHECK(); }
   GraphP gp{b->n_mol, (int)N, E, b->mol_ptr, (const long long*)b->edge_ptr, b->edge_type, w.xt, w.src, w.dst, w.pair, w.etype, w.in_ptr,
             w.dir, w.pair_dist};
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_graph");
   k_tr_graph<<<dim3(b->n_mol, 2), kEW, 0, st>>>(gp);
   LAUNCH_CHECK(); }
 
   // ---- embeddings (embedding.py:68-86,249-261; cpainn.py:70-71): x-independent, shared by both passes ------------------------------
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_embed_in");
   k_tr_embed_in<<<(int)N, kEW, 0, st>>>((int)N, F, n_temp, b->atom_id, b->temp0, b->temp1, b->t, W + o.atom_emb, desc->temp_mean,
                                         desc->temp_range, desc->temp_length, desc->time_length, w.X0);
   LAUNCH_CHECK(); }
   const Seg seg_emb[1] = {{w.X0, (2 + n_temp) * F, nullptr, (2 + n_temp) * F, 1.0f}};
   TRY(mlp_forward(c, W, o.combine, F, seg_emb, 1, w.emb, true));
   LayerAct& A0 = w.layers[0];
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_gather_rows");
   k_tr_gather_rows<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2, F, nullptr, (int)N, w.s0, A0.s_in);
   LAUNCH_CHECK(); }
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_gather_rows");
   k_tr_gather_rows<<<blocks_for(E2 * F, kEW), kEW, 0, st>>>(E2, F, w.etype, 0, W + o.edge_emb, A0.e_in);
   LAUNCH_CHECK(); }
   CUDA_TRY(cudaMemsetAsync(A0.v_in, 0, sizeof(float) * N2 * 3 * F, st));
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_pair_pe");
   k_tr_pair_pe<<<blocks_for(P2 * (F / 2), kEW), kEW, 0, st>>>(P2, F, w.pair_dist, desc->length_scale, w.pe);
   LAUNCH_CHECK(); }
 
@@ -369,21 +475,25 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     float* s_next = l + 1 < L ? w.layers[l + 1].s_in : w.s_last;
     float* v_next = l + 1 < L ? w.layers[l + 1].v_in : w.v_last;
     float* e_next = l + 1 < L ? w.layers[l + 1].e_in : w.e_spare;
+    // the w MLP needs only the pair distances: it runs beside the phi MLP
     const Seg seg_w[1] = {{w.pe, F, nullptr, F, 1.0f}};
+    TRY(c.to_side());
     TRY(mlp_forward(c, W, lo.w, F, seg_w, 1, a.w, true));
+    c.to_main();
     const Seg seg_phi[2] = {{a.s_in, F, w.src, F, kStateScale}, {a.e_in, F, nullptr, F, kStateScale}};
     TRY(mlp_forward(c, W, lo.phi, F, seg_phi, 2, a.phi, true));
+    TRY(c.join());
     CombineP cp{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next};
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_combine_fwd");
     k_tr_combine_fwd<<<node_blocks, kEW, 0, st>>>(cp);
     LAUNCH_CHECK(); }
     TRY(gemm(c, (int)(3 * N2), 2 * F, F, op(a.v_mid, F, 0, kStateScale), op(W + lo.UV, F, 0, 1.0f), a.uvvv, 2 * F, GEMM_STORE));
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_q");
     k_tr_upd_q<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q);
     LAUNCH_CHECK(); }
     const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
     TRY(mlp_forward(c, W, lo.upd, F, seg_upd, 2, a.upd, true));
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_apply");
     k_tr_upd_apply<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, a.s_mid, a.v_mid, s_next, v_next);
     LAUNCH_CHECK(); }
   }
@@ -395,7 +505,7 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   float* bout = out_b ? out_b : w.dX0;      // dX0 is free until the very end ([N][F] >= [2N][3] for F >= 32)
   ReadoutP rp{(int)N2, F, (int)N, w.ro.h2, w.v_last, W + o.readout.W3, W + o.readout.b3, W + o.Vout, w.tgt, bout, w.gate, loss,
               w.dA, w.dv, G + o.readout.W3, G + o.readout.b3, G + o.Vout, am_ro};
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_readout");
   k_tr_readout<<<std::min(blocks_for(N2, 4), c.n_sms * 4), kEW, 2 * F * sizeof(float), st>>>(rp);
   LAUNCH_CHECK(); }
 
@@ -412,20 +522,27 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     const LayerOff& lo = o.layers[l];
     // Update (cpainn.py:345-376)
     float* am_gac = c.new_amax();
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    TRY(c.before_write(w.d_gac));
+    TRY(c.before_write(w.d_uvvv));
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_bwd1");
     k_tr_upd_bwd1<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, w.ds, w.dv, w.d_gac, w.d_uvvv, w.dq, am_gac);
     LAUNCH_CHECK(); }
     const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
     const SegGrad sg_upd[2] = {{w.dq, F, GEMM_ACCUM, nullptr}, {w.ds, F, GEMM_ACCUM, nullptr}};
     TRY(mlp_backward(c, W, G, lo.upd, F, seg_upd, sg_upd, 2, a.upd, w.d_gac, am_gac, w.dA, w.dB));
     float* am_uv = c.new_amax();
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_bwd2");
     k_tr_upd_bwd2<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, w.dq, w.d_uvvv, am_uv);
     LAUNCH_CHECK(); }
+    TRY(c.to_side());
     TRY(gemm(c, 2 * F, F, (int)(3 * N2), op(w.d_uvvv, 2 * F, 1, 1.0f, am_uv), op(a.v_mid, F, 1, kStateScale), G + lo.UV, F, GEMM_ATOMIC,
              nullptr, nullptr, true));
+    TRY(c.side_done(w.d_uvvv));
+    c.to_main();
     TRY(gemm(c, (int)(3 * N2), F, 2 * F, op(w.d_uvvv, 2 * F, 0, 1.0f, am_uv), op(W + lo.UV, F, 1, 1.0f), w.dv, F, GEMM_ACCUM));
     // SE3Message (cpainn.py:263-310)
+    TRY(c.before_write(w.d_w3));
+    TRY(c.before_write(w.d_phi3));
     CUDA_TRY(cudaMemsetAsync(w.d_w3, 0, sizeof(float) * P2 * 5 * F, st));
     CUDA_TRY(cudaMemsetAsync(w.dv_src, 0, sizeof(float) * N2 * 3 * F, st));
     float* am_phi = c.new_amax();
@@ -433,26 +550,30 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     float* e_next = l + 1 < L ? w.layers[l + 1].e_in : w.e_spare;
     CombineBwdP cb{{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next},
                    w.ds, w.dv, w.de, w.d_phi3, w.d_w3, w.dv_src, am_phi, am_w};
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_combine_bwd");
     k_tr_combine_bwd<<<node_blocks, kEW, 0, st>>>(cb);
     LAUNCH_CHECK(); }
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_add");
     k_tr_add<<<blocks_for(N2 * 3 * F, kEW), kEW, 0, st>>>(N2 * 3 * F, w.dv, w.dv_src);
     LAUNCH_CHECK(); }
+    // the w MLP's adjoint produces weight gradients only: all of it runs on the side stream, with its own scratch
+    const Seg seg_w[1] = {{w.pe, F, nullptr, F, 1.0f}};
+    TRY(c.to_side());
+    TRY(mlp_backward(c, W, G, lo.w, F, seg_w, nullptr, 1, a.w, w.d_w3, am_w, w.dAw, w.dBw));
+    TRY(c.side_done(w.d_w3));
+    c.to_main();
     const Seg seg_phi[2] = {{a.s_in, F, w.src, F, kStateScale}, {a.e_in, F, nullptr, F, kStateScale}};
     const SegGrad sg_phi[2] = {{w.ds, F, GEMM_ATOMIC, w.src}, {w.de, F, GEMM_ACCUM, nullptr}};
     TRY(mlp_backward(c, W, G, lo.phi, F, seg_phi, sg_phi, 2, a.phi, w.d_phi3, am_phi, w.dA, w.dB));
-    const Seg seg_w[1] = {{w.pe, F, nullptr, F, 1.0f}};
-    TRY(mlp_backward(c, W, G, lo.w, F, seg_w, nullptr, 1, a.w, w.d_w3, am_w, w.dA, w.dB));
   }
   // embeddings: e0 = Emb4(edge_type), s0 = combine MLP (both passes share it), atom embedding
   {
     const int nb = std::min(blocks_for(E2, 32), c.n_sms * 8);
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_scatter_rows");
     k_tr_scatter_rows<<<nb, kEW, sizeof(float) * desc->n_edge_types * F, st>>>(E2, F, desc->n_edge_types, w.etype, w.de, G + o.edge_emb);
     LAUNCH_CHECK(); }
     float* am_s0 = c.new_amax();
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_fold_passes");
     k_tr_fold_passes<<<blocks_for(N * F, kEW), kEW, 0, st>>>(N * F, w.ds, w.ds0, am_s0);
     LAUNCH_CHECK(); }
     // weight gradients over all input columns; the input gradient only for the first F (the atom embedding) - the
@@ -461,11 +582,13 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     const Seg seg2[2] = {{w.X0, kin, nullptr, F, 1.0f}, {w.X0 + F, kin, nullptr, kin - F, 1.0f}};
     const SegGrad sg2[2] = {{w.dX0, F, GEMM_STORE, nullptr}, {nullptr, 0, 0, nullptr}};
     TRY(mlp_backward(c, W, G, o.combine, F, seg2, sg2, 2, w.emb, w.ds0, am_s0, w.dA, w.dB));
-    const int nb2 = std::min(blocks_for(N, 64), c.n_sms * 2);
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
-    k_tr_scatter_rows<<<nb2, kEW, sizeof(float) * desc->n_types * F, st>>>(N, F, desc->n_types, b->atom_id, w.dX0, G + o.atom_emb);
+    TRY(c.before_write(w.dX0));
+    const int nb2 = std::min(blocks_for(N, 64), c.n_sms);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_scatter_rows");
+    k_tr_scatter_rows<<<nb2, 1024, sizeof(float) * desc->n_types * F, st>>>(N, F, desc->n_types, b->atom_id, w.dX0, G + o.atom_emb);
     LAUNCH_CHECK(); }
   }
+  TRY(c.join());          // the caller's stream owns the complete gradient again
   return 0;
 }
 
@@ -509,12 +632,12 @@ int tib_adam_step(float* weights, const float* grad, float* m, float* v, size_t 
   CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double), st));
   const int nb = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
   if (max_grad_norm > 0.0f) {
-    { Prof pf(TIB_K_TRAIN_OTHER, st);
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_sqnorm");
     k_tr_sqnorm<<<nb, 256, 0, st>>>((long long)n, grad, scratch);
     LAUNCH_CHECK(); }
   }
   const double bc1 = 1.0 - std::pow((double)beta1, step), bc2 = 1.0 - std::pow((double)beta2, step);
-  { Prof pf(TIB_K_TRAIN_OTHER, st);
+  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_adam");
   k_tr_adam<<<nb, 256, 0, st>>>((long long)n, weights, grad, m, v, scratch, max_grad_norm, lr, beta1, beta2, eps, weight_decay,
                                 (float)bc1, (float)std::sqrt(bc2));
   LAUNCH_CHECK(); }
@@ -539,8 +662,8 @@ int tib_gemm_f16x3(int32_t M, int32_t N, int32_t K, const float* A, int64_t lda,
     g_dev_err_device = dev;
   }
   Ctx c{};
-  c.st = (cudaStream_t)stream; c.err = g_dev_err;
-  CUDA_TRY(cudaDeviceGetAttribute(&c.n_sms, cudaDevAttrMultiProcessorCount, dev));
+  TRY(make_ctx(c, (cudaStream_t)stream, g_dev_err, nullptr, 0));
+  c.side = c.main;
   return gemm(c, M, N, K, op(A, lda, trans_a, scale_a, amax_a, idx_a), op(B, ldb, trans_b, scale_b, nullptr, idx_b), C, ldc, mode, bias,
               c_idx, split_k != 0);
 }

@@ -41,6 +41,13 @@ def main():
     for k, (cnt, us, tf) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{us / 1e3:8.3f} ms {100 * us / tot:5.1f}%  {cnt:3d} x {us / cnt:7.1f} us  {tf:6.1f} TFLOP/s  {k}")
     print(f"{tot / 1e3:8.3f} ms in GEMMs per step ({n} molecules)")
+    agg2, tot2 = collections.OrderedDict(), 0.0
+    for m in re.finditer(r"\[kern\] (\w+)\s+([\d.]+) us", err):
+        a = agg2.setdefault(m.group(1), [0, 0.0])
+        a[0] += 1; a[1] += float(m.group(2)); tot2 += float(m.group(2))
+    for k, (cnt, us) in sorted(agg2.items(), key=lambda kv: -kv[1][1]):
+        print(f"{us / 1e3:8.3f} ms {100 * us / max(tot2, 1e-9):5.1f}%  {cnt:3d} x {us / cnt:7.1f} us  {k}")
+    print(f"{tot2 / 1e3:8.3f} ms in the other kernels per step")
 
 
 if __name__ == "__main__":
