@@ -1,5 +1,5 @@
 /*
- * tib.h - C ABI of libtib.so, the B200-native (sm_100a) sampling hot path of
+ * tib.h - C ABI of libtib.so, the B200-native (sm_100a) sampling hot path (and training step) of
  * olsson-group/thermodynamic-interpolation.
  *
  * The reference has no FFI of its own: its seams are three Python call signatures

@@ -274,3 +274,24 @@ def test_training_reduces_the_loss_and_rejects_bad_arguments():
     with pytest.raises(RuntimeError):
         from thermodynamic_interpolation_b200.train import TrainEngine
         TrainEngine(model.hyper, "cpu")
+
+
+def test_cuda_graph_replay_equals_eager_steps():
+    """Trainer(cuda_graph=True) replays the captured launches of both streams: same losses and weights as eager steps,
+    also when the batch changes between replays."""
+    from thermodynamic_interpolation_b200.ambient.interpolants import LinearInterpolant
+    from thermodynamic_interpolation_b200.batch import synthetic_train_batches
+    from thermodynamic_interpolation_b200.synthetic import seeded_ambient_model
+    from thermodynamic_interpolation_b200.train_ambient import Trainer
+    ip = LinearInterpolant(a=1, gamma="sin2")
+    eager = Trainer(seeded_ambient_model(128, 2, seed=5).to(DEV), ip)
+    graph = Trainer(seeded_ambient_model(128, 2, seed=5).to(DEV), ip, cuda_graph=True)
+    g = torch.Generator().manual_seed(0)
+    for step in range(3):
+        b0, b1 = synthetic_train_batches(8, 9, 40 + step)
+        t = torch.rand(8, generator=g).repeat_interleave(9).reshape(-1, 1)
+        z = torch.randn(72, 3, generator=g)
+        le, lg = float(eager.step(b0, b1, t=t, z=z)), float(graph.step(b0, b1, t=t, z=z))
+        assert abs(le - lg) < 1e-5 * max(1.0, abs(le)), (step, le, lg)
+    assert float((eager.weights - graph.weights).abs().max()) < 3.5e-4      # Adam: rounding-level gradients move by <= lr per step
+    assert float((eager.last_grad - graph.last_grad).abs().max()) < 1e-4 * float(eager.last_grad.abs().max())

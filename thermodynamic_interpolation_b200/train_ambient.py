@@ -21,7 +21,8 @@ from .train import TrainEngine, flatten, packed_parameters
 
 class Trainer:
     def __init__(self, model, interpolant, t_distr: str = "uniform", lr: float = 1e-4, weight_decay: float = 0.0,
-                 betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: float = 1.0, process_group=None, data_parallel: bool = False):
+                 betas=(0.9, 0.999), eps: float = 1e-8, max_grad_norm: float = 1.0, process_group=None, data_parallel: bool = False,
+                 cuda_graph: bool = False):
         self.model = model
         self.engine = TrainEngine(model.hyper, model.device)
         self.kind, self.a = interpolant.kind, interpolant.a_value
@@ -35,19 +36,53 @@ class Trainer:
         self.step_no = 0
         self.data_parallel = data_parallel
         self.group = process_group
+        # cuda_graph=True: the ~450 launches of tib_train_loss_grad (both streams) are captured once per batch shape and
+        # replayed; inputs are copied into the captured buffers (the optimiser step stays outside: its bias corrections
+        # are host arguments that change every step)
+        self.cuda_graph = cuda_graph
+        self._graphs = {}
         self.last_grad: Optional[torch.Tensor] = None
         self.last_grad_sqnorm: Optional[torch.Tensor] = None
         if data_parallel:
             import torch.distributed as dist
             dist.broadcast(self.weights, src=0, group=self.group)      # replicas start from rank 0's weights
 
-    def loss_and_grad(self, batch0, batch1, t=None, z=None):
-        tb = self.engine.prepare(batch0, batch1)
+    def loss_and_grad(self, batch0, batch1, t=None, z=None, prepared=None):
+        tb = prepared if prepared is not None else self.engine.prepare(batch0, batch1)
         if t is None:
             t = draw_times(tb.n_atoms, self.t_distr)
         if z is None:
             z = torch.randn(tb.x0.shape)
+        if self.cuda_graph:
+            return self._replay(tb, t, z)
         loss, grad, _ = self.engine.loss_and_grad(self.weights, tb, t, z, gamma=self.kind, a=self.a)
+        return loss, grad
+
+    _STATIC = ("mol_ptr", "edge_ptr", "atom_id", "edge_type", "temp0", "temp1")
+
+    def _replay(self, tb, t, z):
+        dev = self.engine.device
+        t = t.to(dev, torch.float32).reshape(-1)
+        z = z.to(dev, torch.float32)
+        key = (tb.pb.n_mol, tb.pb.n_nodes, tb.pb.n_edges)
+        entry = self._graphs.get(key)
+        if entry is None:
+            st_t, st_z = t.clone(), z.clone()
+            self.engine.loss_and_grad(self.weights, tb, st_t, st_z, gamma=self.kind, a=self.a)      # warm: workspace, streams, events
+            torch.cuda.synchronize(dev)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                loss, grad, _ = self.engine.loss_and_grad(self.weights, tb, st_t, st_z, gamma=self.kind, a=self.a)
+            entry = self._graphs[key] = (graph, tb, st_t, st_z, loss, grad)
+        graph, st_tb, st_t, st_z, loss, grad = entry
+        if tb is not st_tb:
+            for name in self._STATIC:
+                getattr(st_tb.pb, name).copy_(getattr(tb.pb, name))
+            st_tb.x0.copy_(tb.x0)
+            st_tb.x1.copy_(tb.x1)
+        st_t.copy_(t)
+        st_z.copy_(z)
+        graph.replay()
         return loss, grad
 
     def apply(self, grad: torch.Tensor):
@@ -64,7 +99,7 @@ class Trainer:
         """One optimisation step; returns the loss as a device scalar (fp64, shape [1]) without synchronising."""
         loss, grad = self.loss_and_grad(batch0, batch1, t, z)
         self.apply(grad)
-        return loss
+        return loss.clone() if self.cuda_graph else loss
 
     def sync_to_model(self):
         """Copies the flat weights back into the model's parameters (state_dict order and keys untouched)."""
