@@ -423,53 +423,63 @@ def run_train(args):
         trainer.apply(grad)
         losses[i] = loss[0]
 
-    for i in range(W):
-        resident_step(i)
-    barrier()
-    clocks = ClockSampler(local) if rank == 0 else None
     ms_sum = (C.c_double * _lib.N_KERNEL_KINDS)()
     launches = (C.c_uint64 * _lib.N_KERNEL_KINDS)()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    step_no = 0
+    use_graph = bool(args.graph)
+    trainer.cuda_graph = False
+    for _ in range(W):                                         # W untimed warm-up steps (eager launches)
+        resident_step(step_no); step_no += 1
     barrier()
-    lib.tib_launch_count(1)
-    lib.tib_train_gemm_flops(1)
-    lib.tib_profile_begin()
-    t_begin = time.perf_counter()
-    e0.record()
-    for i in range(K):
-        resident_step(W + i)
-    e1.record()
-    barrier()
-    t_end = time.perf_counter()
-    n_launch = int(lib.tib_launch_count(0))
-    gemm_flops = float(lib.tib_train_gemm_flops(0))
-    _lib.check(lib.tib_profile_end(ms_sum, launches), "tib_profile_end")
-    ms_total = max_over_ranks(e0.elapsed_time(e1))
-    clk = clocks.stop(t_begin, t_end) if clocks else None
-    trainer.engine.status()
-    profiled_steps, ms_profiled = K, ms_total
-    if args.graph:
+    profiled_steps, ms_profiled, n_launch_p, gemm_flops_p = 0, 0.0, 0, 0.0
+    if use_graph:
         # a graph replay cannot carry per-launch event pairs (and issues no launches of its own): the kernel-class times of
-        # the roofline come from eager launches of the same kernels on the same inputs, right after the timed region
+        # the roofline come from eager launches of the same kernels on the same inputs, right before the timed region
         profiled_steps = min(K, 5)
-        trainer.cuda_graph = False
-        resident_step(W + K)                                   # eager warm-up
-        barrier()
         lib.tib_launch_count(1)
         lib.tib_train_gemm_flops(1)
         lib.tib_profile_begin()
         p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         p0.record()
-        for i in range(profiled_steps):
-            resident_step(W + K + 1 + i)
+        for _ in range(profiled_steps):
+            resident_step(step_no); step_no += 1
         p1.record()
         barrier()
-        n_launch = int(lib.tib_launch_count(0)) * K // profiled_steps      # kernels per replayed step x K
-        gemm_flops = float(lib.tib_train_gemm_flops(0)) * K / profiled_steps
+        n_launch_p = int(lib.tib_launch_count(0))
+        gemm_flops_p = float(lib.tib_train_gemm_flops(0))
         _lib.check(lib.tib_profile_end(ms_sum, launches), "tib_profile_end")
         ms_profiled = p0.elapsed_time(p1)
         trainer.cuda_graph = True
-    lh = losses[: W + K].cpu()
+        resident_step(step_no); step_no += 1                   # captures the graph (once per batch shape) + one replay
+        barrier()
+    clocks = ClockSampler(local) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    lib.tib_launch_count(1)
+    lib.tib_train_gemm_flops(1)
+    if not use_graph:
+        lib.tib_profile_begin()
+    t_begin = time.perf_counter()
+    e0.record()
+    for _ in range(K):
+        resident_step(step_no); step_no += 1
+    e1.record()
+    barrier()
+    t_end = time.perf_counter()
+    if use_graph:
+        n_launch = n_launch_p * K // profiled_steps            # kernels inside the K replayed steps
+        gemm_flops = gemm_flops_p * K / profiled_steps
+    else:
+        n_launch = int(lib.tib_launch_count(0))
+        gemm_flops = float(lib.tib_train_gemm_flops(0))
+        _lib.check(lib.tib_profile_end(ms_sum, launches), "tib_profile_end")
+        profiled_steps = K
+    ms_total = max_over_ranks(e0.elapsed_time(e1))
+    if not use_graph:
+        ms_profiled = ms_total
+    clk = clocks.stop(t_begin, t_end) if clocks else None
+    trainer.engine.status()
+    lh = losses[:step_no].cpu()
     assert torch.isfinite(lh).all(), "training diverged"
     value = world * args.mols * K / (ms_total * 1e-3)
 
@@ -520,7 +530,7 @@ def run_train(args):
                           peak_source=peaks["source"] + ", bf16 dense sustained", launches=gemm_n,
                           avg_launch_ms=gemm_ms / max(gemm_n, 1), flops_per_step=gemm_flops / K,
                           kernel_time_shares=dict(train_gemm=round(gemm_ms / ms_profiled, 4), train_other=round(other_ms / ms_profiled, 4)),
-                          measured_on=(f"{profiled_steps} eager steps after the timed region ({ms_profiled / profiled_steps:.2f} ms per step; graph "
+                          measured_on=(f"{profiled_steps} eager steps right before the timed region ({ms_profiled / profiled_steps:.2f} ms per step; graph "
                                        "replays carry no per-launch events)" if args.graph else "the timed region"),
                           note="two streams: the kernel-class shares add up to more than the wall time they overlap in"))
         if world == 1 and not args.no_cpu:

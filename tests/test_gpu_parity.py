@@ -266,6 +266,33 @@ def test_euler_maruyama_extension():
         assert torch.allclose(em[k + 1], x, rtol=1e-5, atol=1e-6)
 
 
+def test_euler_maruyama_against_cpu_oracle_drifts():
+    """The same property with nothing of this library on the reference side: x_{k+1} = x_k + dt (b + eps s) + sqrt(2 eps dt) z_k
+     stepped on the CPU with the ORACLE's drift (oracle/cpainn_oracle.py, pinned against the
+    unmodified reference) for both networks, on the noise injected into the CUDA rollout."""
+    from oracle import cpainn_oracle as co
+    from tests._util import oracle_hp_sd
+    model, mb = _cfg2(6, F=32, L=2)
+    score, _ = _cfg2(6, seed=7, F=32, L=2)
+    T, eps = 9, 0.05
+    noise = torch.randn(T - 1, mb.x0.shape[0], 3, generator=torch.Generator().manual_seed(11))
+    em = _integrator("ambient")(model, method="euler", n_step=T, eps=eps, score=score).rollout(mb, noise=noise.to(DEV))[0].cpu()
+    hp, sd = oracle_hp_sd(model)
+    hps, sds = oracle_hp_sd(score)
+    cpu = {k: mb[k].cpu() for k in ("x0", "atoms", "edge_index", "edge_type", "T0", "T1")}
+    times = torch.linspace(0.0, 1.0, T)
+    x = cpu["x0"].clone()
+    worst = 0.0
+    for k in range(T - 1):
+        dt = float(times[k + 1] - times[k])
+        kw = dict(T0=cpu["T0"], T1=cpu["T1"])
+        b = co.drift(sd, hp, x, float(times[k]), cpu["atoms"], cpu["edge_index"], cpu["edge_type"], **kw)
+        sc = co.drift(sds, hps, x, float(times[k]), cpu["atoms"], cpu["edge_index"], cpu["edge_type"], **kw)
+        x = x + dt * b + (dt * eps) * sc + float(np.sqrt(np.float32(2.0 * eps * dt))) * noise[k]
+        worst = max(worst, float((em[k + 1] - x).abs().max() / x.abs().max()))
+    assert worst < 1e-4, worst
+
+
 def test_step_euler_kernel_bit_exact():
     """K1: x + dt*b with product and sum rounded separately == torch eager (torchdiffeq's y0 + dt*f0)."""
     from thermodynamic_interpolation_b200.engine import DriftEngine
