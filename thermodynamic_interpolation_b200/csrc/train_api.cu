@@ -74,11 +74,36 @@ thread_local long long* g_gemm_dbg = nullptr;      // device buffer [64] when ti
 constexpr float kStateScale = tib::tc::kStateScale;
 
 // ---- offsets into the flat weight / gradient vector (order of tib_packed_weight_count, include/tib.h) ------------------------
-struct MlpOff { size_t W1, b1, g1, be1, W2, b2, g2, be2, W3, b3; int k_in, n_out; };
-struct LayerOff { MlpOff phi, w, upd; size_t UV; };          // U [F][F] then V [F][F]: one [2F][F] matrix
+// images of a weight matrix as a pre-packed B operand (train_gemm.cuh::k_pack_operand): byte offsets into the image blob
+struct ImgOff { size_t fwd, tr; int fwd_chunks, tr_chunks; bool ok; };
+struct MlpOff { size_t W1, b1, g1, be1, W2, b2, g2, be2, W3, b3; int k_in, n_out; ImgOff i1, i2, i3; };
+struct LayerOff { MlpOff phi, w, upd; size_t UV; ImgOff iuv; };          // U [F][F] then V [F][F]: one [2F][F] matrix
 struct Offsets {
   size_t edge_emb, atom_emb; MlpOff combine; std::vector<LayerOff> layers; MlpOff readout; size_t Vout; size_t total;
+  PackTable pack; size_t img_bytes;
 };
+
+ImgOff add_image(Offsets& o, size_t src, int ld, int rows_o, int cols_i) {
+  ImgOff im{};
+  if (o.pack.n >= kPackMaxEntries) return im;               // very deep networks: the remaining matrices are built on the fly
+  const int fwd_tiles = (rows_o + 127) / 128, tr_tiles = (cols_i + 127) / 128;
+  im.fwd_chunks = (cols_i + kGemmKC - 1) / kGemmKC;
+  im.tr_chunks = (rows_o + kGemmKC - 1) / kGemmKC;
+  im.fwd = o.img_bytes;
+  im.tr = im.fwd + (size_t)fwd_tiles * im.fwd_chunks * 2 * kGemmHalf;
+  o.img_bytes = im.tr + (size_t)tr_tiles * im.tr_chunks * 2 * kGemmHalf;
+  PackEntry& e = o.pack.e[o.pack.n++];
+  e.src = (long long)src; e.ld = ld; e.rows_o = rows_o; e.cols_i = cols_i; e.fwd_off = (long long)im.fwd; e.tr_off = (long long)im.tr;
+  e.first_block = o.pack.total_blocks; e.pad = 0;
+  o.pack.total_blocks += fwd_tiles * im.fwd_chunks + tr_tiles * im.tr_chunks;
+  im.ok = true;
+  return im;
+}
+void add_mlp_images(Offsets& o, MlpOff& m, int F, bool with_out) {
+  m.i1 = add_image(o, m.W1, m.k_in, F, m.k_in);
+  m.i2 = add_image(o, m.W2, F, F, F);
+  if (with_out) m.i3 = add_image(o, m.W3, F, m.n_out, F);
+}
 
 MlpOff take_mlp(size_t& off, int k_in, int F, int n_out) {
   MlpOff m{};
@@ -106,6 +131,16 @@ Offsets make_offsets(const tib_model_desc& d, int n_temp) {
   o.readout = take_mlp(off, F, F, 2);
   o.Vout = off; off += F;
   o.total = off;
+  // the weight images every forward / data-gradient GEMM reads as its B operand (the readout's 2-row output layer and the
+  // 1-row equivariant readout are not GEMMs)
+  add_mlp_images(o, o.combine, F, true);
+  for (LayerOff& L : o.layers) {
+    add_mlp_images(o, L.phi, F, true);
+    add_mlp_images(o, L.w, F, true);
+    L.iuv = add_image(o, L.UV, F, 2 * F, F);
+    add_mlp_images(o, L.upd, F, true);
+  }
+  add_mlp_images(o, o.readout, F, false);
   return o;
 }
 
@@ -129,13 +164,14 @@ struct Ws {
   float *s_last, *v_last, *e_spare;
   MlpAct ro;
   // backward
+  unsigned char* img;      // pre-packed weight images (B operands)
   float *ds, *dv, *de, *dv_src, *d_phi3, *d_w3, *d_gac, *d_uvvv, *dq, *dA, *dB, *dAw, *dBw, *ds0, *dX0;
   size_t bytes;
 };
 
 size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
-size_t layout(Ws& w, char* base, const tib_model_desc& d, int n_temp, long long N, long long E) {
+size_t layout(Ws& w, char* base, const tib_model_desc& d, int n_temp, long long N, long long E, size_t img_bytes) {
   const int F = d.n_features, L = d.n_layers;
   const long long N2 = 2 * N, E2 = 2 * E, P2 = E;
   size_t off = 0;
@@ -148,6 +184,7 @@ size_t layout(Ws& w, char* base, const tib_model_desc& d, int n_temp, long long 
     a.n2 = tf(rows * F); a.r2 = tf(rows); a.h2 = tf(rows * F);
     a.out = n_out > 0 ? tf(rows * n_out) : nullptr;
   };
+  w.img = (unsigned char*)take(img_bytes);
   w.src = ti(E2); w.dst = ti(E2); w.pair = ti(E2); w.etype = ti(E2); w.in_ptr = ti(N2 + 1);
   w.dir = (float4*)take(sizeof(float4) * (size_t)E2);
   w.pair_dist = tf(P2); w.pe = tf(P2 * F);
@@ -188,6 +225,7 @@ struct Ctx {
   int n_sms;
   int* err;          // device error word (bounded mbarrier waits)
   float* amax; int n_amax, next_amax;
+  const unsigned char* img;      // pre-packed weight images, or nullptr (every B operand built on the fly)
   size_t next_ev;
   struct Pending { const void* ptr; cudaEvent_t ev; } pend[16];
   int n_pend;
@@ -264,10 +302,14 @@ GemmOperand op(const float* ptr, long long ld, int trans, float scale, const flo
   return o;
 }
 
+// a pre-packed B operand: image base, first K chunk of this GEMM, K chunks per n tile of the image
+struct BImg { const unsigned char* p; int chunk0, chunks; };
+
 int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B, float* C, long long ldc, int mode,
-         const float* bias = nullptr, const int* c_idx = nullptr, bool split_k = false) {
+         const float* bias = nullptr, const int* c_idx = nullptr, bool split_k = false, BImg bimg = BImg{nullptr, 0, 0}) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   GemmP p{};
+  p.b_img = bimg.p; p.b_chunk0 = bimg.chunk0; p.b_chunks = bimg.chunks;
   p.M = M; p.N = N; p.K = K; p.A = A; p.B = B; p.C = C; p.ldc = ldc; p.c_idx = c_idx; p.bias = bias; p.mode = mode;
   p.alpha = 1.0f; p.passes = 3; p.err = c.err; p.dbg = g_gemm_dbg;
   const int mt = (M + 127) / 128, nt = (N + 127) / 128, chunks = (K + kGemmKC - 1) / kGemmKC;
@@ -303,6 +345,17 @@ int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B
   return 0;
 }
 
+// forward GEMM over the input columns [k0, k0 + width) of W: chunks k0 / 32 .. of the forward image
+BImg img_fwd(const Ctx& c, const ImgOff& im, int k0) {
+  if (!c.img || !im.ok) return BImg{nullptr, 0, 0};
+  return BImg{c.img + im.fwd, k0 / kGemmKC, im.fwd_chunks};
+}
+// data-gradient GEMM producing the input columns [k0, k0 + width): n tiles k0 / 128 .. of the transposed image
+BImg img_tr(const Ctx& c, const ImgOff& im, int k0) {
+  if (!c.img || !im.ok || k0 % 128 != 0) return BImg{nullptr, 0, 0};
+  return BImg{c.img + im.tr + (size_t)(k0 / 128) * im.tr_chunks * 2 * kGemmHalf, 0, im.tr_chunks};
+}
+
 int blocks_for(long long n, int per_block) { return (int)std::min<long long>((n + per_block - 1) / per_block, 1 << 20); }
 
 // one input segment of an MLP's first Linear: X[:, seg] = rows of `ptr` (optionally gathered), F_seg columns
@@ -315,18 +368,21 @@ int mlp_forward(Ctx& c, const float* W, const MlpOff& m, int F, const Seg* segs,
   int k0 = 0;
   for (int s = 0; s < n_seg; ++s) {
     TRY(gemm(c, R, F, segs[s].width, op(segs[s].ptr, segs[s].ld, 0, segs[s].scale, nullptr, segs[s].idx),
-             op(W + m.W1 + k0, m.k_in, 0, 1.0f), a.n1, F, s == 0 ? GEMM_STORE : GEMM_ACCUM, s == 0 ? W + m.b1 : nullptr));
+             op(W + m.W1 + k0, m.k_in, 0, 1.0f), a.n1, F, s == 0 ? GEMM_STORE : GEMM_ACCUM, s == 0 ? W + m.b1 : nullptr, nullptr, false,
+             img_fwd(c, m.i1, k0)));
     k0 += segs[s].width;
   }
   const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 16);
   { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
   k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1);
   LAUNCH_CHECK(); }
-  TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2));
+  TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2, nullptr, false, img_fwd(c, m.i2, 0)));
   { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
   k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2);
   LAUNCH_CHECK(); }
-  if (with_out) TRY(gemm(c, R, m.n_out, F, op(a.h2, F, 0, 1.0f), op(W + m.W3, F, 0, 1.0f), a.out, m.n_out, GEMM_STORE, W + m.b3));
+  if (with_out)
+    TRY(gemm(c, R, m.n_out, F, op(a.h2, F, 0, 1.0f), op(W + m.W3, F, 0, 1.0f), a.out, m.n_out, GEMM_STORE, W + m.b3, nullptr, false,
+             img_fwd(c, m.i3, 0)));
   return 0;
 }
 
@@ -351,7 +407,8 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
     TRY(c.side_done(dY));
     c.to_main();
     TRY(c.before_write(dA));
-    TRY(gemm(c, R, F, m.n_out, op(dY, m.n_out, 0, 1.0f, amax_dY), op(W + m.W3, F, 1, 1.0f), dA, F, GEMM_STORE));
+    TRY(gemm(c, R, F, m.n_out, op(dY, m.n_out, 0, 1.0f, amax_dY), op(W + m.W3, F, 1, 1.0f), dA, F, GEMM_STORE, nullptr, nullptr, false,
+             img_tr(c, m.i3, 0)));
   }
   float* am2 = c.new_amax();
   { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_bwd");
@@ -362,7 +419,7 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
   TRY(c.side_done(dA));
   c.to_main();
   TRY(c.before_write(dB));
-  TRY(gemm(c, R, F, F, op(dA, F, 0, 1.0f, am2), op(W + m.W2, F, 1, 1.0f), dB, F, GEMM_STORE));
+  TRY(gemm(c, R, F, F, op(dA, F, 0, 1.0f, am2), op(W + m.W2, F, 1, 1.0f), dB, F, GEMM_STORE, nullptr, nullptr, false, img_tr(c, m.i2, 0)));
   float* am1 = c.new_amax();
   { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_bwd");
   ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1);
@@ -380,7 +437,7 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
   for (int s = 0; s < n_seg; ++s) {
     if (sg && sg[s].ptr)
       TRY(gemm(c, R, segs[s].width, F, op(dB, F, 0, 1.0f, am1), op(W + m.W1 + k0, m.k_in, 1, 1.0f), sg[s].ptr, sg[s].ld, sg[s].mode,
-               nullptr, sg[s].c_idx));
+               nullptr, sg[s].c_idx, false, img_tr(c, m.i1, k0)));
     k0 += segs[s].width;
   }
   return 0;
@@ -398,7 +455,7 @@ size_t tib_train_workspace_bytes(const tib_model_desc* desc, int32_t n_mol, int3
   if (!desc) return 0;
   Ws w{};
   const int n_temp = desc->variant == TIB_VARIANT_AMBIENT ? 2 : (desc->variant == TIB_VARIANT_LATENT_MULTI_T ? 1 : 0);
-  return layout(w, nullptr, *desc, n_temp, n_nodes, n_edges);
+  return layout(w, nullptr, *desc, n_temp, n_nodes, n_edges, make_offsets(*desc, n_temp).img_bytes);
 }
 
 int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const tib_train_batch* b, const tib_interpolant* ip,
@@ -414,9 +471,9 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   const int n_temp = 2;
   const long long N = b->n_nodes, E = b->n_edges, N2 = 2 * N, E2 = 2 * E, P2 = E;
   Ws w{};
-  if (layout(w, (char*)workspace, *desc, n_temp, N, E) > workspace_bytes)
-    return fail("tib_train_loss_grad: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
   const Offsets o = make_offsets(*desc, n_temp);
+  if (layout(w, (char*)workspace, *desc, n_temp, N, E, o.img_bytes) > workspace_bytes)
+    return fail("tib_train_loss_grad: workspace too small (%zu < %zu)", workspace_bytes, w.bytes);
   cudaStream_t st = (cudaStream_t)stream;
   int dev = 0;
   CUDA_TRY(cudaGetDevice(&dev));
@@ -434,6 +491,16 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   CUDA_TRY(cudaMemsetAsync(w.amax, 0, w.n_amax * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(w.colsum, 0, 8 * sizeof(float), st));
   CUDA_TRY(cudaMemsetAsync(loss, 0, sizeof(double), st));
+
+  // ---- weight images: every Linear's W as a ready-made B operand for the forward and the data-gradient GEMMs (once per call:
+  // the weights change with every optimiser step)
+  static const bool no_pack = getenv("TIB_TRAIN_NO_PACK") != nullptr;       // diagnostics: build every B operand on the fly
+  if (!no_pack && o.pack.n > 0) {
+    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_pack_operand");
+    k_pack_operand<<<o.pack.total_blocks, kGemmThreads, 0, st>>>(o.pack, W, w.img);
+    LAUNCH_CHECK(); }
+    c.img = w.img;
+  }
 
   // ---- interpolant, targets, graph (interpolants.py:16-33; losses.py:52-57; graph.py:27-29) -----------------------------------------
   { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_interp");
@@ -487,7 +554,8 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_combine_fwd");
     k_tr_combine_fwd<<<node_blocks, kEW, 0, st>>>(cp);
     LAUNCH_CHECK(); }
-    TRY(gemm(c, (int)(3 * N2), 2 * F, F, op(a.v_mid, F, 0, kStateScale), op(W + lo.UV, F, 0, 1.0f), a.uvvv, 2 * F, GEMM_STORE));
+    TRY(gemm(c, (int)(3 * N2), 2 * F, F, op(a.v_mid, F, 0, kStateScale), op(W + lo.UV, F, 0, 1.0f), a.uvvv, 2 * F, GEMM_STORE, nullptr, nullptr,
+             false, img_fwd(c, lo.iuv, 0)));
     { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_q");
     k_tr_upd_q<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q);
     LAUNCH_CHECK(); }
@@ -539,7 +607,8 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
              nullptr, nullptr, true));
     TRY(c.side_done(w.d_uvvv));
     c.to_main();
-    TRY(gemm(c, (int)(3 * N2), F, 2 * F, op(w.d_uvvv, 2 * F, 0, 1.0f, am_uv), op(W + lo.UV, F, 1, 1.0f), w.dv, F, GEMM_ACCUM));
+    TRY(gemm(c, (int)(3 * N2), F, 2 * F, op(w.d_uvvv, 2 * F, 0, 1.0f, am_uv), op(W + lo.UV, F, 1, 1.0f), w.dv, F, GEMM_ACCUM, nullptr, nullptr,
+             false, img_tr(c, lo.iuv, 0)));
     // SE3Message (cpainn.py:263-310)
     TRY(c.before_write(w.d_w3));
     TRY(c.before_write(w.d_phi3));

@@ -55,6 +55,11 @@ struct GemmP {
   int passes;           // 3 = split-f16 x3, 1 = single f16 pass
   int* err;
   long long* dbg;       // optional: clock64() stamps of CTA (0,0,0) thread 0 (pipeline diagnostics), else nullptr
+  // optional pre-packed B operand (k_pack_operand): the split-f16 images of B in (n tile, K chunk) order, 16 KB each.  The
+  // chunk then arrives by one bulk copy of the TMA unit instead of 256 threads loading, converting and storing it - used
+  // for the weights, whose images are made once per optimiser step and shared by every m tile of every GEMM that reads them.
+  const unsigned char* b_img;
+  int b_chunk0, b_chunks;     // first K chunk of this GEMM inside the image, K chunks per n tile of the image
 };
 
 constexpr int kGemmThreads = 256;
@@ -152,10 +157,11 @@ __device__ __forceinline__ void store_tile(unsigned char* img, int trans, float 
 __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
   using namespace tc;
   extern __shared__ __align__(1024) unsigned char smem[];
-  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);   // [0..1] stage free, [2] done
-  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 4);
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + kGemmStages * kGemmStageBytes);   // [0..1] stage free, [2] done,
+  uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(bars + 6);                          // [3..4] packed B chunk arrived
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   volatile int* err = p.err;
+  const bool packed_b = p.b_img != nullptr;
 
   const int n0 = blockIdx.x * 128, m0 = blockIdx.y * 128;
   const int chunks_total = (p.K + kGemmKC - 1) / kGemmKC;
@@ -167,15 +173,19 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
   int di = 0;
   if (dbg) p.dbg[di++] = clock64();
   if (tid == 0) {
-    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1);
+    mbar_init(&bars[0], 1); mbar_init(&bars[1], 1); mbar_init(&bars[2], 1); mbar_init(&bars[3], 1); mbar_init(&bars[4], 1);
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 128);
   // the first chunk's operands are requested before the allocation barrier
-  const TileRows ra = tile_rows(p.A, m0, p.M, warp, lane), rb = tile_rows(p.B, n0, p.N, warp, lane);
+  const TileRows ra = tile_rows(p.A, m0, p.M, warp, lane);
+  TileRows rb{};
   float va[16], vb[16];
   load_tile(va, p.A, ra, m0, p.M, c_begin * kGemmKC, p.K, warp, lane);
-  load_tile(vb, p.B, rb, n0, p.N, c_begin * kGemmKC, p.K, warp, lane);
+  if (!packed_b) {
+    rb = tile_rows(p.B, n0, p.N, warp, lane);
+    load_tile(vb, p.B, rb, n0, p.N, c_begin * kGemmKC, p.K, warp, lane);
+  }
   const float sa = operand_scale(p.A), sb = operand_scale(p.B);
   // a trans-1 thread whose row lies beyond the tile loads a clamped row and stores zeros
   const float sa_t = (p.A.trans && m0 + 32 * (warp & 3) + lane >= p.M) ? 0.0f : sa;
@@ -190,17 +200,22 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
     const int it = c - c_begin, st = it & 1;
     if (it >= kGemmStages) mbar_wait(&bars[st], ((it >> 1) - 1) & 1, err);      // the MMAs that read this stage are done
     unsigned char* const stage = smem + st * kGemmStageBytes;
+    if (packed_b && tid == 0) {                // the B chunk of this stage: one 16 KB bulk copy, under the A conversion
+      mbar_arrive_expect_tx(&bars[3 + st], 2 * kGemmHalf);
+      bulk_g2s(stage + 2 * kGemmHalf, p.b_img + ((size_t)blockIdx.x * p.b_chunks + p.b_chunk0 + c) * (2 * kGemmHalf), 2 * kGemmHalf, &bars[3 + st]);
+    }
     store_tile(stage, p.A.trans, sa_t, warp, lane, va);
-    store_tile(stage + 2 * kGemmHalf, p.B.trans, sb_t, warp, lane, vb);
+    if (!packed_b) store_tile(stage + 2 * kGemmHalf, p.B.trans, sb_t, warp, lane, vb);
     if (c + 1 < c_end) {                       // next chunk's loads fly under the barrier, the MMAs and the next wait
       load_tile(va, p.A, ra, m0, p.M, (c + 1) * kGemmKC, p.K, warp, lane);
-      load_tile(vb, p.B, rb, n0, p.N, (c + 1) * kGemmKC, p.K, warp, lane);
+      if (!packed_b) load_tile(vb, p.B, rb, n0, p.N, (c + 1) * kGemmKC, p.K, warp, lane);
     }
     if (dbg && di < 40) p.dbg[di++] = clock64();          // after the build of this chunk (thread 0's part)
     fence_proxy_async();
     __syncthreads();
     if (dbg && di < 40) p.dbg[di++] = clock64();          // after the barrier
     if (tid == 0) {
+      if (packed_b) mbar_wait(&bars[3 + st], (it >> 1) & 1, err);
       tc_fence_after();
       const uint32_t a = smem_u32(stage), b = a + 2 * kGemmHalf;
       mma_f16x3(tmem, a, kGemmHalf, b, kGemmHalf, kGemmKC / 16, it > 0, p.passes);
@@ -253,6 +268,47 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
   __syncthreads();
   if (warp == 0) tmem_dealloc(tmem, 128);
   if (dbg) { p.dbg[di++] = clock64(); p.dbg[63] = di; }
+}
+
+// ---- operand images in global memory --------------------------------------------------------------------------------------------
+// One entry = one matrix W [rows_o][cols_i] (leading dimension ld, a block of the flat weight vector) packed twice:
+//   fwd : B(n, k) = W[n][k]   (forward GEMMs;       n tiles over rows_o, K chunks over cols_i)   at img + fwd_off
+//   tr  : B(n, k) = W[k][n]   (data-gradient GEMMs; n tiles over cols_i, K chunks over rows_o)   at img + tr_off
+// Chunk (n tile, K chunk) is 16 KB (hi image then lo image) at (n tile * n_chunks + chunk) * 16 KB; rows / columns beyond
+// the matrix are zero.
+struct PackEntry { long long src; int ld, rows_o, cols_i; long long fwd_off, tr_off; int first_block; int pad; };
+constexpr int kPackMaxEntries = 96;
+struct PackTable { PackEntry e[kPackMaxEntries]; int n; int total_blocks; };
+
+__global__ void __launch_bounds__(kGemmThreads) k_pack_operand(const PackTable tab, const float* __restrict__ W,
+                                                                unsigned char* __restrict__ img) {
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int blk = blockIdx.x;
+  int ei = 0;
+  while (ei + 1 < tab.n && tab.e[ei + 1].first_block <= blk) ++ei;          // tab.n <= 96: a short uniform scan
+  const PackEntry& e = tab.e[ei];
+  int local = blk - e.first_block;
+  const int fwd_chunks = (e.cols_i + kGemmKC - 1) / kGemmKC, fwd_tiles = (e.rows_o + 127) / 128;
+  const int tr_chunks = (e.rows_o + kGemmKC - 1) / kGemmKC;
+  GemmOperand o{};
+  o.ptr = W + e.src; o.ld = e.ld; o.idx = nullptr; o.scale = 1.0f; o.amax = nullptr;
+  unsigned char* dst;
+  int r0, r_end, k0, k_end;
+  if (local < fwd_tiles * fwd_chunks) {
+    const int nt = local / fwd_chunks, c = local % fwd_chunks;
+    o.trans = 0; r0 = nt * 128; r_end = e.rows_o; k0 = c * kGemmKC; k_end = e.cols_i;
+    dst = img + e.fwd_off + (size_t)local * (2 * kGemmHalf);
+  } else {
+    local -= fwd_tiles * fwd_chunks;
+    const int nt = local / tr_chunks, c = local % tr_chunks;
+    o.trans = 1; r0 = nt * 128; r_end = e.cols_i; k0 = c * kGemmKC; k_end = e.rows_o;
+    dst = img + e.tr_off + (size_t)local * (2 * kGemmHalf);
+  }
+  const TileRows tr = tile_rows(o, r0, r_end, warp, lane);
+  float v[16];
+  load_tile(v, o, tr, r0, r_end, k0, k_end, warp, lane);
+  const float sc = (o.trans && r0 + 32 * (warp & 3) + lane >= r_end) ? 0.0f : 1.0f;
+  store_tile(dst, o.trans, sc, warp, lane, v);
 }
 
 }  // namespace train
