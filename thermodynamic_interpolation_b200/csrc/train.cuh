@@ -20,10 +20,23 @@ constexpr int kEW = 128;   // threads of the element-wise kernels
 __device__ __forceinline__ void atomic_amax(float* slot, float v) {       // v >= 0
   atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v));
 }
+// One atomicMax per BLOCK (every thread of the block must call it): atomics on one address are serialised in L2 at about
+// 0.7 ns each, so one per warp made the |max| bookkeeping the longest part of the small element-wise kernels
+// (18 k warps -> 13 us) - and of a 46 k-block experiment, 255 us.
 __device__ __forceinline__ void warp_amax(float* slot, float v) {
+  __shared__ float s_amax[32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  if ((threadIdx.x & 31) == 0 && slot) atomic_amax(slot, v);
+  const int warp = threadIdx.x >> 5, nwarps = (blockDim.x + 31) >> 5;
+  if ((threadIdx.x & 31) == 0) s_amax[warp] = v;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    float m = threadIdx.x < nwarps ? s_amax[threadIdx.x] : 0.0f;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0 && slot) atomic_amax(slot, m);
+  }
+  __syncthreads();          // the staging array may be reused by a second call
 }
 
 // ---- interpolant (interpolants.py:16-33, 53-108) and loss targets (losses.py:126-133) -----------------------------------------
