@@ -305,6 +305,37 @@ __global__ void __launch_bounds__(256, 4) k_tr_ln_silu_bwd(long long R, int F, f
   }
 }
 
+// LayerNorm parameter gradients from the by-products of the fused GEMM epilogue (train_gemm.cuh, EPI_LN_BWD):
+//   g_gamma[c] += sum_r dpre[r][c] n[r][c],  g_beta[c] += sum_r dpre[r][c],  g_bias[c] += sum_r dz[r][c]
+// grid = (column blocks, row slabs); runs on the side stream
+__global__ void k_tr_ln_param_grads(long long R, int C, const float* __restrict__ dpre, const float* __restrict__ nrm,
+                                    const float* __restrict__ dz, float* __restrict__ g_gamma, float* __restrict__ g_beta,
+                                    float* __restrict__ g_bias) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= C) return;
+  const long long per = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(R, r0 + per);
+  float ag[2] = {0.0f, 0.0f}, ab[2] = {0.0f, 0.0f}, az[2] = {0.0f, 0.0f};
+  long long r = r0;
+  for (; r + 2 <= r1; r += 2) {
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const float dp = __ldg(dpre + (r + u) * C + c);
+      ag[u] += dp * __ldg(nrm + (r + u) * C + c);
+      ab[u] += dp;
+      az[u] += __ldg(dz + (r + u) * C + c);
+    }
+  }
+  for (; r < r1; ++r) {
+    const float dp = __ldg(dpre + r * C + c);
+    ag[0] += dp * __ldg(nrm + r * C + c);
+    ab[0] += dp;
+    az[0] += __ldg(dz + r * C + c);
+  }
+  atomicAdd(&g_gamma[c], ag[0] + ag[1]);
+  atomicAdd(&g_beta[c], ab[0] + ab[1]);
+  atomicAdd(&g_bias[c], az[0] + az[1]);
+}
+
 // out[c] += sum_r d[r][c]   (bias gradient of an output Linear); also records |max| of d.  grid = (column blocks, row slabs)
 __global__ void k_tr_colsum(long long R, int C, const float* __restrict__ d, float* __restrict__ out, float* amax) {
   const int c = blockIdx.x * blockDim.x + threadIdx.x;

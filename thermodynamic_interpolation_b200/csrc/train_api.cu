@@ -305,11 +305,32 @@ GemmOperand op(const float* ptr, long long ld, int trans, float scale, const flo
 // a pre-packed B operand: image base, first K chunk of this GEMM, K chunks per n tile of the image
 struct BImg { const unsigned char* p; int chunk0, chunks; };
 
+// second A segment and fused LayerNorm epilogue of a GEMM (train_gemm.cuh)
+struct GemmExtra {
+  const GemmOperand* A2 = nullptr; int k1 = 0;          // cat[A (k1 columns), A2] as the A operand
+  int epi = EPI_NONE;
+  const float *gamma = nullptr, *beta = nullptr, *ln_n = nullptr;
+  float *rstd = nullptr, *h = nullptr, *dpre = nullptr, *amax = nullptr;
+};
+
 int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B, float* C, long long ldc, int mode,
-         const float* bias = nullptr, const int* c_idx = nullptr, bool split_k = false, BImg bimg = BImg{nullptr, 0, 0}) {
+         const float* bias = nullptr, const int* c_idx = nullptr, bool split_k = false, BImg bimg = BImg{nullptr, 0, 0},
+         const GemmExtra* ex = nullptr) {
   if (M <= 0 || N <= 0 || K <= 0) return 0;
   GemmP p{};
   p.b_img = bimg.p; p.b_chunk0 = bimg.chunk0; p.b_chunks = bimg.chunks;
+  p.a_split = 1 << 30;
+  if (ex) {
+    if (ex->A2) {
+      if (ex->k1 % kGemmKC || A.trans || ex->A2->trans || A.scale != ex->A2->scale || A.amax || ex->A2->amax)
+        return fail("internal: a two-segment A operand needs row-major segments with one constant scale");
+      p.A2 = *ex->A2; p.a_split = ex->k1 / kGemmKC;
+    }
+    if (ex->epi != EPI_NONE && (N > 128 || split_k || mode != GEMM_STORE || c_idx))
+      return fail("internal: the fused LayerNorm epilogue needs whole rows in one tile (N <= 128), no K split, GEMM_STORE");
+    p.epi = ex->epi; p.ln_gamma = ex->gamma; p.ln_beta = ex->beta; p.ln_n = ex->ln_n; p.ln_rstd = ex->rstd; p.ln_h = ex->h;
+    p.ln_dpre = ex->dpre; p.ln_amax = ex->amax;
+  }
   p.M = M; p.N = N; p.K = K; p.A = A; p.B = B; p.C = C; p.ldc = ldc; p.c_idx = c_idx; p.bias = bias; p.mode = mode;
   p.alpha = 1.0f; p.passes = 3; p.err = c.err; p.dbg = g_gemm_dbg;
   const int mt = (M + 127) / 128, nt = (N + 127) / 128, chunks = (K + kGemmKC - 1) / kGemmKC;
@@ -365,21 +386,40 @@ struct Seg { const float* ptr; long long ld; const int* idx; int width; float sc
 int mlp_forward(Ctx& c, const float* W, const MlpOff& m, int F, const Seg* segs, int n_seg, MlpAct& a, bool with_out) {
   const int R = (int)a.rows;
   g_trace_rows = R;
-  int k0 = 0;
-  for (int s = 0; s < n_seg; ++s) {
-    TRY(gemm(c, R, F, segs[s].width, op(segs[s].ptr, segs[s].ld, 0, segs[s].scale, nullptr, segs[s].idx),
-             op(W + m.W1 + k0, m.k_in, 0, 1.0f), a.n1, F, s == 0 ? GEMM_STORE : GEMM_ACCUM, s == 0 ? W + m.b1 : nullptr, nullptr, false,
-             img_fwd(c, m.i1, k0)));
-    k0 += segs[s].width;
+  static const bool no_fuse = getenv("TIB_TRAIN_NO_LN_FUSION") != nullptr;      // diagnostics: separate LayerNorm kernels
+  if (F <= 128 && n_seg <= 2 && !no_fuse) {
+    // whole rows fit one GEMM tile: LayerNorm + SiLU run in the GEMM epilogue, the input segments are one A operand
+    GemmExtra ex{};
+    GemmOperand a2{};
+    int K = segs[0].width;
+    if (n_seg == 2) {
+      a2 = op(segs[1].ptr, segs[1].ld, 0, segs[1].scale, nullptr, segs[1].idx);
+      ex.A2 = &a2; ex.k1 = segs[0].width; K += segs[1].width;
+    }
+    ex.epi = EPI_LN_FWD; ex.gamma = W + m.g1; ex.beta = W + m.be1; ex.rstd = a.r1; ex.h = a.h1;
+    TRY(gemm(c, R, F, K, op(segs[0].ptr, segs[0].ld, 0, segs[0].scale, nullptr, segs[0].idx), op(W + m.W1, m.k_in, 0, 1.0f), a.n1, F,
+             GEMM_STORE, W + m.b1, nullptr, false, img_fwd(c, m.i1, 0), &ex));
+    GemmExtra ex2{};
+    ex2.epi = EPI_LN_FWD; ex2.gamma = W + m.g2; ex2.beta = W + m.be2; ex2.rstd = a.r2; ex2.h = a.h2;
+    TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2, nullptr, false, img_fwd(c, m.i2, 0),
+             &ex2));
+  } else {
+    int k0 = 0;
+    for (int s = 0; s < n_seg; ++s) {
+      TRY(gemm(c, R, F, segs[s].width, op(segs[s].ptr, segs[s].ld, 0, segs[s].scale, nullptr, segs[s].idx),
+               op(W + m.W1 + k0, m.k_in, 0, 1.0f), a.n1, F, s == 0 ? GEMM_STORE : GEMM_ACCUM, s == 0 ? W + m.b1 : nullptr, nullptr, false,
+               img_fwd(c, m.i1, k0)));
+      k0 += segs[s].width;
+    }
+    const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 16);
+    { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
+    k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1);
+    LAUNCH_CHECK(); }
+    TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2, nullptr, false, img_fwd(c, m.i2, 0)));
+    { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
+    k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2);
+    LAUNCH_CHECK(); }
   }
-  const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 16);
-  { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
-  k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1);
-  LAUNCH_CHECK(); }
-  TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2, nullptr, false, img_fwd(c, m.i2, 0)));
-  { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
-  k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2);
-  LAUNCH_CHECK(); }
   if (with_out)
     TRY(gemm(c, R, m.n_out, F, op(a.h2, F, 0, 1.0f), op(W + m.W3, F, 0, 1.0f), a.out, m.n_out, GEMM_STORE, W + m.b3, nullptr, false,
              img_fwd(c, m.i3, 0)));

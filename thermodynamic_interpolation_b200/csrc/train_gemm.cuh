@@ -26,6 +26,7 @@
 // gradients).  64 KB of shared memory and 128 TMEM columns per CTA, so three CTAs share an SM.  N, ldc, the bias and C
 // must be multiples of 4 floats / 16-byte aligned (every Linear of the network is).
 #pragma once
+#include "common.cuh"
 #include "tc_common.cuh"
 
 namespace tib {
@@ -60,14 +61,25 @@ struct GemmP {
   // for the weights, whose images are made once per optimiser step and shared by every m tile of every GEMM that reads them.
   const unsigned char* b_img;
   int b_chunk0, b_chunks;     // first K chunk of this GEMM inside the image, K chunks per n tile of the image
+  // optional second A segment: K chunks >= a_split read A2 (its columns restart at 0) - cat[x1, x2] W^T as one GEMM
+  GemmOperand A2;
+  int a_split;                // in chunks; >= the chunk count when there is no second segment
+  // optional fused epilogue over whole rows (N <= 128: one n tile, no K split, GEMM_STORE):
+  //   EPI_LN_FWD: z = acc + bias -> C = n = (z - mean) / sqrt(var + 1e-5), ln_rstd[m], ln_h = SiLU(gamma n + beta)
+  //   EPI_LN_BWD: dh = acc -> ln_dpre = dh SiLU'(gamma n + beta), C = dz = the LayerNorm adjoint of gamma dpre  (n = ln_n)
+  int epi;
+  const float *ln_gamma, *ln_beta, *ln_n;
+  float *ln_rstd, *ln_h, *ln_dpre, *ln_amax;
 };
+enum { EPI_NONE = 0, EPI_LN_FWD = 1, EPI_LN_BWD = 2 };
 
 constexpr int kGemmThreads = 256;
 constexpr int kGemmKC = 32;                                   // K per chunk
 constexpr int kGemmStages = 2;
 constexpr uint32_t kGemmHalf = tc::kChunkHalfBytes;           // 8 KB: one [128 x 32] f16 image
 constexpr uint32_t kGemmStageBytes = 4 * kGemmHalf;           // A hi, A lo, B hi, B lo
-constexpr uint32_t kGemmSmem = kGemmStages * kGemmStageBytes + 64;
+constexpr uint32_t kGemmEpiFloats = 3 * 128 + 4 * 128;     // bias / gamma / beta rows + two pairs of per-row partial sums
+constexpr uint32_t kGemmSmem = kGemmStages * kGemmStageBytes + 64 + kGemmEpiFloats * 4;
 
 // power-of-two scale that maps amax into [2^12, 2^13); 1 for an all-zero (or non-finite) tensor
 __device__ __forceinline__ float pow2_scale_for(float amax) {
@@ -179,9 +191,17 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
   if (warp == 0) tmem_alloc(tmem_slot, 128);
   // the first chunk's operands are requested before the allocation barrier
   const TileRows ra = tile_rows(p.A, m0, p.M, warp, lane);
+  const bool two_seg = p.a_split < chunks_total;
+  TileRows ra2{};
+  if (two_seg) ra2 = tile_rows(p.A2, m0, p.M, warp, lane);
+  const int k_split = p.a_split * kGemmKC;                      // columns of the first segment
+  auto load_a = [&](float (&v)[16], int c) {
+    if (c < p.a_split) load_tile(v, p.A, ra, m0, p.M, c * kGemmKC, two_seg ? k_split : p.K, warp, lane);
+    else load_tile(v, p.A2, ra2, m0, p.M, (c - p.a_split) * kGemmKC, p.K - k_split, warp, lane);
+  };
   TileRows rb{};
   float va[16], vb[16];
-  load_tile(va, p.A, ra, m0, p.M, c_begin * kGemmKC, p.K, warp, lane);
+  load_a(va, c_begin);
   if (!packed_b) {
     rb = tile_rows(p.B, n0, p.N, warp, lane);
     load_tile(vb, p.B, rb, n0, p.N, c_begin * kGemmKC, p.K, warp, lane);
@@ -204,10 +224,10 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
       mbar_arrive_expect_tx(&bars[3 + st], 2 * kGemmHalf);
       bulk_g2s(stage + 2 * kGemmHalf, p.b_img + ((size_t)blockIdx.x * p.b_chunks + p.b_chunk0 + c) * (2 * kGemmHalf), 2 * kGemmHalf, &bars[3 + st]);
     }
-    store_tile(stage, p.A.trans, sa_t, warp, lane, va);
+    store_tile(stage, c < p.a_split ? p.A.trans : p.A2.trans, sa_t, warp, lane, va);
     if (!packed_b) store_tile(stage + 2 * kGemmHalf, p.B.trans, sb_t, warp, lane, vb);
     if (c + 1 < c_end) {                       // next chunk's loads fly under the barrier, the MMAs and the next wait
-      load_tile(va, p.A, ra, m0, p.M, (c + 1) * kGemmKC, p.K, warp, lane);
+      load_a(va, c + 1);
       if (!packed_b) load_tile(vb, p.B, rb, n0, p.N, (c + 1) * kGemmKC, p.K, warp, lane);
     }
     if (dbg && di < 40) p.dbg[di++] = clock64();          // after the build of this chunk (thread 0's part)
@@ -228,6 +248,141 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
   tc_fence_after();
   if (dbg) p.dbg[di++] = clock64();            // accumulator complete
 
+  if (p.epi != EPI_NONE) {
+    // ---- fused row epilogues (LayerNorm forward / backward): thread = (tile row, column half); the two halves of a row
+    // exchange their partial sums through shared memory; the accumulators are simply re-read from TMEM for every pass
+    float* const xs = reinterpret_cast<float*>(smem + kGemmStages * kGemmStageBytes + 64);
+    float* const bias_s = xs, *const gam_s = xs + 128, *const bet_s = xs + 256, *const part = xs + 384;     // part[4][128]
+    if (tid < 128) {
+      const bool ok = tid < p.N;
+      bias_s[tid] = (ok && p.bias) ? __ldg(p.bias + tid) : 0.0f;
+      gam_s[tid] = ok ? __ldg(p.ln_gamma + tid) : 0.0f;
+      bet_s[tid] = ok ? __ldg(p.ln_beta + tid) : 0.0f;
+    }
+    __syncthreads();
+    const int hcol = warp >> 2, row = 32 * (warp & 3) + lane, m = m0 + row;
+    const uint32_t tbase = tmem + ((uint32_t)(32 * (warp & 3)) << 16) + 64 * hcol;
+    const float unscale = p.alpha / (sa * sb), inv_n = 1.0f / (float)p.N;
+    float4* const tile = reinterpret_cast<float4*>(smem + warp * 8192);
+    const int j = lane & 15;
+    // coalesced copy of the warp's staged [32 x 64] block to rows of `dst` (leading dimension ldc)
+    auto flush = [&](float* dst) {
+      __syncwarp();
+      const int n = 64 * hcol + 4 * j;
+#pragma unroll 4
+      for (int i = 0; i < 16; ++i) {
+        const int r = 2 * i + (lane >> 4), mm = m0 + 32 * (warp & 3) + r;
+        if (mm < p.M && n < p.N) *reinterpret_cast<float4*>(dst + (long long)mm * p.ldc + n) = tile[r * 16 + (j ^ (r & 15))];
+      }
+      __syncwarp();
+    };
+    if (p.epi == EPI_LN_FWD) {
+      float sum = 0.0f;
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        float v[32];
+        tmem_ld32(tbase + 32 * blk, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) { const int col = 64 * hcol + 32 * blk + i; if (col < p.N) sum += v[i] * unscale + bias_s[col]; }
+      }
+      part[hcol * 128 + row] = sum;
+      __syncthreads();
+      const float mean = (part[row] + part[128 + row]) * inv_n;
+      float sq = 0.0f;
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        float v[32];
+        tmem_ld32(tbase + 32 * blk, v);
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          const int col = 64 * hcol + 32 * blk + i;
+          if (col < p.N) { const float d = (v[i] * unscale + bias_s[col]) - mean; sq += d * d; }
+        }
+      }
+      part[256 + hcol * 128 + row] = sq;
+      __syncthreads();
+      const float rs = 1.0f / sqrtf((part[256 + row] + part[384 + row]) * inv_n + 1e-5f);
+      if (hcol == 0 && m < p.M) p.ln_rstd[m] = rs;
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        float v[32];
+        tmem_ld32(tbase + 32 * blk, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) o[e] = ((v[4 * q + e] * unscale + bias_s[64 * hcol + 32 * blk + 4 * q + e]) - mean) * rs;
+          tile[lane * 16 + ((8 * blk + q) ^ (lane & 15))] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      flush(p.C);                                              // n
+#pragma unroll 4
+      for (int sl = 0; sl < 16; ++sl) {                        // h = SiLU(gamma n + beta), own row, in place
+        float4 x = tile[lane * 16 + (sl ^ (lane & 15))];
+        const int col = 64 * hcol + 4 * sl;
+        x.x = silu(fmaf(x.x, gam_s[col], bet_s[col]));         x.y = silu(fmaf(x.y, gam_s[col + 1], bet_s[col + 1]));
+        x.z = silu(fmaf(x.z, gam_s[col + 2], bet_s[col + 2])); x.w = silu(fmaf(x.w, gam_s[col + 3], bet_s[col + 3]));
+        tile[lane * 16 + (sl ^ (lane & 15))] = x;
+      }
+      flush(p.ln_h);
+    } else {
+      // LayerNorm adjoint: dpre = dh SiLU'(u), u = gamma n + beta; dn = gamma dpre; dz = rstd (dn - mean(dn) - n mean(n dn))
+      const float rs = m < p.M ? __ldg(p.ln_rstd + m) : 0.0f;
+      const float* nrow = p.ln_n + (long long)(m < p.M ? m : 0) * p.ldc;
+      float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 1
+      for (int blk = 0; blk < 2; ++blk) {
+        float v[32];
+        tmem_ld32(tbase + 32 * blk, v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const int col = 64 * hcol + 32 * blk + 4 * q;
+          float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (m < p.M && col < p.N) nn = __ldg(reinterpret_cast<const float4*>(nrow + col));
+          const float nv[4] = {nn.x, nn.y, nn.z, nn.w};
+          float o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float u = fmaf(nv[e], gam_s[col + e], bet_s[col + e]);
+            const float sg = 1.0f / (1.0f + expf(-u));
+            o[e] = (v[4 * q + e] * unscale) * (sg * (1.0f + u * (1.0f - sg)));
+            const float dn = o[e] * gam_s[col + e];
+            s1 += dn;
+            s2 += dn * nv[e];
+          }
+          tile[lane * 16 + ((8 * blk + q) ^ (lane & 15))] = make_float4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      part[hcol * 128 + row] = s1;
+      part[256 + hcol * 128 + row] = s2;
+      flush(p.ln_dpre);                                        // dpre (feeds the d gamma / d beta sums, off the critical path)
+      __syncthreads();
+      s1 = (part[row] + part[128 + row]) * inv_n;
+      s2 = (part[256 + row] + part[384 + row]) * inv_n;
+      float mx = 0.0f;
+#pragma unroll 4
+      for (int sl = 0; sl < 16; ++sl) {
+        float4 x = tile[lane * 16 + (sl ^ (lane & 15))];
+        const int col = 64 * hcol + 4 * sl;
+        float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (m < p.M && col < p.N) nn = __ldg(reinterpret_cast<const float4*>(nrow + col));
+        x.x = (x.x * gam_s[col] - s1 - nn.x * s2) * rs;         x.y = (x.y * gam_s[col + 1] - s1 - nn.y * s2) * rs;
+        x.z = (x.z * gam_s[col + 2] - s1 - nn.z * s2) * rs;     x.w = (x.w * gam_s[col + 3] - s1 - nn.w * s2) * rs;
+        if (col < p.N) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+        tile[lane * 16 + (sl ^ (lane & 15))] = x;
+      }
+      flush(p.C);                                              // dz
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+      if (lane == 0) part[warp] = mx;
+      __syncthreads();
+      if (tid == 0 && p.ln_amax) {
+        float a = 0.0f;
+        for (int w8 = 0; w8 < 8; ++w8) a = fmaxf(a, part[w8]);
+        atomicMax(reinterpret_cast<unsigned int*>(p.ln_amax), __float_as_uint(a));
+      }
+    }
+  } else {
   // ---- epilogue.  Warp w owns TMEM lanes 32 (w & 3) .. +31 (rows) and columns 64 (w >> 2) .. +63; its [32 x 64] block goes
   // through a warp-private 8 KB piece of the (now idle) operand ring so that global rows are written 256 contiguous bytes at
   // a time: element (row r, float4 slot j) sits at r * 256 + ((j ^ (r & 15)) * 16) - conflict-free both ways.
@@ -262,6 +417,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
         else atomicAdd(dst, x);
       }
     }
+  }
   }
   if (dbg) p.dbg[di++] = clock64();            // epilogue done
   tc_fence_before();
