@@ -309,8 +309,8 @@ struct BImg { const unsigned char* p; int chunk0, chunks; };
 struct GemmExtra {
   const GemmOperand* A2 = nullptr; int k1 = 0;          // cat[A (k1 columns), A2] as the A operand
   int epi = EPI_NONE;
-  const float *gamma = nullptr, *beta = nullptr, *ln_n = nullptr;
-  float *rstd = nullptr, *h = nullptr, *dpre = nullptr, *amax = nullptr;
+  const float *gamma = nullptr, *beta = nullptr;
+  float *rstd = nullptr, *h = nullptr;
 };
 
 int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B, float* C, long long ldc, int mode,
@@ -328,8 +328,7 @@ int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B
     }
     if (ex->epi != EPI_NONE && (N > 128 || split_k || mode != GEMM_STORE || c_idx))
       return fail("internal: the fused LayerNorm epilogue needs whole rows in one tile (N <= 128), no K split, GEMM_STORE");
-    p.epi = ex->epi; p.ln_gamma = ex->gamma; p.ln_beta = ex->beta; p.ln_n = ex->ln_n; p.ln_rstd = ex->rstd; p.ln_h = ex->h;
-    p.ln_dpre = ex->dpre; p.ln_amax = ex->amax;
+    p.epi = ex->epi; p.ln_gamma = ex->gamma; p.ln_beta = ex->beta; p.ln_rstd = ex->rstd; p.ln_h = ex->h;
   }
   p.M = M; p.N = N; p.K = K; p.A = A; p.B = B; p.C = C; p.ldc = ldc; p.c_idx = c_idx; p.bias = bias; p.mode = mode;
   p.alpha = 1.0f; p.passes = 3; p.err = c.err; p.dbg = g_gemm_dbg;

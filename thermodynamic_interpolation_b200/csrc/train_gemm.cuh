@@ -66,12 +66,14 @@ struct GemmP {
   int a_split;                // in chunks; >= the chunk count when there is no second segment
   // optional fused epilogue over whole rows (N <= 128: one n tile, no K split, GEMM_STORE):
   //   EPI_LN_FWD: z = acc + bias -> C = n = (z - mean) / sqrt(var + 1e-5), ln_rstd[m], ln_h = SiLU(gamma n + beta)
-  //   EPI_LN_BWD: dh = acc -> ln_dpre = dh SiLU'(gamma n + beta), C = dz = the LayerNorm adjoint of gamma dpre  (n = ln_n)
+  // (the LayerNorm ADJOINT was fused the same way - dz and dpre from the data-gradient GEMM's epilogue, the parameter sums on
+  // the side stream - and measured slower than the separate kernel, 5.21 against 4.96 ms per step: its row-per-thread reads of
+  // the saved n and the exp / divide chain sit badly in a 3-CTA-per-SM GEMM; removed)
   int epi;
-  const float *ln_gamma, *ln_beta, *ln_n;
-  float *ln_rstd, *ln_h, *ln_dpre, *ln_amax;
+  const float *ln_gamma, *ln_beta;
+  float *ln_rstd, *ln_h;
 };
-enum { EPI_NONE = 0, EPI_LN_FWD = 1, EPI_LN_BWD = 2 };
+enum { EPI_NONE = 0, EPI_LN_FWD = 1 };
 
 constexpr int kGemmThreads = 256;
 constexpr int kGemmKC = 32;                                   // K per chunk
@@ -249,7 +251,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
   if (dbg) p.dbg[di++] = clock64();            // accumulator complete
 
   if (p.epi != EPI_NONE) {
-    // ---- fused row epilogues (LayerNorm forward / backward): thread = (tile row, column half); the two halves of a row
+    // ---- fused row epilogue (LayerNorm + SiLU forward): thread = (tile row, column half); the two halves of a row
     // exchange their partial sums through shared memory; the accumulators are simply re-read from TMEM for every pass
     float* const xs = reinterpret_cast<float*>(smem + kGemmStages * kGemmStageBytes + 64);
     float* const bias_s = xs, *const gam_s = xs + 128, *const bet_s = xs + 256, *const part = xs + 384;     // part[4][128]
@@ -276,7 +278,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
       }
       __syncwarp();
     };
-    if (p.epi == EPI_LN_FWD) {
+    {
       float sum = 0.0f;
 #pragma unroll 1
       for (int blk = 0; blk < 2; ++blk) {
@@ -325,62 +327,6 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
         tile[lane * 16 + (sl ^ (lane & 15))] = x;
       }
       flush(p.ln_h);
-    } else {
-      // LayerNorm adjoint: dpre = dh SiLU'(u), u = gamma n + beta; dn = gamma dpre; dz = rstd (dn - mean(dn) - n mean(n dn))
-      const float rs = m < p.M ? __ldg(p.ln_rstd + m) : 0.0f;
-      const float* nrow = p.ln_n + (long long)(m < p.M ? m : 0) * p.ldc;
-      float s1 = 0.0f, s2 = 0.0f;
-#pragma unroll 1
-      for (int blk = 0; blk < 2; ++blk) {
-        float v[32];
-        tmem_ld32(tbase + 32 * blk, v);
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const int col = 64 * hcol + 32 * blk + 4 * q;
-          float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (m < p.M && col < p.N) nn = __ldg(reinterpret_cast<const float4*>(nrow + col));
-          const float nv[4] = {nn.x, nn.y, nn.z, nn.w};
-          float o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float u = fmaf(nv[e], gam_s[col + e], bet_s[col + e]);
-            const float sg = 1.0f / (1.0f + expf(-u));
-            o[e] = (v[4 * q + e] * unscale) * (sg * (1.0f + u * (1.0f - sg)));
-            const float dn = o[e] * gam_s[col + e];
-            s1 += dn;
-            s2 += dn * nv[e];
-          }
-          tile[lane * 16 + ((8 * blk + q) ^ (lane & 15))] = make_float4(o[0], o[1], o[2], o[3]);
-        }
-      }
-      part[hcol * 128 + row] = s1;
-      part[256 + hcol * 128 + row] = s2;
-      flush(p.ln_dpre);                                        // dpre (feeds the d gamma / d beta sums, off the critical path)
-      __syncthreads();
-      s1 = (part[row] + part[128 + row]) * inv_n;
-      s2 = (part[256 + row] + part[384 + row]) * inv_n;
-      float mx = 0.0f;
-#pragma unroll 4
-      for (int sl = 0; sl < 16; ++sl) {
-        float4 x = tile[lane * 16 + (sl ^ (lane & 15))];
-        const int col = 64 * hcol + 4 * sl;
-        float4 nn = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (m < p.M && col < p.N) nn = __ldg(reinterpret_cast<const float4*>(nrow + col));
-        x.x = (x.x * gam_s[col] - s1 - nn.x * s2) * rs;         x.y = (x.y * gam_s[col + 1] - s1 - nn.y * s2) * rs;
-        x.z = (x.z * gam_s[col + 2] - s1 - nn.z * s2) * rs;     x.w = (x.w * gam_s[col + 3] - s1 - nn.w * s2) * rs;
-        if (col < p.N) mx = fmaxf(mx, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
-        tile[lane * 16 + (sl ^ (lane & 15))] = x;
-      }
-      flush(p.C);                                              // dz
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      if (lane == 0) part[warp] = mx;
-      __syncthreads();
-      if (tid == 0 && p.ln_amax) {
-        float a = 0.0f;
-        for (int w8 = 0; w8 < 8; ++w8) a = fmaxf(a, part[w8]);
-        atomicMax(reinterpret_cast<unsigned int*>(p.ln_amax), __float_as_uint(a));
-      }
     }
   } else {
   // ---- epilogue.  Warp w owns TMEM lanes 32 (w & 3) .. +31 (rows) and columns 64 (w >> 2) .. +63; its [32 x 64] block goes
