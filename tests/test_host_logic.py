@@ -177,3 +177,52 @@ def test_regroup_frames_matches_reference_loop():
     assert got.shape == (B, T, n, 3) and np.array_equal(got, ref)
     with pytest.raises(ValueError):
         regroup_frames(xts[:, :-1], batch_idx[:-1])
+
+
+# ---- training host side (no GPU compute) -------------------------------------------------------------------------------------
+def test_packed_parameters_follow_the_library_packing_order():
+    """The flat weight / gradient vector of tib_train_loss_grad uses the order of tib_packed_weight_count: the parameter list,
+    its total length and the reference's state_dict shapes must agree."""
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.engine import model_desc, packed_keys
+    from thermodynamic_interpolation_b200.train import flatten, packed_parameters
+    model = cPaiNN(n_features=64, score_layers=3, temp_length=100)
+    params = packed_parameters(model)
+    keys = packed_keys(model.hyper)
+    sd = model.state_dict()
+    assert len(params) == len(keys)
+    for p, (k, shape) in zip(params, keys):
+        assert tuple(p.shape) == tuple(shape) == tuple(sd[k].shape) and p.data_ptr() == sd[k].data_ptr(), k
+    desc = model_desc(model.hyper)
+    assert flatten(params).numel() == _lib.load().tib_packed_weight_count(C.byref(desc))
+    assert np.array_equal(flatten(params).numpy(), pack_state_dict(sd, model.hyper))
+    # the scalar device_tracker dummies of the reference are not part of the packed vector (they get no gradient)
+    assert all(p.dim() > 0 for p in params) and any(p.dim() == 0 for p in model.parameters())
+
+
+def test_training_is_cuda_only_and_draws_follow_the_reference_order():
+    from thermodynamic_interpolation_b200.ambient import interpolants, losses
+    from thermodynamic_interpolation_b200.ambient.models.cpainn import cPaiNN
+    from thermodynamic_interpolation_b200.train import TrainEngine
+    from oracle import train_oracle as to
+    model = cPaiNN(n_features=32, score_layers=1, temp_length=100)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        TrainEngine(model.hyper, "cpu")
+    torch.manual_seed(7)
+    t = losses.draw_times([9, 4, 9])
+    torch.manual_seed(7)
+    t_ref, _ = to.draw_t_z([9, 4, 9])
+    assert torch.equal(t, t_ref) and t.shape == (22, 1)
+    with pytest.raises(ValueError):
+        losses.draw_times([3], "gaussian")
+    # the drop-in interpolant's callables equal the oracle's restatement of interpolants.py:71-82
+    tt = torch.linspace(0.05, 0.95, 7).unsqueeze(1)
+    for kind in ("sin2", "brownian"):
+        ip = interpolants.LinearInterpolant(a=1, gamma=kind)
+        g, gd = to.gamma_fns(kind, 1.0)
+        assert torch.equal(ip.gamma(tt), g(tt)) and torch.equal(ip.gamma_dot(tt), gd(tt)) and ip.kind == kind
+    x0, x1 = torch.randn(7, 3), torch.randn(7, 3)
+    ip = interpolants.LinearInterpolant(a=1, gamma="sin2")
+    assert torch.allclose(ip.It(tt, x0, x1), (1 - tt) * x0 + tt * x1) and torch.equal(ip.dtIt(tt, x0, x1), -1.0 * x0 + 1.0 * x1)
+    with pytest.raises(NotImplementedError):
+        interpolants.LinearInterpolant(gamma="cubic")
