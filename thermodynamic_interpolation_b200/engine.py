@@ -122,7 +122,7 @@ def pack_node_tiles(n_atoms: np.ndarray, max_nodes: int = 16, max_rows: int = 12
 class PreparedBatch:
     """Device-side view of a batch in the layout `tib_batch` wants; keeps the tensors alive."""
 
-    def __init__(self, batch, hp: Hyper, device: torch.device, validate: bool = True):
+    def __init__(self, batch, hp: Hyper, device: torch.device, validate: bool = True, sampling_tables: bool = True):
         atoms_name = "atoms" if hp.variant == "ambient" else "atom_number"
         atoms = getattr(batch, atoms_name).to(device)
         N = atoms.shape[0]
@@ -164,6 +164,9 @@ class PreparedBatch:
             self.temp1 = batch.T1.to(device, torch.float32).contiguous()
         elif hp.n_temp_encoders == 1:
             self.temp0 = batch.T.to(device, torch.float32).contiguous()
+        if not sampling_tables:      # the training step needs neither the embedding de-duplication nor the node tiling
+            self.c = None
+            return
         # x-independent node embedding: one row per distinct (atom id, T0, T1) triple
         keys = [self.atom_id.to(torch.int64)]
         for tt in (self.temp0, self.temp1):

@@ -31,12 +31,19 @@ class PreparedTrainBatch:
     def __init__(self, batch0, batch1, hp: Hyper, device, validate: bool = True):
         view = MolBatch(atoms=batch0.atoms, batch=batch0.batch, edge_index=batch0.edge_index, edge_type=batch0.edge_type,
                         T0=batch0.T, T1=batch1.T)
-        self.pb = PreparedBatch(view, hp, device, validate)
+        self.pb = PreparedBatch(view, hp, device, validate, sampling_tables=False)
         self.x0 = batch0.x.to(device, torch.float32).contiguous()
         self.x1 = batch1.x.to(device, torch.float32).contiguous()
         if self.x0.shape != (self.pb.n_nodes, 3) or self.x1.shape != self.x0.shape:
             raise ValueError("batch0.x and batch1.x must both be [N,3] for the same molecules")
-        self.n_atoms = torch.diff(self.pb.mol_ptr).tolist()
+        self._n_atoms = None
+
+    @property
+    def n_atoms(self):
+        """Atoms per molecule (host list; only needed to draw the per-molecule times)."""
+        if self._n_atoms is None:
+            self._n_atoms = torch.diff(self.pb.mol_ptr).tolist()
+        return self._n_atoms
 
 
 class TrainEngine:
