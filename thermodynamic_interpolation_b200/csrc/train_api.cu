@@ -10,6 +10,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include <cstdint>
 #include <vector>
 
@@ -50,7 +51,7 @@ struct Prof {      // tib_profile_begin / tib_profile_end: device time per kerne
     if (e0) {
       float ms = 0.0f;
       cudaEventRecord(e1, st); cudaEventSynchronize(e1); cudaEventElapsedTime(&ms, e0, e1);
-      fprintf(stderr, "[kern] %s_rows%lld  %.1f us\n", name, g_trace_rows, ms * 1e3);
+      fprintf(stderr, "[kern] %.*s_rows%lld  %.1f us\n", (int)strcspn(name, "<"), name, g_trace_rows, ms * 1e3);
       cudaEventDestroy(e0); cudaEventDestroy(e1);
     }
   }
@@ -63,6 +64,14 @@ thread_local long long* g_gemm_dbg = nullptr;      // device buffer [64] when ti
     tib_internal::count_launches(1);                                                          \
     cudaError_t _e = cudaGetLastError();                                                      \
     if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
+  } while (0)
+// an element-wise / scatter kernel of the training step: profile scope (kernel class "train_other"; with TIB_TRAIN_TRACE the
+// launch is timed synchronously and printed under the kernel's name) + launch check
+#define TRAIN_LAUNCH(stream, ...)                                                             \
+  do {                                                                                        \
+    Prof pf(TIB_K_TRAIN_OTHER, stream, #__VA_ARGS__);                                         \
+    __VA_ARGS__;                                                                              \
+    LAUNCH_CHECK();                                                                           \
   } while (0)
 #define CUDA_TRY(expr)                                                                        \
   do {                                                                                        \
@@ -411,13 +420,9 @@ int mlp_forward(Ctx& c, const float* W, const MlpOff& m, int F, const Seg* segs,
       k0 += segs[s].width;
     }
     const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 16);
-    { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
-    k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(c.st, k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1));
     TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2, nullptr, false, img_fwd(c, m.i2, 0)));
-    { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_fwd");
-    k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(c.st, k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2));
   }
   if (with_out)
     TRY(gemm(c, R, m.n_out, F, op(a.h2, F, 0, 1.0f), op(W + m.W3, F, 0, 1.0f), a.out, m.n_out, GEMM_STORE, W + m.b3, nullptr, false,
@@ -440,9 +445,7 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
   if (dY) {
     TRY(c.to_side());
     TRY(gemm(c, m.n_out, F, R, op(dY, m.n_out, 1, 1.0f, amax_dY), op(a.h2, F, 1, 1.0f), G + m.W3, F, GEMM_ATOMIC, nullptr, nullptr, true));
-    { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_colsum");
-    k_tr_colsum<<<dim3((m.n_out + kEW - 1) / kEW, std::min(blocks_for(R, 32), 512)), kEW, 0, c.st>>>(R, m.n_out, dY, G + m.b3, nullptr);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(c.st, k_tr_colsum<<<dim3((m.n_out + kEW - 1) / kEW, std::min(blocks_for(R, 32), 512)), kEW, 0, c.st>>>(R, m.n_out, dY, G + m.b3, nullptr));
     TRY(c.side_done(dY));
     c.to_main();
     TRY(c.before_write(dA));
@@ -450,9 +453,7 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
              img_tr(c, m.i3, 0)));
   }
   float* am2 = c.new_amax();
-  { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_bwd");
-  ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dA, a.n2, a.r2, W + m.g2, W + m.be2, G + m.g2, G + m.be2, G + m.b2, am2);
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(c.st, ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dA, a.n2, a.r2, W + m.g2, W + m.be2, G + m.g2, G + m.be2, G + m.b2, am2));
   TRY(c.to_side());
   TRY(gemm(c, F, F, R, op(dA, F, 1, 1.0f, am2), op(a.h1, F, 1, 1.0f), G + m.W2, F, GEMM_ATOMIC, nullptr, nullptr, true));
   TRY(c.side_done(dA));
@@ -460,9 +461,7 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
   TRY(c.before_write(dB));
   TRY(gemm(c, R, F, F, op(dA, F, 0, 1.0f, am2), op(W + m.W2, F, 1, 1.0f), dB, F, GEMM_STORE, nullptr, nullptr, false, img_tr(c, m.i2, 0)));
   float* am1 = c.new_amax();
-  { Prof pf(TIB_K_TRAIN_OTHER, c.st, "k_tr_ln_silu_bwd");
-  ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1);
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(c.st, ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1));
   TRY(c.to_side());
   int k0 = 0;
   for (int s = 0; s < n_seg; ++s) {
@@ -535,43 +534,27 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   // the weights change with every optimiser step)
   static const bool no_pack = getenv("TIB_TRAIN_NO_PACK") != nullptr;       // diagnostics: build every B operand on the fly
   if (!no_pack && o.pack.n > 0) {
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_pack_operand");
-    k_pack_operand<<<o.pack.total_blocks, kGemmThreads, 0, st>>>(o.pack, W, w.img);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_pack_operand<<<o.pack.total_blocks, kGemmThreads, 0, st>>>(o.pack, W, w.img));
     c.img = w.img;
   }
 
   // ---- interpolant, targets, graph (interpolants.py:16-33; losses.py:52-57; graph.py:27-29) -----------------------------------------
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_interp");
-  k_tr_interp<<<std::min(blocks_for(N, kEW), c.n_sms * 4), kEW, 0, st>>>((int)N, b->x0, b->x1, b->t, b->z, ip->gamma_kind, ip->a, w.xt, w.tgt, w.colsum);
-  LAUNCH_CHECK(); }
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_center");
-  k_tr_center<<<blocks_for(6 * N, kEW), kEW, 0, st>>>((int)N, w.xt, w.colsum);
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(st, k_tr_interp<<<std::min(blocks_for(N, kEW), c.n_sms * 4), kEW, 0, st>>>((int)N, b->x0, b->x1, b->t, b->z, ip->gamma_kind, ip->a, w.xt, w.tgt, w.colsum));
+  TRAIN_LAUNCH(st, k_tr_center<<<blocks_for(6 * N, kEW), kEW, 0, st>>>((int)N, w.xt, w.colsum));
   GraphP gp{b->n_mol, (int)N, E, b->mol_ptr, (const long long*)b->edge_ptr, b->edge_type, w.xt, w.src, w.dst, w.pair, w.etype, w.in_ptr,
             w.dir, w.pair_dist};
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_graph");
-  k_tr_graph<<<dim3(b->n_mol, 2), kEW, 0, st>>>(gp);
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(st, k_tr_graph<<<dim3(b->n_mol, 2), kEW, 0, st>>>(gp));
 
   // ---- embeddings (embedding.py:68-86,249-261; cpainn.py:70-71): x-independent, shared by both passes ------------------------------
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_embed_in");
-  k_tr_embed_in<<<(int)N, kEW, 0, st>>>((int)N, F, n_temp, b->atom_id, b->temp0, b->temp1, b->t, W + o.atom_emb, desc->temp_mean,
-                                        desc->temp_range, desc->temp_length, desc->time_length, w.X0);
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(st, k_tr_embed_in<<<(int)N, kEW, 0, st>>>((int)N, F, n_temp, b->atom_id, b->temp0, b->temp1, b->t, W + o.atom_emb, desc->temp_mean,
+                                        desc->temp_range, desc->temp_length, desc->time_length, w.X0));
   const Seg seg_emb[1] = {{w.X0, (2 + n_temp) * F, nullptr, (2 + n_temp) * F, 1.0f}};
   TRY(mlp_forward(c, W, o.combine, F, seg_emb, 1, w.emb, true));
   LayerAct& A0 = w.layers[0];
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_gather_rows");
-  k_tr_gather_rows<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2, F, nullptr, (int)N, w.s0, A0.s_in);
-  LAUNCH_CHECK(); }
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_gather_rows");
-  k_tr_gather_rows<<<blocks_for(E2 * F, kEW), kEW, 0, st>>>(E2, F, w.etype, 0, W + o.edge_emb, A0.e_in);
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(st, k_tr_gather_rows<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2, F, nullptr, (int)N, w.s0, A0.s_in));
+  TRAIN_LAUNCH(st, k_tr_gather_rows<<<blocks_for(E2 * F, kEW), kEW, 0, st>>>(E2, F, w.etype, 0, W + o.edge_emb, A0.e_in));
   CUDA_TRY(cudaMemsetAsync(A0.v_in, 0, sizeof(float) * N2 * 3 * F, st));
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_pair_pe");
-  k_tr_pair_pe<<<blocks_for(P2 * (F / 2), kEW), kEW, 0, st>>>(P2, F, w.pair_dist, desc->length_scale, w.pe);
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(st, k_tr_pair_pe<<<blocks_for(P2 * (F / 2), kEW), kEW, 0, st>>>(P2, F, w.pair_dist, desc->length_scale, w.pe));
 
   // ---- forward through the layers (cpainn.py:138-150) ----------------------------------------------------------------------------------
   const int node_blocks = (int)std::min<long long>(N2, c.n_sms * 16);
@@ -590,19 +573,13 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     TRY(mlp_forward(c, W, lo.phi, F, seg_phi, 2, a.phi, true));
     TRY(c.join());
     CombineP cp{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next};
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_combine_fwd");
-    k_tr_combine_fwd<<<node_blocks, kEW, 0, st>>>(cp);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_combine_fwd<<<node_blocks, kEW, 0, st>>>(cp));
     TRY(gemm(c, (int)(3 * N2), 2 * F, F, op(a.v_mid, F, 0, kStateScale), op(W + lo.UV, F, 0, 1.0f), a.uvvv, 2 * F, GEMM_STORE, nullptr, nullptr,
              false, img_fwd(c, lo.iuv, 0)));
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_q");
-    k_tr_upd_q<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_upd_q<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q));
     const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
     TRY(mlp_forward(c, W, lo.upd, F, seg_upd, 2, a.upd, true));
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_apply");
-    k_tr_upd_apply<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, a.s_mid, a.v_mid, s_next, v_next);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_upd_apply<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, a.s_mid, a.v_mid, s_next, v_next));
   }
 
   // ---- readout, loss and d loss / d b (cpainn.py:425-437; losses.py:126-133) -----------------------------------------------------------
@@ -612,9 +589,7 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   float* bout = out_b ? out_b : w.dX0;      // dX0 is free until the very end ([N][F] >= [2N][3] for F >= 32)
   ReadoutP rp{(int)N2, F, (int)N, w.ro.h2, w.v_last, W + o.readout.W3, W + o.readout.b3, W + o.Vout, w.tgt, bout, w.gate, loss,
               w.dA, w.dv, G + o.readout.W3, G + o.readout.b3, G + o.Vout, am_ro};
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_readout");
-  k_tr_readout<<<std::min(blocks_for(N2, 4), c.n_sms * 4), kEW, 2 * F * sizeof(float), st>>>(rp);
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(st, k_tr_readout<<<std::min(blocks_for(N2, 4), c.n_sms * 4), kEW, 2 * F * sizeof(float), st>>>(rp));
 
   // ---- backward ------------------------------------------------------------------------------------------------------------------------------
   {
@@ -631,16 +606,12 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     float* am_gac = c.new_amax();
     TRY(c.before_write(w.d_gac));
     TRY(c.before_write(w.d_uvvv));
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_bwd1");
-    k_tr_upd_bwd1<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, w.ds, w.dv, w.d_gac, w.d_uvvv, w.dq, am_gac);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_upd_bwd1<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, w.ds, w.dv, w.d_gac, w.d_uvvv, w.dq, am_gac));
     const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
     const SegGrad sg_upd[2] = {{w.dq, F, GEMM_ACCUM, nullptr}, {w.ds, F, GEMM_ACCUM, nullptr}};
     TRY(mlp_backward(c, W, G, lo.upd, F, seg_upd, sg_upd, 2, a.upd, w.d_gac, am_gac, w.dA, w.dB));
     float* am_uv = c.new_amax();
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_upd_bwd2");
-    k_tr_upd_bwd2<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, w.dq, w.d_uvvv, am_uv);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_upd_bwd2<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, w.dq, w.d_uvvv, am_uv));
     TRY(c.to_side());
     TRY(gemm(c, 2 * F, F, (int)(3 * N2), op(w.d_uvvv, 2 * F, 1, 1.0f, am_uv), op(a.v_mid, F, 1, kStateScale), G + lo.UV, F, GEMM_ATOMIC,
              nullptr, nullptr, true));
@@ -658,12 +629,8 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     float* e_next = l + 1 < L ? w.layers[l + 1].e_in : w.e_spare;
     CombineBwdP cb{{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next},
                    w.ds, w.dv, w.de, w.d_phi3, w.d_w3, w.dv_src, am_phi, am_w};
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_combine_bwd");
-    k_tr_combine_bwd<<<node_blocks, kEW, 0, st>>>(cb);
-    LAUNCH_CHECK(); }
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_add");
-    k_tr_add<<<blocks_for(N2 * 3 * F, kEW), kEW, 0, st>>>(N2 * 3 * F, w.dv, w.dv_src);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_combine_bwd<<<node_blocks, kEW, 0, st>>>(cb));
+    TRAIN_LAUNCH(st, k_tr_add<<<blocks_for(N2 * 3 * F, kEW), kEW, 0, st>>>(N2 * 3 * F, w.dv, w.dv_src));
     // the w MLP's adjoint produces weight gradients only: all of it runs on the side stream, with its own scratch
     const Seg seg_w[1] = {{w.pe, F, nullptr, F, 1.0f}};
     TRY(c.to_side());
@@ -677,13 +644,9 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   // embeddings: e0 = Emb4(edge_type), s0 = combine MLP (both passes share it), atom embedding
   {
     const int nb = std::min(blocks_for(E2, 32), c.n_sms * 8);
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_scatter_rows");
-    k_tr_scatter_rows<<<nb, kEW, sizeof(float) * desc->n_edge_types * F, st>>>(E2, F, desc->n_edge_types, w.etype, w.de, G + o.edge_emb);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_scatter_rows<<<nb, kEW, sizeof(float) * desc->n_edge_types * F, st>>>(E2, F, desc->n_edge_types, w.etype, w.de, G + o.edge_emb));
     float* am_s0 = c.new_amax();
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_fold_passes");
-    k_tr_fold_passes<<<blocks_for(N * F, kEW), kEW, 0, st>>>(N * F, w.ds, w.ds0, am_s0);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_fold_passes<<<blocks_for(N * F, kEW), kEW, 0, st>>>(N * F, w.ds, w.ds0, am_s0));
     // weight gradients over all input columns; the input gradient only for the first F (the atom embedding) - the
     // positional-encoding columns carry no parameters
     const int kin = (2 + n_temp) * F;
@@ -692,9 +655,7 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     TRY(mlp_backward(c, W, G, o.combine, F, seg2, sg2, 2, w.emb, w.ds0, am_s0, w.dA, w.dB));
     TRY(c.before_write(w.dX0));
     const int nb2 = std::min(blocks_for(N, 64), c.n_sms);
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_scatter_rows");
-    k_tr_scatter_rows<<<nb2, 1024, sizeof(float) * desc->n_types * F, st>>>(N, F, desc->n_types, b->atom_id, w.dX0, G + o.atom_emb);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_scatter_rows<<<nb2, 1024, sizeof(float) * desc->n_types * F, st>>>(N, F, desc->n_types, b->atom_id, w.dX0, G + o.atom_emb));
   }
   TRY(c.join());          // the caller's stream owns the complete gradient again
   return 0;
@@ -740,15 +701,11 @@ int tib_adam_step(float* weights, const float* grad, float* m, float* v, size_t 
   CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double), st));
   const int nb = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
   if (max_grad_norm > 0.0f) {
-    { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_sqnorm");
-    k_tr_sqnorm<<<nb, 256, 0, st>>>((long long)n, grad, scratch);
-    LAUNCH_CHECK(); }
+    TRAIN_LAUNCH(st, k_tr_sqnorm<<<nb, 256, 0, st>>>((long long)n, grad, scratch));
   }
   const double bc1 = 1.0 - std::pow((double)beta1, step), bc2 = 1.0 - std::pow((double)beta2, step);
-  { Prof pf(TIB_K_TRAIN_OTHER, st, "k_tr_adam");
-  k_tr_adam<<<nb, 256, 0, st>>>((long long)n, weights, grad, m, v, scratch, max_grad_norm, lr, beta1, beta2, eps, weight_decay,
-                                (float)bc1, (float)std::sqrt(bc2));
-  LAUNCH_CHECK(); }
+  TRAIN_LAUNCH(st, k_tr_adam<<<nb, 256, 0, st>>>((long long)n, weights, grad, m, v, scratch, max_grad_norm, lr, beta1, beta2, eps, weight_decay,
+                                (float)bc1, (float)std::sqrt(bc2)));
   return 0;
 }
 
