@@ -17,6 +17,16 @@ namespace train {
 
 constexpr int kEW = 128;   // threads of the element-wise kernels
 
+// sigmoid / SiLU with the MUFU approximations (ex2, rcp; ~2 ulp) - the IEEE expf + divide chain made the LayerNorm kernels
+// instruction-bound (60 instructions per element); the sampling path's tensor-core epilogues use the same approximation
+__device__ __forceinline__ float sigmoid_fast(float z) {
+  float e, r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * -1.4426950408889634f));
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.0f + e));
+  return r;
+}
+__device__ __forceinline__ float silu_mufu(float z) { return z * sigmoid_fast(z); }
+
 __device__ __forceinline__ void atomic_amax(float* slot, float v) {       // v >= 0
   atomicMax(reinterpret_cast<unsigned int*>(slot), __float_as_uint(v));
 }
@@ -231,7 +241,7 @@ __global__ void k_tr_ln_silu_fwd(long long R, int F, float* __restrict__ zn, flo
     for (int f = lane; f < F; f += 32) {
       const float nn = (z[f] - mean) * rs;
       z[f] = nn;
-      h[r * F + f] = silu(fmaf(nn, gamma[f], beta[f]));
+      h[r * F + f] = silu_mufu(fmaf(nn, gamma[f], beta[f]));
     }
   }
 }
@@ -268,7 +278,7 @@ __global__ void __launch_bounds__(256, 4) k_tr_ln_silu_bwd(long long R, int F, f
       dn[k] = nv[k] = 0.0f;
       if (f < F) {
         const float n_ = nn[f], u = fmaf(n_, gam[k], bet[k]);
-        const float sg = 1.0f / (1.0f + expf(-u));
+        const float sg = sigmoid_fast(u);
         const float dpre = d[f] * (sg * (1.0f + u * (1.0f - sg)));       // SiLU'(u)
         a_g[k] += dpre * n_;
         a_b[k] += dpre;

@@ -322,8 +322,8 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
       for (int sl = 0; sl < 16; ++sl) {                        // h = SiLU(gamma n + beta), own row, in place
         float4 x = tile[lane * 16 + (sl ^ (lane & 15))];
         const int col = 64 * hcol + 4 * sl;
-        x.x = silu(fmaf(x.x, gam_s[col], bet_s[col]));         x.y = silu(fmaf(x.y, gam_s[col + 1], bet_s[col + 1]));
-        x.z = silu(fmaf(x.z, gam_s[col + 2], bet_s[col + 2])); x.w = silu(fmaf(x.w, gam_s[col + 3], bet_s[col + 3]));
+        x.x = tc::silu_fast(fmaf(x.x, gam_s[col], bet_s[col]));         x.y = tc::silu_fast(fmaf(x.y, gam_s[col + 1], bet_s[col + 1]));
+        x.z = tc::silu_fast(fmaf(x.z, gam_s[col + 2], bet_s[col + 2])); x.w = tc::silu_fast(fmaf(x.w, gam_s[col + 3], bet_s[col + 3]));
         tile[lane * 16 + (sl ^ (lane & 15))] = x;
       }
       flush(p.ln_h);
