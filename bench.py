@@ -490,8 +490,7 @@ def run_train(args):
 
     def e2e_step(i):
         b0, b1, t, z = host[i % n_host]
-        loss = trainer.step(b0.clone().to(dev, non_blocking=True), b1.clone().to(dev, non_blocking=True),
-                            t=t.to(dev, non_blocking=True), z=z.to(dev, non_blocking=True))
+        loss = trainer.step(b0, b1, t=t.to(dev, non_blocking=True), z=z.to(dev, non_blocking=True))     # pinned host batches
         host_loss.copy_(loss, non_blocking=True)
 
     e2e_step(0)

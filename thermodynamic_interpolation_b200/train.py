@@ -28,12 +28,22 @@ class PreparedTrainBatch:
     """batch0 / batch1 of the training loop (contract of MDQM9MultiTempDataset.process, mdqm9/data/mdqm9_ambient.py:87-107:
     x, T, atoms, edge_index, edge_type, batch) as device arrays in the layout `tib_train_batch` wants."""
 
+    _ARRAYS = ("mol_ptr", "edge_ptr", "atom_id", "edge_type", "temp0", "temp1", "batch_vec")
+
     def __init__(self, batch0, batch1, hp: Hyper, device, validate: bool = True):
         view = MolBatch(atoms=batch0.atoms, batch=batch0.batch, edge_index=batch0.edge_index, edge_type=batch0.edge_type,
                         T0=batch0.T, T1=batch1.T)
-        self.pb = PreparedBatch(view, hp, device, validate, sampling_tables=False)
-        self.x0 = batch0.x.to(device, torch.float32).contiguous()
-        self.x1 = batch1.x.to(device, torch.float32).contiguous()
+        device = torch.device(device)
+        if batch0.atoms.device.type == "cpu" and device.type == "cuda":
+            # host batches (what a DataLoader yields): validate and derive the index arrays on the host - no device
+            # synchronisation, so the preparation of step k + 1 overlaps the device work of step k - then copy
+            self.pb = PreparedBatch(view, hp, torch.device("cpu"), validate, sampling_tables=False)
+            for name in self._ARRAYS:
+                setattr(self.pb, name, getattr(self.pb, name).to(device, non_blocking=True))
+        else:
+            self.pb = PreparedBatch(view, hp, device, validate, sampling_tables=False)
+        self.x0 = batch0.x.to(device, torch.float32, non_blocking=True).contiguous()
+        self.x1 = batch1.x.to(device, torch.float32, non_blocking=True).contiguous()
         if self.x0.shape != (self.pb.n_nodes, 3) or self.x1.shape != self.x0.shape:
             raise ValueError("batch0.x and batch1.x must both be [N,3] for the same molecules")
         self._n_atoms = None
