@@ -699,7 +699,10 @@ int tib_adam_step(float* weights, const float* grad, float* m, float* v, size_t 
   if (step < 1) return fail("tib_adam_step: step counts from 1");
   cudaStream_t st = (cudaStream_t)stream;
   CUDA_TRY(cudaMemsetAsync(scratch, 0, sizeof(double), st));
-  const int nb = (int)std::min<size_t>((n + 255) / 256, 148 * 8);
+  int dev = 0, n_sms = 148;
+  CUDA_TRY(cudaGetDevice(&dev));
+  CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
+  const int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)n_sms * 8);
   if (max_grad_norm > 0.0f) {
     TRAIN_LAUNCH(st, k_tr_sqnorm<<<nb, 256, 0, st>>>((long long)n, grad, scratch));
   }
