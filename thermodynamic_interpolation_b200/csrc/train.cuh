@@ -17,6 +17,12 @@ namespace train {
 
 constexpr int kEW = 128;   // threads of the element-wise kernels
 
+// Programmatic dependent launch (every launch of the training step carries the attribute, train_api.cu::launch_pdl): a kernel
+// first lets the NEXT kernel of the stream be scheduled, then waits until everything before it has completed and is visible.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
+
 // sigmoid / SiLU with the MUFU approximations (ex2, rcp; ~2 ulp) - the IEEE expf + divide chain made the LayerNorm kernels
 // instruction-bound (60 instructions per element); the sampling path's tensor-core epilogues use the same approximation
 __device__ __forceinline__ float sigmoid_fast(float z) {
@@ -69,6 +75,7 @@ __device__ __forceinline__ void gamma_of(int kind, float a, float t, float& g, f
 __global__ void k_tr_interp(int N, const float* __restrict__ x0, const float* __restrict__ x1, const float* __restrict__ t,
                             const float* __restrict__ z, int gamma_kind, float a, float* __restrict__ xt, float* __restrict__ tgt,
                             float* __restrict__ colsum) {
+  pdl_entry();
   __shared__ float red[6];
   if (threadIdx.x < 6) red[threadIdx.x] = 0.0f;
   __syncthreads();
@@ -101,6 +108,7 @@ __global__ void k_tr_interp(int N, const float* __restrict__ x0, const float* __
 
 // losses.py:56-57: xt -= mean over ALL atoms of the batch (per pass)
 __global__ void k_tr_center(int N, float* __restrict__ xt, const float* __restrict__ colsum) {
+  pdl_entry();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 6 * N) return;
   const int p = i / (3 * N), c = i % 3;
@@ -121,6 +129,7 @@ struct GraphP {
 };
 
 __global__ void k_tr_graph(const GraphP g) {
+  pdl_entry();
   const int m = blockIdx.x, pass = blockIdx.y;
   const int nb0 = g.mol_ptr[m], n = g.mol_ptr[m + 1] - nb0;
   const long long eb0 = g.edge_ptr[m];
@@ -152,6 +161,7 @@ __global__ void k_tr_graph(const GraphP g) {
 __global__ void k_tr_embed_in(int N, int F, int n_temp, const int* __restrict__ atoms, const float* __restrict__ T0,
                               const float* __restrict__ T1, const float* __restrict__ t, const float* __restrict__ atom_emb,
                               float temp_mean, float temp_range, float temp_length, float time_length, float* __restrict__ X0) {
+  pdl_entry();
   const int n = blockIdx.x;
   const int width = (2 + n_temp) * F;
   float* row = X0 + (long long)n * width;
@@ -178,6 +188,7 @@ __global__ void k_tr_embed_in(int N, int F, int n_temp, const int* __restrict__ 
 
 // PE of the pair distances [P2][F] (embedding.py:137-160, cpainn.py:282) and e0 = Emb4(edge_type) [E2][F] (cpainn.py:70)
 __global__ void k_tr_pair_pe(long long P2, int F, const float* __restrict__ pair_dist, float length, float* __restrict__ out) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   const int half = F / 2;
   if (i >= P2 * half) return;
@@ -190,6 +201,7 @@ __global__ void k_tr_pair_pe(long long P2, int F, const float* __restrict__ pair
 }
 __global__ void k_tr_gather_rows(long long rows, int F, const int* __restrict__ idx, int idx_mod, const float* __restrict__ table,
                                  float* __restrict__ out) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= rows * F) return;
   const long long r = i / F;
@@ -201,6 +213,7 @@ __global__ void k_tr_gather_rows(long long rows, int F, const int* __restrict__ 
 // (shared-memory atomics: several rows of the block may hit the same table row), then one global atomic per entry and block
 __global__ void k_tr_scatter_rows(long long rows, int F, int table_rows, const int* __restrict__ idx, const float* __restrict__ d,
                                   float* __restrict__ grad_table) {
+  pdl_entry();
   extern __shared__ float acc[];                      // [table_rows][F]
   for (int i = threadIdx.x; i < table_rows * F; i += blockDim.x) acc[i] = 0.0f;
   __syncthreads();
@@ -218,6 +231,7 @@ __global__ void k_tr_scatter_rows(long long rows, int F, int table_rows, const i
 }
 // out[n] = a[n] + a[N + n]  (the two passes share the x-independent embedding)
 __global__ void k_tr_fold_passes(long long n, const float* __restrict__ a, float* __restrict__ out, float* amax) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float v = 0.0f;
   if (i < n) { v = a[i] + a[n + i]; out[i] = v; }
@@ -228,6 +242,7 @@ __global__ void k_tr_fold_passes(long long n, const float* __restrict__ a, float
 // z [R][F] (pre-LayerNorm, bias included) -> n = (z - mean) / sqrt(var + eps) in place, rstd [R], h = SiLU(gamma n + beta)
 __global__ void k_tr_ln_silu_fwd(long long R, int F, float* __restrict__ zn, float* __restrict__ rstd, float* __restrict__ h,
                                  const float* __restrict__ gamma, const float* __restrict__ beta) {
+  pdl_entry();
   const int lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (long long r = (long long)blockIdx.x * wpb + (threadIdx.x >> 5); r < R; r += (long long)gridDim.x * wpb) {
     float* z = zn + r * F;
@@ -253,6 +268,7 @@ __global__ void __launch_bounds__(256, 4) k_tr_ln_silu_bwd(long long R, int F, f
                                                            const float* __restrict__ rstd, const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float* __restrict__ g_gamma,
                                                            float* __restrict__ g_beta, float* __restrict__ g_bias, float* amax) {
+  pdl_entry();
   extern __shared__ float sacc[];                       // [3][F]
   for (int i = threadIdx.x; i < 3 * F; i += blockDim.x) sacc[i] = 0.0f;
   __syncthreads();
@@ -321,6 +337,7 @@ __global__ void __launch_bounds__(256, 4) k_tr_ln_silu_bwd(long long R, int F, f
 __global__ void k_tr_ln_param_grads(long long R, int C, const float* __restrict__ dpre, const float* __restrict__ nrm,
                                     const float* __restrict__ dz, float* __restrict__ g_gamma, float* __restrict__ g_beta,
                                     float* __restrict__ g_bias) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   if (c >= C) return;
   const long long per = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(R, r0 + per);
@@ -348,6 +365,7 @@ __global__ void k_tr_ln_param_grads(long long R, int C, const float* __restrict_
 
 // out[c] += sum_r d[r][c]   (bias gradient of an output Linear); also records |max| of d.  grid = (column blocks, row slabs)
 __global__ void k_tr_colsum(long long R, int C, const float* __restrict__ d, float* __restrict__ out, float* amax) {
+  pdl_entry();
   const int c = blockIdx.x * blockDim.x + threadIdx.x;
   const long long per = (R + gridDim.y - 1) / gridDim.y, r0 = blockIdx.y * per, r1 = min(R, r0 + per);
   float acc[4] = {0.0f, 0.0f, 0.0f, 0.0f}, mx = 0.0f;
@@ -375,6 +393,7 @@ struct CombineP {
 };
 
 __global__ void k_tr_combine_fwd(const CombineP p) {
+  pdl_entry();
   const int F = p.F;
   for (int j = blockIdx.x; j < p.N2; j += gridDim.x) {
     const int r0 = p.in_ptr[j], r1 = p.in_ptr[j + 1];
@@ -420,6 +439,7 @@ struct CombineBwdP {
 };
 
 __global__ void k_tr_combine_bwd(const CombineBwdP q) {
+  pdl_entry();
   const CombineP& p = q.c;
   const int F = p.F;
   float mx_p = 0.0f, mx_w = 0.0f;
@@ -473,6 +493,7 @@ __global__ void k_tr_combine_bwd(const CombineBwdP q) {
 }
 
 __global__ void k_tr_add(long long n, float* __restrict__ a, const float* __restrict__ b) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) a[i] += b[i];
 }
@@ -480,6 +501,7 @@ __global__ void k_tr_add(long long n, float* __restrict__ a, const float* __rest
 // ---- Update (cpainn.py:345-376) ---------------------------------------------------------------------------------------------------
 // uvvv [3 N2][2F] = v [U; V]^T : columns [0, F) = U v, [F, 2F) = V v.   q = |V v| over xyz.
 __global__ void k_tr_upd_q(long long NF, int F, const float* __restrict__ uvvv, float* __restrict__ qv) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NF) return;
   const long long n = i / F;
@@ -492,6 +514,7 @@ __global__ void k_tr_upd_q(long long NF, int F, const float* __restrict__ uvvv, 
 __global__ void k_tr_upd_apply(long long NF, int F, const float* __restrict__ uvvv, const float* __restrict__ qv,
                                const float* __restrict__ gac, const float* __restrict__ s, const float* __restrict__ v,
                                float* __restrict__ s_out, float* __restrict__ v_out) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= NF) return;
   const long long n = i / F;
@@ -505,6 +528,7 @@ __global__ void k_tr_upd_apply(long long NF, int F, const float* __restrict__ uv
 __global__ void k_tr_upd_bwd1(long long NF, int F, const float* __restrict__ uvvv, const float* __restrict__ qv,
                               const float* __restrict__ gac, const float* __restrict__ ds, const float* __restrict__ dv,
                               float* __restrict__ d_gac, float* __restrict__ d_uvvv, float* __restrict__ dq, float* amax_gac) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float mx = 0.0f;
   if (i < NF) {
@@ -530,6 +554,7 @@ __global__ void k_tr_upd_bwd1(long long NF, int F, const float* __restrict__ uvv
 // d (V v)[c] = dq (V v)[c] / q   (0 where q = 0, as torch's norm backward)   -> d_uvvv[:, F:2F]; |max| of all of d_uvvv
 __global__ void k_tr_upd_bwd2(long long NF, int F, const float* __restrict__ uvvv, const float* __restrict__ qv,
                               const float* __restrict__ dq, float* __restrict__ d_uvvv, float* amax) {
+  pdl_entry();
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   float mx = 0.0f;
   if (i < NF) {
@@ -562,6 +587,7 @@ struct ReadoutP {
 };
 
 __global__ void k_tr_readout(const ReadoutP p) {
+  pdl_entry();
   extern __shared__ float sacc[];                    // [2][F]: g_W3 row 1, g_Vout
   const int F = p.F, lane = threadIdx.x & 31, wpb = blockDim.x >> 5;
   for (int i = threadIdx.x; i < 2 * F; i += blockDim.x) sacc[i] = 0.0f;
@@ -620,6 +646,7 @@ __global__ void k_tr_readout(const ReadoutP p) {
 
 // ---- optimiser: clip_grad_norm_(params, max_norm) + torch.optim.Adam (train_ambient.py:96,146-148) ------------------------------
 __global__ void k_tr_sqnorm(long long n, const float* __restrict__ g, double* __restrict__ out) {
+  pdl_entry();
   double acc = 0.0;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const double v = g[i];
@@ -632,6 +659,7 @@ __global__ void k_tr_sqnorm(long long n, const float* __restrict__ g, double* __
 __global__ void k_tr_adam(long long n, float* __restrict__ w, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                           const double* __restrict__ sqnorm, float max_norm, float lr, float beta1, float beta2, float eps,
                           float weight_decay, float bc1, float bc2_sqrt) {
+  pdl_entry();
   float coef = 1.0f;
   if (max_norm > 0.0f) {
     const float total = (float)sqrt(*sqnorm);

@@ -11,6 +11,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <utility>
 #include <cstdint>
 #include <vector>
 
@@ -65,6 +66,32 @@ thread_local long long* g_gemm_dbg = nullptr;      // device buffer [64] when ti
     cudaError_t _e = cudaGetLastError();                                                      \
     if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
+// Launches that cannot fill the GPU (at most one CTA per SM) carry programmatic stream serialisation: the kernel may be
+// scheduled - and run its prologue up to griddepcontrol.wait - while the kernel before it on the stream drains (every kernel
+// triggers its dependents at entry).  Inside the captured graph this takes dependent-launch latency off the small nodes of
+// the main chain (12 molecules: 2.17 -> 2.05 ms per step).  Large grids do not get it: their early CTAs would sit on shared
+// memory and TMEM the running kernel's remaining CTAs need (256 molecules with every launch early: 4.75 -> 4.94 ms).
+bool pdl_enabled() { static const bool on = getenv("TIB_TRAIN_NO_PDL") == nullptr; return on; }
+int pdl_max_ctas() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+  }
+  return n;
+}
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  const long long ctas = (long long)grid.x * grid.y * grid.z;
+  attr[0].val.programmaticStreamSerializationAllowed = (pdl_enabled() && ctas <= pdl_max_ctas()) ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...);      // errors surface in LAUNCH_CHECK (cudaGetLastError)
+}
+
 // an element-wise / scatter kernel of the training step: profile scope (kernel class "train_other"; with TIB_TRAIN_TRACE the
 // launch is timed synchronously and printed under the kernel's name) + launch check
 #define TRAIN_LAUNCH(stream, ...)                                                             \
@@ -361,7 +388,7 @@ int gemm(Ctx& c, int M, int N, int K, const GemmOperand& A, const GemmOperand& B
   if (trace) { cudaEventCreate(&e0); cudaEventCreate(&e1); cudaStreamSynchronize(c.st); cudaEventRecord(e0, c.st); }
   {
     Prof pf(TIB_K_TRAIN_GEMM, c.st);
-    k_gemm_tc<<<dim3(nt, mt, splits), kGemmThreads, kGemmSmem, c.st>>>(p);
+    launch_pdl(k_gemm_tc, dim3(nt, mt, splits), kGemmThreads, kGemmSmem, c.st, p);
     LAUNCH_CHECK();
   }
   if (trace) {
@@ -420,9 +447,9 @@ int mlp_forward(Ctx& c, const float* W, const MlpOff& m, int F, const Seg* segs,
       k0 += segs[s].width;
     }
     const int ln_blocks = std::min(blocks_for(R, 4), c.n_sms * 16);
-    TRAIN_LAUNCH(c.st, k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1));
+    TRAIN_LAUNCH(c.st, launch_pdl(k_tr_ln_silu_fwd, ln_blocks, kEW, 0, c.st, R, F, a.n1, a.r1, a.h1, W + m.g1, W + m.be1));
     TRY(gemm(c, R, F, F, op(a.h1, F, 0, 1.0f), op(W + m.W2, F, 0, 1.0f), a.n2, F, GEMM_STORE, W + m.b2, nullptr, false, img_fwd(c, m.i2, 0)));
-    TRAIN_LAUNCH(c.st, k_tr_ln_silu_fwd<<<ln_blocks, kEW, 0, c.st>>>(R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2));
+    TRAIN_LAUNCH(c.st, launch_pdl(k_tr_ln_silu_fwd, ln_blocks, kEW, 0, c.st, R, F, a.n2, a.r2, a.h2, W + m.g2, W + m.be2));
   }
   if (with_out)
     TRY(gemm(c, R, m.n_out, F, op(a.h2, F, 0, 1.0f), op(W + m.W3, F, 0, 1.0f), a.out, m.n_out, GEMM_STORE, W + m.b3, nullptr, false,
@@ -445,7 +472,7 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
   if (dY) {
     TRY(c.to_side());
     TRY(gemm(c, m.n_out, F, R, op(dY, m.n_out, 1, 1.0f, amax_dY), op(a.h2, F, 1, 1.0f), G + m.W3, F, GEMM_ATOMIC, nullptr, nullptr, true));
-    TRAIN_LAUNCH(c.st, k_tr_colsum<<<dim3((m.n_out + kEW - 1) / kEW, std::min(blocks_for(R, 32), 512)), kEW, 0, c.st>>>(R, m.n_out, dY, G + m.b3, nullptr));
+    TRAIN_LAUNCH(c.st, launch_pdl(k_tr_colsum, dim3((m.n_out + kEW - 1) / kEW, std::min(blocks_for(R, 32), 512)), kEW, 0, c.st, R, m.n_out, dY, G + m.b3, nullptr));
     TRY(c.side_done(dY));
     c.to_main();
     TRY(c.before_write(dA));
@@ -453,7 +480,7 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
              img_tr(c, m.i3, 0)));
   }
   float* am2 = c.new_amax();
-  TRAIN_LAUNCH(c.st, ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dA, a.n2, a.r2, W + m.g2, W + m.be2, G + m.g2, G + m.be2, G + m.b2, am2));
+  TRAIN_LAUNCH(c.st, launch_pdl(ln_bwd, ln_blocks, kLnBwdThreads, ln_smem, c.st, R, F, dA, a.n2, a.r2, W + m.g2, W + m.be2, G + m.g2, G + m.be2, G + m.b2, am2));
   TRY(c.to_side());
   TRY(gemm(c, F, F, R, op(dA, F, 1, 1.0f, am2), op(a.h1, F, 1, 1.0f), G + m.W2, F, GEMM_ATOMIC, nullptr, nullptr, true));
   TRY(c.side_done(dA));
@@ -461,7 +488,7 @@ int mlp_backward(Ctx& c, const float* W, float* G, const MlpOff& m, int F, const
   TRY(c.before_write(dB));
   TRY(gemm(c, R, F, F, op(dA, F, 0, 1.0f, am2), op(W + m.W2, F, 1, 1.0f), dB, F, GEMM_STORE, nullptr, nullptr, false, img_tr(c, m.i2, 0)));
   float* am1 = c.new_amax();
-  TRAIN_LAUNCH(c.st, ln_bwd<<<ln_blocks, kLnBwdThreads, ln_smem, c.st>>>(R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1));
+  TRAIN_LAUNCH(c.st, launch_pdl(ln_bwd, ln_blocks, kLnBwdThreads, ln_smem, c.st, R, F, dB, a.n1, a.r1, W + m.g1, W + m.be1, G + m.g1, G + m.be1, G + m.b1, am1));
   TRY(c.to_side());
   int k0 = 0;
   for (int s = 0; s < n_seg; ++s) {
@@ -534,27 +561,27 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   // the weights change with every optimiser step)
   static const bool no_pack = getenv("TIB_TRAIN_NO_PACK") != nullptr;       // diagnostics: build every B operand on the fly
   if (!no_pack && o.pack.n > 0) {
-    TRAIN_LAUNCH(st, k_pack_operand<<<o.pack.total_blocks, kGemmThreads, 0, st>>>(o.pack, W, w.img));
+    TRAIN_LAUNCH(st, launch_pdl(k_pack_operand, o.pack.total_blocks, kGemmThreads, 0, st, o.pack, W, w.img));
     c.img = w.img;
   }
 
   // ---- interpolant, targets, graph (interpolants.py:16-33; losses.py:52-57; graph.py:27-29) -----------------------------------------
-  TRAIN_LAUNCH(st, k_tr_interp<<<std::min(blocks_for(N, kEW), c.n_sms * 4), kEW, 0, st>>>((int)N, b->x0, b->x1, b->t, b->z, ip->gamma_kind, ip->a, w.xt, w.tgt, w.colsum));
-  TRAIN_LAUNCH(st, k_tr_center<<<blocks_for(6 * N, kEW), kEW, 0, st>>>((int)N, w.xt, w.colsum));
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_interp, std::min(blocks_for(N, kEW), c.n_sms * 4), kEW, 0, st, (int)N, b->x0, b->x1, b->t, b->z, ip->gamma_kind, ip->a, w.xt, w.tgt, w.colsum));
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_center, blocks_for(6 * N, kEW), kEW, 0, st, (int)N, w.xt, w.colsum));
   GraphP gp{b->n_mol, (int)N, E, b->mol_ptr, (const long long*)b->edge_ptr, b->edge_type, w.xt, w.src, w.dst, w.pair, w.etype, w.in_ptr,
             w.dir, w.pair_dist};
-  TRAIN_LAUNCH(st, k_tr_graph<<<dim3(b->n_mol, 2), kEW, 0, st>>>(gp));
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_graph, dim3(b->n_mol, 2), kEW, 0, st, gp));
 
   // ---- embeddings (embedding.py:68-86,249-261; cpainn.py:70-71): x-independent, shared by both passes ------------------------------
-  TRAIN_LAUNCH(st, k_tr_embed_in<<<(int)N, kEW, 0, st>>>((int)N, F, n_temp, b->atom_id, b->temp0, b->temp1, b->t, W + o.atom_emb, desc->temp_mean,
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_embed_in, (int)N, kEW, 0, st, (int)N, F, n_temp, b->atom_id, b->temp0, b->temp1, b->t, W + o.atom_emb, desc->temp_mean,
                                         desc->temp_range, desc->temp_length, desc->time_length, w.X0));
   const Seg seg_emb[1] = {{w.X0, (2 + n_temp) * F, nullptr, (2 + n_temp) * F, 1.0f}};
   TRY(mlp_forward(c, W, o.combine, F, seg_emb, 1, w.emb, true));
   LayerAct& A0 = w.layers[0];
-  TRAIN_LAUNCH(st, k_tr_gather_rows<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2, F, nullptr, (int)N, w.s0, A0.s_in));
-  TRAIN_LAUNCH(st, k_tr_gather_rows<<<blocks_for(E2 * F, kEW), kEW, 0, st>>>(E2, F, w.etype, 0, W + o.edge_emb, A0.e_in));
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_gather_rows, blocks_for(N2 * F, kEW), kEW, 0, st, N2, F, nullptr, (int)N, w.s0, A0.s_in));
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_gather_rows, blocks_for(E2 * F, kEW), kEW, 0, st, E2, F, w.etype, 0, W + o.edge_emb, A0.e_in));
   CUDA_TRY(cudaMemsetAsync(A0.v_in, 0, sizeof(float) * N2 * 3 * F, st));
-  TRAIN_LAUNCH(st, k_tr_pair_pe<<<blocks_for(P2 * (F / 2), kEW), kEW, 0, st>>>(P2, F, w.pair_dist, desc->length_scale, w.pe));
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_pair_pe, blocks_for(P2 * (F / 2), kEW), kEW, 0, st, P2, F, w.pair_dist, desc->length_scale, w.pe));
 
   // ---- forward through the layers (cpainn.py:138-150) ----------------------------------------------------------------------------------
   const int node_blocks = (int)std::min<long long>(N2, c.n_sms * 16);
@@ -573,13 +600,13 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     TRY(mlp_forward(c, W, lo.phi, F, seg_phi, 2, a.phi, true));
     TRY(c.join());
     CombineP cp{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next};
-    TRAIN_LAUNCH(st, k_tr_combine_fwd<<<node_blocks, kEW, 0, st>>>(cp));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_combine_fwd, node_blocks, kEW, 0, st, cp));
     TRY(gemm(c, (int)(3 * N2), 2 * F, F, op(a.v_mid, F, 0, kStateScale), op(W + lo.UV, F, 0, 1.0f), a.uvvv, 2 * F, GEMM_STORE, nullptr, nullptr,
              false, img_fwd(c, lo.iuv, 0)));
-    TRAIN_LAUNCH(st, k_tr_upd_q<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_upd_q, blocks_for(N2 * F, kEW), kEW, 0, st, N2 * F, F, a.uvvv, a.q));
     const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
     TRY(mlp_forward(c, W, lo.upd, F, seg_upd, 2, a.upd, true));
-    TRAIN_LAUNCH(st, k_tr_upd_apply<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, a.s_mid, a.v_mid, s_next, v_next));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_upd_apply, blocks_for(N2 * F, kEW), kEW, 0, st, N2 * F, F, a.uvvv, a.q, a.upd.out, a.s_mid, a.v_mid, s_next, v_next));
   }
 
   // ---- readout, loss and d loss / d b (cpainn.py:425-437; losses.py:126-133) -----------------------------------------------------------
@@ -589,7 +616,7 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   float* bout = out_b ? out_b : w.dX0;      // dX0 is free until the very end ([N][F] >= [2N][3] for F >= 32)
   ReadoutP rp{(int)N2, F, (int)N, w.ro.h2, w.v_last, W + o.readout.W3, W + o.readout.b3, W + o.Vout, w.tgt, bout, w.gate, loss,
               w.dA, w.dv, G + o.readout.W3, G + o.readout.b3, G + o.Vout, am_ro};
-  TRAIN_LAUNCH(st, k_tr_readout<<<std::min(blocks_for(N2, 4), c.n_sms * 4), kEW, 2 * F * sizeof(float), st>>>(rp));
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_readout, std::min(blocks_for(N2, 4), c.n_sms * 4), kEW, 2 * F * sizeof(float), st, rp));
 
   // ---- backward ------------------------------------------------------------------------------------------------------------------------------
   {
@@ -606,12 +633,12 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     float* am_gac = c.new_amax();
     TRY(c.before_write(w.d_gac));
     TRY(c.before_write(w.d_uvvv));
-    TRAIN_LAUNCH(st, k_tr_upd_bwd1<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, a.upd.out, w.ds, w.dv, w.d_gac, w.d_uvvv, w.dq, am_gac));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_upd_bwd1, blocks_for(N2 * F, kEW), kEW, 0, st, N2 * F, F, a.uvvv, a.q, a.upd.out, w.ds, w.dv, w.d_gac, w.d_uvvv, w.dq, am_gac));
     const Seg seg_upd[2] = {{a.q, F, nullptr, F, kStateScale}, {a.s_mid, F, nullptr, F, kStateScale}};
     const SegGrad sg_upd[2] = {{w.dq, F, GEMM_ACCUM, nullptr}, {w.ds, F, GEMM_ACCUM, nullptr}};
     TRY(mlp_backward(c, W, G, lo.upd, F, seg_upd, sg_upd, 2, a.upd, w.d_gac, am_gac, w.dA, w.dB));
     float* am_uv = c.new_amax();
-    TRAIN_LAUNCH(st, k_tr_upd_bwd2<<<blocks_for(N2 * F, kEW), kEW, 0, st>>>(N2 * F, F, a.uvvv, a.q, w.dq, w.d_uvvv, am_uv));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_upd_bwd2, blocks_for(N2 * F, kEW), kEW, 0, st, N2 * F, F, a.uvvv, a.q, w.dq, w.d_uvvv, am_uv));
     TRY(c.to_side());
     TRY(gemm(c, 2 * F, F, (int)(3 * N2), op(w.d_uvvv, 2 * F, 1, 1.0f, am_uv), op(a.v_mid, F, 1, kStateScale), G + lo.UV, F, GEMM_ATOMIC,
              nullptr, nullptr, true));
@@ -629,8 +656,8 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     float* e_next = l + 1 < L ? w.layers[l + 1].e_in : w.e_spare;
     CombineBwdP cb{{(int)N2, F, w.in_ptr, w.src, w.pair, w.dir, a.phi.out, a.w.out, a.s_in, a.v_in, a.e_in, a.s_mid, a.v_mid, e_next},
                    w.ds, w.dv, w.de, w.d_phi3, w.d_w3, w.dv_src, am_phi, am_w};
-    TRAIN_LAUNCH(st, k_tr_combine_bwd<<<node_blocks, kEW, 0, st>>>(cb));
-    TRAIN_LAUNCH(st, k_tr_add<<<blocks_for(N2 * 3 * F, kEW), kEW, 0, st>>>(N2 * 3 * F, w.dv, w.dv_src));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_combine_bwd, node_blocks, kEW, 0, st, cb));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_add, blocks_for(N2 * 3 * F, kEW), kEW, 0, st, N2 * 3 * F, w.dv, w.dv_src));
     // the w MLP's adjoint produces weight gradients only: all of it runs on the side stream, with its own scratch
     const Seg seg_w[1] = {{w.pe, F, nullptr, F, 1.0f}};
     TRY(c.to_side());
@@ -644,9 +671,9 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
   // embeddings: e0 = Emb4(edge_type), s0 = combine MLP (both passes share it), atom embedding
   {
     const int nb = std::min(blocks_for(E2, 32), c.n_sms * 8);
-    TRAIN_LAUNCH(st, k_tr_scatter_rows<<<nb, kEW, sizeof(float) * desc->n_edge_types * F, st>>>(E2, F, desc->n_edge_types, w.etype, w.de, G + o.edge_emb));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_scatter_rows, nb, kEW, sizeof(float) * desc->n_edge_types * F, st, E2, F, desc->n_edge_types, w.etype, w.de, G + o.edge_emb));
     float* am_s0 = c.new_amax();
-    TRAIN_LAUNCH(st, k_tr_fold_passes<<<blocks_for(N * F, kEW), kEW, 0, st>>>(N * F, w.ds, w.ds0, am_s0));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_fold_passes, blocks_for(N * F, kEW), kEW, 0, st, N * F, w.ds, w.ds0, am_s0));
     // weight gradients over all input columns; the input gradient only for the first F (the atom embedding) - the
     // positional-encoding columns carry no parameters
     const int kin = (2 + n_temp) * F;
@@ -655,7 +682,7 @@ int tib_train_loss_grad(const tib_model_desc* desc, const float* weights, const 
     TRY(mlp_backward(c, W, G, o.combine, F, seg2, sg2, 2, w.emb, w.ds0, am_s0, w.dA, w.dB));
     TRY(c.before_write(w.dX0));
     const int nb2 = std::min(blocks_for(N, 64), c.n_sms);
-    TRAIN_LAUNCH(st, k_tr_scatter_rows<<<nb2, 1024, sizeof(float) * desc->n_types * F, st>>>(N, F, desc->n_types, b->atom_id, w.dX0, G + o.atom_emb));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_scatter_rows, nb2, 1024, sizeof(float) * desc->n_types * F, st, N, F, desc->n_types, b->atom_id, w.dX0, G + o.atom_emb));
   }
   TRY(c.join());          // the caller's stream owns the complete gradient again
   return 0;
@@ -704,10 +731,10 @@ int tib_adam_step(float* weights, const float* grad, float* m, float* v, size_t 
   CUDA_TRY(cudaDeviceGetAttribute(&n_sms, cudaDevAttrMultiProcessorCount, dev));
   const int nb = (int)std::min<size_t>((n + 255) / 256, (size_t)n_sms * 8);
   if (max_grad_norm > 0.0f) {
-    TRAIN_LAUNCH(st, k_tr_sqnorm<<<nb, 256, 0, st>>>((long long)n, grad, scratch));
+    TRAIN_LAUNCH(st, launch_pdl(k_tr_sqnorm, nb, 256, 0, st, (long long)n, grad, scratch));
   }
   const double bc1 = 1.0 - std::pow((double)beta1, step), bc2 = 1.0 - std::pow((double)beta2, step);
-  TRAIN_LAUNCH(st, k_tr_adam<<<nb, 256, 0, st>>>((long long)n, weights, grad, m, v, scratch, max_grad_norm, lr, beta1, beta2, eps, weight_decay,
+  TRAIN_LAUNCH(st, launch_pdl(k_tr_adam, nb, 256, 0, st, (long long)n, weights, grad, m, v, scratch, max_grad_norm, lr, beta1, beta2, eps, weight_decay,
                                 (float)bc1, (float)std::sqrt(bc2)));
   return 0;
 }

@@ -28,6 +28,7 @@
 #pragma once
 #include "common.cuh"
 #include "tc_common.cuh"
+#include "train.cuh"
 
 namespace tib {
 namespace train {
@@ -176,6 +177,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   volatile int* err = p.err;
   const bool packed_b = p.b_img != nullptr;
+  pdl_trigger();                             // the next kernel of the stream may be scheduled (it waits at its own griddepcontrol.wait)
 
   const int n0 = blockIdx.x * 128, m0 = blockIdx.y * 128;
   const int chunks_total = (p.K + kGemmKC - 1) / kGemmKC;
@@ -191,6 +193,7 @@ __global__ void __launch_bounds__(kGemmThreads, 3) k_gemm_tc(const GemmP p) {
     fence_mbar_init();
   }
   if (warp == 0) tmem_alloc(tmem_slot, 128);
+  pdl_wait();                                // barriers and TMEM are set up under the previous kernel's tail; its results are needed from here
   // the first chunk's operands are requested before the allocation barrier
   const TileRows ra = tile_rows(p.A, m0, p.M, warp, lane);
   const bool two_seg = p.a_split < chunks_total;
@@ -384,6 +387,7 @@ struct PackTable { PackEntry e[kPackMaxEntries]; int n; int total_blocks; };
 
 __global__ void __launch_bounds__(kGemmThreads) k_pack_operand(const PackTable tab, const float* __restrict__ W,
                                                                 unsigned char* __restrict__ img) {
+  pdl_entry();
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int blk = blockIdx.x;
   int ei = 0;
