@@ -295,3 +295,55 @@ def test_cuda_graph_replay_equals_eager_steps():
         assert abs(le - lg) < 1e-5 * max(1.0, abs(le)), (step, le, lg)
     assert float((eager.weights - graph.weights).abs().max()) < 3.5e-4      # Adam: rounding-level gradients move by <= lr per step
     assert float((eager.last_grad - graph.last_grad).abs().max()) < 1e-4 * float(eager.last_grad.abs().max())
+
+
+def test_edge_cases_tiny_molecules_and_loud_errors():
+    """One diatomic molecule (2 atoms, 2 edges, one pair) and a ragged pair of molecules against oracle autograd; wrong
+    arguments fail loudly through the C ABI."""
+    import ctypes as C
+    from oracle import train_oracle as to
+    from thermodynamic_interpolation_b200 import _lib
+    from thermodynamic_interpolation_b200.batch import synthetic_train_batches
+    from thermodynamic_interpolation_b200.synthetic import seeded_ambient_model
+    from thermodynamic_interpolation_b200.train import TrainEngine, flatten, packed_parameters
+    model = seeded_ambient_model(64, 2, seed=41).to(DEV)
+    hp, sd = oracle_hp_sd(model)
+    eng = TrainEngine(model.hyper, DEV)
+    w = flatten(packed_parameters(model))
+    for sizes in ([2], [3, 2]):
+        b0, b1 = synthetic_train_batches(len(sizes), sizes, 9)
+        torch.manual_seed(6)
+        t, z = to.draw_t_z(sizes)
+        loss, grad, _ = eng.loss_and_grad(w, eng.prepare(b0, b1), t, z, gamma="sin2")
+        eng.status()
+        ref_loss, ref_grads, _, _ = to.loss_and_grads(sd, hp, b0.x, b1.x, t, z, b0.atoms, b0.edge_index, b0.edge_type, b0.T, b1.T, gamma="sin2")
+        assert abs(float(loss) - float(ref_loss)) < 5e-5 * max(1.0, abs(float(ref_loss))), sizes
+        for k, gr in _grad_dict(model, grad).items():
+            ref = ref_grads[k]
+            assert float((gr - ref).abs().max()) <= 3e-4 * max(float(ref.abs().max()), 1e-30) + 1e-9, (sizes, k)
+    # loud errors: workspace too small, unknown gamma, latent descriptor
+    lib = _lib.load()
+    b0, b1 = synthetic_train_batches(2, 9, 1)
+    tb = eng.prepare(b0, b1)
+    t, z = to.draw_t_z([9, 9])
+    t, z = t.to(DEV).reshape(-1).contiguous(), z.to(DEV)
+    loss = torch.empty(1, dtype=torch.float64, device=DEV)
+    grad = torch.empty_like(w)
+    ws = torch.empty(4096, dtype=torch.uint8, device=DEV)
+    pb = tb.pb
+    cb = _lib.TrainBatch(n_mol=pb.n_mol, n_nodes=pb.n_nodes, n_edges=pb.n_edges, mol_ptr=pb.mol_ptr.data_ptr(), edge_ptr=pb.edge_ptr.data_ptr(),
+                         atom_id=pb.atom_id.data_ptr(), edge_type=pb.edge_type.data_ptr(), temp0=pb.temp0.data_ptr(), temp1=pb.temp1.data_ptr(),
+                         x0=tb.x0.data_ptr(), x1=tb.x1.data_ptr(), t=t.data_ptr(), z=z.data_ptr())
+
+    def call(desc, ip, ws_bytes):
+        return lib.tib_train_loss_grad(C.byref(desc), w.data_ptr(), C.byref(cb), C.byref(ip), loss.data_ptr(), grad.data_ptr(), None,
+                                       ws.data_ptr(), ws_bytes, None)
+
+    good_ip = _lib.Interpolant(gamma_kind=_lib.GAMMA_SIN2, a=1.0)
+    assert call(eng.desc, good_ip, 4096) != 0 and b"workspace too small" in lib.tib_last_error()
+    assert call(eng.desc, _lib.Interpolant(gamma_kind=7, a=1.0), 4096) != 0 and b"gamma" in lib.tib_last_error()
+    from thermodynamic_interpolation_b200.engine import Hyper, model_desc
+    latent = model_desc(Hyper(n_features=64, score_layers=2, variant="latent"))
+    assert call(latent, good_ip, 4096) != 0 and b"ambient" in lib.tib_last_error()
+    with pytest.raises(RuntimeError, match="ambient"):
+        TrainEngine(Hyper(n_features=64, score_layers=2, variant="latent"), DEV)
