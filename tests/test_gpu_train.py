@@ -347,3 +347,48 @@ def test_edge_cases_tiny_molecules_and_loud_errors():
     assert call(latent, good_ip, 4096) != 0 and b"ambient" in lib.tib_last_error()
     with pytest.raises(RuntimeError, match="ambient"):
         TrainEngine(Hyper(n_features=64, score_layers=2, variant="latent"), DEV)
+
+
+@pytest.mark.parametrize("wd,max_norm", [(0.0, 1.0), (0.01, 0.0), (0.05, 0.5)])
+def test_adam_step_matches_torch_optimizer(wd, max_norm):
+    """tib_adam_step (clip_grad_norm_ + Adam with L2 weight decay, bias corrections) against torch.optim.Adam over 5 steps."""
+    from thermodynamic_interpolation_b200.engine import Hyper
+    from thermodynamic_interpolation_b200.train import TrainEngine
+    eng = TrainEngine(Hyper(n_features=32, score_layers=1), DEV)
+    g = torch.Generator().manual_seed(3)
+    n = 10007
+    w0 = torch.randn(n, generator=g)
+    p = torch.nn.Parameter(w0.clone().to(DEV))
+    opt = torch.optim.Adam([p], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    w, m, v = w0.clone().to(DEV), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    for step in range(1, 6):
+        grad = (torch.randn(n, generator=g) * 10.0 ** float(torch.randint(-3, 2, (1,), generator=g))).to(DEV)
+        p.grad = grad.clone()
+        if max_norm > 0:
+            total = torch.nn.utils.clip_grad_norm_([p], max_norm)
+        opt.step()
+        sq = eng.adam_step(w, grad.clone(), m, v, step, lr=3e-3, weight_decay=wd, max_grad_norm=max_norm)
+        if max_norm > 0:
+            assert abs(float(sq.sqrt()) - float(total)) < 1e-5 * float(total)
+        assert float((w - p.detach()).abs().max()) < 2e-6, step
+    with pytest.raises(RuntimeError):
+        eng.adam_step(w, grad, m, v, 0)
+    with pytest.raises(ValueError):
+        eng.adam_step(w, grad[:-1], m, v, 1)
+
+
+def test_loss_without_grad_mode_returns_the_same_value():
+    from thermodynamic_interpolation_b200.ambient.interpolants import LinearInterpolant
+    from thermodynamic_interpolation_b200.ambient.losses import StandardVelocityLoss
+    g = load_golden("train_f32")
+    model = golden_model(g, DEV)
+    b0, b1 = _fixture_batches(g)
+    loss_fn = StandardVelocityLoss(LinearInterpolant(a=1, gamma="sin2"))
+    t, z = torch.from_numpy(g["t0"]), torch.from_numpy(g["z0"])
+    with torch.no_grad():
+        l0 = loss_fn(b0, b1, model, t=t, z=z)
+    l1 = loss_fn(b0, b1, model, t=t, z=z)
+    assert not l0.requires_grad and l1.requires_grad
+    assert abs(float(l0) - float(g["loss"][0])) < 1e-5 and abs(float(l0) - float(l1)) < 1e-6
+    with pytest.raises(NotImplementedError):
+        StandardVelocityLoss(LinearInterpolant(a=1, gamma="sig_sum"))(b0, b1, model)
