@@ -14,6 +14,13 @@ namespace tib {
 
 constexpr float kPiF = 3.14159265358979323846f;  // np.pi rounded to fp32 (embedding.py:156-157)
 
+// Programmatic dependent launch: a kernel first lets the NEXT kernel of the stream be scheduled (it runs its prologue and
+// parks at its own wait), then - before it first touches data the previous kernels produce - waits until they have completed
+// and their writes are visible.  Only launches that carry cudaLaunchAttributeProgrammaticStreamSerialization start early;
+// for every other launch both instructions are no-ops.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

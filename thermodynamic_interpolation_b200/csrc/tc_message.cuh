@@ -247,6 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + MsgSmem::BARS + 8 * B_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   volatile int* err = p.err;
+  pdl_trigger();        // programmatic dependent launch: the next kernel of the stream may run its prologue now
   constexpr bool diag = DIAG;
 
   if (tid == 0) {
@@ -270,6 +271,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_message_tc(TcMsgP p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  pdl_wait();           // barriers, TMEM and parameters were set up under the previous kernel; its results are needed from here
   const uint32_t tmem = *tmem_slot;
   const int n_splits = p.first_layer ? 3 : 5;
   // First layer with a phi table: s0 and e0 take a handful of distinct values, so phi's hidden layers were evaluated

@@ -80,6 +80,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_readout_tc(TcRoP p) {
   uint32_t* const tmem_slot = reinterpret_cast<uint32_t*>(smem + RoSmem::BARS + 8 * U_COUNT);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   volatile int* err = p.err;
+  pdl_trigger();        // programmatic dependent launch: the next kernel of the stream may run its prologue now
 
   if (tid == 0) {
     for (int i = 0; i < kStages; ++i) { mbar_init(&bars[U_FULL + i], 1); mbar_init(&bars[U_EMPTY + i], 1); }
@@ -95,6 +96,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_readout_tc(TcRoP p) {
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  if (warp != 16) pdl_wait();      // barriers, TMEM and parameters were set up under the previous kernel; the weight producer
+                                   // (warp 16) reads only weights, which no kernel writes, and starts streaming at once
   const uint32_t tmem = *tmem_slot;
 
   if (warp == 16) {

@@ -79,6 +79,23 @@ struct DeviceGuard {
     if (_e != cudaSuccess) return fail("kernel launch failed: %s (%s:%d)", cudaGetErrorString(_e), __FILE__, __LINE__); \
   } while (0)
 
+// ---- programmatic dependent launch of the tensor-core kernels (common.cuh: pdl_trigger / pdl_wait) -------------------------
+// When a launch leaves SMs idle (fewer tiles than SMs: the reference's own batch sizes of 12 and 64 conformers are 7 - 36
+// tiles), the next kernel of the drift is scheduled on them right away, sets up its barriers, allocates its tensor memory,
+// loads its parameters and - update / readout - starts streaming its weights, and parks at griddepcontrol.wait until the
+// kernel before it has finished.  Full grids get no attribute: there is no idle SM to start on.
+template <typename P>
+void launch_tc(void (*kernel)(P), int grid, int block, size_t smem, cudaStream_t st, int n_sms, const P& prm) {
+  static const bool off = getenv("TIB_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(block); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = (!off && grid < n_sms) ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, prm);          // errors surface in LAUNCH_CHECK (cudaGetLastError)
+}
+
 // ---- packed-weight walking ---------------------------------------------------------------------
 struct MlpShape { int k_in, h, n_out; };
 size_t mlp_floats(const MlpShape& s) {
@@ -389,8 +406,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       tp.length_scale = m->d.length_scale; tp.first_layer = (l == 0); tp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3;
       tp.err = m->dev_err; tp.dbg = m->dev_dbg;
       ProfScope ps(TIB_K_MESSAGE, st);
-      if (tp.dbg) tc::k_message_tc<true><<<std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st>>>(tp);
-      else tc::k_message_tc<false><<<std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st>>>(tp);
+      if (tp.dbg) launch_tc(tc::k_message_tc<true>, std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st, m->n_sms, tp);
+      else launch_tc(tc::k_message_tc<false>, std::min(n_tiles, m->n_sms), tc::kThreads, tc::MsgSmem::TOTAL, st, m->n_sms, tp);
       LAUNCH_CHECK();
     } else {
       MessageP mp{db, L.phi, L.w, x, ws.s[cur], ws.v[cur], ws.s[cur ^ 1], ws.v[cur ^ 1], ws.e, m->d.length_scale, l == 0};
@@ -407,8 +424,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
       up.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3; up.err = m->dev_err;
       up.dbg = m->dev_dbg ? m->dev_dbg + 8 * 1024 : nullptr;   // second half of the diagnostics buffer
       ProfScope ps(TIB_K_UPDATE, st);
-      if (up.dbg) tc::k_update_tc<true><<<std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st>>>(up);
-      else tc::k_update_tc<false><<<std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st>>>(up);
+      if (up.dbg) launch_tc(tc::k_update_tc<true>, std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st, m->n_sms, up);
+      else launch_tc(tc::k_update_tc<false>, std::min(up.n_tiles, m->n_sms), tc::kThreads, tc::UpdSmem::TOTAL, st, m->n_sms, up);
       LAUNCH_CHECK();
     } else {
       UpdateP up{b->n_nodes, L.upd, L.Ut, L.Vt, ws.s[cur], ws.v[cur]};
@@ -426,7 +443,7 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     rp.w3 = m->readout.W3t + F; rp.b3 = m->readout.b3 + 1; rp.vout = m->Vout;
     rp.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3; rp.err = m->dev_err;
     ProfScope ps(TIB_K_READOUT, st);
-    tc::k_readout_tc<<<std::min(rp.n_tiles, m->n_sms), tc::kThreads, tc::RoSmem::TOTAL, st>>>(rp);
+    launch_tc(tc::k_readout_tc, std::min(rp.n_tiles, m->n_sms), tc::kThreads, tc::RoSmem::TOTAL, st, m->n_sms, rp);
   } else {
     ReadoutP rp{b->n_nodes, m->readout, m->Vout, ws.s[cur], ws.v[cur], out};
     ProfScope ps(TIB_K_READOUT, st);

@@ -17,10 +17,8 @@ namespace train {
 
 constexpr int kEW = 128;   // threads of the element-wise kernels
 
-// Programmatic dependent launch (every launch of the training step carries the attribute, train_api.cu::launch_pdl): a kernel
-// first lets the NEXT kernel of the stream be scheduled, then waits until everything before it has completed and is visible.
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Programmatic dependent launch (common.cuh; train_api.cu::launch_pdl sets the attribute on the small launches): the
+// element-wise kernels trigger and wait at entry.
 __device__ __forceinline__ void pdl_entry() { pdl_trigger(); pdl_wait(); }
 
 // sigmoid / SiLU with the MUFU approximations (ex2, rcp; ~2 ulp) - the IEEE expf + divide chain made the LayerNorm kernels
