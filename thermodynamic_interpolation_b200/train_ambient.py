@@ -111,3 +111,77 @@ class Trainer:
                 off += n
         self.engine.status()
         return self.model
+
+
+def trainer(config, make_loaders, model=None, device: Optional[str] = None, data_parallel: bool = False, cuda_graph: bool = True,
+            verbose: bool = True) -> dict:
+    """The epoch loop of the reference's `trainer(config)` (mdqm9/train_ambient.py:22-181) around the native step.
+
+    `config` carries the reference's fields (n_features, score_layers, temp_length, a, gamma, t_distr, learning_rate,
+    weight_decay, n_epochs, seed, model_save_path, model_save_name); `make_loaders(epoch) -> (loader0, loader1)` yields the
+    two batch streams the reference rebuilds every epoch (train_ambient.py:100-117; the RDKit / trajectory datasets behind
+    them are out of scope).  Per batch: loss + gradients + clip_grad_norm_(1) + Adam in libtib.so, a non-finite loss skips
+    the update (train_ambient.py:136-142); per epoch: the mean training loss drives ReduceLROnPlateau(factor 0.5, patience 10),
+    a second pass evaluates the final weights, and two state_dicts are written exactly where the reference writes them -
+    `<name>_<epoch>_weights.pt` and `<name>_best<epoch>_weights.pt` (the weights at the batch with the lowest loss of the
+    epoch).  Returns the per-epoch losses."""
+    import os
+
+    import numpy as np
+
+    from .ambient.interpolants import LinearInterpolant
+    from .ambient.models.cpainn import cPaiNN
+
+    out_dir = os.path.join(config.model_save_path, config.model_save_name)
+    os.makedirs(out_dir, exist_ok=True)
+    np.random.seed(config.seed)
+    torch.manual_seed(config.seed)
+    if model is None:
+        model = cPaiNN(n_features=config.n_features, score_layers=config.score_layers, temp_length=config.temp_length)
+    dev = torch.device(device if device is not None else ("cuda" if torch.cuda.is_available() else "cpu"))
+    model.to(dev)
+    tr = Trainer(model, LinearInterpolant(a=config.a, gamma=config.gamma), t_distr=config.t_distr, lr=config.learning_rate,
+                 weight_decay=config.weight_decay, max_grad_norm=1.0, data_parallel=data_parallel, cuda_graph=cuda_graph)
+    # torch's own plateau scheduler on a stand-in optimiser: its learning rate is copied into the native step
+    knob = torch.optim.SGD([torch.zeros(1, requires_grad=True)], lr=config.learning_rate)
+    sched = torch.optim.lr_scheduler.ReduceLROnPlateau(knob, factor=0.5, patience=10)
+    history = dict(train_loss=[], last_model_train_loss=[], epoch_best_loss=[], lr=[])
+    for epoch in range(config.n_epochs):
+        loader0, loader1 = make_loaders(epoch)
+        total, n_batches, best, best_w = 0.0, 0, float("inf"), None
+        for batch0, batch1 in zip(loader0, loader1):
+            before = tr.weights.clone()
+            loss, grad = tr.loss_and_grad(batch0, batch1)
+            value = float(loss)                       # the reference reads loss.item() every batch too
+            if value < best:                          # "epoch best model": the weights that produced the lowest loss
+                best, best_w = value, before
+            if not np.isfinite(value):
+                if verbose:
+                    print("NaN loss")
+                continue
+            tr.apply(grad)
+            total += value
+            n_batches += 1
+        last = 0.0
+        loader0, loader1 = make_loaders(epoch)
+        for batch0, batch1 in zip(loader0, loader1):   # the final weights of the epoch on the training stream
+            last += float(tr.loss_and_grad(batch0, batch1)[0])
+        n_eval = max(n_batches, 1)
+        total, last = total / n_eval, last / n_eval
+        sched.step(total)
+        tr.lr = knob.param_groups[0]["lr"]
+        history["train_loss"].append(total); history["last_model_train_loss"].append(last)
+        history["epoch_best_loss"].append(best); history["lr"].append(tr.lr)
+        if verbose:
+            print(f"Epoch {epoch + 1}/{config.n_epochs} - Train Loss: {total:.4f} - Last Train Loss: {last:.4f} - Epoch Best Loss: {best:.4f}")
+        tr.sync_to_model()
+        if not data_parallel or torch.distributed.get_rank() == 0:
+            torch.save(model.state_dict(), os.path.join(out_dir, f"{config.model_save_name}_{epoch}_weights.pt"))
+            if best_w is not None:
+                final_w = tr.weights
+                tr.weights = best_w
+                tr.sync_to_model()
+                torch.save(model.state_dict(), os.path.join(out_dir, f"{config.model_save_name}_best{epoch}_weights.pt"))
+                tr.weights = final_w
+                tr.sync_to_model()
+    return history
