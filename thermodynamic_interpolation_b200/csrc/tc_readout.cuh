@@ -16,6 +16,7 @@ constexpr int kRoChunks = 8;       // W1 | W2, 4 chunks each
 
 struct TcRoP {
   int n_nodes, n_tiles;
+  int tile_nodes;               // nodes per tile (<= 128), see tc_tile_nodes
   const float* s;               // [N][F]
   const float* v;               // [N][3][F]
   float* out;                   // [N][3]
@@ -140,8 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_readout_tc(TcRoP p) {
     auto acc_ready = [&]() { mbar_wait(&bars[U_ACC], pacc, err); pacc ^= 1; tc_fence_after(); };
     const float4 vo4 = *reinterpret_cast<const float4*>(PRM + 7 * kF + 4 * lane);
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int node0 = tile * 128;
-      const int rows = min(128, p.n_nodes - node0);
+      const int node0 = tile * p.tile_nodes;
+      const int rows = min(p.tile_nodes, p.n_nodes - node0);
       upd_build(X, wq, grp, lane, rows, p.s + (size_t)node0 * kF, kF);
       ops_done();
       // Vout . v[node][xyz], one node per warp iteration, under the first GEMM          (cpainn.py:434-436)

@@ -32,6 +32,7 @@ __constant__ int kUpdOrder[12] = {0, 7, 0, 7, 0, 7, 1, 2, 3, 6, 4, 5};
 
 struct TcUpdP {
   int n_nodes, n_tiles;
+  int tile_nodes;      // nodes per tile (<= 128 TMEM lanes): 128 for full grids, fewer when the batch is small (tc_tile_nodes)
   float* s;                 // [N][F]    in place
   float* v;                 // [N][3][F] in place
   const unsigned char* wblob;   // 8 matrices x 4 chunks
@@ -216,8 +217,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
     auto ops_done = [&]() { fence_proxy_async(); tc_fence_before(); mbar_arrive(&bars[U_OPS]); };
     auto acc_ready = [&]() { mbar_wait(&bars[U_ACC], pacc, err); pacc ^= 1; tc_fence_after(); };
     for (int tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
-      const int node0 = tile * 128;
-      const int rows = min(128, p.n_nodes - node0);
+      const int node0 = tile * p.tile_nodes;
+      const int rows = min(p.tile_nodes, p.n_nodes - node0);
       const float* vbase = p.v + (size_t)node0 * 3 * kF;
       const bool live = row < rows;
       const size_t node = (size_t)(node0 + row);
@@ -226,9 +227,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_update_tc(TcUpdP p) {
       {
         const int nt = tile + gridDim.x;
         if (nt < p.n_tiles) {
-          const int nrows = min(128, p.n_nodes - nt * 128);
-          const char* vb = reinterpret_cast<const char*>(p.v + (size_t)nt * 128 * 3 * kF);
-          const char* sb = reinterpret_cast<const char*>(p.s + (size_t)nt * 128 * kF);
+          const int nrows = min(p.tile_nodes, p.n_nodes - nt * p.tile_nodes);
+          const char* vb = reinterpret_cast<const char*>(p.v + (size_t)nt * p.tile_nodes * 3 * kF);
+          const char* sb = reinterpret_cast<const char*>(p.s + (size_t)nt * p.tile_nodes * kF);
           for (int i = tid; i < nrows * 12; i += kEpiThreads) asm volatile("prefetch.global.L2 [%0];" ::"l"(vb + (size_t)i * 128));
           if (tid < nrows * 4) asm volatile("prefetch.global.L2 [%0];" ::"l"(sb + (size_t)tid * 128));
         }

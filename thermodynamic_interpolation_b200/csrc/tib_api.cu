@@ -96,6 +96,18 @@ void launch_tc(void (*kernel)(P), int grid, int block, size_t smem, cudaStream_t
   cudaLaunchKernelEx(&cfg, kernel, prm);          // errors surface in LAUNCH_CHECK (cudaGetLastError)
 }
 
+// Nodes per tile of the node-row tensor-core kernels (update, readout).  A tile always occupies the 128 TMEM lanes of one
+// SM, but its memory phases (operand builds from v and s, the residual updates) scale with the rows it holds: when the
+// batch cannot fill the GPU with 128-node tiles, smaller tiles on more SMs cut the latency of the launch - 12 conformers
+// (108 nodes) are one 128-row tile on one SM, or seven 16-row tiles on seven.  Full grids keep 128.  The arithmetic of a
+// node does not depend on its tile (row-local GEMM rows and LayerNorms), so results are bit-identical.
+int tc_tile_nodes(int n_nodes, int n_sms) {
+  static const bool off = getenv("TIB_FIXED_NODE_TILES") != nullptr;
+  if (off) return 128;
+  const int per_sm = (n_nodes + n_sms - 1) / n_sms;
+  return std::min(128, std::max(16, (per_sm + 15) / 16 * 16));
+}
+
 // ---- packed-weight walking ---------------------------------------------------------------------
 struct MlpShape { int k_in, h, n_out; };
 size_t mlp_floats(const MlpShape& s) {
@@ -418,7 +430,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
     cur ^= 1;
     if (use_tc) {
       tc::TcUpdP up{};
-      up.n_nodes = b->n_nodes; up.n_tiles = (b->n_nodes + 127) / 128;
+      up.n_nodes = b->n_nodes; up.tile_nodes = tc_tile_nodes(b->n_nodes, m->n_sms);
+      up.n_tiles = (b->n_nodes + up.tile_nodes - 1) / up.tile_nodes;
       up.s = ws.s[cur]; up.v = ws.v[cur]; up.wblob = L.tc_upd;
       up.b1 = L.upd.b1; up.g1 = L.upd.g1; up.be1 = L.upd.be1; up.b2 = L.upd.b2; up.g2 = L.upd.g2; up.be2 = L.upd.be2; up.b3 = L.upd.b3;
       up.passes = (m->math == TIB_MATH_F16_TC) ? 1 : 3; up.err = m->dev_err;
@@ -436,7 +449,8 @@ int drift_simt(tib_model* m, const tib_batch* b, const float* x, float t, float*
   }
   if (use_tc) {
     tc::TcRoP rp{};
-    rp.n_nodes = b->n_nodes; rp.n_tiles = (b->n_nodes + 127) / 128;
+    rp.n_nodes = b->n_nodes; rp.tile_nodes = tc_tile_nodes(b->n_nodes, m->n_sms);
+    rp.n_tiles = (b->n_nodes + rp.tile_nodes - 1) / rp.tile_nodes;
     rp.s = ws.s[cur]; rp.v = ws.v[cur]; rp.out = out; rp.wblob = m->tc_ro;
     rp.b1 = m->readout.b1; rp.g1 = m->readout.g1; rp.be1 = m->readout.be1;
     rp.b2 = m->readout.b2; rp.g2 = m->readout.g2; rp.be2 = m->readout.be2;
